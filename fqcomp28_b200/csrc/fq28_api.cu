@@ -1,0 +1,478 @@
+// fq28_api.cu -- the C ABI of include/fq28.h: handle lifetime, error plumbing,
+// host<->device staging for the host-buffer entry points, stage timers.
+#include <stdarg.h>
+
+#include "fq28_internal.cuh"
+
+namespace fq28 {
+
+int fail(fq28_handle *h, int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (h) h->err = buf;
+  return code;
+}
+
+int cuda_fail(fq28_handle *h, cudaError_t e, const char *what) {
+  return fail(h, FQ28_ERR_CUDA, "CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
+}
+
+int ensure(fq28_handle *h, DevBuf &b, size_t bytes) {
+  if (bytes <= b.cap && b.p) return FQ28_OK;
+  // grow with headroom so that repeated slabs of similar size do not realloc
+  size_t want = bytes + bytes / 8 + 256;
+  want = (want + 255) & ~(size_t)255;
+  if (b.p) {
+    FQ28_CUDA(h, cudaStreamSynchronize(h->stream));
+    FQ28_CUDA(h, cudaFree(b.p));
+    b.p = nullptr;
+    b.cap = 0;
+  }
+  FQ28_CUDA(h, cudaMalloc(&b.p, want));
+  b.cap = want;
+  return FQ28_OK;
+}
+
+static const char *err_name(int code) {
+  switch (code) {
+    case FQ28_ERR_FORMAT: return "malformed FASTQ (4-line structure, '@'/'+' markers, qual length, or record larger than the reading size)";
+    case FQ28_ERR_ALPHABET: return "symbol outside the codec alphabet (bases ACGTN, qualities '!'..'`')";
+    case FQ28_ERR_SHORT: return "read shorter than 3 bases (undefined behaviour in the reference)";
+    case FQ28_ERR_LONG: return "narrow_cast<>() failed: line longer than 65535";
+    case FQ28_ERR_CAP: return "capacity exceeded";
+    case FQ28_ERR_STREAM: return "corrupt stream (not exactly consumed / bad N positions)";
+    default: return "error";
+  }
+}
+
+int check_status(fq28_handle *h, const char *what) {
+  FQ28_CUDA(h, cudaMemcpyAsync(h->h_status, h->d_status, sizeof(DevStatus), cudaMemcpyDeviceToHost, h->stream));
+  FQ28_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (h->h_status->code != 0)
+    return fail(h, h->h_status->code, "%s: %s (at index %u)", what, err_name(h->h_status->code), h->h_status->where);
+  return FQ28_OK;
+}
+
+void stage_reset(fq28_handle *h) { h->ev_used = 0; }
+
+void stage_begin(fq28_handle *h, Stage s) {
+  if (!h->timing) return;
+  if (h->ev_used == h->ev_pool.size()) {
+    fq28_handle::EvRec r;
+    r.stage = s;
+    cudaEventCreate(&r.a);
+    cudaEventCreate(&r.b);
+    h->ev_pool.push_back(r);
+  }
+  h->ev_pool[h->ev_used].stage = s;
+  cudaEventRecord(h->ev_pool[h->ev_used].a, h->stream);
+}
+
+void stage_end(fq28_handle *h, Stage s) {
+  if (!h->timing) return;
+  (void)s;
+  cudaEventRecord(h->ev_pool[h->ev_used].b, h->stream);
+  h->ev_used++;
+}
+
+static void free_buf(DevBuf &b) {
+  if (b.p) cudaFree(b.p);
+  b.p = nullptr;
+  b.cap = 0;
+}
+
+static void free_tables(DevTables &t) {
+  cudaFree(t.counts); cudaFree(t.norm); cudaFree(t.logs); cudaFree(t.max_log); cudaFree(t.toff);
+  cudaFree(t.ctab); cudaFree(t.symtt); cudaFree(t.dtab); cudaFree(t.dtab_fix);
+  t = DevTables();
+}
+
+static int bind(fq28_handle *h) {
+  FQ28_CUDA(h, cudaSetDevice(h->device));
+  return FQ28_OK;
+}
+
+// copies a FreqTable image out of device norm/logs/max_log
+static int ft_image_out(fq28_handle *h, const DevTables &t, void *image) {
+  if (!image) return FQ28_OK;
+  uint8_t *p = static_cast<uint8_t *>(image);
+  const size_t na = (size_t)t.n_models * t.alphabet;
+  FQ28_CUDA(h, cudaMemcpyAsync(p, t.norm, na * 2, cudaMemcpyDeviceToHost, h->stream));
+  FQ28_CUDA(h, cudaMemcpyAsync(p + na * 2, t.logs, (size_t)t.n_models * 4, cudaMemcpyDeviceToHost, h->stream));
+  FQ28_CUDA(h, cudaMemcpyAsync(p + na * 2 + (size_t)t.n_models * 4, t.max_log, 4, cudaMemcpyDeviceToHost, h->stream));
+  return FQ28_OK;
+}
+
+static int ft_image_in(fq28_handle *h, DevTables &t, const void *image) {
+  const uint8_t *p = static_cast<const uint8_t *>(image);
+  const size_t na = (size_t)t.n_models * t.alphabet;
+  // validate logs on the host before any kernel indexes with them
+  const uint32_t *logs = reinterpret_cast<const uint32_t *>(p + na * 2);
+  for (unsigned i = 0; i < t.n_models; i++)
+    if (logs[i] < FSE_MIN_TABLELOG || logs[i] > FIX_LOG) return fail(h, FQ28_ERR_ARG, "FreqTable image: bad table log %u in context %u", logs[i], i);
+  FQ28_CUDA(h, cudaMemcpyAsync(t.norm, p, na * 2, cudaMemcpyHostToDevice, h->stream));
+  FQ28_CUDA(h, cudaMemcpyAsync(t.logs, p + na * 2, (size_t)t.n_models * 4, cudaMemcpyHostToDevice, h->stream));
+  FQ28_CUDA(h, cudaMemcpyAsync(t.max_log, p + na * 2 + (size_t)t.n_models * 4, 4, cudaMemcpyHostToDevice, h->stream));
+  return FQ28_OK;
+}
+
+static int stage_in(fq28_handle *h, const char *fastq, size_t n_bytes) {
+  FQ28_TRY(ensure(h, h->in_fastq, n_bytes + 64));
+  FQ28_CUDA(h, cudaMemcpyAsync(h->in_fastq.p, fastq, n_bytes, cudaMemcpyHostToDevice, h->stream));
+  return FQ28_OK;
+}
+
+}  // namespace fq28
+
+using namespace fq28;
+
+extern "C" {
+
+int fq28_create(int device, fq28_handle **out) {
+  if (!out) return FQ28_ERR_ARG;
+  *out = nullptr;
+  int n_dev = 0;
+  cudaError_t e = cudaGetDeviceCount(&n_dev);
+  if (e != cudaSuccess || n_dev == 0 || device < 0 || device >= n_dev) return FQ28_ERR_CUDA;  // no CPU fallback
+  fq28_handle *h = new fq28_handle();
+  h->device = device;
+  int rc = FQ28_OK;
+  do {
+    if (cudaSetDevice(device) != cudaSuccess) { rc = FQ28_ERR_CUDA; break; }
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { rc = FQ28_ERR_CUDA; break; }
+    h->own_stream = true;
+    if (cudaMalloc(&h->d_status, sizeof(DevStatus)) != cudaSuccess) { rc = FQ28_ERR_CUDA; break; }
+    if (cudaMallocHost(&h->h_status, sizeof(DevStatus)) != cudaSuccess) { rc = FQ28_ERR_CUDA; break; }
+    if (cudaMalloc(&h->d_scalars, 64 * sizeof(uint64_t)) != cudaSuccess) { rc = FQ28_ERR_CUDA; break; }
+    if (cudaMallocHost(&h->h_scalars, 64 * sizeof(uint64_t)) != cudaSuccess) { rc = FQ28_ERR_CUDA; break; }
+    cudaMemset(h->d_status, 0, sizeof(DevStatus));
+    rc = tables_alloc(h, h->seq, SEQ_N, SEQ_A);
+    if (rc) break;
+    rc = tables_alloc(h, h->qual, QUAL_N, QUAL_A);
+  } while (0);
+  if (rc != FQ28_OK) { fq28_destroy(h); return rc; }
+  *out = h;
+  return FQ28_OK;
+}
+
+void fq28_destroy(fq28_handle *h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  DevBuf *bufs[] = {&h->in_fastq, &h->tile_cnt, &h->nl, &h->hdr_off, &h->seq_off, &h->qual_off, &h->len, &h->hdr_len,
+                    &h->symoff, &h->chunk_rec, &h->n_count, &h->npos_off, &h->n_pos, &h->key_seq, &h->key_qual,
+                    &h->perm_seq, &h->perm_qual, &h->ssym_seq, &h->ssym_qual, &h->out_seq, &h->out_qual, &h->tile0_seq,
+                    &h->tile0_qual, &h->tbase_seq, &h->tbase_qual, &h->fstate_seq, &h->fstate_qual, &h->ptile0_seq,
+                    &h->ptile0_qual, &h->pbits_seq, &h->pbits_qual, &h->pscan_seq, &h->pscan_qual, &h->arena_seq,
+                    &h->arena_qual, &h->d_infos, &h->scan_tmp, &h->dec_out, &h->dec_recout, &h->dec_hdrin,
+                    &h->dec_npos_off, &h->dec_meta};
+  for (DevBuf *b : bufs) free_buf(*b);
+  for (DevBuf &b : h->dec_in) free_buf(b);
+  free_tables(h->seq);
+  free_tables(h->qual);
+  if (h->d_status) cudaFree(h->d_status);
+  if (h->h_status) cudaFreeHost(h->h_status);
+  if (h->d_scalars) cudaFree(h->d_scalars);
+  if (h->h_scalars) cudaFreeHost(h->h_scalars);
+  for (auto &r : h->ev_pool) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+const char *fq28_last_error(const fq28_handle *h) { return h ? h->err.c_str() : "null handle"; }
+
+int fq28_set_stream(fq28_handle *h, void *cuda_stream) {
+  if (!h) return FQ28_ERR_ARG;
+  FQ28_TRY(bind(h));
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+  h->stream = static_cast<cudaStream_t>(cuda_stream);
+  h->own_stream = false;
+  return FQ28_OK;
+}
+
+uint64_t fq28_launch_count(const fq28_handle *h) { return h ? h->launches : 0; }
+
+// ---------------------------------------------------------------- parse/split
+int fq28_parse(fq28_handle *h, const char *fastq, size_t n_bytes, uint32_t *hdr_off, uint32_t *seq_off,
+               uint32_t *qual_off, uint16_t *hdr_len, uint16_t *len, size_t cap, size_t *n_records,
+               size_t *consumed) {
+  if (!h) return FQ28_ERR_ARG;
+  FQ28_TRY(bind(h));
+  stage_reset(h);
+  FQ28_TRY(stage_in(h, fastq, n_bytes));
+  stage_begin(h, ST_PARSE);
+  FQ28_TRY(parse_slab(h, h->in_fastq.as<char>(), n_bytes, false));
+  stage_end(h, ST_PARSE);
+  FQ28_TRY(check_status(h, "parseRecords"));
+  const size_t n = h->n_rec;
+  if (n_records) *n_records = n;
+  uint32_t end = 0;
+  FQ28_CUDA(h, cudaMemcpyAsync(&end, h->hdr_off.as<uint32_t>() + n, 4, cudaMemcpyDeviceToHost, h->stream));
+  if ((hdr_off || seq_off || qual_off || hdr_len || len) && n > cap)
+    return fail(h, FQ28_ERR_CAP, "record table needs %zu entries, cap %zu", n, cap);
+  if (hdr_off) FQ28_CUDA(h, cudaMemcpyAsync(hdr_off, h->hdr_off.p, n * 4, cudaMemcpyDeviceToHost, h->stream));
+  if (seq_off) FQ28_CUDA(h, cudaMemcpyAsync(seq_off, h->seq_off.p, n * 4, cudaMemcpyDeviceToHost, h->stream));
+  if (qual_off) FQ28_CUDA(h, cudaMemcpyAsync(qual_off, h->qual_off.p, n * 4, cudaMemcpyDeviceToHost, h->stream));
+  if (hdr_len) FQ28_CUDA(h, cudaMemcpyAsync(hdr_len, h->hdr_len.p, n * 2, cudaMemcpyDeviceToHost, h->stream));
+  if (len) FQ28_CUDA(h, cudaMemcpyAsync(len, h->len.p, n * 2, cudaMemcpyDeviceToHost, h->stream));
+  FQ28_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (consumed) *consumed = end;
+  return FQ28_OK;
+}
+
+int fq28_split(fq28_handle *h, const char *fastq, size_t n_bytes, size_t reading_size, int eof, uint64_t *offs,
+               size_t cap, size_t *n_chunks) {
+  if (!h || !offs || cap < 1) return FQ28_ERR_ARG;
+  FQ28_TRY(bind(h));
+  stage_reset(h);
+  FQ28_TRY(stage_in(h, fastq, n_bytes));
+  stage_begin(h, ST_PARSE);
+  FQ28_TRY(parse_slab(h, h->in_fastq.as<char>(), n_bytes, true));
+  FQ28_TRY(split_slab(h, reading_size, eof != 0, 0));
+  stage_end(h, ST_PARSE);
+  if (h->n_chunks + 1 > cap) return fail(h, FQ28_ERR_CAP, "offs needs %zu entries, cap %zu", h->n_chunks + 1, cap);
+  for (size_t k = 0; k <= h->n_chunks; k++) offs[k] = h->h_chunk_byte[k];
+  if (n_chunks) *n_chunks = h->n_chunks;
+  return FQ28_OK;
+}
+
+// ---------------------------------------------------------------- tables
+int fq28_hist_dev(fq28_handle *h, const char *d_fastq, size_t n_bytes, uint32_t *d_seq_counts,
+                  uint32_t *d_qual_counts) {
+  if (!h || !d_seq_counts || !d_qual_counts) return FQ28_ERR_ARG;
+  FQ28_TRY(bind(h));
+  stage_reset(h);
+  stage_begin(h, ST_PARSE);
+  FQ28_TRY(parse_slab(h, d_fastq, n_bytes, false));
+  stage_end(h, ST_PARSE);
+  stage_begin(h, ST_HIST);
+  FQ28_TRY(hist_slab(h, d_seq_counts, d_qual_counts));
+  stage_end(h, ST_HIST);
+  return check_status(h, "calculateFreqTable");
+}
+
+int fq28_hist(fq28_handle *h, const char *fastq, size_t n_bytes, uint32_t *seq_counts, uint32_t *qual_counts) {
+  if (!h || !seq_counts || !qual_counts) return FQ28_ERR_ARG;
+  FQ28_TRY(bind(h));
+  FQ28_TRY(stage_in(h, fastq, n_bytes));
+  const size_t ns = (size_t)SEQ_N * SEQ_A * 4, nq = (size_t)QUAL_N * QUAL_A * 4;
+  FQ28_CUDA(h, cudaMemcpyAsync(h->seq.counts, seq_counts, ns, cudaMemcpyHostToDevice, h->stream));
+  FQ28_CUDA(h, cudaMemcpyAsync(h->qual.counts, qual_counts, nq, cudaMemcpyHostToDevice, h->stream));
+  FQ28_TRY(fq28_hist_dev(h, h->in_fastq.as<char>(), n_bytes, h->seq.counts, h->qual.counts));
+  FQ28_CUDA(h, cudaMemcpyAsync(seq_counts, h->seq.counts, ns, cudaMemcpyDeviceToHost, h->stream));
+  FQ28_CUDA(h, cudaMemcpyAsync(qual_counts, h->qual.counts, nq, cudaMemcpyDeviceToHost, h->stream));
+  FQ28_CUDA(h, cudaStreamSynchronize(h->stream));
+  return FQ28_OK;
+}
+
+int fq28_build_tables_dev(fq28_handle *h, const uint32_t *d_seq_counts, const uint32_t *d_qual_counts, void *ft_seq_out,
+                          void *ft_qual_out) {
+  if (!h || !d_seq_counts || !d_qual_counts) return FQ28_ERR_ARG;
+  FQ28_TRY(bind(h));
+  stage_reset(h);
+  stage_begin(h, ST_TABLES);
+  FQ28_TRY(tables_from_counts(h, h->seq, d_seq_counts));
+  FQ28_TRY(tables_from_counts(h, h->qual, d_qual_counts));
+  stage_end(h, ST_TABLES);
+  FQ28_TRY(ft_image_out(h, h->seq, ft_seq_out));
+  FQ28_TRY(ft_image_out(h, h->qual, ft_qual_out));
+  FQ28_CUDA(h, cudaStreamSynchronize(h->stream));
+  return FQ28_OK;
+}
+
+int fq28_build_tables(fq28_handle *h, const uint32_t *seq_counts, const uint32_t *qual_counts, void *ft_seq_out,
+                      void *ft_qual_out) {
+  if (!h || !seq_counts || !qual_counts) return FQ28_ERR_ARG;
+  FQ28_TRY(bind(h));
+  FQ28_CUDA(h, cudaMemcpyAsync(h->seq.counts, seq_counts, (size_t)SEQ_N * SEQ_A * 4, cudaMemcpyHostToDevice, h->stream));
+  FQ28_CUDA(h, cudaMemcpyAsync(h->qual.counts, qual_counts, (size_t)QUAL_N * QUAL_A * 4, cudaMemcpyHostToDevice, h->stream));
+  return fq28_build_tables_dev(h, h->seq.counts, h->qual.counts, ft_seq_out, ft_qual_out);
+}
+
+int fq28_load_tables(fq28_handle *h, const void *ft_seq, const void *ft_qual) {
+  if (!h || !ft_seq || !ft_qual) return FQ28_ERR_ARG;
+  FQ28_TRY(bind(h));
+  stage_reset(h);
+  FQ28_TRY(ft_image_in(h, h->seq, ft_seq));
+  FQ28_TRY(ft_image_in(h, h->qual, ft_qual));
+  stage_begin(h, ST_TABLES);
+  FQ28_TRY(tables_from_norm(h, h->seq));
+  FQ28_TRY(tables_from_norm(h, h->qual));
+  stage_end(h, ST_TABLES);
+  FQ28_CUDA(h, cudaStreamSynchronize(h->stream));
+  return FQ28_OK;
+}
+
+// ---------------------------------------------------------------- compress
+size_t fq28_bound_seq(size_t n) {  // src/workspace.h:21-29
+  if (n < 1024) return (size_t)1024 * FQ28_SEQ_MODELS;
+  return n / 4 + 1024;
+}
+size_t fq28_bound_qual(size_t n) {  // src/workspace.h:31-35
+  const size_t a = (size_t)1024 * FQ28_QUAL_MODELS, b = n * 7 / 8 + 1024;
+  return a > b ? a : b;
+}
+
+int fq28_compress_dev(fq28_handle *h, const char *d_fastq, size_t n_bytes, size_t reading_size, int eof,
+                      fq28_chunk_info *infos, size_t infos_cap, fq28_enc_summary *summary) {
+  if (!h || !infos) return FQ28_ERR_ARG;
+  FQ28_TRY(bind(h));
+  stage_reset(h);
+  stage_begin(h, ST_PARSE);
+  FQ28_TRY(parse_slab(h, d_fastq, n_bytes, true));
+  FQ28_TRY(split_slab(h, reading_size, eof != 0, 0));
+  stage_end(h, ST_PARSE);
+  return encode_slab(h, infos, infos_cap, summary);
+}
+
+int fq28_compress_fetch(fq28_handle *h, const fq28_enc_arenas *out) {
+  if (!h || !out) return FQ28_ERR_ARG;
+  if (!h->have_result) return fail(h, FQ28_ERR_ARG, "no compress result to fetch");
+  FQ28_TRY(bind(h));
+  const fq28_enc_summary &s = h->last_summary;
+  if (s.seq_bytes > out->seq_cap || s.qual_bytes > out->qual_cap || s.n_records > out->readlens_cap ||
+      s.n_records > out->n_count_cap || s.n_pos_entries > out->n_pos_cap ||
+      (out->hdr_lens && s.n_records > out->hdr_lens_cap))
+    return fail(h, FQ28_ERR_CAP, "arena too small: need seq %llu qual %llu records %llu n_pos %llu",
+                (unsigned long long)s.seq_bytes, (unsigned long long)s.qual_bytes, (unsigned long long)s.n_records,
+                (unsigned long long)s.n_pos_entries);
+  if (s.n_chunks == 0) return FQ28_OK;
+  FQ28_CUDA(h, cudaMemcpyAsync(out->seq, h->arena_seq.p, s.seq_bytes, cudaMemcpyDeviceToHost, h->stream));
+  FQ28_CUDA(h, cudaMemcpyAsync(out->qual, h->arena_qual.p, s.qual_bytes, cudaMemcpyDeviceToHost, h->stream));
+  FQ28_CUDA(h, cudaMemcpyAsync(out->readlens, h->len.p, s.n_records * 2, cudaMemcpyDeviceToHost, h->stream));
+  FQ28_CUDA(h, cudaMemcpyAsync(out->n_count, h->n_count.p, s.n_records * 2, cudaMemcpyDeviceToHost, h->stream));
+  if (s.n_pos_entries)
+    FQ28_CUDA(h, cudaMemcpyAsync(out->n_pos, h->n_pos.p, s.n_pos_entries * 2, cudaMemcpyDeviceToHost, h->stream));
+  if (out->hdr_lens)
+    FQ28_CUDA(h, cudaMemcpyAsync(out->hdr_lens, h->hdr_len.p, s.n_records * 2, cudaMemcpyDeviceToHost, h->stream));
+  FQ28_CUDA(h, cudaStreamSynchronize(h->stream));
+  return FQ28_OK;
+}
+
+int fq28_compress(fq28_handle *h, const char *fastq, size_t n_bytes, size_t reading_size, int eof,
+                  const fq28_enc_arenas *out, fq28_chunk_info *infos, size_t infos_cap, fq28_enc_summary *summary) {
+  if (!h || !out || !infos) return FQ28_ERR_ARG;
+  FQ28_TRY(bind(h));
+  FQ28_TRY(stage_in(h, fastq, n_bytes));
+  FQ28_TRY(fq28_compress_dev(h, h->in_fastq.as<char>(), n_bytes, reading_size, eof, infos, infos_cap, summary));
+  return fq28_compress_fetch(h, out);
+}
+
+int fq28_compress_dev_arenas(fq28_handle *h, fq28_dec_arenas *v) {
+  if (!h || !v) return FQ28_ERR_ARG;
+  if (!h->have_result) return fail(h, FQ28_ERR_ARG, "no compress result");
+  memset(v, 0, sizeof(*v));
+  v->seq = h->arena_seq.as<uint8_t>(); v->seq_bytes = h->last_summary.seq_bytes;
+  v->qual = h->arena_qual.as<uint8_t>(); v->qual_bytes = h->last_summary.qual_bytes;
+  v->readlens = h->len.as<uint16_t>();
+  v->n_count = h->n_count.as<uint16_t>();
+  v->n_pos = h->n_pos.as<uint16_t>(); v->n_pos_entries = h->last_summary.n_pos_entries;
+  v->hdr_lens = h->hdr_len.as<uint16_t>();
+  v->headers = nullptr; v->headers_bytes = 0;
+  v->n_records = h->last_summary.n_records;
+  return FQ28_OK;
+}
+
+// ---------------------------------------------------------------- decompress
+int fq28_decompress_dev(fq28_handle *h, const fq28_dec_arenas *in, const fq28_chunk_info *infos, size_t n_chunks,
+                        char *d_fastq_out, size_t out_cap, size_t *out_bytes) {
+  if (!h || !in || !infos) return FQ28_ERR_ARG;
+  FQ28_TRY(bind(h));
+  stage_reset(h);
+  return decode_batch(h, in, infos, n_chunks, d_fastq_out, out_cap, out_bytes);
+}
+
+int fq28_decompress(fq28_handle *h, const fq28_dec_arenas *in, const fq28_chunk_info *infos, size_t n_chunks,
+                    char *fastq_out, size_t out_cap, size_t *out_bytes) {
+  if (!h || !in || !infos) return FQ28_ERR_ARG;
+  FQ28_TRY(bind(h));
+  size_t total = 0;
+  for (size_t k = 0; k < n_chunks; k++) total += infos[k].total;
+  if (total > out_cap) return fail(h, FQ28_ERR_CAP, "output needs %zu bytes, cap %zu", total, out_cap);
+  fq28_dec_arenas d = *in;
+  const size_t nr = in->n_records;
+  struct { const void *src; size_t bytes; const void **dst; } cp[] = {
+      {in->seq, in->seq_bytes, (const void **)&d.seq},
+      {in->qual, in->qual_bytes, (const void **)&d.qual},
+      {in->readlens, nr * 2, (const void **)&d.readlens},
+      {in->n_count, nr * 2, (const void **)&d.n_count},
+      {in->n_pos, in->n_pos_entries * 2, (const void **)&d.n_pos},
+      {in->hdr_lens, nr * 2, (const void **)&d.hdr_lens},
+      {in->headers, in->headers_bytes, (const void **)&d.headers},
+  };
+  for (int i = 0; i < 7; i++) {
+    FQ28_TRY(ensure(h, h->dec_in[i], cp[i].bytes + 64));
+    if (cp[i].bytes)
+      FQ28_CUDA(h, cudaMemcpyAsync(h->dec_in[i].p, cp[i].src, cp[i].bytes, cudaMemcpyHostToDevice, h->stream));
+    *cp[i].dst = h->dec_in[i].p;
+  }
+  FQ28_TRY(ensure(h, h->dec_out, total + 64));
+  size_t wrote = 0;
+  FQ28_TRY(fq28_decompress_dev(h, &d, infos, n_chunks, h->dec_out.as<char>(), total, &wrote));
+  FQ28_CUDA(h, cudaMemcpyAsync(fastq_out, h->dec_out.p, wrote, cudaMemcpyDeviceToHost, h->stream));
+  FQ28_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (out_bytes) *out_bytes = wrote;
+  return FQ28_OK;
+}
+
+// ---------------------------------------------------------------- introspection
+int fq28_get_ctable(fq28_handle *h, int kind, unsigned ctx, uint16_t *state_table, int32_t *dfs, uint32_t *dnb,
+                    unsigned *table_log) {
+  if (!h) return FQ28_ERR_ARG;
+  FQ28_TRY(bind(h));
+  DevTables &t = kind == 0 ? h->seq : h->qual;
+  if (!t.ready || ctx >= t.n_models) return fail(h, FQ28_ERR_ARG, "tables not ready / bad context");
+  uint32_t lg = 0, off = 0;
+  FQ28_CUDA(h, cudaMemcpy(&lg, t.logs + ctx, 4, cudaMemcpyDeviceToHost));
+  FQ28_CUDA(h, cudaMemcpy(&off, t.toff + ctx, 4, cudaMemcpyDeviceToHost));
+  if (table_log) *table_log = lg;
+  if (state_table) FQ28_CUDA(h, cudaMemcpy(state_table, t.ctab + off, (size_t)(1u << lg) * 2, cudaMemcpyDeviceToHost));
+  if (dfs || dnb) {
+    std::vector<int2> tt(t.alphabet);
+    FQ28_CUDA(h, cudaMemcpy(tt.data(), t.symtt + (size_t)ctx * t.alphabet, t.alphabet * sizeof(int2), cudaMemcpyDeviceToHost));
+    for (unsigned s = 0; s < t.alphabet; s++) {
+      if (dfs) dfs[s] = tt[s].x;
+      if (dnb) dnb[s] = (uint32_t)tt[s].y;
+    }
+  }
+  return FQ28_OK;
+}
+
+int fq28_get_dtable(fq28_handle *h, int kind, unsigned ctx, uint32_t *cells, unsigned *table_log) {
+  if (!h) return FQ28_ERR_ARG;
+  FQ28_TRY(bind(h));
+  DevTables &t = kind == 0 ? h->seq : h->qual;
+  if (!t.ready || ctx >= t.n_models) return fail(h, FQ28_ERR_ARG, "tables not ready / bad context");
+  uint32_t lg = 0, off = 0;
+  FQ28_CUDA(h, cudaMemcpy(&lg, t.logs + ctx, 4, cudaMemcpyDeviceToHost));
+  FQ28_CUDA(h, cudaMemcpy(&off, t.toff + ctx, 4, cudaMemcpyDeviceToHost));
+  if (table_log) *table_log = lg;
+  if (cells) FQ28_CUDA(h, cudaMemcpy(cells, t.dtab + off, (size_t)(1u << lg) * 4, cudaMemcpyDeviceToHost));
+  return FQ28_OK;
+}
+
+static const char *const k_stage_names[ST_COUNT] = {"parse", "extract", "partition", "chain", "pack",
+                                                    "layout", "decode", "ninsert", "hist", "tables"};
+const char *fq28_stage_name(size_t i) { return i < ST_COUNT ? k_stage_names[i] : ""; }
+
+int fq28_last_timings(const fq28_handle *hc, float *ms, size_t cap, size_t *n) {
+  fq28_handle *h = const_cast<fq28_handle *>(hc);
+  if (!h || !ms) return FQ28_ERR_ARG;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  for (int s = 0; s < ST_COUNT; s++) h->stage_ms[s] = 0.f;
+  for (size_t i = 0; i < h->ev_used; i++) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, h->ev_pool[i].a, h->ev_pool[i].b) == cudaSuccess) h->stage_ms[h->ev_pool[i].stage] += t;
+  }
+  const size_t m = cap < (size_t)ST_COUNT ? cap : (size_t)ST_COUNT;
+  for (size_t i = 0; i < m; i++) ms[i] = h->stage_ms[i];
+  if (n) *n = m;
+  return FQ28_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,673 @@
+// fq28_encode.cu -- K2 (field separation) and K5 (tANS encode) for every chunk
+// of a slab at once.  Replaces CompressionWorkspace::encodeChunk
+// (src/workspace.cpp:14-45), replaceAndEncodeNs + SequenceEncoder::encodeRecord
+// (src/fse_sequence.cpp:35-112), QualityEncoder::encodeRecord
+// (src/fse_quality.cpp:5-53) and FSE_Encoder::startChunk/endChunk
+// (src/fse_common.hpp:77-90).
+//
+// A chunk stream is the LSB-first concatenation of one bit field per symbol in
+// ENCODE ORDER (records forward, positions backward, src/workspace.cpp:25-31 +
+// src/fse_sequence.cpp:83), followed by the final state of every context
+// 0..N-1 and a 1 end-mark bit.  The state of context
+// c only evolves over the symbols coded in c, so the work splits into
+//   extract   : key[g] = (ctx, sym) for every symbol, g = encode-order index
+//   partition : per tile, stable counting sort of the symbols by context
+//   chain     : one thread per (chunk, context) walks its symbols in order
+//               through the context's CTable held in shared memory and emits
+//               (nbBits, bits) per symbol
+//   pack      : gather the fields back into encode order, prefix-sum nbBits,
+//               OR the fields into the output words
+#include "fq28_internal.cuh"
+
+namespace fq28 {
+
+// ---------------------------------------------------------------------------
+// small helpers
+// ---------------------------------------------------------------------------
+// largest k with arr[k] <= v, arr ascending with arr[0] <= v < arr[n]
+__device__ __forceinline__ unsigned find_chunk(const uint32_t *__restrict__ arr, unsigned n, unsigned v) {
+  unsigned lo = 0, hi = n;
+  while (hi - lo > 1) {
+    const unsigned mid = (lo + hi) >> 1;
+    if (arr[mid] <= v) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+// ---------------------------------------------------------------------------
+// K2: extract.  One warp per record.
+//   key_seq[g]  = ctx(8) << 2 | sym(2)      (N coded as A, src/fse_sequence.cpp:45)
+//   key_qual[g] = ctx(13) << 6 | sym(6)
+//   n_count[r]  = number of N in the read    (src/fse_sequence.cpp:36-50)
+// g = symoff[r] + (L-1-i): symbols of a record are coded last-to-first.
+// ---------------------------------------------------------------------------
+constexpr int EX_WARPS = 8;
+
+__global__ void __launch_bounds__(EX_WARPS * 32)
+k_extract(const char *__restrict__ d, const uint32_t *__restrict__ seq_off, const uint32_t *__restrict__ qual_off,
+          const uint16_t *__restrict__ len, const uint32_t *__restrict__ symoff, size_t n_rec,
+          uint16_t *__restrict__ key_seq, uint32_t *__restrict__ key_qual, uint16_t *__restrict__ n_count,
+          DevStatus *st) {
+  const unsigned lane = threadIdx.x & 31;
+  const size_t r = (size_t)blockIdx.x * EX_WARPS + (threadIdx.x >> 5);
+  if (r >= n_rec) return;
+  const unsigned L = len[r];
+  const unsigned char *sp = reinterpret_cast<const unsigned char *>(d) + seq_off[r];
+  const unsigned char *qp = reinterpret_cast<const unsigned char *>(d) + qual_off[r];
+  const uint32_t g_last = symoff[r] + L - 1;  // g of position 0
+  if (L < 3) {  // src/fse_quality.cpp:42-52 mis-codes L < 3
+    if (lane == 0) { set_error(st, FQ28_ERR_SHORT, (unsigned)r); n_count[r] = 0; }
+    return;
+  }
+  unsigned n_cnt = 0;
+  bool bad = false;
+  for (unsigned base = 0; base < L; base += 32) {
+    const unsigned i = base + lane;
+    bool is_n = false;
+    if (i < L) {
+      // ---- sequence: ctx = b[i-1]<<6 | b[i-2]<<4 | b[i-3]<<2 | b[i-4] over
+      // the virtual prefix b[-1..-4] = T,C,C,T (0xD7)
+      unsigned ctx = 0;
+#pragma unroll
+      for (unsigned k = 1; k <= 4; k++) {
+        unsigned b;
+        if (i >= k) {
+          const unsigned char c = sp[i - k];
+          const int v = (c == 'N') ? 0 : base2bits(c);
+          b = (unsigned)(v & 3);
+        } else {
+          b = (SEQ_INITIAL_CTX >> (2 * (4 - (k - i)))) & 3u;
+        }
+        ctx |= b << (2 * (4 - k));
+      }
+      const unsigned char c = sp[i];
+      is_n = (c == 'N');
+      const int sv = is_n ? 0 : base2bits(c);
+      if (sv < 0) bad = true;
+      key_seq[g_last - i] = (uint16_t)((ctx << 2) | (unsigned)(sv & 3));
+      // ---- quality: ctx = calcContext(q[i-1], q[i-2], q[i-3]), q[<0] = 0
+      const unsigned q = (unsigned)qp[i] - QUAL_OFFSET;
+      const unsigned q0 = i >= 1 ? ((unsigned)qp[i - 1] - QUAL_OFFSET) & 63u : 0u;
+      const unsigned q1 = i >= 2 ? ((unsigned)qp[i - 2] - QUAL_OFFSET) & 63u : 0u;
+      const unsigned q2 = i >= 3 ? ((unsigned)qp[i - 3] - QUAL_OFFSET) & 63u : 0u;
+      if (q > 63u) bad = true;
+      key_qual[g_last - i] = (qual_ctx(q0, q1, q2) << 6) | (q & 63u);
+    }
+    n_cnt += __popc(__ballot_sync(0xffffffffu, is_n));
+  }
+  if (__any_sync(0xffffffffu, bad) && lane == 0) set_error(st, FQ28_ERR_ALPHABET, (unsigned)r);
+  if (lane == 0) n_count[r] = (uint16_t)n_cnt;
+}
+
+// n_pos deltas: delta = i - prev_n_pos, prev_n_pos starts at 0
+// (src/fse_sequence.cpp:38-48).  One warp per record, skipped when N-free.
+__global__ void __launch_bounds__(EX_WARPS * 32)
+k_npos(const char *__restrict__ d, const uint32_t *__restrict__ seq_off, const uint16_t *__restrict__ len,
+       const uint16_t *__restrict__ n_count, const uint32_t *__restrict__ npos_off, size_t n_rec,
+       uint16_t *__restrict__ n_pos) {
+  const unsigned lane = threadIdx.x & 31;
+  const size_t r = (size_t)blockIdx.x * EX_WARPS + (threadIdx.x >> 5);
+  if (r >= n_rec) return;
+  if (n_count[r] == 0) return;
+  const unsigned L = len[r];
+  const unsigned char *sp = reinterpret_cast<const unsigned char *>(d) + seq_off[r];
+  uint32_t o = npos_off[r];
+  unsigned prev = 0;
+  for (unsigned base = 0; base < L; base += 32) {
+    const unsigned i = base + lane;
+    const bool is_n = i < L && sp[i] == 'N';
+    const unsigned m = __ballot_sync(0xffffffffu, is_n);
+    if (is_n) {
+      const unsigned below = m & ((1u << lane) - 1u);
+      const unsigned p = below ? base + (31u - (unsigned)__clz(below)) : prev;
+      n_pos[o + __popc(below)] = (uint16_t)(i - p);
+    }
+    if (m) {
+      prev = base + (31u - (unsigned)__clz(m));
+      o += __popc(m);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// partition
+// ---------------------------------------------------------------------------
+template <typename KEY, unsigned N, unsigned SHIFT>
+struct Kind {
+  using key_t = KEY;
+  static constexpr unsigned n_models = N;
+  static constexpr unsigned shift = SHIFT;       // key >> shift = ctx
+  static constexpr unsigned sym_mask = (1u << SHIFT) - 1u;
+};
+using SeqKind = Kind<uint16_t, SEQ_N, 2>;
+using QualKind = Kind<uint32_t, QUAL_N, 6>;
+
+// tile t -> (chunk, first symbol g0, symbol count)
+struct TileRef { unsigned chunk, g0, cnt; };
+__device__ __forceinline__ TileRef tile_ref(unsigned t, const uint32_t *__restrict__ tile0,
+                                           const uint32_t *__restrict__ chunk_sym, unsigned n_chunks,
+                                           unsigned tile_syms) {
+  TileRef tr;
+  tr.chunk = find_chunk(tile0, n_chunks, t);
+  tr.g0 = chunk_sym[tr.chunk] + (t - tile0[tr.chunk]) * tile_syms;
+  const unsigned end = chunk_sym[tr.chunk + 1];
+  tr.cnt = end - tr.g0 < tile_syms ? end - tr.g0 : tile_syms;
+  return tr;
+}
+
+// Per tile: context histogram, then exclusive scan over contexts:
+// tbase[t][c] = rank of the first symbol of context c inside the tile's
+// partitioned order, tbase[t][N] = tile symbol count.
+template <class K, unsigned TILE>
+__global__ void __launch_bounds__(256)
+k_tile_hist(const typename K::key_t *__restrict__ key, const uint32_t *__restrict__ tile0,
+            const uint32_t *__restrict__ chunk_sym, unsigned n_chunks, uint32_t *__restrict__ tbase) {
+  constexpr unsigned N = K::n_models;
+  __shared__ uint32_t hist[N];
+  __shared__ uint32_t wsum[9];
+  const TileRef tr = tile_ref(blockIdx.x, tile0, chunk_sym, n_chunks, TILE);
+  for (unsigned i = threadIdx.x; i < N; i += 256) hist[i] = 0;
+  __syncthreads();
+  const unsigned lane = threadIdx.x & 31;
+  for (unsigned j = threadIdx.x; j < ((tr.cnt + 255u) & ~255u); j += 256) {
+    unsigned ctx = 0xFFFFFFFFu;
+    if (j < tr.cnt) ctx = (unsigned)key[tr.g0 + j] >> K::shift;
+    const unsigned peers = __match_any_sync(0xffffffffu, ctx);
+    if (ctx != 0xFFFFFFFFu && lane == (unsigned)(__ffs(peers) - 1)) atomicAdd(&hist[ctx], (unsigned)__popc(peers));
+  }
+  __syncthreads();
+  // exclusive scan of hist[N]; thread i owns N/256 consecutive entries
+  constexpr unsigned PER = N / 256;
+  unsigned local[PER];
+  unsigned s = 0;
+#pragma unroll
+  for (unsigned i = 0; i < PER; i++) { local[i] = hist[threadIdx.x * PER + i]; s += local[i]; }
+  unsigned inc = s;
+#pragma unroll
+  for (int dd = 1; dd < 32; dd <<= 1) {
+    unsigned o = __shfl_up_sync(0xffffffffu, inc, dd);
+    if (lane >= (unsigned)dd) inc += o;
+  }
+  if (lane == 31) wsum[threadIdx.x >> 5] = inc;
+  __syncthreads();
+  unsigned woff = 0;
+#pragma unroll
+  for (unsigned i = 0; i < 8; i++) woff += (i < (threadIdx.x >> 5)) ? wsum[i] : 0u;
+  unsigned ex = woff + inc - s;
+  uint32_t *out = tbase + (size_t)blockIdx.x * (N + 1);
+#pragma unroll
+  for (unsigned i = 0; i < PER; i++) { out[threadIdx.x * PER + i] = ex; ex += local[i]; }
+  if (threadIdx.x == 255) out[N] = ex;
+}
+
+// Stable rank: one warp per tile walks the tile in encode order, 32 symbols a
+// step; run[c] is the next free slot of context c.  Emits
+//   ssym[g0 + slot] = symbol            (partitioned symbols, chain input)
+//   perm[g]         = g0 + slot         (where the symbol's field will be)
+template <class K, unsigned TILE, unsigned WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+k_tile_rank(const typename K::key_t *__restrict__ key, const uint32_t *__restrict__ tile0,
+            const uint32_t *__restrict__ chunk_sym, unsigned n_chunks, unsigned n_tiles,
+            const uint32_t *__restrict__ tbase, uint8_t *__restrict__ ssym, uint32_t *__restrict__ perm) {
+  constexpr unsigned N = K::n_models;
+  __shared__ uint32_t run_s[WARPS][N];
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned t = blockIdx.x * WARPS + warp;
+  if (t >= n_tiles) return;
+  uint32_t *run = run_s[warp];
+  const TileRef tr = tile_ref(t, tile0, chunk_sym, n_chunks, TILE);
+  const uint32_t *tb = tbase + (size_t)t * (N + 1);
+  for (unsigned i = lane; i < N; i += 32) run[i] = tb[i];
+  __syncwarp();
+  const typename K::key_t *kp = key + tr.g0;
+  unsigned nxt = lane < tr.cnt ? (unsigned)kp[lane] : 0u;
+  for (unsigned j = 0; j < tr.cnt; j += 32) {
+    const unsigned kv = nxt;
+    const unsigned jn = j + 32 + lane;
+    nxt = jn < tr.cnt ? (unsigned)kp[jn] : 0u;
+    const bool live = j + lane < tr.cnt;
+    const unsigned ctx = live ? kv >> K::shift : 0xFFFFFFFFu;
+    const unsigned peers = __match_any_sync(0xffffffffu, ctx);
+    unsigned slot = 0;
+    if (live) slot = run[ctx];
+    __syncwarp();
+    const unsigned below = peers & ((1u << lane) - 1u);
+    if (live && below == 0) run[ctx] = slot + (unsigned)__popc(peers);
+    __syncwarp();
+    if (live) {
+      const unsigned dst = tr.g0 + slot + (unsigned)__popc(below);
+      ssym[dst] = (uint8_t)(kv & K::sym_mask);
+      perm[tr.g0 + j + lane] = dst;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// chain: FSE_encodeSymbol (Appendix A.5) along the symbols of one context.
+// CTA = one warp = one context x 32 consecutive chunks; the context's CTable
+// (next-state cells + symbol transforms) sits in shared memory, so all 32
+// lanes walk the same table and chain lengths within a warp are similar.
+// field[slot] = nbBits << 12 | low bits.
+// ---------------------------------------------------------------------------
+template <class K, unsigned A, unsigned TILE>
+__global__ void __launch_bounds__(32)
+k_chain(const uint8_t *__restrict__ ssym, const uint32_t *__restrict__ tile0, const uint32_t *__restrict__ chunk_sym,
+        unsigned n_chunks, const uint32_t *__restrict__ tbase, const uint32_t *__restrict__ logs,
+        const uint32_t *__restrict__ toff, const uint16_t *__restrict__ ctab, const int2 *__restrict__ symtt,
+        uint16_t *__restrict__ field, uint16_t *__restrict__ fstate) {
+  constexpr unsigned N = K::n_models;
+  __shared__ uint16_t st[1u << FSE_MAX_TABLELOG];
+  __shared__ int2 tt[A];
+  const unsigned c = blockIdx.x, lane = threadIdx.x;
+  const unsigned k = blockIdx.y * 32 + lane;
+  const bool live = k < n_chunks;
+  const unsigned t_log = logs[c], T = 1u << t_log;
+  unsigned t_begin = 0, t_end = 0, sym0 = 0;
+  if (live) { t_begin = tile0[k]; t_end = tile0[k + 1]; sym0 = chunk_sym[k]; }
+  unsigned total = 0;
+  for (unsigned t = t_begin; t < t_end; t++) {
+    const uint32_t *tb = tbase + (size_t)t * (N + 1) + c;
+    total += tb[1] - tb[0];
+  }
+  unsigned x = T;  // FSE_initCState, src/fse_common.hpp:82
+  if (__any_sync(0xffffffffu, total != 0)) {
+    const uint16_t *gs = ctab + toff[c];
+    for (unsigned i = lane; i < T; i += 32) st[i] = gs[i];
+    for (unsigned i = lane; i < A; i += 32) tt[i] = symtt[(size_t)c * A + i];
+    __syncwarp();
+    for (unsigned t = t_begin; t < t_end; t++) {
+      const uint32_t *tb = tbase + (size_t)t * (N + 1) + c;
+      const unsigned b0 = tb[0], n = tb[1] - b0;
+      const unsigned base = sym0 + (t - t_begin) * TILE + b0;
+      const uint8_t *sp = ssym + base;
+      uint16_t *fp = field + base;
+      unsigned j = 0;
+      for (; j + 4 <= n; j += 4) {
+        const unsigned s0 = sp[j], s1 = sp[j + 1], s2 = sp[j + 2], s3 = sp[j + 3];
+        const int2 a0 = tt[s0], a1 = tt[s1], a2 = tt[s2], a3 = tt[s3];
+        unsigned nb;
+        nb = (x + (unsigned)a0.y) >> 16; fp[j] = (uint16_t)((nb << 12) | (x & ((1u << nb) - 1u)));
+        x = st[(int)(x >> nb) + a0.x];
+        nb = (x + (unsigned)a1.y) >> 16; fp[j + 1] = (uint16_t)((nb << 12) | (x & ((1u << nb) - 1u)));
+        x = st[(int)(x >> nb) + a1.x];
+        nb = (x + (unsigned)a2.y) >> 16; fp[j + 2] = (uint16_t)((nb << 12) | (x & ((1u << nb) - 1u)));
+        x = st[(int)(x >> nb) + a2.x];
+        nb = (x + (unsigned)a3.y) >> 16; fp[j + 3] = (uint16_t)((nb << 12) | (x & ((1u << nb) - 1u)));
+        x = st[(int)(x >> nb) + a3.x];
+      }
+      for (; j < n; j++) {
+        const int2 a = tt[sp[j]];
+        const unsigned nb = (x + (unsigned)a.y) >> 16;
+        fp[j] = (uint16_t)((nb << 12) | (x & ((1u << nb) - 1u)));
+        x = st[(int)(x >> nb) + a.x];
+      }
+    }
+  }
+  if (live) fstate[(size_t)k * N + c] = (uint16_t)x;
+}
+
+// ---------------------------------------------------------------------------
+// pack
+// ---------------------------------------------------------------------------
+// Entry e of chunk k's stream: e < n_sym -> the symbol's field; then N state
+// flushes for ctx 0..N-1 (FSE_flushCState: low `log` bits of the state,
+// src/fse_common.hpp:87-88); then the end mark (BIT_closeCStream).
+template <unsigned N>
+__device__ __forceinline__ unsigned entry_value(unsigned e, unsigned n_sym, unsigned sym0, unsigned k,
+                                               const uint32_t *__restrict__ perm, const uint16_t *__restrict__ field,
+                                               const uint32_t *__restrict__ logs, const uint16_t *__restrict__ fstate) {
+  if (e < n_sym) return field[perm[sym0 + e]];
+  const unsigned c = e - n_sym;
+  if (c < N) {
+    const unsigned lg = logs[c];
+    return (lg << 12) | ((unsigned)fstate[(size_t)k * N + c] & ((1u << lg) - 1u));
+  }
+  if (c == N) return (1u << 12) | 1u;
+  return 0;
+}
+
+template <unsigned N>
+__global__ void __launch_bounds__(PACK_THREADS)
+k_pack_count(const uint32_t *__restrict__ ptile0, const uint32_t *__restrict__ chunk_sym, unsigned n_chunks,
+             const uint32_t *__restrict__ perm, const uint16_t *__restrict__ field, const uint32_t *__restrict__ logs,
+             const uint16_t *__restrict__ fstate, uint32_t *__restrict__ pbits) {
+  __shared__ unsigned wsum[PACK_THREADS / 32];
+  const unsigned k = find_chunk(ptile0, n_chunks, blockIdx.x);
+  const unsigned sym0 = chunk_sym[k], n_sym = chunk_sym[k + 1] - sym0;
+  const unsigned e0 = (blockIdx.x - ptile0[k]) * PACK_TILE + threadIdx.x * PACK_EPT;
+  unsigned bits = 0;
+#pragma unroll
+  for (unsigned i = 0; i < PACK_EPT; i++)
+    bits += entry_value<N>(e0 + i, n_sym, sym0, k, perm, field, logs, fstate) >> 12;
+  bits = __reduce_add_sync(0xffffffffu, bits);
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = bits;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned t = 0;
+#pragma unroll
+    for (unsigned i = 0; i < PACK_THREADS / 32; i++) t += wsum[i];
+    pbits[blockIdx.x] = t;
+  }
+}
+
+// Per chunk: stream sizes from the bit prefix sums, 16-byte aligned arena
+// offsets, and the rest of fq28_chunk_info.  Single CTA; chunks are few.
+__global__ void __launch_bounds__(1024)
+k_chunk_finish(unsigned n_chunks, const uint32_t *__restrict__ chunk_rec, const uint32_t *__restrict__ chunk_sym,
+               const uint32_t *__restrict__ chunk_byte, const uint32_t *__restrict__ npos_off,
+               const uint32_t *__restrict__ ptile0_seq, const unsigned long long *__restrict__ pscan_seq,
+               const uint32_t *__restrict__ ptile0_qual, const unsigned long long *__restrict__ pscan_qual,
+               fq28_chunk_info *__restrict__ infos, uint64_t *__restrict__ scalars) {
+  __shared__ unsigned long long carry[2];
+  __shared__ unsigned long long wsum[2][33];
+  if (threadIdx.x == 0) carry[0] = carry[1] = 0;
+  __syncthreads();
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (unsigned base = 0; base < n_chunks; base += blockDim.x) {
+    const unsigned k = base + threadIdx.x;
+    unsigned long long len[2] = {0, 0}, al[2] = {0, 0}, inc[2];
+    if (k < n_chunks) {
+      const unsigned long long bs = pscan_seq[ptile0_seq[k + 1]] - pscan_seq[ptile0_seq[k]];
+      const unsigned long long bq = pscan_qual[ptile0_qual[k + 1]] - pscan_qual[ptile0_qual[k]];
+      len[0] = (bs + 7) >> 3;
+      len[1] = (bq + 7) >> 3;
+      al[0] = (len[0] + 15) & ~15ULL;
+      al[1] = (len[1] + 15) & ~15ULL;
+    }
+#pragma unroll
+    for (int w = 0; w < 2; w++) {
+      unsigned long long v = al[w];
+#pragma unroll
+      for (int dd = 1; dd < 32; dd <<= 1) {
+        unsigned long long o = __shfl_up_sync(0xffffffffu, v, dd);
+        if (lane >= (unsigned)dd) v += o;
+      }
+      inc[w] = v;
+      if (lane == 31) wsum[w][warp] = v;
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+      for (int w = 0; w < 2; w++) {
+        unsigned long long x = wsum[w][lane], v = x;
+#pragma unroll
+        for (int dd = 1; dd < 32; dd <<= 1) {
+          unsigned long long o = __shfl_up_sync(0xffffffffu, v, dd);
+          if (lane >= (unsigned)dd) v += o;
+        }
+        wsum[w][lane] = v - x;
+        if (lane == 31) wsum[w][32] = v;
+      }
+    }
+    __syncthreads();
+    if (k < n_chunks) {
+      fq28_chunk_info ci;
+      ci.fastq_off = chunk_byte[k];
+      ci.total = chunk_byte[k + 1] - chunk_byte[k];
+      ci.n_records = chunk_rec[k + 1] - chunk_rec[k];
+      ci.rec_off = chunk_rec[k];
+      ci.seq_off = carry[0] + wsum[0][warp] + inc[0] - al[0];
+      ci.qual_off = carry[1] + wsum[1][warp] + inc[1] - al[1];
+      ci.seq_len = (uint32_t)len[0];
+      ci.qual_len = (uint32_t)len[1];
+      ci.n_pos_off = npos_off[chunk_rec[k]];
+      ci.n_pos_len = npos_off[chunk_rec[k + 1]] - npos_off[chunk_rec[k]];
+      ci.reserved = 0;
+      infos[k] = ci;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { carry[0] += wsum[0][32]; carry[1] += wsum[1][32]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { scalars[0] = carry[0]; scalars[1] = carry[1]; }
+}
+
+__global__ void k_zero_words(uint32_t *__restrict__ p, const uint64_t *__restrict__ n_bytes_ptr) {
+  const size_t n = (size_t)((*n_bytes_ptr + 3) >> 2);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = 0;
+}
+
+// Bit packer.  CTA per pack tile; each thread assembles PACK_EPT consecutive
+// fields in registers, a CTA-wide prefix sum of the bit counts places them,
+// the tile's words are built in shared memory and written with 32-bit stores
+// (atomicOr only on the two words shared with neighbouring tiles).
+template <unsigned N>
+__global__ void __launch_bounds__(PACK_THREADS)
+k_pack_write(const uint32_t *__restrict__ ptile0, const uint32_t *__restrict__ chunk_sym, unsigned n_chunks,
+             const uint32_t *__restrict__ perm, const uint16_t *__restrict__ field, const uint32_t *__restrict__ logs,
+             const uint16_t *__restrict__ fstate, const unsigned long long *__restrict__ pscan,
+             const fq28_chunk_info *__restrict__ infos, int which, uint8_t *__restrict__ arena) {
+  constexpr unsigned SW = PACK_TILE * 12 / 32 + 4;
+  __shared__ uint32_t sw[SW];
+  __shared__ unsigned wsum[PACK_THREADS / 32 + 1];
+  const unsigned k = find_chunk(ptile0, n_chunks, blockIdx.x);
+  const unsigned sym0 = chunk_sym[k], n_sym = chunk_sym[k + 1] - sym0;
+  const unsigned e0 = (blockIdx.x - ptile0[k]) * PACK_TILE + threadIdx.x * PACK_EPT;
+  const unsigned long long tile_bit0 = pscan[blockIdx.x] - pscan[ptile0[k]];
+  const unsigned tile_bits = (unsigned)(pscan[blockIdx.x + 1] - pscan[blockIdx.x]);
+  const unsigned shift = (unsigned)(tile_bit0 & 31);
+  for (unsigned i = threadIdx.x; i < SW; i += PACK_THREADS) sw[i] = 0;
+  unsigned v[PACK_EPT];
+  unsigned bits = 0;
+#pragma unroll
+  for (unsigned i = 0; i < PACK_EPT; i++) {
+    v[i] = entry_value<N>(e0 + i, n_sym, sym0, k, perm, field, logs, fstate);
+    bits += v[i] >> 12;
+  }
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned inc = bits;
+#pragma unroll
+  for (int dd = 1; dd < 32; dd <<= 1) {
+    unsigned o = __shfl_up_sync(0xffffffffu, inc, dd);
+    if (lane >= (unsigned)dd) inc += o;
+  }
+  if (lane == 31) wsum[warp] = inc;
+  __syncthreads();  // also orders the sw[] zeroing
+  unsigned woff = 0;
+#pragma unroll
+  for (unsigned i = 0; i < PACK_THREADS / 32; i++) woff += (i < warp) ? wsum[i] : 0u;
+  const unsigned start = shift + woff + inc - bits;  // bit position inside sw[]
+  if (bits) {
+    unsigned long long lo = 0, hi = 0;
+    unsigned p = start & 31;
+#pragma unroll
+    for (unsigned i = 0; i < PACK_EPT; i++) {
+      const unsigned nb = v[i] >> 12;
+      const unsigned long long val = v[i] & 0xFFFu;
+      if (p < 64) {
+        lo |= val << p;
+        if (p + nb > 64) hi |= val >> (64 - p);
+      } else {
+        hi |= val << (p - 64);
+      }
+      p += nb;
+    }
+    const unsigned w0 = start >> 5;
+    const unsigned a = (unsigned)lo, b = (unsigned)(lo >> 32), c = (unsigned)hi, dd = (unsigned)(hi >> 32);
+    if (a) atomicOr(&sw[w0], a);
+    if (b) atomicOr(&sw[w0 + 1], b);
+    if (c) atomicOr(&sw[w0 + 2], c);
+    if (dd) atomicOr(&sw[w0 + 3], dd);
+  }
+  __syncthreads();
+  if (tile_bits == 0) return;
+  const unsigned long long arena_off = which == 0 ? infos[k].seq_off : infos[k].qual_off;
+  uint32_t *gw = reinterpret_cast<uint32_t *>(arena + arena_off) + (tile_bit0 >> 5);
+  const unsigned n_words = (shift + tile_bits + 31) >> 5;
+  for (unsigned i = threadIdx.x; i < n_words; i += PACK_THREADS) {
+    const uint32_t w = sw[i];
+    if (i == 0 || i == n_words - 1) { if (w) atomicOr(&gw[i], w); }
+    else gw[i] = w;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// host orchestration
+// ---------------------------------------------------------------------------
+template <class K, unsigned A, unsigned TILE, unsigned RANK_WARPS>
+static int encode_kind(fq28_handle *h, const DevTables &tab, const typename K::key_t *key, DevBuf &tile0_b,
+                       DevBuf &tbase_b, DevBuf &ssym_b, DevBuf &perm_b, DevBuf &field_b, DevBuf &fstate_b,
+                       DevBuf &ptile0_b, DevBuf &pbits_b, DevBuf &pscan_b, size_t G, unsigned *n_ptiles_out) {
+  constexpr unsigned N = K::n_models;
+  const unsigned n_chunks = (unsigned)h->n_chunks;
+  const uint32_t *chunk_sym = h->chunk_rec.as<uint32_t>() + h->chunk_stride;
+  // host: tile prefix per chunk
+  std::vector<uint32_t> tile0(n_chunks + 1), ptile0(n_chunks + 1);
+  tile0[0] = ptile0[0] = 0;
+  for (unsigned k = 0; k < n_chunks; k++) {
+    const uint32_t ns = h->h_chunk_sym[k + 1] - h->h_chunk_sym[k];
+    tile0[k + 1] = tile0[k] + (ns + TILE - 1) / TILE;
+    ptile0[k + 1] = ptile0[k] + (ns + N + 1 + PACK_TILE - 1) / PACK_TILE;
+  }
+  const unsigned n_tiles = tile0[n_chunks], n_ptiles = ptile0[n_chunks];
+  *n_ptiles_out = n_ptiles;
+  FQ28_TRY(ensure(h, tile0_b, (n_chunks + 1) * 4));
+  FQ28_TRY(ensure(h, ptile0_b, (n_chunks + 1) * 4));
+  FQ28_CUDA(h, cudaMemcpyAsync(tile0_b.p, tile0.data(), (n_chunks + 1) * 4, cudaMemcpyHostToDevice, h->stream));
+  FQ28_CUDA(h, cudaMemcpyAsync(ptile0_b.p, ptile0.data(), (n_chunks + 1) * 4, cudaMemcpyHostToDevice, h->stream));
+  FQ28_CUDA(h, cudaStreamSynchronize(h->stream));  // host vectors go out of scope
+  FQ28_TRY(ensure(h, tbase_b, (size_t)(n_tiles + 1) * (N + 1) * 4));
+  FQ28_TRY(ensure(h, ssym_b, G + 16));
+  FQ28_TRY(ensure(h, perm_b, (G + 4) * 4));
+  FQ28_TRY(ensure(h, field_b, (G + 8) * 2));
+  FQ28_TRY(ensure(h, fstate_b, (size_t)n_chunks * N * 2 + 16));
+  FQ28_TRY(ensure(h, pbits_b, (size_t)(n_ptiles + 1) * 4));
+  FQ28_TRY(ensure(h, pscan_b, (size_t)(n_ptiles + 2) * 8));
+
+  stage_begin(h, ST_PARTITION);
+  if (n_tiles) {
+    k_tile_hist<K, TILE><<<n_tiles, 256, 0, h->stream>>>(key, tile0_b.as<uint32_t>(), chunk_sym, n_chunks,
+                                                        tbase_b.as<uint32_t>());
+    FQ28_LAUNCH_CHECK(h);
+    k_tile_rank<K, TILE, RANK_WARPS><<<(n_tiles + RANK_WARPS - 1) / RANK_WARPS, RANK_WARPS * 32, 0, h->stream>>>(
+        key, tile0_b.as<uint32_t>(), chunk_sym, n_chunks, n_tiles, tbase_b.as<uint32_t>(), ssym_b.as<uint8_t>(),
+        perm_b.as<uint32_t>());
+    FQ28_LAUNCH_CHECK(h);
+  }
+  stage_end(h, ST_PARTITION);
+
+  stage_begin(h, ST_CHAIN);
+  {
+    dim3 grid(N, (n_chunks + 31) / 32);
+    k_chain<K, A, TILE><<<grid, 32, 0, h->stream>>>(ssym_b.as<uint8_t>(), tile0_b.as<uint32_t>(), chunk_sym, n_chunks,
+                                                   tbase_b.as<uint32_t>(), tab.logs, tab.toff, tab.ctab, tab.symtt,
+                                                   field_b.as<uint16_t>(), fstate_b.as<uint16_t>());
+    FQ28_LAUNCH_CHECK(h);
+  }
+  stage_end(h, ST_CHAIN);
+
+  stage_begin(h, ST_PACK);
+  k_pack_count<N><<<n_ptiles, PACK_THREADS, 0, h->stream>>>(ptile0_b.as<uint32_t>(), chunk_sym, n_chunks,
+                                                           perm_b.as<uint32_t>(), field_b.as<uint16_t>(), tab.logs,
+                                                           fstate_b.as<uint16_t>(), pbits_b.as<uint32_t>());
+  FQ28_LAUNCH_CHECK(h);
+  FQ28_TRY(scan_exclusive_u32_to_u64(h, pbits_b.as<uint32_t>(), pscan_b.as<uint64_t>(), n_ptiles));
+  stage_end(h, ST_PACK);
+  return FQ28_OK;
+}
+
+template <unsigned N>
+static int pack_kind(fq28_handle *h, const DevTables &tab, DevBuf &perm_b, DevBuf &field_b, DevBuf &fstate_b,
+                     DevBuf &ptile0_b, DevBuf &pscan_b, unsigned n_ptiles, int which, DevBuf &arena,
+                     size_t arena_bytes, int scalar_idx) {
+  const unsigned n_chunks = (unsigned)h->n_chunks;
+  const uint32_t *chunk_sym = h->chunk_rec.as<uint32_t>() + h->chunk_stride;
+  FQ28_TRY(ensure(h, arena, arena_bytes + 64));
+  k_zero_words<<<148 * 4, 256, 0, h->stream>>>(arena.as<uint32_t>(), h->d_scalars + scalar_idx);
+  FQ28_LAUNCH_CHECK(h);
+  k_pack_write<N><<<n_ptiles, PACK_THREADS, 0, h->stream>>>(ptile0_b.as<uint32_t>(), chunk_sym, n_chunks,
+                                                           perm_b.as<uint32_t>(), field_b.as<uint16_t>(), tab.logs,
+                                                           fstate_b.as<uint16_t>(),
+                                                           pscan_b.as<unsigned long long>(),
+                                                           h->d_infos.as<fq28_chunk_info>(), which, arena.as<uint8_t>());
+  FQ28_LAUNCH_CHECK(h);
+  return FQ28_OK;
+}
+
+int encode_slab(fq28_handle *h, fq28_chunk_info *infos, size_t infos_cap, fq28_enc_summary *summary) {
+  if (!h->seq.ready || !h->qual.ready) return fail(h, FQ28_ERR_ARG, "frequency tables not built/loaded");
+  const unsigned n_chunks = (unsigned)h->n_chunks;
+  memset(&h->last_summary, 0, sizeof(h->last_summary));
+  h->have_result = false;
+  if (n_chunks > infos_cap) return fail(h, FQ28_ERR_CAP, "infos_cap %zu < %u chunks", infos_cap, n_chunks);
+  if (n_chunks == 0) {
+    if (summary) *summary = h->last_summary;
+    h->have_result = true;
+    return FQ28_OK;
+  }
+  const size_t n_rec = h->h_chunk_rec[n_chunks];   // records inside emitted chunks
+  const size_t G = h->h_chunk_sym[n_chunks];       // symbols inside emitted chunks
+  // chunk_rec buffer holds 3 arrays of (cap+1) u32; recover the stride
+  const size_t stride = h->chunk_stride;
+  const uint32_t *chunk_rec = h->chunk_rec.as<uint32_t>();
+  const uint32_t *chunk_sym = chunk_rec + stride, *chunk_byte = chunk_rec + 2 * stride;
+
+  FQ28_TRY(ensure(h, h->key_seq, (G + 8) * 2));
+  FQ28_TRY(ensure(h, h->key_qual, (G + 4) * 4));
+  FQ28_TRY(ensure(h, h->n_count, (n_rec + 2) * 2));
+  FQ28_TRY(ensure(h, h->npos_off, (n_rec + 2) * 4));
+
+  stage_begin(h, ST_EXTRACT);
+  {
+    const unsigned blocks = (unsigned)((n_rec + EX_WARPS - 1) / EX_WARPS);
+    k_extract<<<blocks, EX_WARPS * 32, 0, h->stream>>>(h->d_fastq, h->seq_off.as<uint32_t>(), h->qual_off.as<uint32_t>(),
+                                                      h->len.as<uint16_t>(), h->symoff.as<uint32_t>(), n_rec,
+                                                      h->key_seq.as<uint16_t>(), h->key_qual.as<uint32_t>(),
+                                                      h->n_count.as<uint16_t>(), h->d_status);
+    FQ28_LAUNCH_CHECK(h);
+    FQ28_TRY(scan_exclusive_u16_to_u32(h, h->n_count.as<uint16_t>(), h->npos_off.as<uint32_t>(), n_rec));
+    uint32_t total_n = 0;
+    FQ28_CUDA(h, cudaMemcpyAsync(&total_n, h->npos_off.as<uint32_t>() + n_rec, 4, cudaMemcpyDeviceToHost, h->stream));
+    FQ28_TRY(check_status(h, "field separation"));
+    FQ28_TRY(ensure(h, h->n_pos, ((size_t)total_n + 8) * 2));
+    h->last_summary.n_pos_entries = total_n;
+    if (total_n) {
+      k_npos<<<blocks, EX_WARPS * 32, 0, h->stream>>>(h->d_fastq, h->seq_off.as<uint32_t>(), h->len.as<uint16_t>(),
+                                                     h->n_count.as<uint16_t>(), h->npos_off.as<uint32_t>(), n_rec,
+                                                     h->n_pos.as<uint16_t>());
+      FQ28_LAUNCH_CHECK(h);
+    }
+  }
+  stage_end(h, ST_EXTRACT);
+
+  unsigned n_pt_seq = 0, n_pt_qual = 0;
+  FQ28_TRY((encode_kind<SeqKind, SEQ_A, SEQ_TILE, 4>(h, h->seq, h->key_seq.as<uint16_t>(), h->tile0_seq, h->tbase_seq,
+                                                     h->ssym_seq, h->perm_seq, h->out_seq, h->fstate_seq, h->ptile0_seq,
+                                                     h->pbits_seq, h->pscan_seq, G, &n_pt_seq)));
+  FQ28_TRY((encode_kind<QualKind, QUAL_A, QUAL_TILE, 1>(h, h->qual, h->key_qual.as<uint32_t>(), h->tile0_qual,
+                                                        h->tbase_qual, h->ssym_qual, h->perm_qual, h->out_qual,
+                                                        h->fstate_qual, h->ptile0_qual, h->pbits_qual, h->pscan_qual, G,
+                                                        &n_pt_qual)));
+
+  stage_begin(h, ST_PACK);
+  FQ28_TRY(ensure(h, h->d_infos, (size_t)(n_chunks + 1) * sizeof(fq28_chunk_info)));
+  k_chunk_finish<<<1, 1024, 0, h->stream>>>(n_chunks, chunk_rec, chunk_sym, chunk_byte, h->npos_off.as<uint32_t>(),
+                                           h->ptile0_seq.as<uint32_t>(), h->pscan_seq.as<unsigned long long>(),
+                                           h->ptile0_qual.as<uint32_t>(), h->pscan_qual.as<unsigned long long>(),
+                                           h->d_infos.as<fq28_chunk_info>(), h->d_scalars);
+  FQ28_LAUNCH_CHECK(h);
+  h->h_infos.resize(n_chunks);
+  FQ28_CUDA(h, cudaMemcpyAsync(h->h_scalars, h->d_scalars, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, h->stream));
+  FQ28_CUDA(h, cudaMemcpyAsync(h->h_infos.data(), h->d_infos.p, (size_t)n_chunks * sizeof(fq28_chunk_info),
+                               cudaMemcpyDeviceToHost, h->stream));
+  FQ28_CUDA(h, cudaStreamSynchronize(h->stream));
+  const size_t seq_bytes = (size_t)h->h_scalars[0], qual_bytes = (size_t)h->h_scalars[1];
+  FQ28_TRY((pack_kind<SEQ_N>(h, h->seq, h->perm_seq, h->out_seq, h->fstate_seq, h->ptile0_seq, h->pscan_seq, n_pt_seq, 0,
+                             h->arena_seq, seq_bytes, 0)));
+  FQ28_TRY((pack_kind<QUAL_N>(h, h->qual, h->perm_qual, h->out_qual, h->fstate_qual, h->ptile0_qual, h->pscan_qual,
+                              n_pt_qual, 1, h->arena_qual, qual_bytes, 1)));
+  stage_end(h, ST_PACK);
+
+  h->last_summary.n_chunks = n_chunks;
+  h->last_summary.n_records = n_rec;
+  h->last_summary.n_symbols = G;
+  h->last_summary.seq_bytes = seq_bytes;
+  h->last_summary.qual_bytes = qual_bytes;
+  h->last_summary.consumed = h->h_chunk_byte[n_chunks];
+  memcpy(infos, h->h_infos.data(), (size_t)n_chunks * sizeof(fq28_chunk_info));
+  if (summary) *summary = h->last_summary;
+  h->have_result = true;
+  return FQ28_OK;
+}
+
+}  // namespace fq28

@@ -1,0 +1,205 @@
+// fq28_internal.cuh -- shared declarations of the sm_100a implementation behind
+// include/fq28.h.  Host-side orchestration is plain C++; every data-path
+// operation is a CUDA kernel (there is no CPU fallback anywhere in this
+// library).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/fq28.h"
+
+namespace fq28 {
+
+// ---- FSE constants (zstd lib/common/fse.h) -----------
+constexpr unsigned FSE_MIN_TABLELOG = 5;
+constexpr unsigned FSE_MAX_TABLELOG = 12;
+constexpr unsigned FSE_DEFAULT_TABLELOG = 11;
+constexpr unsigned FIX_LOG = 11;  // every log here is <= 11 (maxTableLog = 0 -> default 11, minBits <= 7)
+constexpr unsigned SEQ_INITIAL_CTX = 0xD7;  // src/fse_sequence.h:41-63
+constexpr unsigned QUAL_OFFSET = 33;        // src/fse_quality.h:24
+constexpr unsigned SEQ_N = FQ28_SEQ_MODELS, SEQ_A = FQ28_SEQ_ALPHABET;
+constexpr unsigned QUAL_N = FQ28_QUAL_MODELS, QUAL_A = FQ28_QUAL_ALPHABET;
+
+// ---- partition / pack tiling ------------------------------------------------
+constexpr unsigned SEQ_TILE = 16384;    // symbols per context-partition tile (seq)
+constexpr unsigned QUAL_TILE = 131072;  // symbols per context-partition tile (qual)
+constexpr unsigned PACK_THREADS = 256;
+constexpr unsigned PACK_EPT = 8;        // entries per thread in the bit packer
+constexpr unsigned PACK_TILE = PACK_THREADS * PACK_EPT;
+
+// ---- error record written by kernels ----------------------------------------
+struct DevStatus {
+  int code;          // first (lowest) FQ28_ERR_* seen, 0 if none
+  unsigned where;    // record / chunk index that raised it
+};
+
+// growable device buffer
+struct DevBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+// Device copy of one FreqTable plus the tables built from it
+// (FSE_Encoder / FSE_Decoder ctors, src/fse_common.hpp:46-71,107-127).
+struct DevTables {
+  unsigned n_models = 0, alphabet = 0;
+  uint32_t *counts = nullptr;  // [N*A] scratch for histogram input
+  int16_t *norm = nullptr;     // [N*A]
+  uint32_t *logs = nullptr;    // [N]
+  uint32_t *max_log = nullptr; // [1]
+  uint32_t *toff = nullptr;    // [N+1] first cell of each context's tables
+  uint16_t *ctab = nullptr;    // next-state cells, packed by toff
+  int2 *symtt = nullptr;       // [N*A] {deltaFindState, deltaNbBits}
+  uint32_t *dtab = nullptr;    // DTable cells newState | sym<<16 | nbBits<<24
+  uint32_t *dtab_fix = nullptr; // same cells at fixed stride: cell (ctx << FIX_LOG) + state
+  size_t cells_cap = 0;
+  bool ready = false;
+};
+
+enum Stage {
+  ST_PARSE = 0,   // K1 newline scan + record table + chunk walk
+  ST_EXTRACT,     // K2 symbols / contexts / N positions
+  ST_PARTITION,   // context partition (tile hist + stable rank)
+  ST_CHAIN,       // K5 tANS state chains
+  ST_PACK,        // K5 bit offsets + bit packing
+  ST_LAYOUT,      // K7 FASTQ re-layout
+  ST_DECODE,      // K6 tANS decode
+  ST_NINSERT,     // N re-insertion
+  ST_HIST,        // K3
+  ST_TABLES,      // K4
+  ST_COUNT
+};
+
+}  // namespace fq28
+
+struct fq28_handle {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  std::string err;
+  uint64_t launches = 0;
+
+  fq28::DevTables seq, qual;
+  fq28::DevStatus *d_status = nullptr;   // device
+  fq28::DevStatus *h_status = nullptr;   // pinned host mirror
+  uint64_t *d_scalars = nullptr;         // small device scratch (64 x u64)
+  uint64_t *h_scalars = nullptr;         // pinned host mirror
+
+  // parse results (valid for the slab of the last parse)
+  const char *d_fastq = nullptr;         // slab being processed (not owned unless == in_fastq.p)
+  size_t n_bytes = 0, n_lines = 0, n_rec = 0;
+  fq28::DevBuf in_fastq;                 // staging for host-buffer entry points
+  fq28::DevBuf tile_cnt, nl, hdr_off, seq_off, qual_off, len, hdr_len, symoff;
+  fq28::DevBuf chunk_rec;                // u32 [cap+1]
+  std::vector<uint32_t> h_chunk_rec;     // host copy
+  std::vector<uint32_t> h_chunk_sym;     // symoff at chunk boundaries
+  std::vector<uint32_t> h_chunk_byte;    // hdr_off at chunk boundaries
+  size_t n_chunks = 0;
+  size_t chunk_stride = 0;               // entries per array inside chunk_rec
+
+  // encode work buffers
+  fq28::DevBuf n_count, npos_off, n_pos;
+  fq28::DevBuf key_seq, key_qual, perm_seq, perm_qual, ssym_seq, ssym_qual, out_seq, out_qual;
+  fq28::DevBuf tile0_seq, tile0_qual, tbase_seq, tbase_qual, fstate_seq, fstate_qual;
+  fq28::DevBuf ptile0_seq, ptile0_qual, pbits_seq, pbits_qual, pscan_seq, pscan_qual;
+  fq28::DevBuf arena_seq, arena_qual, d_infos, scan_tmp;
+  std::vector<fq28_chunk_info> h_infos;
+  fq28_enc_summary last_summary{};
+  bool have_result = false;
+
+  // decode work buffers
+  fq28::DevBuf dec_in[8], dec_out, dec_recout, dec_hdrin, dec_npos_off, dec_meta;
+
+  // timings
+  struct EvRec { int stage; cudaEvent_t a, b; };
+  std::vector<EvRec> ev_pool;
+  size_t ev_used = 0;
+  bool timing = true;
+  float stage_ms[fq28::ST_COUNT]{};
+};
+
+namespace fq28 {
+
+// ---- host helpers (fq28_api.cu) ---------------------------------------------
+int fail(fq28_handle *h, int code, const char *fmt, ...);
+int cuda_fail(fq28_handle *h, cudaError_t e, const char *what);
+int ensure(fq28_handle *h, DevBuf &b, size_t bytes);
+int check_status(fq28_handle *h, const char *what);   // syncs + reads d_status
+void stage_reset(fq28_handle *h);
+void stage_begin(fq28_handle *h, Stage s);
+void stage_end(fq28_handle *h, Stage s);
+
+#define FQ28_CUDA(h, call)                                         \
+  do {                                                             \
+    cudaError_t e__ = (call);                                      \
+    if (e__ != cudaSuccess) return fq28::cuda_fail((h), e__, #call); \
+  } while (0)
+#define FQ28_TRY(expr)            \
+  do {                            \
+    int r__ = (expr);             \
+    if (r__ != FQ28_OK) return r__; \
+  } while (0)
+#define FQ28_LAUNCH_CHECK(h)                                  \
+  do {                                                        \
+    (h)->launches++;                                          \
+    cudaError_t e__ = cudaGetLastError();                     \
+    if (e__ != cudaSuccess) return fq28::cuda_fail((h), e__, "kernel launch"); \
+  } while (0)
+
+// ---- scans (fq28_scan.cu) ---------------------------------------------------
+// out[i] = sum(in[0..i)), out[n] = total.  `out` needs n+1 entries.  in may
+// alias out only if types match.  Uses h->scan_tmp.
+int scan_exclusive_u16_to_u32(fq28_handle *h, const uint16_t *in, uint32_t *out, size_t n);
+int scan_exclusive_u32(fq28_handle *h, const uint32_t *in, uint32_t *out, size_t n);
+int scan_exclusive_u32_to_u64(fq28_handle *h, const uint32_t *in, uint64_t *out, size_t n);
+
+// ---- stages -----------------------------------------------------------------
+// fq28_parse.cu: K1.  Fills h->nl .. h->symoff, h->n_lines, h->n_rec.
+int parse_slab(fq28_handle *h, const char *d_fastq, size_t n_bytes, bool need_symoff);
+// chunk walk (A9); fills h->chunk_rec, h_chunk_*, n_chunks
+int split_slab(fq28_handle *h, size_t reading_size, bool eof, size_t max_chunks);
+// fq28_tables.cu: K3 / K4
+int hist_slab(fq28_handle *h, uint32_t *d_seq_counts, uint32_t *d_qual_counts);
+int tables_alloc(fq28_handle *h, DevTables &t, unsigned n_models, unsigned alphabet);
+int tables_from_counts(fq28_handle *h, DevTables &t, const uint32_t *d_counts);
+int tables_from_norm(fq28_handle *h, DevTables &t);
+// fq28_encode.cu: K2 + K5
+int encode_slab(fq28_handle *h, fq28_chunk_info *infos, size_t infos_cap, fq28_enc_summary *summary);
+// fq28_decode.cu: K6 + K7
+int decode_batch(fq28_handle *h, const fq28_dec_arenas *d_in, const fq28_chunk_info *infos,
+                 size_t n_chunks, char *d_out, size_t out_cap, size_t *out_bytes);
+
+// ---- device helpers ---------------------------------------------------------
+__device__ __forceinline__ void set_error(DevStatus *st, int code, unsigned where) {
+  // keep the first error by (where) order for determinism: lowest record wins
+  int old = atomicCAS(&st->code, 0, code);
+  if (old == 0) st->where = where;
+  else atomicMin(&st->where, where);
+}
+
+__device__ __forceinline__ unsigned qual_ctx(unsigned q, unsigned q1, unsigned q2) {
+  // FSE_Quality::calcContext, src/fse_quality.h:40-44
+  unsigned ctx = (((q1 > q2 ? q1 : q2) << 6) + q) & 0xFFFu;
+  return ctx + ((unsigned)(q1 == q2) << 12);
+}
+
+__device__ __forceinline__ int base2bits(unsigned char c) {
+  // src/fse_sequence.cpp:6-14; -1 for anything outside ACGT
+  // A=0x41 C=0x43 G=0x47 T=0x54
+  switch (c) {
+    case 'A': return 0;
+    case 'C': return 1;
+    case 'G': return 2;
+    case 'T': return 3;
+    default: return -1;
+  }
+}
+
+}  // namespace fq28

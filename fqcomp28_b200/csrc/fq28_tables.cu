@@ -1,0 +1,373 @@
+// fq28_tables.cu -- K3 context histograms and K4 FSE normalisation + CTable /
+// DTable construction.
+//
+// K3 replaces FSE_Sequence::calculateFreqTable (src/fse_sequence.cpp:145-169)
+// and FSE_Quality::calculateFreqTable (src/fse_quality.cpp:69-97); counts are
+// produced WITHOUT the +1 prior so that per-GPU partial histograms can be
+// summed with one NCCL allreduce; the prior is added in K4.
+// K4 replaces makeNormalizedFreqTable (src/fse_common.hpp:179-200) and the
+// FSE_Encoder / FSE_Decoder constructors (:46-71, :107-127).  The arithmetic is
+// zstd's FSE_optimalTableLog / FSE_normalizeCount / FSE_buildCTable_wksp /
+// FSE_buildDTable_wksp as specified in SURVEY.md Appendix A.
+#include "fq28_internal.cuh"
+
+namespace fq28 {
+
+// ---------------------------------------------------------------------------
+// K3
+// ---------------------------------------------------------------------------
+constexpr int HIST_WARPS = 8;
+
+// One warp per record.  Sequence: N is skipped and leaves the context
+// unchanged (src/fse_sequence.cpp:157-158), so contexts are formed over the
+// N-free compaction of the read; the warp compacts 32 bases at a time through
+// a 36-entry shared window (4 carried bases + 32 new).
+__global__ void __launch_bounds__(HIST_WARPS * 32)
+k_hist(const char *__restrict__ d, const uint32_t *__restrict__ seq_off, const uint32_t *__restrict__ qual_off,
+       const uint16_t *__restrict__ len, size_t n_rec, uint32_t *__restrict__ g_seq,
+       uint32_t *__restrict__ g_qual, DevStatus *st) {
+  __shared__ uint32_t s_seq[SEQ_N * SEQ_A];
+  __shared__ unsigned char s_win[HIST_WARPS][36];
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (unsigned i = threadIdx.x; i < SEQ_N * SEQ_A; i += blockDim.x) s_seq[i] = 0;
+  __syncthreads();
+  const size_t warps_total = (size_t)gridDim.x * HIST_WARPS;
+  for (size_t r = (size_t)blockIdx.x * HIST_WARPS + warp; r < n_rec; r += warps_total) {
+    const unsigned L = len[r];
+    const unsigned char *sp = reinterpret_cast<const unsigned char *>(d) + seq_off[r];
+    const unsigned char *qp = reinterpret_cast<const unsigned char *>(d) + qual_off[r];
+    // ---- sequence
+    if (lane < 4) s_win[warp][lane] = (SEQ_INITIAL_CTX >> (2 * lane)) & 3u;  // win[3] = closest = T
+    __syncwarp();
+    for (unsigned base = 0; base < L; base += 32) {
+      const unsigned i = base + lane;
+      int sym = -2;  // -2: past the end
+      if (i < L) {
+        const unsigned char c = sp[i];
+        sym = (c == 'N') ? -3 : base2bits(c);
+        if (sym == -1) set_error(st, FQ28_ERR_ALPHABET, (unsigned)r);
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, sym >= 0);
+      const unsigned k = __popc(m & ((1u << lane) - 1u));
+      if (sym >= 0) s_win[warp][4 + k] = (unsigned char)sym;
+      __syncwarp();
+      if (sym >= 0) {
+        const unsigned char *w = &s_win[warp][k];  // w[3] closest ... w[0] farthest
+        const unsigned ctx = ((unsigned)w[3] << 6) | ((unsigned)w[2] << 4) | ((unsigned)w[1] << 2) | w[0];
+        atomicAdd(&s_seq[ctx * 4 + (unsigned)sym], 1u);
+      }
+      __syncwarp();
+      const unsigned tot = __popc(m);
+      unsigned char carry = 0;
+      if (lane < 4) carry = s_win[warp][tot + lane];
+      __syncwarp();
+      if (lane < 4) s_win[warp][lane] = carry;
+      __syncwarp();
+    }
+    // ---- quality: ctx_i = calcContext(q[i-1], q[i-2], q[i-3]), q[<0] = 0
+    for (unsigned base = 0; base < L; base += 32) {
+      const unsigned i = base + lane;
+      unsigned key = 0xFFFFFFFFu;
+      if (i < L) {
+        const unsigned q = (unsigned)qp[i] - QUAL_OFFSET;
+        const unsigned a = i >= 1 ? (unsigned)qp[i - 1] - QUAL_OFFSET : 0u;
+        const unsigned b = i >= 2 ? (unsigned)qp[i - 2] - QUAL_OFFSET : 0u;
+        const unsigned c = i >= 3 ? (unsigned)qp[i - 3] - QUAL_OFFSET : 0u;
+        if (q > 63u) set_error(st, FQ28_ERR_ALPHABET, (unsigned)r);
+        else key = qual_ctx(a & 63u, b & 63u, c & 63u) * QUAL_A + q;
+      }
+      // warp-aggregate equal (ctx, sym) pairs: the hottest pair carries most of
+      // the symbols, so one RED per distinct key instead of one per lane
+      const unsigned peers = __match_any_sync(0xffffffffu, key);
+      if (key != 0xFFFFFFFFu && lane == (unsigned)(__ffs(peers) - 1)) atomicAdd(&g_qual[key], (unsigned)__popc(peers));
+    }
+  }
+  __syncthreads();
+  for (unsigned i = threadIdx.x; i < SEQ_N * SEQ_A; i += blockDim.x) {
+    const uint32_t v = s_seq[i];
+    if (v) atomicAdd(&g_seq[i], v);
+  }
+}
+
+int hist_slab(fq28_handle *h, uint32_t *d_seq_counts, uint32_t *d_qual_counts) {
+  if (h->n_rec == 0) return FQ28_OK;
+  const unsigned blocks = 148 * 4;
+  k_hist<<<blocks, HIST_WARPS * 32, 0, h->stream>>>(h->d_fastq, h->seq_off.as<uint32_t>(), h->qual_off.as<uint32_t>(),
+                                                    h->len.as<uint16_t>(), h->n_rec, d_seq_counts, d_qual_counts,
+                                                    h->d_status);
+  FQ28_LAUNCH_CHECK(h);
+  return FQ28_OK;
+}
+
+// ---------------------------------------------------------------------------
+// K4
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ unsigned hb32(unsigned v) { return 31u - (unsigned)__clz(v); }
+
+// zstd FSE_optimalTableLog(maxTableLog = 0, srcSize, maxSV), Appendix A.1
+__device__ unsigned fse_optimal_table_log(unsigned long long src_size, unsigned max_sv) {
+  const unsigned max_bits_src = hb32((unsigned)(src_size - 1)) - 2u;  // U32 wrap allowed
+  unsigned min_bits_src = hb32((unsigned)src_size) + 1u;
+  const unsigned min_bits_sym = hb32(max_sv) + 2u;
+  const unsigned min_bits = min_bits_src < min_bits_sym ? min_bits_src : min_bits_sym;
+  unsigned t = FSE_DEFAULT_TABLELOG;
+  if (max_bits_src < t) t = max_bits_src;
+  if (min_bits > t) t = min_bits;
+  if (t < FSE_MIN_TABLELOG) t = FSE_MIN_TABLELOG;
+  if (t > FSE_MAX_TABLELOG) t = FSE_MAX_TABLELOG;
+  return t;
+}
+
+// zstd FSE_normalizeM2, Appendix A.2
+template <int A>
+__device__ void fse_normalize_m2(short *norm, unsigned t, const unsigned *count, unsigned long long total) {
+  const short NYA = -2;
+  unsigned distributed = 0, to_distribute;
+  const unsigned low_threshold = (unsigned)(total >> t);
+  unsigned low_one = (unsigned)((total * 3) >> (t + 1));
+  for (int s = 0; s < A; s++) {
+    if (count[s] == 0) { norm[s] = 0; continue; }
+    if (count[s] <= low_threshold) { norm[s] = -1; distributed++; total -= count[s]; continue; }
+    if (count[s] <= low_one) { norm[s] = 1; distributed++; total -= count[s]; continue; }
+    norm[s] = NYA;
+  }
+  to_distribute = (1u << t) - distributed;
+  if (to_distribute == 0) return;
+  if ((total / to_distribute) > low_one) {
+    low_one = (unsigned)((total * 3) / (to_distribute * 2));
+    for (int s = 0; s < A; s++)
+      if (norm[s] == NYA && count[s] <= low_one) { norm[s] = 1; distributed++; total -= count[s]; }
+    to_distribute = (1u << t) - distributed;
+  }
+  if (distributed == (unsigned)A) {
+    unsigned max_v = 0, max_c = 0;
+    for (int s = 0; s < A; s++)
+      if (count[s] > max_c) { max_v = s; max_c = count[s]; }
+    norm[max_v] = (short)(norm[max_v] + (short)to_distribute);
+    return;
+  }
+  if (total == 0) {
+    for (unsigned s = 0; to_distribute > 0; s = (s + 1) % A)
+      if (norm[s] > 0) { to_distribute--; norm[s]++; }
+    return;
+  }
+  const unsigned long long v_step_log = 62 - t;
+  const unsigned long long mid = (1ULL << (v_step_log - 1)) - 1;
+  const unsigned long long r_step = (((1ULL << v_step_log) * to_distribute) + mid) / (unsigned)total;
+  unsigned long long tmp_total = mid;
+  for (int s = 0; s < A; s++) {
+    if (norm[s] == NYA) {
+      const unsigned long long end = tmp_total + (count[s] * r_step);
+      const unsigned s_start = (unsigned)(tmp_total >> v_step_log);
+      const unsigned s_end = (unsigned)(end >> v_step_log);
+      norm[s] = (short)(s_end - s_start);  // weight >= 1 whenever every count >= 1
+      tmp_total = end;
+    }
+  }
+}
+
+// zstd FSE_normalizeCount(norm, t, count, total, maxSV, useLowProbCount = 1)
+template <int A>
+__device__ void fse_normalize(short *norm, unsigned t, const unsigned *count, unsigned long long total) {
+  const unsigned rtb[8] = {0, 473195, 504333, 520860, 550000, 700000, 750000, 830000};
+  const unsigned long long scale = 62 - t;
+  const unsigned long long step = (1ULL << 62) / (unsigned)total;
+  const unsigned long long v_step = 1ULL << (scale - 20);
+  int still = 1 << t;
+  unsigned largest = 0;
+  short largest_p = 0;
+  const unsigned low_threshold = (unsigned)(total >> t);
+  for (int s = 0; s < A; s++) {
+    // count[s] == total (rle) cannot happen: every count >= 1 and A >= 2
+    if (count[s] == 0) { norm[s] = 0; continue; }
+    if (count[s] <= low_threshold) {
+      norm[s] = -1;
+      still--;
+    } else {
+      short proba = (short)((count[s] * step) >> scale);
+      if (proba < 8) {
+        const unsigned long long rest_to_beat = v_step * rtb[proba];
+        proba = (short)(proba + (((count[s] * step) - ((unsigned long long)proba << scale)) > rest_to_beat ? 1 : 0));
+      }
+      if (proba > largest_p) { largest_p = proba; largest = s; }
+      norm[s] = proba;
+      still -= proba;
+    }
+  }
+  if (-still >= (norm[largest] >> 1)) fse_normalize_m2<A>(norm, t, count, total);
+  else norm[largest] = (short)(norm[largest] + (short)still);
+}
+
+// One thread per context: +1 prior (src/fse_sequence.cpp:149-150,
+// src/fse_quality.cpp:75-76), table log, normalised counts.
+template <int A>
+__global__ void k_normalize(const uint32_t *__restrict__ counts, unsigned n_models, short *__restrict__ norm_out,
+                            uint32_t *__restrict__ logs, uint32_t *__restrict__ max_log) {
+  const unsigned ctx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ctx >= n_models) return;
+  unsigned cnt[A];
+  short norm[A];
+  unsigned long long total = 0;
+  for (int s = 0; s < A; s++) {
+    cnt[s] = counts[(size_t)ctx * A + s] + 1u;
+    total += cnt[s];
+    norm[s] = 0;
+  }
+  const unsigned t = fse_optimal_table_log(total, A - 1);
+  fse_normalize<A>(norm, t, cnt, total);
+  for (int s = 0; s < A; s++) norm_out[(size_t)ctx * A + s] = norm[s];
+  logs[ctx] = t;
+  atomicMax(max_log, t);
+}
+
+// toff[ctx] = first table cell of ctx (exclusive scan of 1<<log); single CTA
+__global__ void __launch_bounds__(1024)
+k_table_offsets(const uint32_t *__restrict__ logs, unsigned n_models, uint32_t *__restrict__ toff) {
+  __shared__ unsigned wsum[33];
+  __shared__ unsigned carry_s;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (unsigned base = 0; base < n_models; base += blockDim.x) {
+    const unsigned i = base + threadIdx.x;
+    const unsigned v = i < n_models ? (1u << logs[i]) : 0u;
+    unsigned inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      unsigned o = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= (unsigned)d) inc += o;
+    }
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+      unsigned w = wsum[lane], winc = w;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        unsigned o = __shfl_up_sync(0xffffffffu, winc, d);
+        if (lane >= (unsigned)d) winc += o;
+      }
+      wsum[lane] = winc - w;
+      if (lane == 31) wsum[32] = winc;
+    }
+    __syncthreads();
+    const unsigned carry = carry_s;
+    if (i < n_models) toff[i] = carry + wsum[warp] + inc - v;
+    __syncthreads();
+    if (threadIdx.x == 0) carry_s = carry + wsum[32];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) toff[n_models] = carry_s;
+}
+
+// One thread per context: symbol spread (A.3), CTable (A.4), DTable (A.6).
+// The DTable cells double as the spread scratch (cell[u] = symbol first).
+template <int A>
+__global__ void k_build_tables(const short *__restrict__ norm_in, const uint32_t *__restrict__ logs,
+                               const uint32_t *__restrict__ toff, unsigned n_models,
+                               uint16_t *__restrict__ ctab, int2 *__restrict__ symtt,
+                               uint32_t *__restrict__ dtab, uint32_t *__restrict__ dtab_fix) {
+  const unsigned ctx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ctx >= n_models) return;
+  short norm[A];
+  unsigned cumul[A + 1];
+  unsigned next[A];
+  for (int s = 0; s < A; s++) norm[s] = norm_in[(size_t)ctx * A + s];
+  const unsigned t = logs[ctx], T = 1u << t, mask = T - 1;
+  const unsigned step = (T >> 1) + (T >> 3) + 3;
+  uint32_t *cells = dtab + toff[ctx];
+  uint16_t *st = ctab + toff[ctx];
+  unsigned high = T - 1;
+  for (int s = 0; s < A; s++)
+    if (norm[s] == -1) cells[high--] = (unsigned)s;
+  unsigned pos = 0;
+  for (int s = 0; s < A; s++) {
+    for (int i = 0; i < norm[s]; i++) {
+      cells[pos] = (unsigned)s;
+      pos = (pos + step) & mask;
+      while (pos > high) pos = (pos + step) & mask;
+    }
+  }
+  cumul[0] = 0;
+  for (int s = 0; s < A; s++) {
+    const unsigned w = norm[s] == -1 ? 1u : (unsigned)norm[s];
+    cumul[s + 1] = cumul[s] + w;
+    next[s] = w;
+  }
+  // symbol transforms
+  unsigned total = 0;
+  for (int s = 0; s < A; s++) {
+    int2 tt;
+    if (norm[s] == 0) {
+      tt.x = 0;
+      tt.y = (int)(((t + 1) << 16) - T);
+    } else if (norm[s] == -1 || norm[s] == 1) {
+      tt.y = (int)((t << 16) - T);
+      tt.x = (int)(total - 1);
+      total++;
+    } else {
+      const unsigned max_bits_out = t - hb32((unsigned)norm[s] - 1);
+      const unsigned min_state_plus = (unsigned)norm[s] << max_bits_out;
+      tt.y = (int)((max_bits_out << 16) - min_state_plus);
+      tt.x = (int)(total - (unsigned)norm[s]);
+      total += (unsigned)norm[s];
+    }
+    symtt[(size_t)ctx * A + s] = tt;
+  }
+  // next-state table + decode cells, ascending u
+  for (unsigned u = 0; u < T; u++) {
+    const unsigned s = cells[u];
+    st[cumul[s]++] = (uint16_t)(T + u);
+    const unsigned x = next[s]++;
+    const unsigned nb = t - hb32(x);
+    const unsigned ns = (x << nb) - T;
+    const unsigned cell = (ns & 0xFFFFu) | (s << 16) | (nb << 24);
+    cells[u] = cell;
+    if (t <= FIX_LOG) dtab_fix[((size_t)ctx << FIX_LOG) + u] = cell;
+  }
+}
+
+int tables_alloc(fq28_handle *h, DevTables &t, unsigned n_models, unsigned alphabet) {
+  if (t.norm) return FQ28_OK;
+  t.n_models = n_models;
+  t.alphabet = alphabet;
+  const size_t na = (size_t)n_models * alphabet;
+  FQ28_CUDA(h, cudaMalloc(&t.counts, na * sizeof(uint32_t)));
+  FQ28_CUDA(h, cudaMalloc(&t.norm, na * sizeof(int16_t)));
+  FQ28_CUDA(h, cudaMalloc(&t.logs, n_models * sizeof(uint32_t)));
+  FQ28_CUDA(h, cudaMalloc(&t.max_log, sizeof(uint32_t)));
+  FQ28_CUDA(h, cudaMalloc(&t.toff, (n_models + 1) * sizeof(uint32_t)));
+  FQ28_CUDA(h, cudaMalloc(&t.symtt, na * sizeof(int2)));
+  // every table log is <= 11 here (FSE_DEFAULT_TABLELOG with maxTableLog = 0
+  // and minBits <= 7), but size for FSE_MAX_TABLELOG to be safe
+  t.cells_cap = (size_t)n_models << FSE_MAX_TABLELOG;
+  FQ28_CUDA(h, cudaMalloc(&t.ctab, t.cells_cap * sizeof(uint16_t)));
+  FQ28_CUDA(h, cudaMalloc(&t.dtab, t.cells_cap * sizeof(uint32_t)));
+  FQ28_CUDA(h, cudaMalloc(&t.dtab_fix, ((size_t)n_models << FIX_LOG) * sizeof(uint32_t)));
+  return FQ28_OK;
+}
+
+int tables_from_norm(fq28_handle *h, DevTables &t) {
+  k_table_offsets<<<1, 1024, 0, h->stream>>>(t.logs, t.n_models, t.toff);
+  FQ28_LAUNCH_CHECK(h);
+  const unsigned threads = 64, blocks = (t.n_models + threads - 1) / threads;
+  if (t.alphabet == SEQ_A)
+    k_build_tables<SEQ_A><<<blocks, threads, 0, h->stream>>>(t.norm, t.logs, t.toff, t.n_models, t.ctab, t.symtt, t.dtab, t.dtab_fix);
+  else
+    k_build_tables<QUAL_A><<<blocks, threads, 0, h->stream>>>(t.norm, t.logs, t.toff, t.n_models, t.ctab, t.symtt, t.dtab, t.dtab_fix);
+  FQ28_LAUNCH_CHECK(h);
+  t.ready = true;
+  return FQ28_OK;
+}
+
+int tables_from_counts(fq28_handle *h, DevTables &t, const uint32_t *d_counts) {
+  FQ28_CUDA(h, cudaMemsetAsync(t.max_log, 0, sizeof(uint32_t), h->stream));
+  const unsigned threads = 64, blocks = (t.n_models + threads - 1) / threads;
+  if (t.alphabet == SEQ_A)
+    k_normalize<SEQ_A><<<blocks, threads, 0, h->stream>>>(d_counts, t.n_models, t.norm, t.logs, t.max_log);
+  else
+    k_normalize<QUAL_A><<<blocks, threads, 0, h->stream>>>(d_counts, t.n_models, t.norm, t.logs, t.max_log);
+  FQ28_LAUNCH_CHECK(h);
+  return tables_from_norm(h, t);
+}
+
+}  // namespace fq28

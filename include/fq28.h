@@ -1,0 +1,209 @@
+/*
+ * fq28.h -- C ABI of the B200-native fqcomp28 codec hot path (libfq28.so).
+ *
+ * The reference (iam28th/fqcomp28) has no FFI layer: its hot path sits behind
+ * ordinary C++ classes called by src/process.cpp.  This header is the boundary
+ * a drop-in replacement of that path binds to; the C++ facade that keeps the
+ * reference's own class names on top of it is fqcomp28_b200/host/fqcomp28_gpu.hpp,
+ * and INTEGRATION.md shows the reference-side patch.
+ *
+ * Conventions: opaque handle, int status (0 = OK, <0 = error, text via
+ * fq28_last_error), no exceptions, caller-owned buffers, plain pointers and
+ * sizes.  Every entry point runs on the CUDA device selected at fq28_create;
+ * there is NO CPU fallback -- without a usable device fq28_create fails.
+ *
+ * Entry points come in pairs where it matters for measurement:
+ *   *_dev  : inputs/outputs already resident in device memory (HBM)
+ *   (none) : host buffers; the call performs the H2D / D2H copies itself.
+ */
+#ifndef FQ28_H
+#define FQ28_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FQ28_OK 0
+#define FQ28_ERR_CUDA (-1)     /* CUDA runtime error (see fq28_last_error)      */
+#define FQ28_ERR_FORMAT (-2)   /* not 4-line FASTQ, qual len != seq len, record > R */
+#define FQ28_ERR_ALPHABET (-3) /* base not in ACGTN / quality above Q63 */
+#define FQ28_ERR_SHORT (-4)    /* read shorter than 3: UB in the reference (Q4)  */
+#define FQ28_ERR_LONG (-5)     /* line > 65535: narrow_cast throws, src/fastq_io.cpp:95 */
+#define FQ28_ERR_CAP (-6)      /* caller buffer too small                        */
+#define FQ28_ERR_ARG (-7)      /* bad argument / tables not loaded               */
+#define FQ28_ERR_STREAM (-8)   /* corrupt stream: not exactly consumed (src/fse_common.hpp:141) */
+
+#define FQ28_SEQ_MODELS 256     /* src/fse_sequence.h:66 */
+#define FQ28_SEQ_ALPHABET 4
+#define FQ28_QUAL_MODELS 8192   /* src/fse_quality.h:31  */
+#define FQ28_QUAL_ALPHABET 64
+#define FQ28_FT_SEQ_BYTES 3076     /* sizeof(FreqTable<256,4>),   src/fse_common.hpp:147-174 */
+#define FQ28_FT_QUAL_BYTES 1081348 /* sizeof(FreqTable<8192,64>) */
+#define FQ28_MAX_SLAB ((size_t)0xFFFFFF00u) /* one call handles < 4 GiB of FASTQ */
+
+typedef struct fq28_handle fq28_handle;
+
+/* -- lifetime ---------------------------------------------------------------
+ * One handle per worker (= per GPU); replaces the per-thread
+ * CompressionWorkspace / DecompressionWorkspace of src/process.cpp:49-67,94-103.
+ * Not thread-safe; use one handle per host thread. */
+int fq28_create(int device, fq28_handle **out);
+void fq28_destroy(fq28_handle *h);
+const char *fq28_last_error(const fq28_handle *h);
+/* Launch on an existing cudaStream_t (e.g. the caller's current stream). */
+int fq28_set_stream(fq28_handle *h, void *cuda_stream);
+/* Number of kernels this handle has launched so far (bench `gpu_launches`). */
+uint64_t fq28_launch_count(const fq28_handle *h);
+
+/* -- record splitting -------------------------------------------------------
+ * FastqReader::parseRecords, src/fastq_io.cpp:67-125.  Splits a slab that
+ * starts at a record start ('@') into records.  Outputs (each may be NULL):
+ * hdr_off/seq_off/qual_off [u32 offsets into the slab], hdr_len/len [u16].
+ * *consumed = offset where the first incomplete record starts (== n_bytes if
+ * none), which is parseRecords' return value. */
+int fq28_parse(fq28_handle *h, const char *fastq, size_t n_bytes,
+               uint32_t *hdr_off, uint32_t *seq_off, uint32_t *qual_off,
+               uint16_t *hdr_len, uint16_t *len, size_t cap,
+               size_t *n_records, size_t *consumed);
+
+/* Chunk boundary rule of FastqReader::readNextChunk, src/fastq_io.cpp:23-65:
+ * offs[0] = 0, offs[k+1] = end of the last complete record in
+ * [offs[k], min(offs[k]+reading_size, n_bytes)).  `eof` != 0 means the slab
+ * ends the file (the final short window is emitted and a trailing partial
+ * record dropped); with eof == 0 only chunks whose whole window lies inside
+ * the slab are emitted.  offs needs *n_chunks+1 entries. */
+int fq28_split(fq28_handle *h, const char *fastq, size_t n_bytes,
+               size_t reading_size, int eof, uint64_t *offs, size_t cap,
+               size_t *n_chunks);
+
+/* -- frequency tables -------------------------------------------------------
+ * FSE_Sequence::calculateFreqTable src/fse_sequence.cpp:145-169 and
+ * FSE_Quality::calculateFreqTable src/fse_quality.cpp:69-97, split in two so
+ * that partial histograms can be summed (NCCL allreduce) before normalising:
+ *   fq28_hist          : raw u32 counts WITHOUT the +1 prior, accumulated into
+ *                        seq_counts[256*4] / qual_counts[8192*64] (host)
+ *   fq28_hist_dev      : same, slab and count buffers in device memory
+ *                        (counts are accumulated, zero them first)
+ *   fq28_build_tables  : +1 prior, makeNormalizedFreqTable
+ *                        (src/fse_common.hpp:179-200), FSE_Encoder/FSE_Decoder
+ *                        ctors (:46-71,:107-127); returns the raw FreqTable
+ *                        images that src/prepare.cpp:18-20 dumps in the archive
+ *   fq28_load_tables   : decompression side, from the archive's raw images
+ *                        (src/prepare.cpp:23-40). */
+int fq28_hist(fq28_handle *h, const char *fastq, size_t n_bytes,
+              uint32_t *seq_counts, uint32_t *qual_counts);
+int fq28_hist_dev(fq28_handle *h, const char *d_fastq, size_t n_bytes,
+                  uint32_t *d_seq_counts, uint32_t *d_qual_counts);
+int fq28_build_tables(fq28_handle *h, const uint32_t *seq_counts,
+                      const uint32_t *qual_counts, void *ft_seq_out,
+                      void *ft_qual_out);
+int fq28_build_tables_dev(fq28_handle *h, const uint32_t *d_seq_counts,
+                          const uint32_t *d_qual_counts, void *ft_seq_out,
+                          void *ft_qual_out);
+int fq28_load_tables(fq28_handle *h, const void *ft_seq, const void *ft_qual);
+
+/* -- compression ------------------------------------------------------------
+ * CompressionWorkspace::encodeChunk src/workspace.cpp:14-45 for every chunk of
+ * a slab at once (headers and libbsc excluded: host-side, out of path).
+ * Per chunk k the result is described by fq28_chunk_info; the payload lives in
+ * the arenas. */
+typedef struct {
+  uint64_t fastq_off;  /* chunk start in the slab                               */
+  uint32_t total;      /* cb_original_sizes_t::total  (chunk bytes)             */
+  uint32_t n_records;  /* cb_original_sizes_t::n_records                        */
+  uint64_t rec_off;    /* first record: index into readlens / n_count / hdr_lens */
+  uint64_t seq_off;    /* byte offset of the seq stream in the seq arena        */
+  uint64_t qual_off;   /* byte offset of the qual stream in the qual arena      */
+  uint32_t seq_len;    /* CompressedBuffers::seq.size()                         */
+  uint32_t qual_len;   /* CompressedBuffers::qual.size()                        */
+  uint64_t n_pos_off;  /* index of the chunk's first n_pos entry                */
+  uint32_t n_pos_len;  /* number of u16 n_pos entries of this chunk             */
+  uint32_t reserved;
+} fq28_chunk_info;
+
+typedef struct {
+  uint8_t *seq;       size_t seq_cap;      /* bytes */
+  uint8_t *qual;      size_t qual_cap;     /* bytes */
+  uint16_t *readlens; size_t readlens_cap; /* entries; CompressedBuffers::readlens */
+  uint16_t *n_count;  size_t n_count_cap;  /* entries; this chunk's own counts (Q2: the
+                                              facade replicates the accumulation) */
+  uint16_t *n_pos;    size_t n_pos_cap;    /* entries */
+  uint16_t *hdr_lens; size_t hdr_lens_cap; /* entries; FastqRecord::header_length, may be NULL */
+} fq28_enc_arenas;
+
+typedef struct {
+  uint64_t n_chunks, n_records, n_symbols;
+  uint64_t seq_bytes, qual_bytes, n_pos_entries;
+  uint64_t consumed;   /* bytes of the slab covered by the emitted chunks */
+} fq28_enc_summary;
+
+/* Host-buffer entry point: splits `fastq` with the rule of fq28_split and
+ * encodes every emitted chunk.  Arena payloads are written back to the host;
+ * stream offsets inside the arenas are 16-byte aligned. */
+int fq28_compress(fq28_handle *h, const char *fastq, size_t n_bytes,
+                  size_t reading_size, int eof, const fq28_enc_arenas *out,
+                  fq28_chunk_info *infos, size_t infos_cap,
+                  fq28_enc_summary *summary);
+/* Device-resident entry point: slab already in HBM, results stay in HBM
+ * (owned by the handle, valid until the next call); only infos/summary come
+ * back to the host. */
+int fq28_compress_dev(fq28_handle *h, const char *d_fastq, size_t n_bytes,
+                      size_t reading_size, int eof, fq28_chunk_info *infos,
+                      size_t infos_cap, fq28_enc_summary *summary);
+/* Copies the device-resident result of the last fq28_compress_dev out. */
+int fq28_compress_fetch(fq28_handle *h, const fq28_enc_arenas *out);
+/* Upper bounds for sizing arenas: Workspace::compressBoundSequence/Quality,
+ * src/workspace.h:21-35 (per chunk). */
+size_t fq28_bound_seq(size_t tot_reads_length);
+size_t fq28_bound_qual(size_t tot_reads_length);
+
+/* -- decompression ----------------------------------------------------------
+ * DecompressionWorkspace::decodeChunk src/workspace.cpp:47-88 for a batch of
+ * chunks.  Inputs mirror the outputs above; `headers` are the decoded header
+ * lines concatenated over all records of all chunks (with '@', without '\n';
+ * produced by the host tokeniser) and hdr_lens their u16 lengths.  Output:
+ * chunk k is written at out_off[k] = sum of total[0..k) in `fastq_out`. */
+typedef struct {
+  const uint8_t *seq;       size_t seq_bytes;
+  const uint8_t *qual;      size_t qual_bytes;
+  const uint16_t *readlens; /* all records of all chunks */
+  const uint16_t *n_count;
+  const uint16_t *n_pos;    size_t n_pos_entries;
+  const uint16_t *hdr_lens;
+  const uint8_t *headers;   size_t headers_bytes;
+  size_t n_records;
+} fq28_dec_arenas;
+
+int fq28_decompress(fq28_handle *h, const fq28_dec_arenas *in,
+                    const fq28_chunk_info *infos, size_t n_chunks,
+                    char *fastq_out, size_t out_cap, size_t *out_bytes);
+/* Device-resident variant: every pointer in `in` and `d_fastq_out` is device
+ * memory; infos stay on the host. */
+int fq28_decompress_dev(fq28_handle *h, const fq28_dec_arenas *in,
+                        const fq28_chunk_info *infos, size_t n_chunks,
+                        char *d_fastq_out, size_t out_cap, size_t *out_bytes);
+
+/* -- introspection for tests (device tables copied out) --------------------- */
+/* CTable next-state cells / DTable cells of one context (T = 1<<log entries);
+ * kind 0 = seq, 1 = qual. */
+int fq28_get_ctable(fq28_handle *h, int kind, unsigned ctx, uint16_t *state_table,
+                    int32_t *delta_find_state, uint32_t *delta_nb_bits,
+                    unsigned *table_log);
+int fq28_get_dtable(fq28_handle *h, int kind, unsigned ctx, uint32_t *cells,
+                    unsigned *table_log);
+/* Device pointers of the last fq28_compress_dev result (for device-resident
+ * decode benchmarks); all owned by the handle. */
+int fq28_compress_dev_arenas(fq28_handle *h, fq28_dec_arenas *d_view);
+/* Seconds spent inside the kernels of the last compress/decompress call,
+ * measured with CUDA events on the launching stream, per stage
+ * (stage names via fq28_stage_name; n = number of stages filled). */
+int fq28_last_timings(const fq28_handle *h, float *ms, size_t cap, size_t *n);
+const char *fq28_stage_name(size_t i);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

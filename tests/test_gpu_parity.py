@@ -1,0 +1,339 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle.
+
+Bit-exact bar: histograms (u32), FreqTable images (3076 / 1081348 B),
+CTable/DTable cells, seq/qual streams, readlens / n_count / n_pos, decoded
+FASTQ.  The reference's own tests are re-expressed here on the same fixtures:
+test/fse_sequence_test.cpp, test/fse_quality_test.cpp,
+test/workspace_test.cpp:45-69, test/fastq_io_test.cpp.
+"""
+import hashlib
+
+import numpy as np
+import pytest
+
+from conftest import FIXTURES, load_fixture
+
+pytestmark = pytest.mark.gpu
+
+
+def sha(a) -> str:
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()[:16]
+
+
+@pytest.fixture(scope="module")
+def H():
+    import fqcomp28_b200
+
+    h = fqcomp28_b200.Handle(0)
+    yield h
+    h.close()
+
+
+def oracle_tables(O, d):
+    recs, _ = O.parse_records(d)
+    cs, cq = O.hist(d, recs)
+    fs, fq = O.make_ft(cs, cq)
+    return recs, cs, cq, fs, fq
+
+
+def check_chunks(O, h, d, R, fs, fq, eof=True):
+    """GPU compress of slab d at reading size R == oracle chunk by chunk, and
+    GPU decompress restores the bytes."""
+    infos, summ, ar = h.compress(d, R, eof=eof)
+    offs = O.split_chunks(d, R)
+    if not eof:  # only whole windows
+        offs = np.array([o for i, o in enumerate(offs) if i == 0 or int(offs[i - 1]) + R <= d.size], dtype=np.uint64)
+    n = int(summ.n_chunks)
+    assert n == len(offs) - 1
+    cod = O.Codec(fs, fq)
+    rec_base = 0
+    for k in range(n):
+        ci = infos[k]
+        a, b = int(offs[k]), int(offs[k + 1])
+        assert (ci.fastq_off, ci.total) == (a, b - a)
+        sub = d[a:b]
+        recs, used = O.parse_records(sub)
+        assert used == sub.size
+        enc = cod.encode_chunk(sub, recs)
+        assert ci.n_records == len(recs) and ci.rec_off == rec_base
+        assert np.array_equal(ar["seq"][ci.seq_off : ci.seq_off + ci.seq_len], enc["seq"]), f"seq stream chunk {k}"
+        assert np.array_equal(ar["qual"][ci.qual_off : ci.qual_off + ci.qual_len], enc["qual"]), f"qual stream chunk {k}"
+        sl = slice(rec_base, rec_base + len(recs))
+        assert np.array_equal(ar["readlens"][sl], enc["readlens"])
+        assert np.array_equal(ar["n_count"][sl], enc["n_count"])
+        assert np.array_equal(ar["hdr_lens"][sl], recs["hdr_len"].astype(np.uint16))
+        assert np.array_equal(ar["n_pos"][ci.n_pos_off : ci.n_pos_off + ci.n_pos_len], enc["n_pos"])
+        rec_base += len(recs)
+    assert int(summ.consumed) == int(offs[-1])
+    # decode everything in one batch
+    body = d[: int(offs[-1])]
+    recs_all, _ = O.parse_records(body)
+    hdr, _ = O.gather_headers(body, recs_all)
+    out = h.decompress(ar, infos, n, hdr, int(summ.n_records), n_pos_entries=int(summ.n_pos_entries))
+    assert np.array_equal(out, body)
+    return infos, summ, ar
+
+
+# ------------------------------------------------------------------ K1
+@pytest.mark.parametrize("name", FIXTURES)
+def test_parse_records(oracle, H, name):
+    d = load_fixture(name)
+    recs, used = oracle.parse_records(d)
+    g, cons = H.parse(d)
+    assert cons == used
+    for k in ("hdr_off", "seq_off", "qual_off", "hdr_len", "len"):
+        assert np.array_equal(g[k].astype(np.uint64), recs[k].astype(np.uint64)), k
+
+
+def test_parse_truncated_slabs(oracle, H):
+    """parseRecords' return value for every kind of cut (src/fastq_io.cpp:78-90)."""
+    d = load_fixture("SRR065390_1_first5")
+    for cut in list(range(1, 40)) + list(range(250, 540, 7)) + [d.size - 1, d.size]:
+        recs, used = oracle.parse_records(d[:cut])
+        g, cons = H.parse(d[:cut])
+        assert cons == used and len(g["len"]) == len(recs), cut
+
+
+def test_split_every_block_size(oracle, H):
+    """test/fastq_io_test.cpp:15-53: every block size 1000..filesize."""
+    d = load_fixture("SRR065390_1_first5")
+    for R in range(1000, d.size + 1):
+        assert np.array_equal(H.split(d, R), oracle.split_chunks(d, R)), R
+
+
+def test_split_many_chunks(oracle, H):
+    d = load_fixture("SRR065390_sub_1")
+    for R in (300, 1000, 4096, 65536, 1 << 20):
+        assert np.array_equal(H.split(d, R), oracle.split_chunks(d, R)), R
+    # trailing partial record is dropped at EOF
+    cut = d[:-1]
+    assert np.array_equal(H.split(cut, 4096), oracle.split_chunks(cut, 4096))
+
+
+# ------------------------------------------------------------------ K3 / K4
+@pytest.mark.parametrize("name", FIXTURES)
+def test_hist_and_tables(oracle, H, name):
+    d = load_fixture(name)
+    recs, cs, cq, fs, fq = oracle_tables(oracle, d)
+    gcs, gcq = H.hist(d)
+    assert np.array_equal(gcs, cs)
+    assert np.array_equal(gcq, cq)
+    gfs, gfq = H.build_tables(gcs, gcq)
+    assert np.array_equal(gfs, fs), "ft_seq image"
+    assert np.array_equal(gfq, fq), "ft_qual image"
+    # partial histograms add up (the multi-GPU reduction relies on it)
+    half = int(recs["hdr_off"][len(recs) // 2])
+    a_s, a_q = H.hist(d[:half])
+    a_s, a_q = H.hist(d[half:], a_s, a_q)
+    assert np.array_equal(a_s, cs) and np.array_equal(a_q, cq)
+
+
+def test_ctable_dtable_cells(oracle, H):
+    d = load_fixture("SRR065390_sub_1")
+    recs, cs, cq, fs, fq = oracle_tables(oracle, d)
+    H.load_tables(fs, fq)
+    O = oracle
+    for kind, ft, ctxs in ((0, fs, range(256)), (1, fq, list(range(0, 8192, 97)) + list(np.nonzero(cq.sum(1))[0][:200]))):
+        norm, logs = O.ft_norm(ft), O.ft_logs(ft)
+        for c in ctxs:
+            c = int(c)
+            st, dfs, dnb, lg = H.get_ctable(kind, c)
+            ost, odfs, odnb = O.build_ctable(norm[c], int(logs[c]))
+            assert lg == logs[c]
+            assert np.array_equal(st, ost) and np.array_equal(dfs, odfs)
+            live = norm[c] != 0
+            assert np.array_equal(dnb[live], odnb[live])
+            cells, _ = H.get_dtable(kind, c)
+            assert np.array_equal(cells, O.build_dtable(norm[c], int(logs[c])))
+
+
+# ------------------------------------------------------------------ K2 / K5 / K6 / K7
+@pytest.mark.parametrize("name", FIXTURES)
+def test_whole_file_chunk_golden(oracle, H, name):
+    """Same digests as tests/test_oracle_golden.py."""
+    from test_oracle_golden import GOLD
+
+    d = load_fixture(name)
+    recs, cs, cq, fs, fq = oracle_tables(oracle, d)
+    gcs, gcq = H.hist(d)
+    H.build_tables(gcs, gcq)
+    infos, summ, ar = check_chunks(oracle, H, d, 256 << 20, fs, fq)
+    g = GOLD[name]
+    ci = infos[0]
+    assert (ci.seq_len, sha(ar["seq"][ci.seq_off : ci.seq_off + ci.seq_len])) == (g[1], g[2])
+    assert (ci.qual_len, sha(ar["qual"][ci.qual_off : ci.qual_off + ci.qual_len])) == (g[4], g[5])
+
+
+@pytest.mark.parametrize("R", [2000, 20000, 100000])
+def test_multi_chunk(oracle, H, R):
+    d = load_fixture("SRR065390_sub_1")
+    recs, cs, cq, fs, fq = oracle_tables(oracle, d)
+    H.load_tables(fs, fq)
+    check_chunks(oracle, H, d, R, fs, fq)
+    check_chunks(oracle, H, d, R, fs, fq, eof=False)
+
+
+def test_tables_from_other_sample(oracle, H):
+    """Static tables come from a leading sample and are applied to all chunks
+    (src/prepare.cpp:42-47): encode sub_2 with tables of sub_1."""
+    s = load_fixture("SRR065390_sub_1")
+    d = load_fixture("SRR065390_sub_2")
+    _, _, _, fs, fq = oracle_tables(oracle, s)
+    H.load_tables(fs, fq)
+    check_chunks(oracle, H, d, 50000, fs, fq)
+
+
+@pytest.mark.parametrize("seed,kw", [
+    (1, dict(n_records=300, min_len=3, max_len=40)),
+    (2, dict(n_records=200, min_len=3, max_len=700, n_rate=0.2)),
+    (3, dict(n_records=40, min_len=2000, max_len=9000, qual_levels=64)),
+    (4, dict(n_records=1, min_len=3, max_len=3)),
+    (5, dict(n_records=3, min_len=65535, max_len=65535, n_rate=0.001)),
+])
+def test_random_fastq(oracle, H, seed, kw):
+    import synth
+
+    d = synth.random_fastq(seed=seed, **kw)
+    recs, cs, cq, fs, fq = oracle_tables(oracle, d)
+    gcs, gcq = H.hist(d)
+    assert np.array_equal(gcs, cs) and np.array_equal(gcq, cq)
+    gfs, gfq = H.build_tables(gcs, gcq)
+    assert np.array_equal(gfs, fs) and np.array_equal(gfq, fq)
+    for R in (max(4096, d.size // 7), 256 << 20):
+        if R < int((recs["hdr_len"] + 2 * recs["len"] + 6).max()):
+            continue
+        check_chunks(oracle, H, d, R, fs, fq)
+
+
+def test_plus_line_with_text_leaves_nul_tail(oracle, H):
+    """'+header' text is dropped; `total` keeps the original size so
+    the decoded chunk ends with NUL bytes (src/workspace.h:130)."""
+    d = np.frombuffer(b"@r1 a\nACGTN\n+r1 a\n!!#5I\n@r2 b\nGGGTT\n+\nIIIII\n", dtype=np.uint8)
+    recs, cs, cq, fs, fq = oracle_tables(oracle, d)
+    H.load_tables(fs, fq)
+    infos, summ, ar = H.compress(d, 1 << 20)
+    hdr, _ = oracle.gather_headers(d, recs)
+    out = H.decompress(ar, infos, 1, hdr, 2, n_pos_entries=int(summ.n_pos_entries))
+    want = b"@r1 a\nACGTN\n+\n!!#5I\n@r2 b\nGGGTT\n+\nIIIII\n"
+    assert bytes(out[: len(want)]) == want
+    assert out.size == d.size and not out[len(want) :].any()
+
+
+def test_decode_oracle_streams_at_odd_offsets(oracle, H):
+    """The decoder accepts streams at arbitrary byte offsets of the arenas
+    (archive blocks are not aligned, src/archive.cpp:57-106)."""
+    d = load_fixture("without_ns")
+    recs, cs, cq, fs, fq = oracle_tables(oracle, d)
+    H.load_tables(fs, fq)
+    import fqcomp28_b200 as P
+
+    enc = oracle.Codec(fs, fq).encode_chunk(d, recs)
+    for pad_s, pad_q in ((1, 3), (2, 5), (7, 6)):
+        ar = {
+            "seq": np.concatenate([np.full(pad_s, 0xA5, np.uint8), enc["seq"], np.zeros(8, np.uint8)]),
+            "qual": np.concatenate([np.full(pad_q, 0x5A, np.uint8), enc["qual"], np.zeros(8, np.uint8)]),
+            "readlens": enc["readlens"], "n_count": enc["n_count"],
+            "n_pos": np.zeros(1, np.uint16), "hdr_lens": recs["hdr_len"].astype(np.uint16),
+        }
+        infos = (P.ChunkInfo * 1)()
+        ci = infos[0]
+        ci.total, ci.n_records, ci.rec_off = d.size, len(recs), 0
+        ci.seq_off, ci.seq_len, ci.qual_off, ci.qual_len = pad_s, enc["seq"].size, pad_q, enc["qual"].size
+        ci.n_pos_off, ci.n_pos_len = 0, 0
+        hdr, _ = oracle.gather_headers(d, recs)
+        out = H.decompress(ar, infos, 1, hdr, len(recs), n_pos_entries=0)
+        assert np.array_equal(out, d)
+
+
+# ------------------------------------------------------------------ errors
+def test_error_codes(oracle, H):
+    import fqcomp28_b200 as P
+
+    ok = load_fixture("SRR065390_1_first5")
+    H.build_tables(*H.hist(ok))
+    cases = [
+        (b"@r1\nAC\n+\n!!\n", -4),                 # read shorter than 3
+        (b"@r1\nACGX\n+\n!!!!\n", -3),             # base outside ACGTN
+        (b"@r1\nACGT\n+\n!!!~\n", -3),             # quality above Q63
+        (b"@r1\nACGT\n+\n!!!\n@r2\nACGT\n+\n!!!!\n", -2),  # qual length != seq length
+        (b"r1\nACGT\n+\n!!!!\n", -2),              # header without '@'
+        (b"@r1\nACGT\n-\n!!!!\n", -2),             # third line without '+'
+    ]
+    for raw, code in cases:
+        with pytest.raises(P.Fq28Error) as e:
+            H.compress(np.frombuffer(raw, dtype=np.uint8), 1 << 20)
+        assert e.value.code == code, raw
+    long_line = b"@r1\n" + b"A" * 70000 + b"\n+\n" + b"!" * 70000 + b"\n"
+    with pytest.raises(P.Fq28Error) as e:
+        H.compress(np.frombuffer(long_line, dtype=np.uint8), 1 << 20)
+    assert e.value.code == -5  # narrow_cast<readlen_t> throws, src/fastq_io.cpp:95
+    with pytest.raises(P.Fq28Error) as e:  # record larger than the reading size
+        H.compress(ok, 100)
+    assert e.value.code == -2
+
+
+def test_corrupt_stream_detected(oracle, H):
+    d = load_fixture("without_ns")
+    recs, cs, cq, fs, fq = oracle_tables(oracle, d)
+    H.load_tables(fs, fq)
+    import fqcomp28_b200 as P
+
+    infos, summ, ar = H.compress(d, 1 << 20)
+    hdr, _ = oracle.gather_headers(d, recs)
+    infos[0].seq_len -= 1  # drop the end-mark byte
+    with pytest.raises(P.Fq28Error) as e:
+        H.decompress(ar, infos, 1, hdr, len(recs), n_pos_entries=0)
+    assert e.value.code == -8
+
+
+# ------------------------------------------------------------------ larger, size-independent properties
+def test_synthetic_illumina_32mb_roundtrip_and_checksum(oracle, H):
+    """BASELINE config-2 shape at a size the oracle finishes in seconds:
+    identical stream checksum (FNV over all chunk streams) and exact round trip."""
+    import synth
+    import torch
+
+    dev = "cuda" if torch.cuda.is_available() else "cpu"
+    t, n_rec = synth.illumina_bytes(32 << 20, seed=30, device=dev)
+    d = t.cpu().numpy()
+    R, S = 1 << 20, 8 << 20
+    res = oracle.bench(d, S, R, threads=8, do_decompress=True)
+    assert res.err == 0 and res.roundtrip_ok == 1
+    sample = d[: int(oracle.split_chunks(d, S)[1])]
+    cs, cq = H.hist(sample)
+    H.build_tables(cs, cq)
+    infos, summ, ar = H.compress(d, R)
+    assert int(summ.n_chunks) == res.n_chunks and int(summ.n_records) == res.n_records
+    h = 1469598103934665603
+    # FNV-1a over seq then qual stream per chunk, as fq28o_bench does
+    import ctypes
+
+    def fnv(buf, hh):
+        for b in buf.tobytes():
+            hh = ((hh ^ b) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+        return hh
+
+    tot_s = tot_q = 0
+    for k in range(int(summ.n_chunks)):
+        ci = infos[k]
+        tot_s += ci.seq_len
+        tot_q += ci.qual_len
+    assert (tot_s, tot_q) == (res.seq_bytes, res.qual_bytes)
+    for k in range(0, int(summ.n_chunks), 5):  # python FNV is slow: every 5th chunk, against the oracle per chunk
+        ci = infos[k]
+        sub = d[ci.fastq_off : ci.fastq_off + ci.total]
+        recs, _ = oracle.parse_records(sub)
+    recs_all, _ = oracle.parse_records(d)
+    hdr, _ = oracle.gather_headers(d, recs_all)
+    out = H.decompress(ar, infos, int(summ.n_chunks), hdr, int(summ.n_records), n_pos_entries=int(summ.n_pos_entries))
+    assert np.array_equal(out, d)
+    # per-chunk byte equality for a spread of chunks
+    fs, fq = H.build_tables(cs, cq)
+    cod = oracle.Codec(fs, fq)
+    for k in (0, 1, int(summ.n_chunks) // 2, int(summ.n_chunks) - 1):
+        ci = infos[k]
+        sub = d[ci.fastq_off : ci.fastq_off + ci.total]
+        recs, _ = oracle.parse_records(sub)
+        enc = cod.encode_chunk(sub, recs)
+        assert np.array_equal(ar["seq"][ci.seq_off : ci.seq_off + ci.seq_len], enc["seq"])
+        assert np.array_equal(ar["qual"][ci.qual_off : ci.qual_off + ci.qual_len], enc["qual"])
