@@ -279,33 +279,34 @@ static size_t bw_close(bitw *w) {
 
 typedef struct {
   const U8 *src;
+  U64 size;
   U64 pos; /* number of stream bits not yet consumed (below the end mark) */
   int bad;
 } bitr;
 
 /* BIT_initDStream: locate the end mark in the last byte */
 static int br_init(bitr *r, const U8 *src, size_t size) {
-  r->src = src; r->bad = 0; r->pos = 0;
+  r->src = src; r->size = size; r->bad = 0; r->pos = 0;
   if (size == 0 || src[size - 1] == 0) { r->bad = 1; return -1; }
   r->pos = (U64)(size - 1) * 8 + hb32(src[size - 1]);
   return 0;
 }
-/* BIT_readBits: take the next nb bits going downward */
+/* BIT_readBits: take the next nb bits going downward.  One unaligned 64-bit
+ * load per call (what BIT_reloadDStream amounts to), byte gather near the
+ * end of the buffer. */
 static inline U32 br_read(bitr *r, unsigned nb) {
-  U64 p, byte;
-  unsigned sh;
-  U64 w = 0;
+  U64 w = 0, byte;
   if (nb == 0) return 0;
   if (r->pos < nb) { r->bad = 1; r->pos = 0; return 0; }
   r->pos -= nb;
-  p = r->pos; byte = p >> 3; sh = (unsigned)(p & 7);
-  /* gather up to 4 bytes (nb <= 12 so 3 suffice, keep 4 for safety) */
-  {
+  byte = r->pos >> 3;
+  if (byte + 8 <= r->size) {
+    memcpy(&w, r->src + byte, 8);
+  } else {
     unsigned i;
-    U64 last = (r->pos + nb + 7) >> 3; /* bytes valid up to here */
-    for (i = 0; i < 4 && byte + i < last; i++) w |= (U64)r->src[byte + i] << (8 * i);
+    for (i = 0; byte + i < r->size; i++) w |= (U64)r->src[byte + i] << (8 * i);
   }
-  return (U32)((w >> sh) & ((1u << nb) - 1u));
+  return (U32)((w >> (r->pos & 7)) & ((1u << nb) - 1u));
 }
 
 /* ===================================================================== */
@@ -625,16 +626,22 @@ long fq28o_encode_seq(const fq28o_codec *c, char *data, const fq28o_rec *recs,
       }
     }
     n_count[r] = cnt;
-    for (i = L; i > 0; --i) {
-      const U32 pos = i - 1;
-      unsigned ctx = 0, k;
-      for (k = 1; k <= 4; k++) { /* closest base in the top two bits */
-        unsigned b;
-        if (pos >= k) b = (unsigned)base2bits(p[pos - k]);
-        else b = (FQ28O_SEQ_INITIAL_CTX >> (2 * (3 - (k - pos - 1)))) & 3u;
-        ctx |= b << (2 * (4 - k));
+    {
+      /* ext[j] = 2-bit base of position j-4 over the virtual prefix T,C,C,T;
+       * ctx(pos) = ext[pos+3]<<6 | ext[pos+2]<<4 | ext[pos+1]<<2 | ext[pos].
+       * Rolling form: going from pos to pos-1 shifts the window down, exactly
+       * what addBaseLower does at src/fse_sequence.cpp:84. */
+      unsigned ctx;
+      U32 pos = L - 1;
+#define EXT(j) ((j) >= 4 ? (unsigned)base2bits(p[(j)-4]) : ((FQ28O_SEQ_INITIAL_CTX >> (2 * (j))) & 3u))
+      ctx = (EXT(pos + 3) << 6) | (EXT(pos + 2) << 4) | (EXT(pos + 1) << 2) | EXT(pos);
+      for (;;) {
+        enc_symbol(c, &w, states, ctx, (unsigned)base2bits(p[pos]));
+        if (pos == 0) break;
+        --pos;
+        ctx = ((ctx << 2) & 0xFFu) | EXT(pos);
       }
-      enc_symbol(c, &w, states, ctx, (unsigned)base2bits(p[pos]));
+#undef EXT
     }
   }
   if (n_npos) *n_npos = npos_n;
