@@ -49,7 +49,8 @@ class ChunkInfo(C.Structure):
         ("qual_len", C.c_uint32),
         ("n_pos_off", C.c_uint64),
         ("n_pos_len", C.c_uint32),
-        ("reserved", C.c_uint32),
+        ("hdr_bytes", C.c_uint32),
+        ("hdr_off", C.c_uint64),
     ]
 
 
@@ -61,6 +62,7 @@ class EncArenas(C.Structure):
         ("n_count", C.c_void_p), ("n_count_cap", C.c_size_t),
         ("n_pos", C.c_void_p), ("n_pos_cap", C.c_size_t),
         ("hdr_lens", C.c_void_p), ("hdr_lens_cap", C.c_size_t),
+        ("headers", C.c_void_p), ("headers_cap", C.c_size_t),
     ]
 
 
@@ -68,7 +70,7 @@ class EncSummary(C.Structure):
     _fields_ = [
         ("n_chunks", C.c_uint64), ("n_records", C.c_uint64), ("n_symbols", C.c_uint64),
         ("seq_bytes", C.c_uint64), ("qual_bytes", C.c_uint64), ("n_pos_entries", C.c_uint64),
-        ("consumed", C.c_uint64),
+        ("consumed", C.c_uint64), ("hdr_bytes", C.c_uint64),
     ]
 
 
@@ -126,8 +128,8 @@ def load() -> C.CDLL:
     L.fq28_build_tables.argtypes = [vp, vp, vp, vp, vp]
     L.fq28_build_tables_dev.argtypes = [vp, vp, vp, vp, vp]
     L.fq28_load_tables.argtypes = [vp, vp, vp]
-    L.fq28_compress.argtypes = [vp, vp, sz, sz, i32, C.POINTER(EncArenas), C.POINTER(ChunkInfo), sz, C.POINTER(EncSummary)]
-    L.fq28_compress_dev.argtypes = [vp, vp, sz, sz, i32, C.POINTER(ChunkInfo), sz, C.POINTER(EncSummary)]
+    L.fq28_compress.argtypes = [vp, vp, sz, sz, sz, i32, vp, vp, C.POINTER(EncArenas), C.POINTER(ChunkInfo), sz, C.POINTER(EncSummary)]
+    L.fq28_compress_dev.argtypes = [vp, vp, sz, sz, sz, i32, vp, vp, C.POINTER(ChunkInfo), sz, C.POINTER(EncSummary)]
     L.fq28_compress_fetch.argtypes = [vp, C.POINTER(EncArenas)]
     L.fq28_bound_seq.argtypes = [sz]
     L.fq28_bound_seq.restype = sz
@@ -264,8 +266,11 @@ class Handle:
         return cells[: 1 << lg.value].copy(), lg.value
 
     # ------------------------------------------------------------ compress
-    def compress(self, data: np.ndarray, reading_size: int, eof: bool = True, arenas: dict | None = None):
-        """fq28_compress on a host slab -> (infos, summary, arenas dict of numpy arrays)."""
+    def compress(self, data: np.ndarray, reading_size: int, eof: bool = True, arenas: dict | None = None,
+                 sample_bytes: int = 0, ft_out: tuple | None = None):
+        """fq28_compress on a host slab -> (infos, summary, arenas dict of numpy arrays).
+        sample_bytes > 0 runs analyzeDataset on the leading sample first; ft_out =
+        (ft_seq, ft_qual) uint8 arrays then receive the FreqTable images."""
         data = np.ascontiguousarray(data, dtype=np.uint8)
         n = data.size
         max_chunks = 2 * (n // max(1, reading_size)) + 8
@@ -278,28 +283,35 @@ class Handle:
                 "n_count": np.zeros(max_rec, np.uint16),
                 "n_pos": np.zeros(n // 2 + 16, np.uint16),
                 "hdr_lens": np.zeros(max_rec, np.uint16),
+                "headers": np.zeros(n // 2 + 64, np.uint8),
             }
         ea = self._enc_arenas(arenas)
         infos = (ChunkInfo * max_chunks)()
         summ = EncSummary()
-        self._ck(self.L.fq28_compress(self.h, _ptr(data), n, reading_size, int(eof), C.byref(ea), infos, max_chunks, C.byref(summ)))
+        fs, fq = ft_out if ft_out is not None else (None, None)
+        self._ck(self.L.fq28_compress(self.h, _ptr(data), n, sample_bytes, reading_size, int(eof), _ptr(fs), _ptr(fq),
+                                      C.byref(ea), infos, max_chunks, C.byref(summ)))
         return infos, summ, arenas
 
     @staticmethod
     def _enc_arenas(a: dict) -> EncArenas:
         ea = EncArenas()
-        for k in ("seq", "qual", "readlens", "n_count", "n_pos", "hdr_lens"):
+        for k in ("seq", "qual", "readlens", "n_count", "n_pos", "hdr_lens", "headers"):
             arr = a.get(k)
             setattr(ea, k, _ptr(arr) if arr is not None else None)
             setattr(ea, k + "_cap", int(arr.size) if arr is not None else 0)
         return ea
 
-    def compress_dev(self, d_fastq: int, n_bytes: int, reading_size: int, eof: bool = True, max_chunks: int | None = None):
+    def compress_dev(self, d_fastq: int, n_bytes: int, reading_size: int, eof: bool = True, max_chunks: int | None = None,
+                     sample_bytes: int = 0, ft_out: tuple | None = None, infos=None):
         if max_chunks is None:
             max_chunks = 2 * (n_bytes // max(1, reading_size)) + 8
-        infos = (ChunkInfo * max_chunks)()
+        if infos is None:
+            infos = (ChunkInfo * max_chunks)()
         summ = EncSummary()
-        self._ck(self.L.fq28_compress_dev(self.h, d_fastq, n_bytes, reading_size, int(eof), infos, max_chunks, C.byref(summ)))
+        fs, fq = ft_out if ft_out is not None else (None, None)
+        self._ck(self.L.fq28_compress_dev(self.h, d_fastq, n_bytes, sample_bytes, reading_size, int(eof), _ptr(fs), _ptr(fq),
+                                          infos, max_chunks, C.byref(summ)))
         return infos, summ
 
     def compress_fetch(self, arenas: dict):

@@ -167,7 +167,7 @@ void fq28_destroy(fq28_handle *h) {
                     &h->perm_seq, &h->perm_qual, &h->ssym_seq, &h->ssym_qual, &h->out_seq, &h->out_qual, &h->tile0_seq,
                     &h->tile0_qual, &h->tbase_seq, &h->tbase_qual, &h->fstate_seq, &h->fstate_qual, &h->ptile0_seq,
                     &h->ptile0_qual, &h->pbits_seq, &h->pbits_qual, &h->pscan_seq, &h->pscan_qual, &h->arena_seq,
-                    &h->arena_qual, &h->d_infos, &h->scan_tmp, &h->dec_out, &h->dec_recout, &h->dec_hdrin,
+                    &h->arena_qual, &h->d_infos, &h->scan_tmp, &h->hdrscan, &h->hdr_arena, &h->dec_out, &h->dec_recout, &h->dec_hdrin,
                     &h->dec_npos_off, &h->dec_meta};
   for (DevBuf *b : bufs) free_buf(*b);
   for (DevBuf &b : h->dec_in) free_buf(b);
@@ -317,11 +317,33 @@ size_t fq28_bound_qual(size_t n) {  // src/workspace.h:31-35
   return a > b ? a : b;
 }
 
-int fq28_compress_dev(fq28_handle *h, const char *d_fastq, size_t n_bytes, size_t reading_size, int eof,
-                      fq28_chunk_info *infos, size_t infos_cap, fq28_enc_summary *summary) {
+int fq28_compress_dev(fq28_handle *h, const char *d_fastq, size_t n_bytes, size_t sample_bytes, size_t reading_size,
+                      int eof, void *ft_seq_out, void *ft_qual_out, fq28_chunk_info *infos, size_t infos_cap,
+                      fq28_enc_summary *summary) {
   if (!h || !infos) return FQ28_ERR_ARG;
   FQ28_TRY(bind(h));
   stage_reset(h);
+  if (sample_bytes > 0) {
+    // analyzeDataset (src/prepare.cpp:42-47): first chunk of a reader whose
+    // reading size is the sample size = records wholly inside the window
+    const size_t win = sample_bytes < n_bytes ? sample_bytes : n_bytes;
+    stage_begin(h, ST_PARSE);
+    FQ28_TRY(parse_slab(h, d_fastq, win, false));
+    stage_end(h, ST_PARSE);
+    if (h->n_rec == 0) return fail(h, FQ28_ERR_FORMAT, "sample window of %zu bytes holds no complete record", win);
+    stage_begin(h, ST_HIST);
+    FQ28_CUDA(h, cudaMemsetAsync(h->seq.counts, 0, (size_t)SEQ_N * SEQ_A * 4, h->stream));
+    FQ28_CUDA(h, cudaMemsetAsync(h->qual.counts, 0, (size_t)QUAL_N * QUAL_A * 4, h->stream));
+    FQ28_TRY(hist_slab(h, h->seq.counts, h->qual.counts));
+    stage_end(h, ST_HIST);
+    stage_begin(h, ST_TABLES);
+    FQ28_TRY(tables_from_counts(h, h->seq, h->seq.counts));
+    FQ28_TRY(tables_from_counts(h, h->qual, h->qual.counts));
+    stage_end(h, ST_TABLES);
+    FQ28_TRY(check_status(h, "analyzeDataset"));
+    FQ28_TRY(ft_image_out(h, h->seq, ft_seq_out));
+    FQ28_TRY(ft_image_out(h, h->qual, ft_qual_out));
+  }
   stage_begin(h, ST_PARSE);
   FQ28_TRY(parse_slab(h, d_fastq, n_bytes, true));
   FQ28_TRY(split_slab(h, reading_size, eof != 0, 0));
@@ -336,7 +358,7 @@ int fq28_compress_fetch(fq28_handle *h, const fq28_enc_arenas *out) {
   const fq28_enc_summary &s = h->last_summary;
   if (s.seq_bytes > out->seq_cap || s.qual_bytes > out->qual_cap || s.n_records > out->readlens_cap ||
       s.n_records > out->n_count_cap || s.n_pos_entries > out->n_pos_cap ||
-      (out->hdr_lens && s.n_records > out->hdr_lens_cap))
+      (out->hdr_lens && s.n_records > out->hdr_lens_cap) || (out->headers && s.hdr_bytes > out->headers_cap))
     return fail(h, FQ28_ERR_CAP, "arena too small: need seq %llu qual %llu records %llu n_pos %llu",
                 (unsigned long long)s.seq_bytes, (unsigned long long)s.qual_bytes, (unsigned long long)s.n_records,
                 (unsigned long long)s.n_pos_entries);
@@ -349,16 +371,20 @@ int fq28_compress_fetch(fq28_handle *h, const fq28_enc_arenas *out) {
     FQ28_CUDA(h, cudaMemcpyAsync(out->n_pos, h->n_pos.p, s.n_pos_entries * 2, cudaMemcpyDeviceToHost, h->stream));
   if (out->hdr_lens)
     FQ28_CUDA(h, cudaMemcpyAsync(out->hdr_lens, h->hdr_len.p, s.n_records * 2, cudaMemcpyDeviceToHost, h->stream));
+  if (out->headers && s.hdr_bytes)
+    FQ28_CUDA(h, cudaMemcpyAsync(out->headers, h->hdr_arena.p, s.hdr_bytes, cudaMemcpyDeviceToHost, h->stream));
   FQ28_CUDA(h, cudaStreamSynchronize(h->stream));
   return FQ28_OK;
 }
 
-int fq28_compress(fq28_handle *h, const char *fastq, size_t n_bytes, size_t reading_size, int eof,
-                  const fq28_enc_arenas *out, fq28_chunk_info *infos, size_t infos_cap, fq28_enc_summary *summary) {
+int fq28_compress(fq28_handle *h, const char *fastq, size_t n_bytes, size_t sample_bytes, size_t reading_size, int eof,
+                  void *ft_seq_out, void *ft_qual_out, const fq28_enc_arenas *out, fq28_chunk_info *infos,
+                  size_t infos_cap, fq28_enc_summary *summary) {
   if (!h || !out || !infos) return FQ28_ERR_ARG;
   FQ28_TRY(bind(h));
   FQ28_TRY(stage_in(h, fastq, n_bytes));
-  FQ28_TRY(fq28_compress_dev(h, h->in_fastq.as<char>(), n_bytes, reading_size, eof, infos, infos_cap, summary));
+  FQ28_TRY(fq28_compress_dev(h, h->in_fastq.as<char>(), n_bytes, sample_bytes, reading_size, eof, ft_seq_out, ft_qual_out,
+                             infos, infos_cap, summary));
   return fq28_compress_fetch(h, out);
 }
 
@@ -372,7 +398,7 @@ int fq28_compress_dev_arenas(fq28_handle *h, fq28_dec_arenas *v) {
   v->n_count = h->n_count.as<uint16_t>();
   v->n_pos = h->n_pos.as<uint16_t>(); v->n_pos_entries = h->last_summary.n_pos_entries;
   v->hdr_lens = h->hdr_len.as<uint16_t>();
-  v->headers = nullptr; v->headers_bytes = 0;
+  v->headers = h->hdr_arena.as<uint8_t>(); v->headers_bytes = h->last_summary.hdr_bytes;
   v->n_records = h->last_summary.n_records;
   return FQ28_OK;
 }
@@ -455,8 +481,8 @@ int fq28_get_dtable(fq28_handle *h, int kind, unsigned ctx, uint32_t *cells, uns
   return FQ28_OK;
 }
 
-static const char *const k_stage_names[ST_COUNT] = {"parse", "extract", "partition", "chain", "pack",
-                                                    "layout", "decode", "ninsert", "hist", "tables"};
+static const char *const k_stage_names[ST_COUNT] = {"parse", "extract", "partition", "chain_seq", "chain_qual", "pack",
+                                                    "layout", "decode_seq", "decode_qual", "ninsert", "hist", "tables"};
 const char *fq28_stage_name(size_t i) { return i < ST_COUNT ? k_stage_names[i] : ""; }
 
 int fq28_last_timings(const fq28_handle *hc, float *ms, size_t cap, size_t *n) {

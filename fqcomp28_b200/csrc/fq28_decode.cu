@@ -246,7 +246,7 @@ int decode_batch(fq28_handle *h, const fq28_dec_arenas *in, const fq28_chunk_inf
   FQ28_LAUNCH_CHECK(h);
   stage_end(h, ST_LAYOUT);
 
-  stage_begin(h, ST_DECODE);
+  stage_begin(h, ST_DECODE_SEQ);
   {
     const size_t smem = (size_t)SEQ_N * SEQ_STREAMS * sizeof(uint16_t);
     k_decode<SEQ_N, SEQ_STREAMS, true><<<(unsigned)((n_chunks + SEQ_STREAMS - 1) / SEQ_STREAMS), SEQ_STREAMS, smem, h->stream>>>(
@@ -254,6 +254,8 @@ int decode_batch(fq28_handle *h, const fq28_dec_arenas *in, const fq28_chunk_inf
         h->d_status);
     FQ28_LAUNCH_CHECK(h);
   }
+  stage_end(h, ST_DECODE_SEQ);
+  stage_begin(h, ST_DECODE_QUAL);
   {
     const size_t smem = (size_t)QUAL_N * QUAL_STREAMS * sizeof(uint16_t);
     static bool attr_set = false;
@@ -267,7 +269,7 @@ int decode_batch(fq28_handle *h, const fq28_dec_arenas *in, const fq28_chunk_inf
         h->d_status);
     FQ28_LAUNCH_CHECK(h);
   }
-  stage_end(h, ST_DECODE);
+  stage_end(h, ST_DECODE_QUAL);
 
   stage_begin(h, ST_NINSERT);
   if (n_rec && in->n_pos_entries) {

@@ -129,6 +129,20 @@ k_npos(const char *__restrict__ d, const uint32_t *__restrict__ seq_off, const u
   }
 }
 
+// Header lines ('@'.., without '\n') back to back: the input of the host-side
+// header tokeniser (src/workspace.cpp:95-125, out of path).  One warp per record.
+__global__ void __launch_bounds__(EX_WARPS * 32)
+k_gather_headers(const char *__restrict__ d, const uint32_t *__restrict__ hdr_off, const uint16_t *__restrict__ hdr_len,
+                 const uint32_t *__restrict__ hdrscan, size_t n_rec, uint8_t *__restrict__ out) {
+  const unsigned lane = threadIdx.x & 31;
+  const size_t r = (size_t)blockIdx.x * EX_WARPS + (threadIdx.x >> 5);
+  if (r >= n_rec) return;
+  const unsigned hl = hdr_len[r];
+  const char *src = d + hdr_off[r];
+  uint8_t *dst = out + hdrscan[r];
+  for (unsigned i = lane; i < hl; i += 32) dst[i] = (uint8_t)src[i];
+}
+
 // ---------------------------------------------------------------------------
 // partition
 // ---------------------------------------------------------------------------
@@ -355,7 +369,7 @@ k_pack_count(const uint32_t *__restrict__ ptile0, const uint32_t *__restrict__ c
 __global__ void __launch_bounds__(1024)
 k_chunk_finish(unsigned n_chunks, const uint32_t *__restrict__ chunk_rec, const uint32_t *__restrict__ chunk_sym,
                const uint32_t *__restrict__ chunk_byte, const uint32_t *__restrict__ npos_off,
-               const uint32_t *__restrict__ ptile0_seq, const unsigned long long *__restrict__ pscan_seq,
+               const uint32_t *__restrict__ hdrscan, const uint32_t *__restrict__ ptile0_seq, const unsigned long long *__restrict__ pscan_seq,
                const uint32_t *__restrict__ ptile0_qual, const unsigned long long *__restrict__ pscan_qual,
                fq28_chunk_info *__restrict__ infos, uint64_t *__restrict__ scalars) {
   __shared__ unsigned long long carry[2];
@@ -412,7 +426,8 @@ k_chunk_finish(unsigned n_chunks, const uint32_t *__restrict__ chunk_rec, const 
       ci.qual_len = (uint32_t)len[1];
       ci.n_pos_off = npos_off[chunk_rec[k]];
       ci.n_pos_len = npos_off[chunk_rec[k + 1]] - npos_off[chunk_rec[k]];
-      ci.reserved = 0;
+      ci.hdr_off = hdrscan[chunk_rec[k]];
+      ci.hdr_bytes = hdrscan[chunk_rec[k + 1]] - hdrscan[chunk_rec[k]];
       infos[k] = ci;
     }
     __syncthreads();
@@ -546,7 +561,7 @@ static int encode_kind(fq28_handle *h, const DevTables &tab, const typename K::k
   }
   stage_end(h, ST_PARTITION);
 
-  stage_begin(h, ST_CHAIN);
+  stage_begin(h, N == SEQ_N ? ST_CHAIN_SEQ : ST_CHAIN_QUAL);
   {
     dim3 grid(N, (n_chunks + 31) / 32);
     k_chain<K, A, TILE><<<grid, 32, 0, h->stream>>>(ssym_b.as<uint8_t>(), tile0_b.as<uint32_t>(), chunk_sym, n_chunks,
@@ -554,7 +569,7 @@ static int encode_kind(fq28_handle *h, const DevTables &tab, const typename K::k
                                                    field_b.as<uint16_t>(), fstate_b.as<uint16_t>());
     FQ28_LAUNCH_CHECK(h);
   }
-  stage_end(h, ST_CHAIN);
+  stage_end(h, N == SEQ_N ? ST_CHAIN_SEQ : ST_CHAIN_QUAL);
 
   stage_begin(h, ST_PACK);
   k_pack_count<N><<<n_ptiles, PACK_THREADS, 0, h->stream>>>(ptile0_b.as<uint32_t>(), chunk_sym, n_chunks,
@@ -616,11 +631,20 @@ int encode_slab(fq28_handle *h, fq28_chunk_info *infos, size_t infos_cap, fq28_e
                                                       h->n_count.as<uint16_t>(), h->d_status);
     FQ28_LAUNCH_CHECK(h);
     FQ28_TRY(scan_exclusive_u16_to_u32(h, h->n_count.as<uint16_t>(), h->npos_off.as<uint32_t>(), n_rec));
-    uint32_t total_n = 0;
+    FQ28_TRY(ensure(h, h->hdrscan, (n_rec + 2) * 4));
+    FQ28_TRY(scan_exclusive_u16_to_u32(h, h->hdr_len.as<uint16_t>(), h->hdrscan.as<uint32_t>(), n_rec));
+    uint32_t total_n = 0, total_h = 0;
     FQ28_CUDA(h, cudaMemcpyAsync(&total_n, h->npos_off.as<uint32_t>() + n_rec, 4, cudaMemcpyDeviceToHost, h->stream));
+    FQ28_CUDA(h, cudaMemcpyAsync(&total_h, h->hdrscan.as<uint32_t>() + n_rec, 4, cudaMemcpyDeviceToHost, h->stream));
     FQ28_TRY(check_status(h, "field separation"));
     FQ28_TRY(ensure(h, h->n_pos, ((size_t)total_n + 8) * 2));
     h->last_summary.n_pos_entries = total_n;
+    h->last_summary.hdr_bytes = total_h;
+    FQ28_TRY(ensure(h, h->hdr_arena, (size_t)total_h + 64));
+    k_gather_headers<<<blocks, EX_WARPS * 32, 0, h->stream>>>(h->d_fastq, h->hdr_off.as<uint32_t>(),
+                                                             h->hdr_len.as<uint16_t>(), h->hdrscan.as<uint32_t>(), n_rec,
+                                                             h->hdr_arena.as<uint8_t>());
+    FQ28_LAUNCH_CHECK(h);
     if (total_n) {
       k_npos<<<blocks, EX_WARPS * 32, 0, h->stream>>>(h->d_fastq, h->seq_off.as<uint32_t>(), h->len.as<uint16_t>(),
                                                      h->n_count.as<uint16_t>(), h->npos_off.as<uint32_t>(), n_rec,
@@ -642,7 +666,7 @@ int encode_slab(fq28_handle *h, fq28_chunk_info *infos, size_t infos_cap, fq28_e
   stage_begin(h, ST_PACK);
   FQ28_TRY(ensure(h, h->d_infos, (size_t)(n_chunks + 1) * sizeof(fq28_chunk_info)));
   k_chunk_finish<<<1, 1024, 0, h->stream>>>(n_chunks, chunk_rec, chunk_sym, chunk_byte, h->npos_off.as<uint32_t>(),
-                                           h->ptile0_seq.as<uint32_t>(), h->pscan_seq.as<unsigned long long>(),
+                                           h->hdrscan.as<uint32_t>(), h->ptile0_seq.as<uint32_t>(), h->pscan_seq.as<unsigned long long>(),
                                            h->ptile0_qual.as<uint32_t>(), h->pscan_qual.as<unsigned long long>(),
                                            h->d_infos.as<fq28_chunk_info>(), h->d_scalars);
   FQ28_LAUNCH_CHECK(h);

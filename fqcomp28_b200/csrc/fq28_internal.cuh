@@ -67,10 +67,12 @@ enum Stage {
   ST_PARSE = 0,   // K1 newline scan + record table + chunk walk
   ST_EXTRACT,     // K2 symbols / contexts / N positions
   ST_PARTITION,   // context partition (tile hist + stable rank)
-  ST_CHAIN,       // K5 tANS state chains
+  ST_CHAIN_SEQ,   // K5 tANS state chains, sequence
+  ST_CHAIN_QUAL,  // K5 tANS state chains, quality
   ST_PACK,        // K5 bit offsets + bit packing
   ST_LAYOUT,      // K7 FASTQ re-layout
-  ST_DECODE,      // K6 tANS decode
+  ST_DECODE_SEQ,  // K6 tANS decode, sequence
+  ST_DECODE_QUAL, // K6 tANS decode, quality
   ST_NINSERT,     // N re-insertion
   ST_HIST,        // K3
   ST_TABLES,      // K4
@@ -105,7 +107,7 @@ struct fq28_handle {
   size_t chunk_stride = 0;               // entries per array inside chunk_rec
 
   // encode work buffers
-  fq28::DevBuf n_count, npos_off, n_pos;
+  fq28::DevBuf n_count, npos_off, n_pos, hdrscan, hdr_arena;
   fq28::DevBuf key_seq, key_qual, perm_seq, perm_qual, ssym_seq, ssym_qual, out_seq, out_qual;
   fq28::DevBuf tile0_seq, tile0_qual, tbase_seq, tbase_qual, fstate_seq, fstate_qual;
   fq28::DevBuf ptile0_seq, ptile0_qual, pbits_seq, pbits_qual, pscan_seq, pscan_qual;

@@ -121,7 +121,8 @@ typedef struct {
   uint32_t qual_len;   /* CompressedBuffers::qual.size()                        */
   uint64_t n_pos_off;  /* index of the chunk's first n_pos entry                */
   uint32_t n_pos_len;  /* number of u16 n_pos entries of this chunk             */
-  uint32_t reserved;
+  uint32_t hdr_bytes;  /* sum of the chunk's header line lengths                */
+  uint64_t hdr_off;    /* byte offset of the chunk's first header in `headers`  */
 } fq28_chunk_info;
 
 typedef struct {
@@ -132,27 +133,39 @@ typedef struct {
                                               facade replicates the accumulation) */
   uint16_t *n_pos;    size_t n_pos_cap;    /* entries */
   uint16_t *hdr_lens; size_t hdr_lens_cap; /* entries; FastqRecord::header_length, may be NULL */
+  uint8_t *headers;   size_t headers_cap;  /* bytes; header lines ('@'.., no '\n') back to back:
+                                              the input of the host header tokeniser, may be NULL */
 } fq28_enc_arenas;
 
 typedef struct {
   uint64_t n_chunks, n_records, n_symbols;
   uint64_t seq_bytes, qual_bytes, n_pos_entries;
   uint64_t consumed;   /* bytes of the slab covered by the emitted chunks */
+  uint64_t hdr_bytes;  /* total header bytes of the emitted chunks         */
 } fq28_enc_summary;
 
 /* Host-buffer entry point: splits `fastq` with the rule of fq28_split and
  * encodes every emitted chunk.  Arena payloads are written back to the host;
- * stream offsets inside the arenas are 16-byte aligned. */
+ * stream offsets inside the arenas are 16-byte aligned.
+ * sample_bytes > 0: first run analyzeDataset (src/prepare.cpp:42-47) on the
+ * leading sample_bytes of this slab -- records wholly inside
+ * [0, min(sample_bytes, n_bytes)) -- and build the tables from it, which is
+ * what `fqcomp28 c` does when it opens the archive (src/archive.cpp:13-20);
+ * the raw FreqTable images are returned in ft_seq_out / ft_qual_out (may be
+ * NULL).  sample_bytes == 0: use the tables already built / loaded. */
 int fq28_compress(fq28_handle *h, const char *fastq, size_t n_bytes,
-                  size_t reading_size, int eof, const fq28_enc_arenas *out,
-                  fq28_chunk_info *infos, size_t infos_cap,
-                  fq28_enc_summary *summary);
+                  size_t sample_bytes, size_t reading_size, int eof,
+                  void *ft_seq_out, void *ft_qual_out,
+                  const fq28_enc_arenas *out, fq28_chunk_info *infos,
+                  size_t infos_cap, fq28_enc_summary *summary);
 /* Device-resident entry point: slab already in HBM, results stay in HBM
  * (owned by the handle, valid until the next call); only infos/summary come
  * back to the host. */
 int fq28_compress_dev(fq28_handle *h, const char *d_fastq, size_t n_bytes,
-                      size_t reading_size, int eof, fq28_chunk_info *infos,
-                      size_t infos_cap, fq28_enc_summary *summary);
+                      size_t sample_bytes, size_t reading_size, int eof,
+                      void *ft_seq_out, void *ft_qual_out,
+                      fq28_chunk_info *infos, size_t infos_cap,
+                      fq28_enc_summary *summary);
 /* Copies the device-resident result of the last fq28_compress_dev out. */
 int fq28_compress_fetch(fq28_handle *h, const fq28_enc_arenas *out);
 /* Upper bounds for sizing arenas: Workspace::compressBoundSequence/Quality,
