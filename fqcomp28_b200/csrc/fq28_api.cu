@@ -78,6 +78,36 @@ void stage_end(fq28_handle *h, Stage s) {
   h->ev_used++;
 }
 
+static void stage_begin_on(fq28_handle *h, Stage s, cudaStream_t strm) {
+  if (!h->timing) return;
+  if (h->ev_used == h->ev_pool.size()) {
+    fq28_handle::EvRec r;
+    r.stage = s;
+    cudaEventCreate(&r.a);
+    cudaEventCreate(&r.b);
+    h->ev_pool.push_back(r);
+  }
+  h->ev_pool[h->ev_used].stage = s;
+  cudaEventRecord(h->ev_pool[h->ev_used].a, strm);
+}
+void side_stage_begin(fq28_handle *h, Stage s) { stage_begin_on(h, s, h->side); }
+void side_stage_end(fq28_handle *h, Stage s) {
+  if (!h->timing) return;
+  (void)s;
+  cudaEventRecord(h->ev_pool[h->ev_used].b, h->side);
+  h->ev_used++;
+}
+int side_fork(fq28_handle *h) {
+  FQ28_CUDA(h, cudaEventRecord(h->ev_fork, h->stream));
+  FQ28_CUDA(h, cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+  return FQ28_OK;
+}
+int side_join(fq28_handle *h) {
+  FQ28_CUDA(h, cudaEventRecord(h->ev_join, h->side));
+  FQ28_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_join, 0));
+  return FQ28_OK;
+}
+
 static void free_buf(DevBuf &b) {
   if (b.p) cudaFree(b.p);
   b.p = nullptr;
@@ -87,6 +117,7 @@ static void free_buf(DevBuf &b) {
 static void free_tables(DevTables &t) {
   cudaFree(t.counts); cudaFree(t.norm); cudaFree(t.logs); cudaFree(t.max_log); cudaFree(t.toff);
   cudaFree(t.ctab); cudaFree(t.symtt); cudaFree(t.dtab); cudaFree(t.dtab_fix);
+  cudaFree(t.logsuf); cudaFree(t.seqdec); cudaFree(t.cid); cudaFree(t.n_touched);
   t = DevTables();
 }
 
@@ -144,6 +175,9 @@ int fq28_create(int device, fq28_handle **out) {
     if (cudaSetDevice(device) != cudaSuccess) { rc = FQ28_ERR_CUDA; break; }
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { rc = FQ28_ERR_CUDA; break; }
     h->own_stream = true;
+    if (cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess) { rc = FQ28_ERR_CUDA; break; }
+    if (cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess) { rc = FQ28_ERR_CUDA; break; }
+    if (cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess) { rc = FQ28_ERR_CUDA; break; }
     if (cudaMalloc(&h->d_status, sizeof(DevStatus)) != cudaSuccess) { rc = FQ28_ERR_CUDA; break; }
     if (cudaMallocHost(&h->h_status, sizeof(DevStatus)) != cudaSuccess) { rc = FQ28_ERR_CUDA; break; }
     if (cudaMalloc(&h->d_scalars, 64 * sizeof(uint64_t)) != cudaSuccess) { rc = FQ28_ERR_CUDA; break; }
@@ -168,7 +202,7 @@ void fq28_destroy(fq28_handle *h) {
                     &h->tile0_qual, &h->tbase_seq, &h->tbase_qual, &h->fstate_seq, &h->fstate_qual, &h->ptile0_seq,
                     &h->ptile0_qual, &h->pbits_seq, &h->pbits_qual, &h->pscan_seq, &h->pscan_qual, &h->arena_seq,
                     &h->arena_qual, &h->d_infos, &h->scan_tmp, &h->hdrscan, &h->hdr_arena, &h->dec_out, &h->dec_recout, &h->dec_hdrin,
-                    &h->dec_npos_off, &h->dec_meta};
+                    &h->dec_npos_off, &h->dec_meta, &h->dec_cold};
   for (DevBuf *b : bufs) free_buf(*b);
   for (DevBuf &b : h->dec_in) free_buf(b);
   free_tables(h->seq);
@@ -178,6 +212,9 @@ void fq28_destroy(fq28_handle *h) {
   if (h->d_scalars) cudaFree(h->d_scalars);
   if (h->h_scalars) cudaFreeHost(h->h_scalars);
   for (auto &r : h->ev_pool) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  if (h->side) { cudaStreamSynchronize(h->side); cudaStreamDestroy(h->side); }
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }

@@ -33,6 +33,20 @@ constexpr unsigned PACK_THREADS = 256;
 constexpr unsigned PACK_EPT = 8;        // entries per thread in the bit packer
 constexpr unsigned PACK_TILE = PACK_THREADS * PACK_EPT;
 
+// ---- compressed sequence DTables (shared-memory resident in the decoder) ----
+// A DTable cell is (symbol, nbBits, newState) with newState = (x << nbBits) - T,
+// nbBits = log - hb(x), x = symbolNext[sym] + rank, rank = number of cells
+// below u holding the same symbol (Appendix A.6).  So 2 bits per cell (the
+// symbol) plus a two-level rank directory reproduce the cell exactly:
+// 840 B per context instead of 8 KB, all 256 contexts fit in one SM's smem.
+struct SeqDecTables {
+  uint32_t symtab[SEQ_N][128];    // 16 two-bit symbols per word, cell u at word u>>4
+  uint8_t fine[SEQ_N][64][4];     // rank of each symbol at the start of 32-cell block b, relative to its coarse block
+  uint16_t coarse[SEQ_N][8][4];   // rank of each symbol at the start of 256-cell block
+  uint16_t snext[SEQ_N][4];       // symbolNext: norm count (-1 counts as 1) in bits 0..11;
+                                  // bits 12..15 of snext[ctx][0] hold the context's table log
+};
+
 // ---- error record written by kernels ----------------------------------------
 struct DevStatus {
   int code;          // first (lowest) FQ28_ERR_* seen, 0 if none
@@ -59,6 +73,13 @@ struct DevTables {
   int2 *symtt = nullptr;       // [N*A] {deltaFindState, deltaNbBits}
   uint32_t *dtab = nullptr;    // DTable cells newState | sym<<16 | nbBits<<24
   uint32_t *dtab_fix = nullptr; // same cells at fixed stride: cell (ctx << FIX_LOG) + state
+  // decoder side structures
+  uint32_t *logsuf = nullptr;   // [N+1] logsuf[c] = sum of logs[c'] for c' > c (initial-state bit offsets)
+  uint8_t *seqdec = nullptr;    // sequence only: compressed DTables (SeqDecTables), copied to smem by the decoder
+  uint16_t *cid = nullptr;      // quality only: [N] compact id of every context whose table differs from the
+                                // untouched (prior-only) pattern, 0xFFFF otherwise
+  uint32_t *n_touched = nullptr;   // quality only: [1] number of compact ids
+  uint32_t h_n_touched = 0;
   size_t cells_cap = 0;
   bool ready = false;
 };
@@ -117,7 +138,11 @@ struct fq28_handle {
   bool have_result = false;
 
   // decode work buffers
-  fq28::DevBuf dec_in[8], dec_out, dec_recout, dec_hdrin, dec_npos_off, dec_meta;
+  fq28::DevBuf dec_in[8], dec_out, dec_recout, dec_hdrin, dec_npos_off, dec_meta, dec_cold;
+
+  // side stream: the sequence and quality pipelines are independent
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 
   // timings
   struct EvRec { int stage; cudaEvent_t a, b; };
@@ -137,6 +162,12 @@ int check_status(fq28_handle *h, const char *what);   // syncs + reads d_status
 void stage_reset(fq28_handle *h);
 void stage_begin(fq28_handle *h, Stage s);
 void stage_end(fq28_handle *h, Stage s);
+// side stream: fork = side waits for everything queued on the main stream,
+// join = main waits for the side stream; side_stage_* time a stage on it
+int side_fork(fq28_handle *h);
+int side_join(fq28_handle *h);
+void side_stage_begin(fq28_handle *h, Stage s);
+void side_stage_end(fq28_handle *h, Stage s);
 
 #define FQ28_CUDA(h, call)                                         \
   do {                                                             \

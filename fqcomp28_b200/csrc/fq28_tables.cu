@@ -326,6 +326,69 @@ __global__ void k_build_tables(const short *__restrict__ norm_in, const uint32_t
   }
 }
 
+// ---- decoder-side structures ----------------------------------------------
+// logsuf[c] = sum of logs[c'] for c' > c: FSE_Decoder::startChunk reads the
+// initial states for ctx N-1 .. 0 (src/fse_common.hpp:134-138), so the state
+// of context c starts logsuf[c] bits below the end mark.  Single thread.
+__global__ void k_logsuf(const uint32_t *__restrict__ logs, unsigned n_models, uint32_t *__restrict__ logsuf) {
+  unsigned acc = 0;
+  logsuf[n_models] = 0;
+  for (unsigned c = n_models; c > 0; --c) {
+    logsuf[c - 1] = acc;
+    acc += logs[c - 1];
+  }
+  logsuf[n_models] = acc;  // total bits of the state block
+}
+
+// Compressed sequence DTables (SeqDecTables), one thread per context.
+__global__ void k_build_seqdec(const short *__restrict__ norm, const uint32_t *__restrict__ logs,
+                               const uint32_t *__restrict__ dtab_fix, SeqDecTables *__restrict__ out) {
+  const unsigned ctx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ctx >= SEQ_N) return;
+  const unsigned t = logs[ctx], T = 1u << t;
+  unsigned run[4] = {0, 0, 0, 0}, coarse_base[4] = {0, 0, 0, 0};
+  unsigned word = 0;
+  for (unsigned u = 0; u < (1u << FIX_LOG); u++) {
+    if ((u & 255) == 0) {
+      for (int s = 0; s < 4; s++) { out->coarse[ctx][u >> 8][s] = (uint16_t)run[s]; coarse_base[s] = run[s]; }
+    }
+    if ((u & 31) == 0) {
+      for (int s = 0; s < 4; s++) out->fine[ctx][u >> 5][s] = (uint8_t)(run[s] - coarse_base[s]);
+    }
+    unsigned sym = 0;
+    if (u < T) {
+      sym = (dtab_fix[((size_t)ctx << FIX_LOG) + u] >> 16) & 3u;
+      run[sym]++;
+    }
+    word |= sym << (2 * (u & 15));
+    if ((u & 15) == 15) { out->symtab[ctx][u >> 4] = word; word = 0; }
+  }
+  for (int s = 0; s < 4; s++) {
+    const short n = norm[ctx * 4 + s];
+    out->snext[ctx][s] = (uint16_t)((n == -1 ? 1 : n) | (s == 0 ? (t << 12) : 0u));
+  }
+}
+
+// Quality: compact ids for the contexts whose table is not the untouched
+// pattern (64 symbols with norm 2 at log 7 = only the +1 prior was seen).
+// Single CTA: flag per context, then an in-order prefix.
+__global__ void __launch_bounds__(1024)
+k_qual_cid(const short *__restrict__ norm, const uint32_t *__restrict__ logs, uint16_t *__restrict__ cid,
+           uint32_t *__restrict__ n_touched) {
+  __shared__ unsigned flags[QUAL_N];
+  for (unsigned c = threadIdx.x; c < QUAL_N; c += blockDim.x) {
+    bool touched = logs[c] != 7;
+    for (int s = 0; s < (int)QUAL_A && !touched; s++) touched = norm[(size_t)c * QUAL_A + s] != 2;
+    flags[c] = touched ? 1u : 0u;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned n = 0;
+    for (unsigned c = 0; c < QUAL_N; c++) cid[c] = flags[c] ? (uint16_t)(n++) : (uint16_t)0xFFFF;
+    *n_touched = n;
+  }
+}
+
 int tables_alloc(fq28_handle *h, DevTables &t, unsigned n_models, unsigned alphabet) {
   if (t.norm) return FQ28_OK;
   t.n_models = n_models;
@@ -343,6 +406,13 @@ int tables_alloc(fq28_handle *h, DevTables &t, unsigned n_models, unsigned alpha
   FQ28_CUDA(h, cudaMalloc(&t.ctab, t.cells_cap * sizeof(uint16_t)));
   FQ28_CUDA(h, cudaMalloc(&t.dtab, t.cells_cap * sizeof(uint32_t)));
   FQ28_CUDA(h, cudaMalloc(&t.dtab_fix, ((size_t)n_models << FIX_LOG) * sizeof(uint32_t)));
+  FQ28_CUDA(h, cudaMalloc(&t.logsuf, (n_models + 1) * sizeof(uint32_t)));
+  if (alphabet == SEQ_A) {
+    FQ28_CUDA(h, cudaMalloc(&t.seqdec, sizeof(SeqDecTables)));
+  } else {
+    FQ28_CUDA(h, cudaMalloc(&t.cid, n_models * sizeof(uint16_t)));
+    FQ28_CUDA(h, cudaMalloc(&t.n_touched, sizeof(uint32_t)));
+  }
   return FQ28_OK;
 }
 
@@ -355,6 +425,17 @@ int tables_from_norm(fq28_handle *h, DevTables &t) {
   else
     k_build_tables<QUAL_A><<<blocks, threads, 0, h->stream>>>(t.norm, t.logs, t.toff, t.n_models, t.ctab, t.symtt, t.dtab, t.dtab_fix);
   FQ28_LAUNCH_CHECK(h);
+  k_logsuf<<<1, 1, 0, h->stream>>>(t.logs, t.n_models, t.logsuf);
+  FQ28_LAUNCH_CHECK(h);
+  if (t.alphabet == SEQ_A) {
+    k_build_seqdec<<<(SEQ_N + 63) / 64, 64, 0, h->stream>>>(t.norm, t.logs, t.dtab_fix, reinterpret_cast<SeqDecTables *>(t.seqdec));
+    FQ28_LAUNCH_CHECK(h);
+  } else {
+    k_qual_cid<<<1, 1024, 0, h->stream>>>(t.norm, t.logs, t.cid, t.n_touched);
+    FQ28_LAUNCH_CHECK(h);
+    FQ28_CUDA(h, cudaMemcpyAsync(&t.h_n_touched, t.n_touched, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    FQ28_CUDA(h, cudaStreamSynchronize(h->stream));
+  }
   t.ready = true;
   return FQ28_OK;
 }
