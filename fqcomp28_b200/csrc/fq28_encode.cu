@@ -169,9 +169,11 @@ __device__ __forceinline__ TileRef tile_ref(unsigned t, const uint32_t *__restri
   return tr;
 }
 
-// Per tile: context histogram, then exclusive scan over contexts:
-// tbase[t][c] = rank of the first symbol of context c inside the tile's
-// partitioned order, tbase[t][N] = tile symbol count.
+// Per tile: context histogram, then exclusive scan over contexts of the counts
+// rounded up to 16 (every context's run starts 16-byte aligned so that the
+// chain kernel can move it with 128-bit loads):
+// tbase[t][c] = first slot of context c inside the tile's partitioned region
+// (a multiple of 16) | (count & 15); tbase[t][N] = padded size of the region.
 template <class K, unsigned TILE>
 __global__ void __launch_bounds__(256)
 k_tile_hist(const typename K::key_t *__restrict__ key, const uint32_t *__restrict__ tile0,
@@ -195,7 +197,7 @@ k_tile_hist(const typename K::key_t *__restrict__ key, const uint32_t *__restric
   unsigned local[PER];
   unsigned s = 0;
 #pragma unroll
-  for (unsigned i = 0; i < PER; i++) { local[i] = hist[threadIdx.x * PER + i]; s += local[i]; }
+  for (unsigned i = 0; i < PER; i++) { local[i] = hist[threadIdx.x * PER + i]; s += (local[i] + 15u) & ~15u; }
   unsigned inc = s;
 #pragma unroll
   for (int dd = 1; dd < 32; dd <<= 1) {
@@ -210,15 +212,15 @@ k_tile_hist(const typename K::key_t *__restrict__ key, const uint32_t *__restric
   unsigned ex = woff + inc - s;
   uint32_t *out = tbase + (size_t)blockIdx.x * (N + 1);
 #pragma unroll
-  for (unsigned i = 0; i < PER; i++) { out[threadIdx.x * PER + i] = ex; ex += local[i]; }
+  for (unsigned i = 0; i < PER; i++) { out[threadIdx.x * PER + i] = ex | (local[i] & 15u); ex += (local[i] + 15u) & ~15u; }
   if (threadIdx.x == 255) out[N] = ex;
 }
 
 // Stable rank: one warp per tile walks the tile in encode order, 32 symbols a
 // step; run[c] is the next free slot of context c.  Emits
-//   ssym[g0 + slot] = symbol            (partitioned symbols, chain input)
-//   perm[g]         = g0 + slot         (where the symbol's field will be)
-template <class K, unsigned TILE, unsigned WARPS>
+//   ssym[t * STRIDE + slot] = symbol    (partitioned symbols, chain input)
+//   perm[g]                 = t * STRIDE + slot   (where the symbol's field will be)
+template <class K, unsigned TILE, unsigned STRIDE, unsigned WARPS>
 __global__ void __launch_bounds__(WARPS * 32)
 k_tile_rank(const typename K::key_t *__restrict__ key, const uint32_t *__restrict__ tile0,
             const uint32_t *__restrict__ chunk_sym, unsigned n_chunks, unsigned n_tiles,
@@ -231,7 +233,7 @@ k_tile_rank(const typename K::key_t *__restrict__ key, const uint32_t *__restric
   uint32_t *run = run_s[warp];
   const TileRef tr = tile_ref(t, tile0, chunk_sym, n_chunks, TILE);
   const uint32_t *tb = tbase + (size_t)t * (N + 1);
-  for (unsigned i = lane; i < N; i += 32) run[i] = tb[i];
+  for (unsigned i = lane; i < N; i += 32) run[i] = tb[i] & ~15u;
   __syncwarp();
   const typename K::key_t *kp = key + tr.g0;
   unsigned nxt = lane < tr.cnt ? (unsigned)kp[lane] : 0u;
@@ -249,7 +251,7 @@ k_tile_rank(const typename K::key_t *__restrict__ key, const uint32_t *__restric
     if (live && below == 0) run[ctx] = slot + (unsigned)__popc(peers);
     __syncwarp();
     if (live) {
-      const unsigned dst = tr.g0 + slot + (unsigned)__popc(below);
+      const unsigned dst = t * STRIDE + slot + (unsigned)__popc(below);
       ssym[dst] = (uint8_t)(kv & K::sym_mask);
       perm[tr.g0 + j + lane] = dst;
     }
@@ -262,13 +264,19 @@ k_tile_rank(const typename K::key_t *__restrict__ key, const uint32_t *__restric
 // (next-state cells + symbol transforms) sits in shared memory, so all 32
 // lanes walk the same table and chain lengths within a warp are similar.
 // field[slot] = nbBits << 12 | low bits.
+//
+// The lanes advance in ROUNDS of one 16-symbol group each: every lane loads its
+// next group with one 128-bit load at the start of a round -- all lanes in the
+// same instruction, one full round (16 dependent table steps) before the data
+// is used -- and ends the round with two 128-bit stores of the 16 fields.  The
+// only latency on the critical path is the shared-memory next-state lookup.
 // ---------------------------------------------------------------------------
-template <class K, unsigned A, unsigned TILE>
+template <class K, unsigned A, unsigned TILE, unsigned STRIDE>
 __global__ void __launch_bounds__(32)
-k_chain(const uint8_t *__restrict__ ssym, const uint32_t *__restrict__ tile0, const uint32_t *__restrict__ chunk_sym,
-        unsigned n_chunks, const uint32_t *__restrict__ tbase, const uint32_t *__restrict__ logs,
-        const uint32_t *__restrict__ toff, const uint16_t *__restrict__ ctab, const int2 *__restrict__ symtt,
-        uint16_t *__restrict__ field, uint16_t *__restrict__ fstate) {
+k_chain(const uint8_t *__restrict__ ssym, const uint32_t *__restrict__ tile0, unsigned n_chunks,
+        const uint32_t *__restrict__ tbase, const uint32_t *__restrict__ logs, const uint32_t *__restrict__ toff,
+        const uint16_t *__restrict__ ctab, const int2 *__restrict__ symtt, uint16_t *__restrict__ field,
+        uint16_t *__restrict__ fstate) {
   constexpr unsigned N = K::n_models;
   __shared__ uint16_t st[1u << FSE_MAX_TABLELOG];
   __shared__ int2 tt[A];
@@ -276,44 +284,63 @@ k_chain(const uint8_t *__restrict__ ssym, const uint32_t *__restrict__ tile0, co
   const unsigned k = blockIdx.y * 32 + lane;
   const bool live = k < n_chunks;
   const unsigned t_log = logs[c], T = 1u << t_log;
-  unsigned t_begin = 0, t_end = 0, sym0 = 0;
-  if (live) { t_begin = tile0[k]; t_end = tile0[k + 1]; sym0 = chunk_sym[k]; }
-  unsigned total = 0;
-  for (unsigned t = t_begin; t < t_end; t++) {
-    const uint32_t *tb = tbase + (size_t)t * (N + 1) + c;
-    total += tb[1] - tb[0];
-  }
+  unsigned t = 0, t_end = 0;
+  if (live) { t = tile0[k]; t_end = tile0[k + 1]; }
+  // run cursor
+  unsigned grp_left = 0, last_valid = 16;
+  size_t slot = 0;                       // slot of the next group to load
+  uint4 nxtv = make_uint4(0, 0, 0, 0);   // the group loaded in the previous round
+  unsigned nxt_valid = 0;
+  size_t nxt_slot = 0;
+  auto fetch = [&]() {                   // advance to the next non-empty run if needed, load one group
+    while (grp_left == 0 && t < t_end) {
+      const uint32_t *tb = tbase + (size_t)t * (N + 1) + c;
+      const unsigned a0 = tb[0], a1 = tb[1];
+      const unsigned b0 = a0 & ~15u, padded = (a1 & ~15u) - b0;
+      if (padded) {
+        grp_left = padded >> 4;
+        last_valid = (a0 & 15u) ? (a0 & 15u) : 16u;
+        slot = (size_t)t * STRIDE + b0;
+      }
+      ++t;
+    }
+    nxt_valid = 0;
+    if (grp_left) {
+      nxtv = __ldg(reinterpret_cast<const uint4 *>(ssym + slot));
+      nxt_valid = grp_left == 1 ? last_valid : 16u;
+      nxt_slot = slot;
+      slot += 16;
+      --grp_left;
+    }
+  };
+  fetch();
   unsigned x = T;  // FSE_initCState, src/fse_common.hpp:82
-  if (__any_sync(0xffffffffu, total != 0)) {
+  if (__any_sync(0xffffffffu, nxt_valid != 0)) {
     const uint16_t *gs = ctab + toff[c];
     for (unsigned i = lane; i < T; i += 32) st[i] = gs[i];
     for (unsigned i = lane; i < A; i += 32) tt[i] = symtt[(size_t)c * A + i];
     __syncwarp();
-    for (unsigned t = t_begin; t < t_end; t++) {
-      const uint32_t *tb = tbase + (size_t)t * (N + 1) + c;
-      const unsigned b0 = tb[0], n = tb[1] - b0;
-      const unsigned base = sym0 + (t - t_begin) * TILE + b0;
-      const uint8_t *sp = ssym + base;
-      uint16_t *fp = field + base;
-      unsigned j = 0;
-      for (; j + 4 <= n; j += 4) {
-        const unsigned s0 = sp[j], s1 = sp[j + 1], s2 = sp[j + 2], s3 = sp[j + 3];
-        const int2 a0 = tt[s0], a1 = tt[s1], a2 = tt[s2], a3 = tt[s3];
-        unsigned nb;
-        nb = (x + (unsigned)a0.y) >> 16; fp[j] = (uint16_t)((nb << 12) | (x & ((1u << nb) - 1u)));
-        x = st[(int)(x >> nb) + a0.x];
-        nb = (x + (unsigned)a1.y) >> 16; fp[j + 1] = (uint16_t)((nb << 12) | (x & ((1u << nb) - 1u)));
-        x = st[(int)(x >> nb) + a1.x];
-        nb = (x + (unsigned)a2.y) >> 16; fp[j + 2] = (uint16_t)((nb << 12) | (x & ((1u << nb) - 1u)));
-        x = st[(int)(x >> nb) + a2.x];
-        nb = (x + (unsigned)a3.y) >> 16; fp[j + 3] = (uint16_t)((nb << 12) | (x & ((1u << nb) - 1u)));
-        x = st[(int)(x >> nb) + a3.x];
-      }
-      for (; j < n; j++) {
-        const int2 a = tt[sp[j]];
-        const unsigned nb = (x + (unsigned)a.y) >> 16;
-        fp[j] = (uint16_t)((nb << 12) | (x & ((1u << nb) - 1u)));
-        x = st[(int)(x >> nb) + a.x];
+    while (__any_sync(0xffffffffu, nxt_valid != 0)) {
+      const uint4 cur = nxtv;
+      const unsigned valid = nxt_valid;
+      const size_t cur_slot = nxt_slot;
+      fetch();  // next round's group: issued now, consumed after 16 table steps
+      if (valid) {
+        const unsigned w[4] = {cur.x, cur.y, cur.z, cur.w};
+        unsigned f[8];
+#pragma unroll
+        for (unsigned i = 0; i < 16; i++) {
+          const unsigned s = (w[i >> 2] >> (8 * (i & 3))) & (A - 1);  // padding bytes are masked into range
+          const int2 a = tt[s];
+          const unsigned nb = (x + (unsigned)a.y) >> 16;
+          const unsigned fv = (nb << 12) | (x & ((1u << nb) - 1u));
+          const unsigned xn = st[(int)(x >> nb) + a.x];
+          if (i < valid) x = xn;
+          if (i & 1) f[i >> 1] |= fv << 16; else f[i >> 1] = fv;
+        }
+        uint4 *fp = reinterpret_cast<uint4 *>(field + cur_slot);
+        fp[0] = make_uint4(f[0], f[1], f[2], f[3]);
+        fp[1] = make_uint4(f[4], f[5], f[6], f[7]);
       }
     }
   }
@@ -519,7 +546,7 @@ k_pack_write(const uint32_t *__restrict__ ptile0, const uint32_t *__restrict__ c
 // ---------------------------------------------------------------------------
 // host orchestration
 // ---------------------------------------------------------------------------
-template <class K, unsigned A, unsigned TILE, unsigned RANK_WARPS>
+template <class K, unsigned A, unsigned TILE, unsigned STRIDE, unsigned RANK_WARPS>
 static int encode_kind(fq28_handle *h, const DevTables &tab, const typename K::key_t *key, DevBuf &tile0_b,
                        DevBuf &tbase_b, DevBuf &ssym_b, DevBuf &perm_b, DevBuf &field_b, DevBuf &fstate_b,
                        DevBuf &ptile0_b, DevBuf &pbits_b, DevBuf &pscan_b, size_t G, unsigned *n_ptiles_out) {
@@ -542,9 +569,9 @@ static int encode_kind(fq28_handle *h, const DevTables &tab, const typename K::k
   FQ28_CUDA(h, cudaMemcpyAsync(ptile0_b.p, ptile0.data(), (n_chunks + 1) * 4, cudaMemcpyHostToDevice, h->stream));
   FQ28_CUDA(h, cudaStreamSynchronize(h->stream));  // host vectors go out of scope
   FQ28_TRY(ensure(h, tbase_b, (size_t)(n_tiles + 1) * (N + 1) * 4));
-  FQ28_TRY(ensure(h, ssym_b, G + 16));
+  FQ28_TRY(ensure(h, ssym_b, (size_t)n_tiles * STRIDE + 64));
   FQ28_TRY(ensure(h, perm_b, (G + 4) * 4));
-  FQ28_TRY(ensure(h, field_b, (G + 8) * 2));
+  FQ28_TRY(ensure(h, field_b, ((size_t)n_tiles * STRIDE + 64) * 2));
   FQ28_TRY(ensure(h, fstate_b, (size_t)n_chunks * N * 2 + 16));
   FQ28_TRY(ensure(h, pbits_b, (size_t)(n_ptiles + 1) * 4));
   FQ28_TRY(ensure(h, pscan_b, (size_t)(n_ptiles + 2) * 8));
@@ -554,7 +581,7 @@ static int encode_kind(fq28_handle *h, const DevTables &tab, const typename K::k
     k_tile_hist<K, TILE><<<n_tiles, 256, 0, h->stream>>>(key, tile0_b.as<uint32_t>(), chunk_sym, n_chunks,
                                                         tbase_b.as<uint32_t>());
     FQ28_LAUNCH_CHECK(h);
-    k_tile_rank<K, TILE, RANK_WARPS><<<(n_tiles + RANK_WARPS - 1) / RANK_WARPS, RANK_WARPS * 32, 0, h->stream>>>(
+    k_tile_rank<K, TILE, STRIDE, RANK_WARPS><<<(n_tiles + RANK_WARPS - 1) / RANK_WARPS, RANK_WARPS * 32, 0, h->stream>>>(
         key, tile0_b.as<uint32_t>(), chunk_sym, n_chunks, n_tiles, tbase_b.as<uint32_t>(), ssym_b.as<uint8_t>(),
         perm_b.as<uint32_t>());
     FQ28_LAUNCH_CHECK(h);
@@ -564,7 +591,7 @@ static int encode_kind(fq28_handle *h, const DevTables &tab, const typename K::k
   stage_begin(h, N == SEQ_N ? ST_CHAIN_SEQ : ST_CHAIN_QUAL);
   {
     dim3 grid(N, (n_chunks + 31) / 32);
-    k_chain<K, A, TILE><<<grid, 32, 0, h->stream>>>(ssym_b.as<uint8_t>(), tile0_b.as<uint32_t>(), chunk_sym, n_chunks,
+    k_chain<K, A, TILE, STRIDE><<<grid, 32, 0, h->stream>>>(ssym_b.as<uint8_t>(), tile0_b.as<uint32_t>(), n_chunks,
                                                    tbase_b.as<uint32_t>(), tab.logs, tab.toff, tab.ctab, tab.symtt,
                                                    field_b.as<uint16_t>(), fstate_b.as<uint16_t>());
     FQ28_LAUNCH_CHECK(h);
@@ -655,10 +682,10 @@ int encode_slab(fq28_handle *h, fq28_chunk_info *infos, size_t infos_cap, fq28_e
   stage_end(h, ST_EXTRACT);
 
   unsigned n_pt_seq = 0, n_pt_qual = 0;
-  FQ28_TRY((encode_kind<SeqKind, SEQ_A, SEQ_TILE, 4>(h, h->seq, h->key_seq.as<uint16_t>(), h->tile0_seq, h->tbase_seq,
+  FQ28_TRY((encode_kind<SeqKind, SEQ_A, SEQ_TILE, SEQ_STRIDE, 4>(h, h->seq, h->key_seq.as<uint16_t>(), h->tile0_seq, h->tbase_seq,
                                                      h->ssym_seq, h->perm_seq, h->out_seq, h->fstate_seq, h->ptile0_seq,
                                                      h->pbits_seq, h->pscan_seq, G, &n_pt_seq)));
-  FQ28_TRY((encode_kind<QualKind, QUAL_A, QUAL_TILE, 1>(h, h->qual, h->key_qual.as<uint32_t>(), h->tile0_qual,
+  FQ28_TRY((encode_kind<QualKind, QUAL_A, QUAL_TILE, QUAL_STRIDE, 1>(h, h->qual, h->key_qual.as<uint32_t>(), h->tile0_qual,
                                                         h->tbase_qual, h->ssym_qual, h->perm_qual, h->out_qual,
                                                         h->fstate_qual, h->ptile0_qual, h->pbits_qual, h->pscan_qual, G,
                                                         &n_pt_qual)));

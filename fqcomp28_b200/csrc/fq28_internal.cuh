@@ -29,6 +29,9 @@ constexpr unsigned QUAL_N = FQ28_QUAL_MODELS, QUAL_A = FQ28_QUAL_ALPHABET;
 // ---- partition / pack tiling ------------------------------------------------
 constexpr unsigned SEQ_TILE = 16384;    // symbols per context-partition tile (seq)
 constexpr unsigned QUAL_TILE = 131072;  // symbols per context-partition tile (qual)
+// slots per tile region: every non-empty context run is padded to a multiple of 16
+constexpr unsigned SEQ_STRIDE = SEQ_TILE + 16 * SEQ_N;
+constexpr unsigned QUAL_STRIDE = 2 * QUAL_TILE;   // >= QUAL_TILE + 15 * QUAL_N
 constexpr unsigned PACK_THREADS = 256;
 constexpr unsigned PACK_EPT = 8;        // entries per thread in the bit packer
 constexpr unsigned PACK_TILE = PACK_THREADS * PACK_EPT;
