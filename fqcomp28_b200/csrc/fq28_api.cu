@@ -518,7 +518,7 @@ int fq28_get_dtable(fq28_handle *h, int kind, unsigned ctx, uint32_t *cells, uns
   return FQ28_OK;
 }
 
-static const char *const k_stage_names[ST_COUNT] = {"parse", "extract", "partition", "chain_seq", "chain_qual", "pack",
+static const char *const k_stage_names[ST_COUNT] = {"parse", "extract", "part_seq", "part_qual", "chain_seq", "chain_qual", "pack",
                                                     "layout", "decode_seq", "decode_qual", "ninsert", "hist", "tables"};
 const char *fq28_stage_name(size_t i) { return i < ST_COUNT ? k_stage_names[i] : ""; }
 

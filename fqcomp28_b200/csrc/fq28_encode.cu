@@ -258,6 +258,140 @@ k_tile_rank(const typename K::key_t *__restrict__ key, const uint32_t *__restric
   }
 }
 
+// Fused histogram + stable rank for a small context space (sequence, 256
+// contexts).  One warp per tile; lane l owns the l-th contiguous 1/32 of the
+// tile, so the order inside a context is (lane, position in the lane's
+// segment) and no two lanes ever touch the same counter:
+//   load    keys -> shared memory, coalesced (segment rows padded to an odd
+//           word stride so that the per-lane walks are bank-conflict free)
+//   pass 1  cnt[ctx][lane]++                       (u16, lane-private column)
+//   scan    per context: exclusive scan over the lanes -> each lane's first
+//           slot inside the context's run; per tile: exclusive scan over the
+//           contexts of the 16-padded totals -> tbase (same format as
+//           k_tile_hist)
+//   pass 2  slot = cbase[ctx] + cnt[ctx][lane]++; the symbol goes to
+//           region[slot] in shared memory, the slot replaces the key
+//   store   region -> ssym and slots -> perm, coalesced
+// No match_any, no cross-lane dependency inside the passes, and every global
+// access is a full-width coalesced transaction.
+template <class K, unsigned TILE, unsigned STRIDE>
+struct PartSmall {
+  static constexpr unsigned N = K::n_models;
+  static constexpr unsigned SEG = TILE / 32;           // keys per lane
+  static constexpr unsigned ROW = SEG + 2;             // u16 per padded row: (SEG + 2) / 2 words is odd
+  static_assert(N % 32 == 0 && TILE % 64 == 0 && STRIDE < 65536 && ((ROW / 2) & 1) == 1, "layout");
+  static constexpr size_t KEYS_BYTES = (size_t)32 * ROW * 2;
+  static constexpr size_t CNT_BYTES = (size_t)N * 32 * 2;
+  static constexpr size_t CBASE_BYTES = (size_t)N * 4;
+  static constexpr size_t SMEM = KEYS_BYTES + CNT_BYTES + CBASE_BYTES + STRIDE;
+};
+
+template <class K, unsigned TILE, unsigned STRIDE>
+__global__ void __launch_bounds__(32)
+k_tile_part_small(const typename K::key_t *__restrict__ key, const uint32_t *__restrict__ tile0,
+                  const uint32_t *__restrict__ chunk_sym, unsigned n_chunks, unsigned n_tiles,
+                  uint32_t *__restrict__ tbase, uint8_t *__restrict__ ssym, uint32_t *__restrict__ perm) {
+  using P = PartSmall<K, TILE, STRIDE>;
+  constexpr unsigned N = P::N, SEG = P::SEG, ROW = P::ROW;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint16_t *keys = reinterpret_cast<uint16_t *>(smem_raw);                      // [32][ROW]
+  uint16_t *cnt = reinterpret_cast<uint16_t *>(smem_raw + P::KEYS_BYTES);       // [N][32]
+  uint32_t *cbase = reinterpret_cast<uint32_t *>(smem_raw + P::KEYS_BYTES + P::CNT_BYTES);
+  uint8_t *region = smem_raw + P::KEYS_BYTES + P::CNT_BYTES + P::CBASE_BYTES;   // [STRIDE]
+  const unsigned lane = threadIdx.x;
+  const unsigned t = blockIdx.x;
+  if (t >= n_tiles) return;
+  const TileRef tr = tile_ref(t, tile0, chunk_sym, n_chunks, TILE);
+  for (unsigned i = lane; i < N * 16; i += 32) reinterpret_cast<uint32_t *>(cnt)[i] = 0u;
+  const typename K::key_t *kp = key + tr.g0;
+  for (unsigned j = lane; j < tr.cnt; j += 32) keys[(j / SEG) * ROW + (j % SEG)] = (uint16_t)kp[j];
+  __syncwarp();
+  const unsigned j0 = lane * SEG < tr.cnt ? lane * SEG : tr.cnt;
+  const unsigned j1 = (lane + 1) * SEG < tr.cnt ? (lane + 1) * SEG : tr.cnt;
+  uint16_t *myk = keys + lane * ROW;
+  const unsigned nk = j1 - j0;
+  {
+    unsigned j = 0;
+    for (; j + 4 <= nk; j += 4) {  // key loads hoisted: only the counter updates are ordered
+      const unsigned c0 = (unsigned)myk[j] >> K::shift, c1 = (unsigned)myk[j + 1] >> K::shift;
+      const unsigned c2 = (unsigned)myk[j + 2] >> K::shift, c3 = (unsigned)myk[j + 3] >> K::shift;
+      cnt[c0 * 32 + lane]++;
+      cnt[c1 * 32 + lane]++;
+      cnt[c2 * 32 + lane]++;
+      cnt[c3 * 32 + lane]++;
+    }
+    for (; j < nk; j++) cnt[((unsigned)myk[j] >> K::shift) * 32 + lane]++;
+  }
+  __syncwarp();
+  // per context: exclusive scan over lanes; lane (c & 31) keeps the total of context c
+  unsigned tot[N / 32];
+#pragma unroll
+  for (unsigned i = 0; i < N / 32; i++) {
+#pragma unroll 1
+    for (unsigned cl = 0; cl < 32; cl++) {
+      const unsigned c = 32 * i + cl;
+      const unsigned v = cnt[c * 32 + lane];
+      unsigned inc = v;
+#pragma unroll
+      for (int dd = 1; dd < 32; dd <<= 1) {
+        const unsigned o = __shfl_up_sync(0xffffffffu, inc, dd);
+        if (lane >= (unsigned)dd) inc += o;
+      }
+      cnt[c * 32 + lane] = (uint16_t)(inc - v);
+      const unsigned total = __shfl_sync(0xffffffffu, inc, 31);
+      if (lane == cl) tot[i] = total;
+    }
+  }
+  // context bases in context order c = 32 i + lane: scan over lanes, carry over i
+  uint32_t *tb = tbase + (size_t)t * (N + 1);
+  unsigned carry = 0;
+#pragma unroll
+  for (unsigned i = 0; i < N / 32; i++) {
+    const unsigned v = (tot[i] + 15u) & ~15u;
+    unsigned inc = v;
+#pragma unroll
+    for (int dd = 1; dd < 32; dd <<= 1) {
+      const unsigned o = __shfl_up_sync(0xffffffffu, inc, dd);
+      if (lane >= (unsigned)dd) inc += o;
+    }
+    const unsigned base = carry + inc - v;
+    cbase[32 * i + lane] = base;
+    tb[32 * i + lane] = base | (tot[i] & 15u);
+    carry += __shfl_sync(0xffffffffu, inc, 31);
+  }
+  if (lane == 0) tb[N] = carry;
+  __syncwarp();
+  {
+    auto place = [&](unsigned j, unsigned kv, unsigned cb) {
+      const unsigned ctx = kv >> K::shift;
+      const unsigned o = cnt[ctx * 32 + lane];
+      cnt[ctx * 32 + lane] = (uint16_t)(o + 1);
+      const unsigned slot = cb + o;
+      region[slot] = (uint8_t)(kv & K::sym_mask);
+      myk[j] = (uint16_t)slot;
+    };
+    unsigned j = 0;
+    for (; j + 4 <= nk; j += 4) {
+      const unsigned k0 = myk[j], k1 = myk[j + 1], k2 = myk[j + 2], k3 = myk[j + 3];
+      const unsigned b0 = cbase[k0 >> K::shift], b1 = cbase[k1 >> K::shift];
+      const unsigned b2 = cbase[k2 >> K::shift], b3 = cbase[k3 >> K::shift];
+      place(j, k0, b0);
+      place(j + 1, k1, b1);
+      place(j + 2, k2, b2);
+      place(j + 3, k3, b3);
+    }
+    for (; j < nk; j++) { const unsigned kv = myk[j]; place(j, kv, cbase[kv >> K::shift]); }
+  }
+  __syncwarp();
+  const unsigned t_slot0 = t * STRIDE;
+  uint32_t *pp = perm + tr.g0;
+  for (unsigned j = lane; j < tr.cnt; j += 32) pp[j] = t_slot0 + keys[(j / SEG) * ROW + (j % SEG)];
+  // carry = padded size of the tile's region (multiple of 16)
+  const uint4 *rsrc = reinterpret_cast<const uint4 *>(region);
+  uint4 *rdst = reinterpret_cast<uint4 *>(ssym + (size_t)t_slot0);
+  for (unsigned i = lane; i < (carry >> 4); i += 32) rdst[i] = rsrc[i];
+}
+
 // ---------------------------------------------------------------------------
 // chain: FSE_encodeSymbol (Appendix A.5) along the symbols of one context.
 // CTA = one warp = one context x 32 consecutive chunks; the context's CTable
@@ -576,8 +710,20 @@ static int encode_kind(fq28_handle *h, const DevTables &tab, const typename K::k
   FQ28_TRY(ensure(h, pbits_b, (size_t)(n_ptiles + 1) * 4));
   FQ28_TRY(ensure(h, pscan_b, (size_t)(n_ptiles + 2) * 8));
 
-  stage_begin(h, ST_PARTITION);
-  if (n_tiles) {
+  stage_begin(h, N == SEQ_N ? ST_PART_SEQ : ST_PART_QUAL);
+  if (n_tiles && N == SEQ_N) {
+    using P = PartSmall<SeqKind, SEQ_TILE, SEQ_STRIDE>;
+    static bool attr_set = false;
+    if (!attr_set) {
+      FQ28_CUDA(h, cudaFuncSetAttribute(k_tile_part_small<SeqKind, SEQ_TILE, SEQ_STRIDE>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P::SMEM));
+      attr_set = true;
+    }
+    k_tile_part_small<SeqKind, SEQ_TILE, SEQ_STRIDE><<<n_tiles, 32, P::SMEM, h->stream>>>(
+        reinterpret_cast<const uint16_t *>(key), tile0_b.as<uint32_t>(), chunk_sym, n_chunks, n_tiles,
+        tbase_b.as<uint32_t>(), ssym_b.as<uint8_t>(), perm_b.as<uint32_t>());
+    FQ28_LAUNCH_CHECK(h);
+  } else if (n_tiles) {
     k_tile_hist<K, TILE><<<n_tiles, 256, 0, h->stream>>>(key, tile0_b.as<uint32_t>(), chunk_sym, n_chunks,
                                                         tbase_b.as<uint32_t>());
     FQ28_LAUNCH_CHECK(h);
@@ -586,7 +732,7 @@ static int encode_kind(fq28_handle *h, const DevTables &tab, const typename K::k
         perm_b.as<uint32_t>());
     FQ28_LAUNCH_CHECK(h);
   }
-  stage_end(h, ST_PARTITION);
+  stage_end(h, N == SEQ_N ? ST_PART_SEQ : ST_PART_QUAL);
 
   stage_begin(h, N == SEQ_N ? ST_CHAIN_SEQ : ST_CHAIN_QUAL);
   {

@@ -90,7 +90,8 @@ struct DevTables {
 enum Stage {
   ST_PARSE = 0,   // K1 newline scan + record table + chunk walk
   ST_EXTRACT,     // K2 symbols / contexts / N positions
-  ST_PARTITION,   // context partition (tile hist + stable rank)
+  ST_PART_SEQ,    // context partition, sequence (fused hist + stable rank)
+  ST_PART_QUAL,   // context partition, quality (tile hist + stable rank)
   ST_CHAIN_SEQ,   // K5 tANS state chains, sequence
   ST_CHAIN_QUAL,  // K5 tANS state chains, quality
   ST_PACK,        // K5 bit offsets + bit packing

@@ -141,13 +141,16 @@ k_chunk_walk(const uint32_t *__restrict__ hdr_off, const uint32_t *__restrict__ 
   const unsigned lane = threadIdx.x;
   size_t s_rec = 0, k = 0;
   if (lane == 0) { chunk_rec[0] = 0; chunk_sym[0] = 0; chunk_byte[0] = 0; }
+  // average record size: the first probe of every chunk brackets the expected
+  // answer, which settles fixed-length data in ONE dependent load per chunk
+  const size_t avg = n_rec ? ((size_t)hdr_off[n_rec] - hdr_off[0] + n_rec - 1) / n_rec : 1;
+  size_t s = n_rec ? hdr_off[0] : 0;  // byte start of the current chunk (carried, never re-loaded)
   for (;;) {
     if (s_rec >= n_rec) {
       // bytes left but no complete record: in the reference this is a
       // zero-record chunk (malformed tail); reported only at EOF
       break;
     }
-    const size_t s = hdr_off[s_rec];
     const size_t limit = s + R;
     const bool reaches_eof = limit >= n_bytes;
     if (!eof && limit > n_bytes) break;
@@ -155,18 +158,40 @@ k_chunk_walk(const uint32_t *__restrict__ hdr_off, const uint32_t *__restrict__ 
     size_t lo = s_rec;
     size_t hi = s_rec + R / 12 + 1;  // a record is at least 12 bytes
     if (hi > n_rec) hi = n_rec;
+    size_t lo_val = s;               // hdr_off[lo]
+    {  // bracket probe: 32 consecutive records around the estimate
+      size_t est = s_rec + (L - s) / (avg ? avg : 1);
+      if (est > hi) est = hi;
+      size_t p0 = est >= s_rec + 16 ? est - 16 : s_rec;
+      if (p0 + 31 > hi) p0 = hi >= 31 && hi - 31 >= s_rec ? hi - 31 : s_rec;
+      size_t p = p0 + lane;
+      if (p > hi) p = hi;
+      const size_t v = hdr_off[p];
+      const bool ok = v <= L;
+      const unsigned m = __ballot_sync(0xffffffffu, ok);
+      if (m & 1u) {                  // p0 is a valid lower bound
+        const unsigned c = __popc(m);  // ok is monotone: a prefix of the lanes
+        lo = p0 + c - 1 > hi ? hi : p0 + c - 1;
+        lo_val = __shfl_sync(0xffffffffu, v, c - 1);
+        if (c < 32) hi = lo;         // lane c is the first record that does not fit
+      } else {
+        hi = p0 - 1;                 // answer is below the bracket (p0 > s_rec here)
+      }
+    }
     while (lo < hi) {
       const size_t step = (hi - lo + 31) / 32;
       size_t p = lo + (size_t)(lane + 1) * step;
       if (p > hi) p = hi;
-      const bool ok = (size_t)hdr_off[p] <= L;
+      const size_t v = hdr_off[p];
+      const bool ok = v <= L;
       const unsigned m = __ballot_sync(0xffffffffu, ok);
       const unsigned c = __popc(m);
-      if (c == 32) { lo = hi; break; }
+      if (c == 32) { lo = hi; lo_val = __shfl_sync(0xffffffffu, v, 31); break; }
       size_t nlo = lo + (size_t)c * step;          // p_c (== lo when c == 0)
       if (nlo > hi) nlo = hi;
       size_t nhi = lo + (size_t)(c + 1) * step;    // p_{c+1}, not ok
       if (nhi > hi) nhi = hi;
+      if (c) lo_val = __shfl_sync(0xffffffffu, v, c - 1);
       lo = nlo;
       hi = nhi - 1;
     }
@@ -183,9 +208,10 @@ k_chunk_walk(const uint32_t *__restrict__ hdr_off, const uint32_t *__restrict__ 
     if (lane == 0) {
       chunk_rec[k] = (uint32_t)lo;
       chunk_sym[k] = symoff ? symoff[lo] : 0u;
-      chunk_byte[k] = hdr_off[lo];
+      chunk_byte[k] = (uint32_t)lo_val;
     }
     s_rec = lo;
+    s = lo_val;
     if (reaches_eof) break;
   }
   if (lane == 0) *n_chunks_out = k;
