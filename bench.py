@@ -185,6 +185,7 @@ def run_ours(args):
     import torch.distributed as dist
 
     import fqcomp28_b200 as P
+    from fqcomp28_b200 import multigpu as MG
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -209,7 +210,7 @@ def run_ours(args):
             k[0] = int((d_fastq[: min(S, n_bytes)] == 10).sum().item()) // 4
         dist.broadcast(k, 0)
         K = int(k.item())
-        a, b = K * rank // world, K * (rank + 1) // world
+        a, b = MG.shard_range(K, rank, world)
         d_sample = synth.illumina(a, b - a, seed=30, profile=args.profile, device=str(dev))
         sample_window = d_sample.numel()
     else:
@@ -231,8 +232,7 @@ def run_ours(args):
         cq.zero_()
         h.hist_dev(d_sample.data_ptr(), sample_window, cs.data_ptr(), cq.data_ptr())
         if world > 1:
-            dist.all_reduce(cs)  # the path's only collective (C1): 525 312 u32 counters
-            dist.all_reduce(cq)
+            MG.allreduce_counts(cs, cq)  # the path's only collective (C1): 525 312 u32 counters over NCCL
         f = h.build_tables_dev(cs.data_ptr(), cq.data_ptr())
         state["ft"] = f
 
@@ -310,8 +310,7 @@ def run_ours(args):
             d_tmp = torch.empty(sample_window + 64, dtype=torch.uint8, device=dev)
             d_tmp[:sample_window].copy_(hp["sample_t"], non_blocking=True)
             h.hist_dev(d_tmp.data_ptr(), sample_window, cs.data_ptr(), cq.data_ptr())
-            dist.all_reduce(cs)
-            dist.all_reduce(cq)
+            MG.allreduce_counts(cs, cq)
             h.build_tables_dev(cs.data_ptr(), cq.data_ptr())
             _, summ, _ = h.compress(hp["fastq"], R, eof=True, arenas=hp["arenas"])
         else:
