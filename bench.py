@@ -45,10 +45,25 @@ def parse_args():
     ap.add_argument("--reading-mb", type=int, default=1, help="-R, chunk size in MB")
     ap.add_argument("--sample-mb", type=int, default=128, help="-S, sample size in MB")
     ap.add_argument("--profile", default="novaseq", choices=["novaseq", "hiseq"])
-    ap.add_argument("--cpu-mb", type=int, default=1024, help="bounded sample for the CPU legs")
+    ap.add_argument("--cpu-mb", type=int, default=2048, help="bounded sample (MB of the slab) for the CPU legs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--threads", type=int, default=0, help="CPU threads (0 = all)")
     return ap.parse_args()
+
+
+def load_traffic():
+    """Per-symbol DRAM traffic of the stage kernels from the latest committed
+    ncu --set full capture (profiles/traffic_rNN.json, written by
+    profiles/summarize.py)."""
+    import glob
+
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "traffic_r*.json")))
+    if not files:
+        return {}
+    try:
+        return json.load(open(files[-1]))
+    except Exception:
+        return {}
 
 
 def load_peaks():
@@ -366,6 +381,7 @@ def run_ours(args):
         dist.all_reduce(tot_bytes)
     total_mb = float(tot_bytes.item()) / 1e6
     peak, peak_src = load_peaks()
+    traffic_db = load_traffic()
     nsym = int(summ.n_symbols)
     side = 2 * int(summ.n_records) * 2 + 2 * int(summ.n_pos_entries) + int(summ.hdr_bytes)
     algo_pipeline = n_bytes + int(summ.seq_bytes) + int(summ.qual_bytes) + side  # SURVEY 8(d) `B`
@@ -385,7 +401,9 @@ def run_ours(args):
         kern_ms = sum(stage_ms.values())
         return {
             "bound": "hbm", "kernel": name, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-            "traffic": None, "peak_source": peak_src, "kernel_ms": stage_ms[name], "kernel_share_of_step": stage_ms[name] / kern_ms,
+            "traffic": (traffic_db.get(name, {}).get("dram_bytes_per_symbol") or 0) * nsym or None,
+            "traffic_source": "ncu dram__bytes_read+write per symbol of the committed capture x symbols of this run" if name in traffic_db else None,
+            "peak_source": peak_src, "kernel_ms": stage_ms[name], "kernel_share_of_step": stage_ms[name] / kern_ms,
             "stage_ms": {k: round(v, 4) for k, v in stage_ms.items()},
             "pipeline": {"algorithmic_bytes": algo_pipeline, "kernels_ms": kern_ms,
                          "achieved": algo_pipeline / (kern_ms * 1e-3) / 1e9, "frac": algo_pipeline / (kern_ms * 1e-3) / 1e9 / peak},
@@ -404,6 +422,16 @@ def run_ours(args):
                 "h2d_bytes_per_step": out_bytes_c, "d2h_bytes_per_step": n_bytes},
         "gpu_launches": int(launches_d), "roofline": roofline(t_d, "d"),
     }
+
+    def gpu_fnv(O):
+        """FNV-1a over (seq stream, qual stream) of every chunk in order, on the
+        bytes the e2e leg fetched to the host -- same walk as fq28o_bench."""
+        ar, hh = state["hp"]["arenas"], 1469598103934665603
+        for kk in range(int(summ.n_chunks)):
+            ci = state["dec_infos"][kk]
+            hh = O.fnv1a(ar["seq"][ci.seq_off : ci.seq_off + ci.seq_len], hh)
+            hh = O.fnv1a(ar["qual"][ci.qual_off : ci.qual_off + ci.qual_len], hh)
+        return hh
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -424,7 +452,8 @@ def run_ours(args):
                 "value": vc if args.mode == "compress" else vd, "unit": "MB/s", "cores": threads, "kind": "port",
                 "sample": f"leading {host.size} bytes of the rank-0 slab ({res.n_chunks} chunks), one pass",
                 "compress_MBps": vc, "decompress_MBps": vd, "roundtrip_ok": bool(res.roundtrip_ok),
-                "streams_match_gpu": bool(host.size == n_bytes and res.seq_bytes == int(summ.seq_bytes) and res.qual_bytes == int(summ.qual_bytes)),
+                "streams_match_gpu": bool(host.size == n_bytes and res.seq_bytes == int(summ.seq_bytes)
+                                          and res.qual_bytes == int(summ.qual_bytes) and res.checksum == gpu_fnv(O)),
             }
         except Exception as e:  # the oracle is a checker, never a dependency of the product arm
             cpu_baseline = {"error": repr(e)}

@@ -872,6 +872,12 @@ static void run_workers(bench_ctx *b, int threads) {
   free(th);
 }
 
+uint64_t fq28o_fnv1a(const uint8_t *p, size_t n, uint64_t h) {
+  size_t i;
+  for (i = 0; i < n; i++) { h ^= p[i]; h *= 1099511628211ULL; }
+  return h;
+}
+
 int fq28o_bench(const char *fastq, size_t size, size_t sample_bytes,
                 size_t reading_size, int threads, int do_decompress,
                 fq28o_bench_result *res) {

@@ -168,6 +168,8 @@ typedef struct {
   int roundtrip_ok;      /* decoded FASTQ == input */
   int err;
 } fq28o_bench_result;
+/* FNV-1a, chained: the checksum fq28o_bench computes over the streams */
+uint64_t fq28o_fnv1a(const uint8_t *p, size_t n, uint64_t h);
 int fq28o_bench(const char *fastq, size_t size, size_t sample_bytes,
                 size_t reading_size, int threads, int do_decompress,
                 fq28o_bench_result *res);

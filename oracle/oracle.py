@@ -107,6 +107,8 @@ def lib() -> C.CDLL:
     L.fq28o_decode_qual.restype = i32
     L.fq28o_layout_chunk.argtypes = [vp, sz, vp, vp, vp, sz, vp]
     L.fq28o_layout_chunk.restype = sz
+    L.fq28o_fnv1a.argtypes = [vp, sz, C.c_uint64]
+    L.fq28o_fnv1a.restype = C.c_uint64
     L.fq28o_bench.argtypes = [vp, sz, sz, sz, i32, i32, C.POINTER(BenchResult)]
     L.fq28o_bench.restype = i32
     _lib = L
@@ -300,6 +302,11 @@ def gather_headers(data: np.ndarray, recs: np.ndarray):
     parts = [data[int(o) : int(o) + int(l)] for o, l in zip(recs["hdr_off"], lens)]
     hdr = np.concatenate(parts) if parts else np.zeros(0, dtype=np.uint8)
     return hdr, lens
+
+
+def fnv1a(data: np.ndarray, h: int = 1469598103934665603) -> int:
+    data = np.ascontiguousarray(data, dtype=np.uint8)
+    return int(lib().fq28o_fnv1a(_p(data), data.size, h))
 
 
 def bench(data: np.ndarray, sample_bytes: int, reading_size: int, threads: int, do_decompress: bool = True) -> BenchResult:
