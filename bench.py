@@ -392,7 +392,7 @@ def run_ours(args):
             "chain_seq": nsym * 3, "chain_qual": nsym * 3,          # 1 B symbol read + 2 B field written
             "decode_seq": nsym + int(summ.seq_bytes), "decode_qual": nsym + int(summ.qual_bytes),  # stream read + 1 B/sym written
             "part_seq": nsym * (2 + 1 + 4), "part_qual": nsym * (4 + 4 + 1 + 4),
-            "pack": nsym * 2 * (4 + 2) * 2, "extract": 2 * nsym + nsym * 6, "parse": 2 * n_bytes,
+            "pack_seq": nsym * (4 + 2) * 2, "pack_qual": nsym * (4 + 2) * 2, "extract": 2 * nsym + nsym * 6, "parse": 2 * n_bytes,
             "layout": int(summ.hdr_bytes) * 2 + 5 * int(summ.n_records), "hist": 2 * min(S, n_bytes), "tables": 8448 * 2048 * 10,
             "ninsert": 4 * int(summ.n_records),
         }

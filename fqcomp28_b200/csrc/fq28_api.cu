@@ -97,6 +97,23 @@ void side_stage_end(fq28_handle *h, Stage s) {
   cudaEventRecord(h->ev_pool[h->ev_used].b, h->side);
   h->ev_used++;
 }
+int stage_open(fq28_handle *h, Stage s, cudaStream_t strm) {
+  if (!h->timing) return -1;
+  if (h->ev_used == h->ev_pool.size()) {
+    fq28_handle::EvRec r;
+    r.stage = s;
+    cudaEventCreate(&r.a);
+    cudaEventCreate(&r.b);
+    h->ev_pool.push_back(r);
+  }
+  const int slot = (int)h->ev_used++;
+  h->ev_pool[slot].stage = s;
+  cudaEventRecord(h->ev_pool[slot].a, strm);
+  return slot;
+}
+void stage_close(fq28_handle *h, int slot, cudaStream_t strm) {
+  if (slot >= 0) cudaEventRecord(h->ev_pool[slot].b, strm);
+}
 int side_fork(fq28_handle *h) {
   FQ28_CUDA(h, cudaEventRecord(h->ev_fork, h->stream));
   FQ28_CUDA(h, cudaStreamWaitEvent(h->side, h->ev_fork, 0));
@@ -117,7 +134,7 @@ static void free_buf(DevBuf &b) {
 static void free_tables(DevTables &t) {
   cudaFree(t.counts); cudaFree(t.norm); cudaFree(t.logs); cudaFree(t.max_log); cudaFree(t.toff);
   cudaFree(t.ctab); cudaFree(t.symtt); cudaFree(t.dtab); cudaFree(t.dtab_fix);
-  cudaFree(t.logsuf); cudaFree(t.seqdec); cudaFree(t.cid); cudaFree(t.n_touched);
+  cudaFree(t.logsuf); cudaFree(t.seqdec); cudaFree(t.cid); cudaFree(t.n_touched); cudaFree(t.dom_sym);
   t = DevTables();
 }
 
@@ -175,7 +192,11 @@ int fq28_create(int device, fq28_handle **out) {
     if (cudaSetDevice(device) != cudaSuccess) { rc = FQ28_ERR_CUDA; break; }
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { rc = FQ28_ERR_CUDA; break; }
     h->own_stream = true;
-    if (cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess) { rc = FQ28_ERR_CUDA; break; }
+    {  // the side stream carries the latency-bound chains: its CTAs must not queue behind bulk kernels
+      int lo = 0, hi = 0;
+      cudaDeviceGetStreamPriorityRange(&lo, &hi);
+      if (cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, hi) != cudaSuccess) { rc = FQ28_ERR_CUDA; break; }
+    }
     if (cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess) { rc = FQ28_ERR_CUDA; break; }
     if (cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess) { rc = FQ28_ERR_CUDA; break; }
     if (cudaMalloc(&h->d_status, sizeof(DevStatus)) != cudaSuccess) { rc = FQ28_ERR_CUDA; break; }
@@ -201,7 +222,7 @@ void fq28_destroy(fq28_handle *h) {
                     &h->perm_seq, &h->perm_qual, &h->ssym_seq, &h->ssym_qual, &h->out_seq, &h->out_qual, &h->tile0_seq,
                     &h->tile0_qual, &h->tbase_seq, &h->tbase_qual, &h->fstate_seq, &h->fstate_qual, &h->ptile0_seq,
                     &h->ptile0_qual, &h->pbits_seq, &h->pbits_qual, &h->pscan_seq, &h->pscan_qual, &h->arena_seq,
-                    &h->arena_qual, &h->d_infos, &h->scan_tmp, &h->hdrscan, &h->hdr_arena, &h->dec_out, &h->dec_recout, &h->dec_hdrin,
+                    &h->arena_qual, &h->d_infos, &h->scan_tmp, &h->scan_tmp_side, &h->dom_list, &h->hdrscan, &h->hdr_arena, &h->dec_out, &h->dec_recout, &h->dec_hdrin,
                     &h->dec_npos_off, &h->dec_meta, &h->dec_cold};
   for (DevBuf *b : bufs) free_buf(*b);
   for (DevBuf &b : h->dec_in) free_buf(b);
@@ -518,7 +539,7 @@ int fq28_get_dtable(fq28_handle *h, int kind, unsigned ctx, uint32_t *cells, uns
   return FQ28_OK;
 }
 
-static const char *const k_stage_names[ST_COUNT] = {"parse", "extract", "part_seq", "part_qual", "chain_seq", "chain_qual", "pack",
+static const char *const k_stage_names[ST_COUNT] = {"parse", "extract", "part_seq", "part_qual", "chain_seq", "chain_qual", "pack_seq", "pack_qual",
                                                     "layout", "decode_seq", "decode_qual", "ninsert", "hist", "tables"};
 const char *fq28_stage_name(size_t i) { return i < ST_COUNT ? k_stage_names[i] : ""; }
 

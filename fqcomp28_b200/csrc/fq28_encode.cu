@@ -17,6 +17,10 @@
 //               (nbBits, bits) per symbol
 //   pack      : gather the fields back into encode order, prefix-sum nbBits,
 //               OR the fields into the output words
+#include <stdlib.h>
+
+#include <algorithm>
+
 #include "fq28_internal.cuh"
 
 namespace fq28 {
@@ -304,7 +308,17 @@ k_tile_part_small(const typename K::key_t *__restrict__ key, const uint32_t *__r
   const TileRef tr = tile_ref(t, tile0, chunk_sym, n_chunks, TILE);
   for (unsigned i = lane; i < N * 16; i += 32) reinterpret_cast<uint32_t *>(cnt)[i] = 0u;
   const typename K::key_t *kp = key + tr.g0;
-  for (unsigned j = lane; j < tr.cnt; j += 32) keys[(j / SEG) * ROW + (j % SEG)] = (uint16_t)kp[j];
+  {  // coalesced key load, 8 loads in flight per lane
+    unsigned j = lane;
+    for (; j + 7 * 32 < tr.cnt; j += 8 * 32) {
+      uint16_t v[8];
+#pragma unroll
+      for (unsigned u = 0; u < 8; u++) v[u] = (uint16_t)kp[j + u * 32];
+#pragma unroll
+      for (unsigned u = 0; u < 8; u++) { const unsigned jj = j + u * 32; keys[(jj / SEG) * ROW + (jj % SEG)] = v[u]; }
+    }
+    for (; j < tr.cnt; j += 32) keys[(j / SEG) * ROW + (j % SEG)] = (uint16_t)kp[j];
+  }
   __syncwarp();
   const unsigned j0 = lane * SEG < tr.cnt ? lane * SEG : tr.cnt;
   const unsigned j1 = (lane + 1) * SEG < tr.cnt ? (lane + 1) * SEG : tr.cnt;
@@ -328,18 +342,24 @@ k_tile_part_small(const typename K::key_t *__restrict__ key, const uint32_t *__r
 #pragma unroll
   for (unsigned i = 0; i < N / 32; i++) {
 #pragma unroll 1
-    for (unsigned cl = 0; cl < 32; cl++) {
-      const unsigned c = 32 * i + cl;
-      const unsigned v = cnt[c * 32 + lane];
-      unsigned inc = v;
+    for (unsigned cl = 0; cl < 32; cl += 4) {  // four independent rows per step: the shuffle latencies overlap
+      unsigned v[4], inc[4];
+#pragma unroll
+      for (unsigned u = 0; u < 4; u++) { v[u] = cnt[(32 * i + cl + u) * 32 + lane]; inc[u] = v[u]; }
 #pragma unroll
       for (int dd = 1; dd < 32; dd <<= 1) {
-        const unsigned o = __shfl_up_sync(0xffffffffu, inc, dd);
-        if (lane >= (unsigned)dd) inc += o;
+#pragma unroll
+        for (unsigned u = 0; u < 4; u++) {
+          const unsigned o = __shfl_up_sync(0xffffffffu, inc[u], dd);
+          if (lane >= (unsigned)dd) inc[u] += o;
+        }
       }
-      cnt[c * 32 + lane] = (uint16_t)(inc - v);
-      const unsigned total = __shfl_sync(0xffffffffu, inc, 31);
-      if (lane == cl) tot[i] = total;
+#pragma unroll
+      for (unsigned u = 0; u < 4; u++) {
+        cnt[(32 * i + cl + u) * 32 + lane] = (uint16_t)(inc[u] - v[u]);
+        const unsigned total = __shfl_sync(0xffffffffu, inc[u], 31);
+        if (lane == cl + u) tot[i] = total;
+      }
     }
   }
   // context bases in context order c = 32 i + lane: scan over lanes, carry over i
@@ -385,12 +405,21 @@ k_tile_part_small(const typename K::key_t *__restrict__ key, const uint32_t *__r
   __syncwarp();
   const unsigned t_slot0 = t * STRIDE;
   uint32_t *pp = perm + tr.g0;
+#pragma unroll 8
   for (unsigned j = lane; j < tr.cnt; j += 32) pp[j] = t_slot0 + keys[(j / SEG) * ROW + (j % SEG)];
   // carry = padded size of the tile's region (multiple of 16)
   const uint4 *rsrc = reinterpret_cast<const uint4 *>(region);
   uint4 *rdst = reinterpret_cast<uint4 *>(ssym + (size_t)t_slot0);
   for (unsigned i = lane; i < (carry >> 4); i += 32) rdst[i] = rsrc[i];
 }
+
+// symbols of a context inside a tile, from the packed tbase entries
+__device__ __forceinline__ unsigned run_count(const uint32_t *__restrict__ tb) {
+  const unsigned a0 = tb[0], a1 = tb[1];
+  const unsigned padded = (a1 & ~15u) - (a0 & ~15u);
+  return (a0 & 15u) ? padded - 16u + (a0 & 15u) : padded;
+}
+constexpr unsigned DOM_MIN = 16384;  // chain length from which a (chunk, context) pair goes to k_chain_dom
 
 // ---------------------------------------------------------------------------
 // chain: FSE_encodeSymbol (Appendix A.5) along the symbols of one context.
@@ -410,16 +439,21 @@ __global__ void __launch_bounds__(32)
 k_chain(const uint8_t *__restrict__ ssym, const uint32_t *__restrict__ tile0, unsigned n_chunks,
         const uint32_t *__restrict__ tbase, const uint32_t *__restrict__ logs, const uint32_t *__restrict__ toff,
         const uint16_t *__restrict__ ctab, const int2 *__restrict__ symtt, uint16_t *__restrict__ field,
-        uint16_t *__restrict__ fstate) {
+        uint16_t *__restrict__ fstate, const int8_t *__restrict__ dom_sym) {
   constexpr unsigned N = K::n_models;
   __shared__ uint16_t st[1u << FSE_MAX_TABLELOG];
   __shared__ int2 tt[A];
   const unsigned c = blockIdx.x, lane = threadIdx.x;
   const unsigned k = blockIdx.y * 32 + lane;
-  const bool live = k < n_chunks;
+  bool live = k < n_chunks;
   const unsigned t_log = logs[c], T = 1u << t_log;
   unsigned t = 0, t_end = 0;
   if (live) { t = tile0[k]; t_end = tile0[k + 1]; }
+  if (dom_sym && dom_sym[c] >= 0 && live) {  // long chains of dominant-symbol contexts go to k_chain_dom
+    unsigned total = 0;
+    for (unsigned tt_ = t; tt_ < t_end; tt_++) total += run_count(tbase + (size_t)tt_ * (N + 1) + c);
+    if (total >= DOM_MIN) { live = false; t = t_end; }
+  }
   // run cursor
   unsigned grp_left = 0, last_valid = 16;
   size_t slot = 0;                       // slot of the next group to load
@@ -479,6 +513,158 @@ k_chain(const uint8_t *__restrict__ ssym, const uint32_t *__restrict__ tile0, un
     }
   }
   if (live) fstate[(size_t)k * N + c] = (uint16_t)x;
+}
+
+// ---------------------------------------------------------------------------
+// Long chains in contexts with a DOMINANT symbol (norm > T/2, so every step
+// with it emits 0 or 1 bit): binned qualities put > 80 % of a chunk's symbols
+// into one such chain, and its length bounds the whole encoder.  One warp per
+// (chunk, context) pair:
+//   * P8[x] = effect of 8 consecutive dominant symbols on state x: next state
+//     (11 bits) | nbBits of the 8 steps (8 bits) | emitted bits (8 bits),
+//     built in shared memory from the CTable;
+//   * per block of 32 groups (512 symbols): every lane loads one group and
+//     tests its two 8-symbol halves against the dominant pattern (parallel),
+//     the warp then walks the 64 halves serially -- ONE table lookup for an
+//     all-dominant half, 8 ordinary steps otherwise -- and finally every lane
+//     expands and stores the 16 fields of its group (parallel).
+// ---------------------------------------------------------------------------
+template <class K>
+__global__ void k_dom_list(const uint32_t *__restrict__ tile0, unsigned n_chunks, const uint32_t *__restrict__ tbase,
+                           const int8_t *__restrict__ dom_sym, uint32_t *__restrict__ list, unsigned cap,
+                           unsigned long long *__restrict__ count) {
+  constexpr unsigned N = K::n_models;
+  const unsigned c = blockIdx.x;
+  if (dom_sym[c] < 0) return;
+  const unsigned k = blockIdx.y * blockDim.x + threadIdx.x;
+  if (k >= n_chunks) return;
+  unsigned total = 0;
+  for (unsigned t = tile0[k]; t < tile0[k + 1]; t++) total += run_count(tbase + (size_t)t * (N + 1) + c);
+  if (total >= DOM_MIN) {
+    const unsigned long long i = atomicAdd(count, 1ULL);
+    if (i < cap) list[i] = c | (k << 13);
+  }
+}
+
+template <class K, unsigned A, unsigned STRIDE>
+__global__ void __launch_bounds__(32)
+k_chain_dom(const uint32_t *__restrict__ list, const unsigned long long *__restrict__ count,
+            const uint8_t *__restrict__ ssym, const uint32_t *__restrict__ tile0, const uint32_t *__restrict__ tbase,
+            const uint32_t *__restrict__ logs, const uint32_t *__restrict__ toff, const uint16_t *__restrict__ ctab,
+            const int2 *__restrict__ symtt, const int8_t *__restrict__ dom_sym, uint16_t *__restrict__ field,
+            uint16_t *__restrict__ fstate) {
+  constexpr unsigned N = K::n_models;
+  constexpr unsigned SLOW = 0xFFFFFFFFu;
+  __shared__ uint16_t st[1u << FSE_MAX_TABLELOG];
+  __shared__ int2 tt[A];
+  __shared__ uint32_t P8[1u << FIX_LOG];
+  __shared__ uint32_t E[64];
+  __shared__ uint16_t F[512];
+  if (blockIdx.x >= *count) return;
+  const unsigned lane = threadIdx.x;
+  const unsigned ent = list[blockIdx.x];
+  const unsigned c = ent & 0x1FFFu, k = ent >> 13;
+  const unsigned t_log = logs[c], T = 1u << t_log;
+  const unsigned sdom = (unsigned)dom_sym[c];
+  {
+    const uint16_t *gs = ctab + toff[c];
+    for (unsigned i = lane; i < T; i += 32) st[i] = gs[i];
+    for (unsigned i = lane; i < A; i += 32) tt[i] = symtt[(size_t)c * A + i];
+  }
+  __syncwarp();
+  {
+    const int2 a = tt[sdom];
+    for (unsigned x0 = T + lane; x0 < 2 * T; x0 += 32) {
+      unsigned x = x0, nbm = 0, vm = 0;
+#pragma unroll
+      for (unsigned i = 0; i < 8; i++) {
+        const unsigned nb = (x + (unsigned)a.y) >> 16;  // 0 or 1
+        nbm |= nb << i;
+        vm |= (x & nb) << i;
+        x = st[(int)(x >> nb) + a.x];
+      }
+      P8[x0 - T] = (x - T) | (nbm << 11) | (vm << 19);
+    }
+  }
+  __syncwarp();
+  const unsigned pat = sdom * 0x01010101u;
+  unsigned x = T;  // FSE_initCState
+  auto slow_half = [&](unsigned wa, unsigned wb, unsigned cnt, unsigned fbase) {
+    // cnt ordinary FSE_encodeSymbol steps over the bytes of (wa, wb); uniform across the warp
+    for (unsigned i = 0; i < cnt; i++) {
+      const unsigned s = ((i < 4 ? wa >> (8 * i) : wb >> (8 * (i - 4))) & 0xFFu) & (A - 1);
+      const int2 a = tt[s];
+      const unsigned nb = (x + (unsigned)a.y) >> 16;
+      if (lane == 0) F[fbase + i] = (uint16_t)((nb << 12) | (x & ((1u << nb) - 1u)));
+      x = st[(int)(x >> nb) + a.x];
+    }
+  };
+  for (unsigned t = tile0[k]; t < tile0[k + 1]; t++) {
+    const uint32_t *tb = tbase + (size_t)t * (N + 1) + c;
+    const unsigned a0 = tb[0], a1 = tb[1];
+    const unsigned b0 = a0 & ~15u, padded = (a1 & ~15u) - b0;
+    if (!padded) continue;
+    const unsigned groups = padded >> 4;
+    const unsigned last_valid = (a0 & 15u) ? (a0 & 15u) : 16u;
+    const size_t slot0 = (size_t)t * STRIDE + b0;
+    for (unsigned blk0 = 0; blk0 < groups; blk0 += 32) {
+      const unsigned g = blk0 + lane;
+      const bool have = g < groups;
+      uint4 w = make_uint4(0, 0, 0, 0);
+      if (have) w = __ldg(reinterpret_cast<const uint4 *>(ssym + slot0 + (size_t)g * 16));
+      const unsigned valid_g = have ? (g == groups - 1 ? last_valid : 16u) : 0u;
+      const unsigned m0 = __ballot_sync(0xffffffffu, valid_g >= 8 && w.x == pat && w.y == pat);
+      const unsigned m1 = __ballot_sync(0xffffffffu, valid_g == 16 && w.z == pat && w.w == pat);
+      const unsigned nb_groups = groups - blk0 < 32 ? groups - blk0 : 32;
+      for (unsigned j = 0; j < nb_groups; j++) {
+        const unsigned vj = __shfl_sync(0xffffffffu, valid_g, j);
+        if ((m0 >> j) & 1u) {
+          const unsigned e = P8[x - T];
+          if (lane == 0) E[2 * j] = e;
+          x = T + (e & 0x7FFu);
+        } else {
+          const unsigned wa = __shfl_sync(0xffffffffu, w.x, j), wb = __shfl_sync(0xffffffffu, w.y, j);
+          slow_half(wa, wb, vj < 8 ? vj : 8u, j * 16);
+          if (lane == 0) E[2 * j] = SLOW;
+        }
+        if ((m1 >> j) & 1u) {
+          const unsigned e = P8[x - T];
+          if (lane == 0) E[2 * j + 1] = e;
+          x = T + (e & 0x7FFu);
+        } else {
+          const unsigned wa = __shfl_sync(0xffffffffu, w.z, j), wb = __shfl_sync(0xffffffffu, w.w, j);
+          slow_half(wa, wb, vj > 8 ? vj - 8 : 0u, j * 16 + 8);
+          if (lane == 0) E[2 * j + 1] = SLOW;
+        }
+      }
+      __syncwarp();
+      if (have) {
+        unsigned f[8];
+#pragma unroll
+        for (unsigned hh = 0; hh < 2; hh++) {
+          const unsigned e = E[2 * lane + hh];
+          if (e != SLOW) {
+            const unsigned nbm = (e >> 11) & 0xFFu, vm = (e >> 19) & 0xFFu;
+#pragma unroll
+            for (unsigned i = 0; i < 8; i += 2) {
+              const unsigned n0 = (nbm >> i) & 1u, n1 = (nbm >> (i + 1)) & 1u;
+              const unsigned f0 = (n0 << 12) | (n0 & (vm >> i)), f1 = (n1 << 12) | (n1 & (vm >> (i + 1)));
+              f[hh * 4 + (i >> 1)] = f0 | (f1 << 16);
+            }
+          } else {
+#pragma unroll
+            for (unsigned i = 0; i < 8; i += 2)
+              f[hh * 4 + (i >> 1)] = (unsigned)F[lane * 16 + hh * 8 + i] | ((unsigned)F[lane * 16 + hh * 8 + i + 1] << 16);
+          }
+        }
+        uint4 *fp = reinterpret_cast<uint4 *>(field + slot0 + (size_t)g * 16);
+        fp[0] = make_uint4(f[0], f[1], f[2], f[3]);
+        fp[1] = make_uint4(f[4], f[5], f[6], f[7]);
+      }
+      __syncwarp();
+    }
+  }
+  if (lane == 0) fstate[(size_t)k * N + c] = (uint16_t)x;
 }
 
 // ---------------------------------------------------------------------------
@@ -680,14 +866,20 @@ k_pack_write(const uint32_t *__restrict__ ptile0, const uint32_t *__restrict__ c
 // ---------------------------------------------------------------------------
 // host orchestration
 // ---------------------------------------------------------------------------
-template <class K, unsigned A, unsigned TILE, unsigned STRIDE, unsigned RANK_WARPS>
-static int encode_kind(fq28_handle *h, const DevTables &tab, const typename K::key_t *key, DevBuf &tile0_b,
-                       DevBuf &tbase_b, DevBuf &ssym_b, DevBuf &perm_b, DevBuf &field_b, DevBuf &fstate_b,
-                       DevBuf &ptile0_b, DevBuf &pbits_b, DevBuf &pscan_b, size_t G, unsigned *n_ptiles_out) {
+// Per stream type: tile tables + buffers (prep, main stream), then partition ->
+// chain -> bit counts (run) on `strm`.  The sequence and quality pipelines are
+// independent, so they run concurrently on the main and the side stream: the
+// quality chain is latency-bound on a handful of SMs and leaves the rest of
+// the machine to the sequence kernels.
+struct KindBufs {
+  DevBuf &tile0, &tbase, &ssym, &perm, &field, &fstate, &ptile0, &pbits, &pscan;
+  unsigned n_tiles = 0, n_ptiles = 0, dom_cap = 0;
+};
+
+template <class K, unsigned TILE, unsigned STRIDE>
+static int prep_kind(fq28_handle *h, KindBufs &b, size_t G) {
   constexpr unsigned N = K::n_models;
   const unsigned n_chunks = (unsigned)h->n_chunks;
-  const uint32_t *chunk_sym = h->chunk_rec.as<uint32_t>() + h->chunk_stride;
-  // host: tile prefix per chunk
   std::vector<uint32_t> tile0(n_chunks + 1), ptile0(n_chunks + 1);
   tile0[0] = ptile0[0] = 0;
   for (unsigned k = 0; k < n_chunks; k++) {
@@ -695,22 +887,43 @@ static int encode_kind(fq28_handle *h, const DevTables &tab, const typename K::k
     tile0[k + 1] = tile0[k] + (ns + TILE - 1) / TILE;
     ptile0[k + 1] = ptile0[k] + (ns + N + 1 + PACK_TILE - 1) / PACK_TILE;
   }
-  const unsigned n_tiles = tile0[n_chunks], n_ptiles = ptile0[n_chunks];
-  *n_ptiles_out = n_ptiles;
-  FQ28_TRY(ensure(h, tile0_b, (n_chunks + 1) * 4));
-  FQ28_TRY(ensure(h, ptile0_b, (n_chunks + 1) * 4));
-  FQ28_CUDA(h, cudaMemcpyAsync(tile0_b.p, tile0.data(), (n_chunks + 1) * 4, cudaMemcpyHostToDevice, h->stream));
-  FQ28_CUDA(h, cudaMemcpyAsync(ptile0_b.p, ptile0.data(), (n_chunks + 1) * 4, cudaMemcpyHostToDevice, h->stream));
+  b.n_tiles = tile0[n_chunks];
+  b.n_ptiles = ptile0[n_chunks];
+  FQ28_TRY(ensure(h, b.tile0, (n_chunks + 1) * 4));
+  FQ28_TRY(ensure(h, b.ptile0, (n_chunks + 1) * 4));
+  FQ28_CUDA(h, cudaMemcpyAsync(b.tile0.p, tile0.data(), (n_chunks + 1) * 4, cudaMemcpyHostToDevice, h->stream));
+  FQ28_CUDA(h, cudaMemcpyAsync(b.ptile0.p, ptile0.data(), (n_chunks + 1) * 4, cudaMemcpyHostToDevice, h->stream));
   FQ28_CUDA(h, cudaStreamSynchronize(h->stream));  // host vectors go out of scope
-  FQ28_TRY(ensure(h, tbase_b, (size_t)(n_tiles + 1) * (N + 1) * 4));
-  FQ28_TRY(ensure(h, ssym_b, (size_t)n_tiles * STRIDE + 64));
-  FQ28_TRY(ensure(h, perm_b, (G + 4) * 4));
-  FQ28_TRY(ensure(h, field_b, ((size_t)n_tiles * STRIDE + 64) * 2));
-  FQ28_TRY(ensure(h, fstate_b, (size_t)n_chunks * N * 2 + 16));
-  FQ28_TRY(ensure(h, pbits_b, (size_t)(n_ptiles + 1) * 4));
-  FQ28_TRY(ensure(h, pscan_b, (size_t)(n_ptiles + 2) * 8));
+  FQ28_TRY(ensure(h, b.tbase, (size_t)(b.n_tiles + 1) * (N + 1) * 4));
+  FQ28_TRY(ensure(h, b.ssym, (size_t)b.n_tiles * STRIDE + 64));
+  FQ28_TRY(ensure(h, b.perm, (G + 4) * 4));
+  FQ28_TRY(ensure(h, b.field, ((size_t)b.n_tiles * STRIDE + 64) * 2));
+  FQ28_TRY(ensure(h, b.fstate, (size_t)n_chunks * N * 2 + 16));
+  FQ28_TRY(ensure(h, b.pbits, (size_t)(b.n_ptiles + 1) * 4));
+  FQ28_TRY(ensure(h, b.pscan, (size_t)(b.n_ptiles + 2) * 8));
+  if (N == QUAL_N) {  // every (chunk, context) pair with >= DOM_MIN symbols fits
+    uint32_t max_syms = 0;
+    for (unsigned k = 0; k < n_chunks; k++) max_syms = std::max(max_syms, h->h_chunk_sym[k + 1] - h->h_chunk_sym[k]);
+    b.dom_cap = n_chunks * (max_syms / DOM_MIN + 1);
+    if (getenv("FQ28_NO_DOM")) b.dom_cap = 0;
+    FQ28_TRY(ensure(h, h->dom_list, (size_t)b.dom_cap * 4 + 16));
+  }
+  // scan scratch of the side stream must exist before the pipelines fork
+  FQ28_TRY(ensure(h, h->scan_tmp, ((size_t)b.n_ptiles / 4096 + 8) * 8));
+  FQ28_TRY(ensure(h, h->scan_tmp_side, ((size_t)b.n_ptiles / 4096 + 8) * 8));
+  return FQ28_OK;
+}
 
-  stage_begin(h, N == SEQ_N ? ST_PART_SEQ : ST_PART_QUAL);
+template <class K, unsigned A, unsigned TILE, unsigned STRIDE, unsigned RANK_WARPS>
+static int run_kind(fq28_handle *h, const DevTables &tab, const typename K::key_t *key, KindBufs &b, bool side,
+                    cudaEvent_t after_partition = nullptr) {
+  constexpr unsigned N = K::n_models;
+  cudaStream_t strm = side ? h->side : h->stream;
+  const unsigned n_chunks = (unsigned)h->n_chunks;
+  const uint32_t *chunk_sym = h->chunk_rec.as<uint32_t>() + h->chunk_stride;
+  const unsigned n_tiles = b.n_tiles, n_ptiles = b.n_ptiles;
+
+  int slot = stage_open(h, N == SEQ_N ? ST_PART_SEQ : ST_PART_QUAL, strm);
   if (n_tiles && N == SEQ_N) {
     using P = PartSmall<SeqKind, SEQ_TILE, SEQ_STRIDE>;
     static bool attr_set = false;
@@ -719,56 +932,74 @@ static int encode_kind(fq28_handle *h, const DevTables &tab, const typename K::k
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P::SMEM));
       attr_set = true;
     }
-    k_tile_part_small<SeqKind, SEQ_TILE, SEQ_STRIDE><<<n_tiles, 32, P::SMEM, h->stream>>>(
-        reinterpret_cast<const uint16_t *>(key), tile0_b.as<uint32_t>(), chunk_sym, n_chunks, n_tiles,
-        tbase_b.as<uint32_t>(), ssym_b.as<uint8_t>(), perm_b.as<uint32_t>());
+    k_tile_part_small<SeqKind, SEQ_TILE, SEQ_STRIDE><<<n_tiles, 32, P::SMEM, strm>>>(
+        reinterpret_cast<const uint16_t *>(key), b.tile0.as<uint32_t>(), chunk_sym, n_chunks, n_tiles,
+        b.tbase.as<uint32_t>(), b.ssym.as<uint8_t>(), b.perm.as<uint32_t>());
     FQ28_LAUNCH_CHECK(h);
   } else if (n_tiles) {
-    k_tile_hist<K, TILE><<<n_tiles, 256, 0, h->stream>>>(key, tile0_b.as<uint32_t>(), chunk_sym, n_chunks,
-                                                        tbase_b.as<uint32_t>());
+    k_tile_hist<K, TILE><<<n_tiles, 256, 0, strm>>>(key, b.tile0.as<uint32_t>(), chunk_sym, n_chunks,
+                                                   b.tbase.as<uint32_t>());
     FQ28_LAUNCH_CHECK(h);
-    k_tile_rank<K, TILE, STRIDE, RANK_WARPS><<<(n_tiles + RANK_WARPS - 1) / RANK_WARPS, RANK_WARPS * 32, 0, h->stream>>>(
-        key, tile0_b.as<uint32_t>(), chunk_sym, n_chunks, n_tiles, tbase_b.as<uint32_t>(), ssym_b.as<uint8_t>(),
-        perm_b.as<uint32_t>());
+    k_tile_rank<K, TILE, STRIDE, RANK_WARPS><<<(n_tiles + RANK_WARPS - 1) / RANK_WARPS, RANK_WARPS * 32, 0, strm>>>(
+        key, b.tile0.as<uint32_t>(), chunk_sym, n_chunks, n_tiles, b.tbase.as<uint32_t>(), b.ssym.as<uint8_t>(),
+        b.perm.as<uint32_t>());
     FQ28_LAUNCH_CHECK(h);
   }
-  stage_end(h, N == SEQ_N ? ST_PART_SEQ : ST_PART_QUAL);
+  stage_close(h, slot, strm);
+  if (after_partition) FQ28_CUDA(h, cudaEventRecord(after_partition, strm));
 
-  stage_begin(h, N == SEQ_N ? ST_CHAIN_SEQ : ST_CHAIN_QUAL);
+  slot = stage_open(h, N == SEQ_N ? ST_CHAIN_SEQ : ST_CHAIN_QUAL, strm);
   {
+    const bool use_dom = (N == QUAL_N) && b.dom_cap > 0;
+    unsigned long long *dom_count = reinterpret_cast<unsigned long long *>(h->d_scalars + 8);
+    if (use_dom) {
+      FQ28_CUDA(h, cudaMemsetAsync(dom_count, 0, sizeof(unsigned long long), strm));
+      dim3 lgrid(N, (n_chunks + 127) / 128);
+      k_dom_list<K><<<lgrid, 128, 0, strm>>>(b.tile0.as<uint32_t>(), n_chunks, b.tbase.as<uint32_t>(), tab.dom_sym,
+                                            h->dom_list.as<uint32_t>(), b.dom_cap, dom_count);
+      FQ28_LAUNCH_CHECK(h);
+    }
     dim3 grid(N, (n_chunks + 31) / 32);
-    k_chain<K, A, TILE, STRIDE><<<grid, 32, 0, h->stream>>>(ssym_b.as<uint8_t>(), tile0_b.as<uint32_t>(), n_chunks,
-                                                   tbase_b.as<uint32_t>(), tab.logs, tab.toff, tab.ctab, tab.symtt,
-                                                   field_b.as<uint16_t>(), fstate_b.as<uint16_t>());
+    k_chain<K, A, TILE, STRIDE><<<grid, 32, 0, strm>>>(b.ssym.as<uint8_t>(), b.tile0.as<uint32_t>(), n_chunks,
+                                                      b.tbase.as<uint32_t>(), tab.logs, tab.toff, tab.ctab, tab.symtt,
+                                                      b.field.as<uint16_t>(), b.fstate.as<uint16_t>(),
+                                                      use_dom ? tab.dom_sym : nullptr);
     FQ28_LAUNCH_CHECK(h);
+    if (use_dom) {
+      k_chain_dom<K, A, STRIDE><<<b.dom_cap, 32, 0, strm>>>(h->dom_list.as<uint32_t>(), dom_count, b.ssym.as<uint8_t>(),
+                                                           b.tile0.as<uint32_t>(), b.tbase.as<uint32_t>(), tab.logs, tab.toff,
+                                                           tab.ctab, tab.symtt, tab.dom_sym, b.field.as<uint16_t>(),
+                                                           b.fstate.as<uint16_t>());
+      FQ28_LAUNCH_CHECK(h);
+    }
   }
-  stage_end(h, N == SEQ_N ? ST_CHAIN_SEQ : ST_CHAIN_QUAL);
+  stage_close(h, slot, strm);
 
-  stage_begin(h, ST_PACK);
-  k_pack_count<N><<<n_ptiles, PACK_THREADS, 0, h->stream>>>(ptile0_b.as<uint32_t>(), chunk_sym, n_chunks,
-                                                           perm_b.as<uint32_t>(), field_b.as<uint16_t>(), tab.logs,
-                                                           fstate_b.as<uint16_t>(), pbits_b.as<uint32_t>());
+  slot = stage_open(h, N == SEQ_N ? ST_PACK_SEQ : ST_PACK_QUAL, strm);
+  k_pack_count<N><<<n_ptiles, PACK_THREADS, 0, strm>>>(b.ptile0.as<uint32_t>(), chunk_sym, n_chunks,
+                                                      b.perm.as<uint32_t>(), b.field.as<uint16_t>(), tab.logs,
+                                                      b.fstate.as<uint16_t>(), b.pbits.as<uint32_t>());
   FQ28_LAUNCH_CHECK(h);
-  FQ28_TRY(scan_exclusive_u32_to_u64(h, pbits_b.as<uint32_t>(), pscan_b.as<uint64_t>(), n_ptiles));
-  stage_end(h, ST_PACK);
+  FQ28_TRY(scan_exclusive_u32_to_u64(h, b.pbits.as<uint32_t>(), b.pscan.as<uint64_t>(), n_ptiles, side));
+  stage_close(h, slot, strm);
   return FQ28_OK;
 }
 
 template <unsigned N>
-static int pack_kind(fq28_handle *h, const DevTables &tab, DevBuf &perm_b, DevBuf &field_b, DevBuf &fstate_b,
-                     DevBuf &ptile0_b, DevBuf &pscan_b, unsigned n_ptiles, int which, DevBuf &arena,
-                     size_t arena_bytes, int scalar_idx) {
+static int pack_kind(fq28_handle *h, const DevTables &tab, KindBufs &b, int which, DevBuf &arena, int scalar_idx,
+                     bool side) {
+  cudaStream_t strm = side ? h->side : h->stream;
   const unsigned n_chunks = (unsigned)h->n_chunks;
   const uint32_t *chunk_sym = h->chunk_rec.as<uint32_t>() + h->chunk_stride;
-  FQ28_TRY(ensure(h, arena, arena_bytes + 64));
-  k_zero_words<<<148 * 4, 256, 0, h->stream>>>(arena.as<uint32_t>(), h->d_scalars + scalar_idx);
+  const int slot = stage_open(h, N == SEQ_N ? ST_PACK_SEQ : ST_PACK_QUAL, strm);
+  k_zero_words<<<148 * 4, 256, 0, strm>>>(arena.as<uint32_t>(), h->d_scalars + scalar_idx);
   FQ28_LAUNCH_CHECK(h);
-  k_pack_write<N><<<n_ptiles, PACK_THREADS, 0, h->stream>>>(ptile0_b.as<uint32_t>(), chunk_sym, n_chunks,
-                                                           perm_b.as<uint32_t>(), field_b.as<uint16_t>(), tab.logs,
-                                                           fstate_b.as<uint16_t>(),
-                                                           pscan_b.as<unsigned long long>(),
-                                                           h->d_infos.as<fq28_chunk_info>(), which, arena.as<uint8_t>());
+  k_pack_write<N><<<b.n_ptiles, PACK_THREADS, 0, strm>>>(b.ptile0.as<uint32_t>(), chunk_sym, n_chunks,
+                                                        b.perm.as<uint32_t>(), b.field.as<uint16_t>(), tab.logs,
+                                                        b.fstate.as<uint16_t>(), b.pscan.as<unsigned long long>(),
+                                                        h->d_infos.as<fq28_chunk_info>(), which, arena.as<uint8_t>());
   FQ28_LAUNCH_CHECK(h);
+  stage_close(h, slot, strm);
   return FQ28_OK;
 }
 
@@ -827,17 +1058,25 @@ int encode_slab(fq28_handle *h, fq28_chunk_info *infos, size_t infos_cap, fq28_e
   }
   stage_end(h, ST_EXTRACT);
 
-  unsigned n_pt_seq = 0, n_pt_qual = 0;
-  FQ28_TRY((encode_kind<SeqKind, SEQ_A, SEQ_TILE, SEQ_STRIDE, 4>(h, h->seq, h->key_seq.as<uint16_t>(), h->tile0_seq, h->tbase_seq,
-                                                     h->ssym_seq, h->perm_seq, h->out_seq, h->fstate_seq, h->ptile0_seq,
-                                                     h->pbits_seq, h->pscan_seq, G, &n_pt_seq)));
-  FQ28_TRY((encode_kind<QualKind, QUAL_A, QUAL_TILE, QUAL_STRIDE, 1>(h, h->qual, h->key_qual.as<uint32_t>(), h->tile0_qual,
-                                                        h->tbase_qual, h->ssym_qual, h->perm_qual, h->out_qual,
-                                                        h->fstate_qual, h->ptile0_qual, h->pbits_qual, h->pscan_qual, G,
-                                                        &n_pt_qual)));
-
-  stage_begin(h, ST_PACK);
+  KindBufs bs{h->tile0_seq, h->tbase_seq, h->ssym_seq, h->perm_seq, h->out_seq, h->fstate_seq, h->ptile0_seq, h->pbits_seq, h->pscan_seq};
+  KindBufs bq{h->tile0_qual, h->tbase_qual, h->ssym_qual, h->perm_qual, h->out_qual, h->fstate_qual, h->ptile0_qual, h->pbits_qual, h->pscan_qual};
+  FQ28_TRY((prep_kind<SeqKind, SEQ_TILE, SEQ_STRIDE>(h, bs, G)));
+  FQ28_TRY((prep_kind<QualKind, QUAL_TILE, QUAL_STRIDE>(h, bq, G)));
   FQ28_TRY(ensure(h, h->d_infos, (size_t)(n_chunks + 1) * sizeof(fq28_chunk_info)));
+  const bool overlap = getenv("FQ28_SERIAL") == nullptr;
+  if (overlap) {
+    FQ28_TRY(side_fork(h));
+    // quality partition first with the whole GPU; its chain is latency-bound on a
+    // few SMs, so the complete sequence pipeline runs underneath it
+    FQ28_TRY((run_kind<QualKind, QUAL_A, QUAL_TILE, QUAL_STRIDE, 1>(h, h->qual, h->key_qual.as<uint32_t>(), bq, true, h->ev_join)));
+    if (getenv("FQ28_SEQ_AFTER_QPART")) FQ28_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_join, 0));
+    FQ28_TRY((run_kind<SeqKind, SEQ_A, SEQ_TILE, SEQ_STRIDE, 4>(h, h->seq, h->key_seq.as<uint16_t>(), bs, false)));
+    FQ28_TRY(side_join(h));
+  } else {
+    FQ28_TRY((run_kind<QualKind, QUAL_A, QUAL_TILE, QUAL_STRIDE, 1>(h, h->qual, h->key_qual.as<uint32_t>(), bq, false)));
+    FQ28_TRY((run_kind<SeqKind, SEQ_A, SEQ_TILE, SEQ_STRIDE, 4>(h, h->seq, h->key_seq.as<uint16_t>(), bs, false)));
+  }
+
   k_chunk_finish<<<1, 1024, 0, h->stream>>>(n_chunks, chunk_rec, chunk_sym, chunk_byte, h->npos_off.as<uint32_t>(),
                                            h->hdrscan.as<uint32_t>(), h->ptile0_seq.as<uint32_t>(), h->pscan_seq.as<unsigned long long>(),
                                            h->ptile0_qual.as<uint32_t>(), h->pscan_qual.as<unsigned long long>(),
@@ -849,11 +1088,12 @@ int encode_slab(fq28_handle *h, fq28_chunk_info *infos, size_t infos_cap, fq28_e
                                cudaMemcpyDeviceToHost, h->stream));
   FQ28_CUDA(h, cudaStreamSynchronize(h->stream));
   const size_t seq_bytes = (size_t)h->h_scalars[0], qual_bytes = (size_t)h->h_scalars[1];
-  FQ28_TRY((pack_kind<SEQ_N>(h, h->seq, h->perm_seq, h->out_seq, h->fstate_seq, h->ptile0_seq, h->pscan_seq, n_pt_seq, 0,
-                             h->arena_seq, seq_bytes, 0)));
-  FQ28_TRY((pack_kind<QUAL_N>(h, h->qual, h->perm_qual, h->out_qual, h->fstate_qual, h->ptile0_qual, h->pscan_qual,
-                              n_pt_qual, 1, h->arena_qual, qual_bytes, 1)));
-  stage_end(h, ST_PACK);
+  FQ28_TRY(ensure(h, h->arena_seq, seq_bytes + 64));
+  FQ28_TRY(ensure(h, h->arena_qual, qual_bytes + 64));
+  FQ28_TRY(side_fork(h));
+  FQ28_TRY((pack_kind<QUAL_N>(h, h->qual, bq, 1, h->arena_qual, 1, true)));
+  FQ28_TRY((pack_kind<SEQ_N>(h, h->seq, bs, 0, h->arena_seq, 0, false)));
+  FQ28_TRY(side_join(h));
 
   h->last_summary.n_chunks = n_chunks;
   h->last_summary.n_records = n_rec;

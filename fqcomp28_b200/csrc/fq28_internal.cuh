@@ -74,6 +74,7 @@ struct DevTables {
   uint32_t *toff = nullptr;    // [N+1] first cell of each context's tables
   uint16_t *ctab = nullptr;    // next-state cells, packed by toff
   int2 *symtt = nullptr;       // [N*A] {deltaFindState, deltaNbBits}
+  int8_t *dom_sym = nullptr;   // [N] symbol with norm > T/2 (nbBits in {0,1}), or -1
   uint32_t *dtab = nullptr;    // DTable cells newState | sym<<16 | nbBits<<24
   uint32_t *dtab_fix = nullptr; // same cells at fixed stride: cell (ctx << FIX_LOG) + state
   // decoder side structures
@@ -94,7 +95,8 @@ enum Stage {
   ST_PART_QUAL,   // context partition, quality (tile hist + stable rank)
   ST_CHAIN_SEQ,   // K5 tANS state chains, sequence
   ST_CHAIN_QUAL,  // K5 tANS state chains, quality
-  ST_PACK,        // K5 bit offsets + bit packing
+  ST_PACK_SEQ,    // K5 bit offsets + bit packing, sequence
+  ST_PACK_QUAL,   // K5 bit offsets + bit packing, quality
   ST_LAYOUT,      // K7 FASTQ re-layout
   ST_DECODE_SEQ,  // K6 tANS decode, sequence
   ST_DECODE_QUAL, // K6 tANS decode, quality
@@ -136,7 +138,7 @@ struct fq28_handle {
   fq28::DevBuf key_seq, key_qual, perm_seq, perm_qual, ssym_seq, ssym_qual, out_seq, out_qual;
   fq28::DevBuf tile0_seq, tile0_qual, tbase_seq, tbase_qual, fstate_seq, fstate_qual;
   fq28::DevBuf ptile0_seq, ptile0_qual, pbits_seq, pbits_qual, pscan_seq, pscan_qual;
-  fq28::DevBuf arena_seq, arena_qual, d_infos, scan_tmp;
+  fq28::DevBuf arena_seq, arena_qual, d_infos, scan_tmp, scan_tmp_side, dom_list;
   std::vector<fq28_chunk_info> h_infos;
   fq28_enc_summary last_summary{};
   bool have_result = false;
@@ -172,6 +174,9 @@ int side_fork(fq28_handle *h);
 int side_join(fq28_handle *h);
 void side_stage_begin(fq28_handle *h, Stage s);
 void side_stage_end(fq28_handle *h, Stage s);
+// re-entrant form for stages that overlap on two streams: open returns a slot
+int stage_open(fq28_handle *h, Stage s, cudaStream_t strm);
+void stage_close(fq28_handle *h, int slot, cudaStream_t strm);
 
 #define FQ28_CUDA(h, call)                                         \
   do {                                                             \
@@ -193,9 +198,10 @@ void side_stage_end(fq28_handle *h, Stage s);
 // ---- scans (fq28_scan.cu) ---------------------------------------------------
 // out[i] = sum(in[0..i)), out[n] = total.  `out` needs n+1 entries.  in may
 // alias out only if types match.  Uses h->scan_tmp.
-int scan_exclusive_u16_to_u32(fq28_handle *h, const uint16_t *in, uint32_t *out, size_t n);
-int scan_exclusive_u32(fq28_handle *h, const uint32_t *in, uint32_t *out, size_t n);
-int scan_exclusive_u32_to_u64(fq28_handle *h, const uint32_t *in, uint64_t *out, size_t n);
+// `side` = run on h->side with its own scratch (for the overlapped pipelines).
+int scan_exclusive_u16_to_u32(fq28_handle *h, const uint16_t *in, uint32_t *out, size_t n, bool side = false);
+int scan_exclusive_u32(fq28_handle *h, const uint32_t *in, uint32_t *out, size_t n, bool side = false);
+int scan_exclusive_u32_to_u64(fq28_handle *h, const uint32_t *in, uint64_t *out, size_t n, bool side = false);
 
 // ---- stages -----------------------------------------------------------------
 // fq28_parse.cu: K1.  Fills h->nl .. h->symoff, h->n_lines, h->n_rec.

@@ -91,33 +91,35 @@ k_scan_add(TOut *__restrict__ out, const TOut *__restrict__ sums, size_t n) {
 }
 
 template <typename TIn, typename TOut>
-static int scan_impl(fq28_handle *h, const TIn *in, TOut *out, size_t n) {
+static int scan_impl(fq28_handle *h, const TIn *in, TOut *out, size_t n, bool side) {
+  cudaStream_t strm = side ? h->side : h->stream;
+  DevBuf &tmpb = side ? h->scan_tmp_side : h->scan_tmp;
   if (n == 0) {
-    FQ28_CUDA(h, cudaMemsetAsync(out, 0, sizeof(TOut), h->stream));
+    FQ28_CUDA(h, cudaMemsetAsync(out, 0, sizeof(TOut), strm));
     return FQ28_OK;
   }
   const size_t n_tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
-  FQ28_TRY(ensure(h, h->scan_tmp, (n_tiles + 1) * sizeof(TOut)));
-  TOut *sums = h->scan_tmp.as<TOut>();
-  k_scan_tiles<TIn, TOut><<<(unsigned)n_tiles, SCAN_THREADS, 0, h->stream>>>(in, out, sums, n);
+  FQ28_TRY(ensure(h, tmpb, (n_tiles + 1) * sizeof(TOut)));
+  TOut *sums = tmpb.as<TOut>();
+  k_scan_tiles<TIn, TOut><<<(unsigned)n_tiles, SCAN_THREADS, 0, strm>>>(in, out, sums, n);
   FQ28_LAUNCH_CHECK(h);
-  k_scan_sums<TOut><<<1, SCAN_THREADS, 0, h->stream>>>(sums, n_tiles, out + n);
+  k_scan_sums<TOut><<<1, SCAN_THREADS, 0, strm>>>(sums, n_tiles, out + n);
   FQ28_LAUNCH_CHECK(h);
   if (n_tiles > 1) {
-    k_scan_add<TOut><<<(unsigned)n_tiles, SCAN_THREADS, 0, h->stream>>>(out, sums, n);
+    k_scan_add<TOut><<<(unsigned)n_tiles, SCAN_THREADS, 0, strm>>>(out, sums, n);
     FQ28_LAUNCH_CHECK(h);
   }
   return FQ28_OK;
 }
 
-int scan_exclusive_u16_to_u32(fq28_handle *h, const uint16_t *in, uint32_t *out, size_t n) {
-  return scan_impl<uint16_t, uint32_t>(h, in, out, n);
+int scan_exclusive_u16_to_u32(fq28_handle *h, const uint16_t *in, uint32_t *out, size_t n, bool side) {
+  return scan_impl<uint16_t, uint32_t>(h, in, out, n, side);
 }
-int scan_exclusive_u32(fq28_handle *h, const uint32_t *in, uint32_t *out, size_t n) {
-  return scan_impl<uint32_t, uint32_t>(h, in, out, n);
+int scan_exclusive_u32(fq28_handle *h, const uint32_t *in, uint32_t *out, size_t n, bool side) {
+  return scan_impl<uint32_t, uint32_t>(h, in, out, n, side);
 }
-int scan_exclusive_u32_to_u64(fq28_handle *h, const uint32_t *in, uint64_t *out, size_t n) {
-  return scan_impl<uint32_t, unsigned long long>(h, in, reinterpret_cast<unsigned long long *>(out), n);
+int scan_exclusive_u32_to_u64(fq28_handle *h, const uint32_t *in, uint64_t *out, size_t n, bool side) {
+  return scan_impl<uint32_t, unsigned long long>(h, in, reinterpret_cast<unsigned long long *>(out), n, side);
 }
 
 }  // namespace fq28

@@ -265,7 +265,7 @@ template <int A>
 __global__ void k_build_tables(const short *__restrict__ norm_in, const uint32_t *__restrict__ logs,
                                const uint32_t *__restrict__ toff, unsigned n_models,
                                uint16_t *__restrict__ ctab, int2 *__restrict__ symtt,
-                               uint32_t *__restrict__ dtab, uint32_t *__restrict__ dtab_fix) {
+                               uint32_t *__restrict__ dtab, uint32_t *__restrict__ dtab_fix, int8_t *__restrict__ dom_sym) {
   const unsigned ctx = blockIdx.x * blockDim.x + threadIdx.x;
   if (ctx >= n_models) return;
   short norm[A];
@@ -312,6 +312,12 @@ __global__ void k_build_tables(const short *__restrict__ norm_in, const uint32_t
       total += (unsigned)norm[s];
     }
     symtt[(size_t)ctx * A + s] = tt;
+  }
+  {  // dominant symbol: norm > T/2 <=> every step with it emits 0 or 1 bit (maxBitsOut == 1)
+    int d = -1;
+    for (int s = 0; s < A; s++)
+      if (norm[s] > (int)(T >> 1)) d = s;
+    dom_sym[ctx] = (int8_t)d;
   }
   // next-state table + decode cells, ascending u
   for (unsigned u = 0; u < T; u++) {
@@ -400,6 +406,7 @@ int tables_alloc(fq28_handle *h, DevTables &t, unsigned n_models, unsigned alpha
   FQ28_CUDA(h, cudaMalloc(&t.max_log, sizeof(uint32_t)));
   FQ28_CUDA(h, cudaMalloc(&t.toff, (n_models + 1) * sizeof(uint32_t)));
   FQ28_CUDA(h, cudaMalloc(&t.symtt, na * sizeof(int2)));
+  FQ28_CUDA(h, cudaMalloc(&t.dom_sym, n_models));
   // every table log is <= 11 here (FSE_DEFAULT_TABLELOG with maxTableLog = 0
   // and minBits <= 7), but size for FSE_MAX_TABLELOG to be safe
   t.cells_cap = (size_t)n_models << FSE_MAX_TABLELOG;
@@ -421,9 +428,9 @@ int tables_from_norm(fq28_handle *h, DevTables &t) {
   FQ28_LAUNCH_CHECK(h);
   const unsigned threads = 64, blocks = (t.n_models + threads - 1) / threads;
   if (t.alphabet == SEQ_A)
-    k_build_tables<SEQ_A><<<blocks, threads, 0, h->stream>>>(t.norm, t.logs, t.toff, t.n_models, t.ctab, t.symtt, t.dtab, t.dtab_fix);
+    k_build_tables<SEQ_A><<<blocks, threads, 0, h->stream>>>(t.norm, t.logs, t.toff, t.n_models, t.ctab, t.symtt, t.dtab, t.dtab_fix, t.dom_sym);
   else
-    k_build_tables<QUAL_A><<<blocks, threads, 0, h->stream>>>(t.norm, t.logs, t.toff, t.n_models, t.ctab, t.symtt, t.dtab, t.dtab_fix);
+    k_build_tables<QUAL_A><<<blocks, threads, 0, h->stream>>>(t.norm, t.logs, t.toff, t.n_models, t.ctab, t.symtt, t.dtab, t.dtab_fix, t.dom_sym);
   FQ28_LAUNCH_CHECK(h);
   k_logsuf<<<1, 1, 0, h->stream>>>(t.logs, t.n_models, t.logsuf);
   FQ28_LAUNCH_CHECK(h);
