@@ -1,0 +1,480 @@
+// fqcomp28_cli.cpp -- `fqcomp28 c|d` on top of the GPU codec path (row N1 of
+// SURVEY.md section 8(f)): the reference's command line (src/app.cpp:27-80),
+// worker loops (src/process.cpp:32-105) and archive framing
+// (src/archive.cpp:22-163, src/archive.h:10-29) around
+// CompressionWorkspace::encodeChunks / DecompressionWorkspace::decodeChunks.
+//
+// Everything that touches bases or qualities runs on the GPU (libfq28.so).
+// Host-side, out of the hot path (north_star):
+//   * header tokenisation -- same field model as src/headers.cpp:43-133
+//     (alnum fields, NUMERIC = int32 delta, STRING = is-different flag +
+//     content + 1-byte length), context reset to the dataset's first header at
+//     every chunk (src/workspace.cpp:90-93);
+//   * the generic coder of the misc buffers.  The reference uses libbsc
+//     (src/memcompress.cpp), which is not available offline, so this build
+//     writes a STORED container (28-byte header like LIBBSC_HEADER_SIZE, then
+//     the raw bytes).  The block framing, the meta section, the seq/qual
+//     streams and every integer field are the reference's; only the payload
+//     of the bsc-coded buffers differs, so archives are self-consistent but
+//     not exchangeable with a libbsc build.  Magic "FQ28STOR" marks them.
+// Divergence kept on purpose: n_count / n_pos are written per block, not
+// accumulated across blocks (SURVEY Q2 makes archives quadratic in size).
+#include <charconv>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <iostream>
+#include <variant>
+
+#include "fqcomp28_gpu.hpp"
+
+namespace fqcomp28 {
+
+// ---------------------------------------------------------------- settings
+struct Settings {  // src/settings.h:15-39
+  std::string mates1, archive;
+  unsigned sample_mb = 128, reading_mb = 256, n_threads = 1;
+  bool verbose = false;
+  std::size_t slab_mb = 1024;  // FASTQ bytes handed to the GPU per pass
+};
+
+// ---------------------------------------------------------------- headers
+namespace headers {
+enum class FieldType { NUMERIC = 0, STRING };
+using numeric_t = int32_t;
+constexpr std::size_t FIELDLEN_MAX = 255;
+
+struct Format {  // HeaderFormatSpeciciation, src/headers.h:29-42
+  std::vector<FieldType> field_types;
+  std::vector<char> separators;
+  std::size_t n_fields() const { return field_types.size(); }
+  static Format fromHeader(std::string_view header) {  // src/headers.cpp:43-73
+    if (header.empty() || header[0] != '@') throw std::invalid_argument("header must start with '@'");
+    Format fmt;
+    const char *p = header.data() + 1, *end = header.data() + header.size();
+    for (;;) {
+      const char *sep = std::find_if_not(p, end, [](char c) { return std::isalnum(static_cast<unsigned char>(c)); });
+      const bool numeric = std::all_of(p, sep, [](char c) { return std::isdigit(static_cast<unsigned char>(c)); });
+      fmt.field_types.push_back(numeric ? FieldType::NUMERIC : FieldType::STRING);
+      if (sep == end) break;
+      if (sep == end - 1) throw std::invalid_argument(std::string(header) + ": header should end in alnum char");
+      fmt.separators.push_back(*sep);
+      p = sep + 1;
+    }
+    return fmt;
+  }
+};
+
+struct FieldStorage {  // src/headers.h:50-82
+  std::vector<std::byte> isDifferentFlag, content, contentLength;
+  void clear() { isDifferentFlag.clear(); content.clear(); contentLength.clear(); }
+};
+
+using field_t = std::variant<numeric_t, std::string>;
+
+inline std::vector<field_t> fieldsOf(std::string_view header, const Format &fmt) {  // src/headers.cpp:25-41
+  std::vector<field_t> f(fmt.n_fields());
+  const char *p = header.data() + 1, *end = header.data() + header.size();
+  for (std::size_t i = 0; i < fmt.n_fields(); ++i) {
+    const char *e = i + 1 < fmt.n_fields() ? std::find(p + 1, end, fmt.separators[i]) : end;
+    if (fmt.field_types[i] == FieldType::NUMERIC) {
+      numeric_t v = 0;
+      std::from_chars(p, e, v);
+      f[i] = v;
+    } else {
+      f[i] = std::string(p, e);
+    }
+    p = e + 1;
+  }
+  return f;
+}
+
+/** encodeHeader for every header of a chunk (src/workspace.cpp:95-125) */
+inline void tokenize(const std::vector<std::byte> &raw, const std::vector<readlen_t> &lens, const Format &fmt,
+                     const std::vector<field_t> &first, std::vector<FieldStorage> &out) {
+  out.assign(fmt.n_fields(), {});
+  std::vector<field_t> prev = first;  // startNewChunk, src/workspace.cpp:90-93
+  const char *h = reinterpret_cast<const char *>(raw.data());
+  for (readlen_t hl : lens) {
+    const char *p = h + 1, *end = h + hl;
+    for (std::size_t i = 0; i < fmt.n_fields(); ++i) {
+      const char *e = i + 1 < fmt.n_fields() ? std::find(std::min(p + 1, end), end, fmt.separators[i]) : end;
+      auto &st = out[i];
+      if (fmt.field_types[i] == FieldType::STRING) {  // storeString, src/headers.cpp:75-89
+        auto &pv = std::get<std::string>(prev[i]);
+        const std::string_view val(p, static_cast<std::size_t>(e - p));
+        if (val == pv) {
+          st.isDifferentFlag.push_back(std::byte{0});
+        } else {
+          if (val.size() >= FIELDLEN_MAX) throw std::invalid_argument("header field longer than 254 characters");
+          st.isDifferentFlag.push_back(std::byte{1});
+          st.content.insert(st.content.end(), reinterpret_cast<const std::byte *>(val.data()),
+                            reinterpret_cast<const std::byte *>(val.data()) + val.size());
+          st.contentLength.push_back(static_cast<std::byte>(val.size()));
+          pv.assign(val);
+        }
+      } else {  // storeNumeric, src/headers.cpp:108-118
+        numeric_t v = 0;
+        std::from_chars(p, e, v);
+        auto &pv = std::get<numeric_t>(prev[i]);
+        const numeric_t delta = v - pv;
+        st.content.insert(st.content.end(), reinterpret_cast<const std::byte *>(&delta),
+                          reinterpret_cast<const std::byte *>(&delta) + sizeof(delta));
+        pv = v;
+      }
+      p = e < end ? e + 1 : end;
+    }
+    h += hl;
+  }
+}
+
+/** decodeHeader for n_records headers (src/workspace.cpp:127-157) */
+inline void detokenize(const std::vector<FieldStorage> &in, const Format &fmt, const std::vector<field_t> &first,
+                       std::size_t n_records, std::vector<std::byte> &raw, std::vector<readlen_t> &lens) {
+  std::vector<field_t> prev = first;
+  std::vector<std::size_t> dpos(fmt.n_fields(), 0), cpos(fmt.n_fields(), 0), lpos(fmt.n_fields(), 0);
+  raw.clear();
+  lens.clear();
+  std::string line;
+  char num[16];
+  for (std::size_t r = 0; r < n_records; ++r) {
+    line.assign("@");
+    for (std::size_t i = 0; i < fmt.n_fields(); ++i) {
+      const auto &st = in[i];
+      if (fmt.field_types[i] == FieldType::STRING) {  // loadNextString, src/headers.cpp:91-106
+        auto &pv = std::get<std::string>(prev[i]);
+        if (st.isDifferentFlag.at(dpos[i]++) != std::byte{0}) {
+          const std::size_t len = static_cast<unsigned char>(st.contentLength.at(lpos[i]++));
+          if (cpos[i] + len > st.content.size()) throw std::runtime_error("header content underflow");
+          pv.assign(reinterpret_cast<const char *>(st.content.data()) + cpos[i], len);
+          cpos[i] += len;
+        }
+        line += pv;
+      } else {  // loadNextNumeric, src/headers.cpp:120-133
+        numeric_t delta;
+        if (cpos[i] + sizeof(delta) > st.content.size()) throw std::runtime_error("header content underflow");
+        std::memcpy(&delta, st.content.data() + cpos[i], sizeof(delta));
+        cpos[i] += sizeof(delta);
+        auto &pv = std::get<numeric_t>(prev[i]);
+        pv += delta;
+        const auto res = std::to_chars(num, num + sizeof(num), pv);
+        line.append(num, res.ptr);
+      }
+      if (i + 1 < fmt.n_fields()) line.push_back(fmt.separators[i]);
+    }
+    raw.insert(raw.end(), reinterpret_cast<const std::byte *>(line.data()),
+               reinterpret_cast<const std::byte *>(line.data()) + line.size());
+    lens.push_back(narrow_cast<readlen_t>(line.size()));
+  }
+}
+}  // namespace headers
+
+// ---------------------------------------------------------------- misc buffer container
+// Stand-in for memcompress/memdecompress (src/memcompress.h:14-28): STORED.
+constexpr std::size_t STORED_HEADER = 28;  // = LIBBSC_HEADER_SIZE, src/workspace.h:18
+inline std::vector<std::byte> memcompress(const std::vector<std::byte> &src) {
+  std::vector<std::byte> dst(STORED_HEADER + src.size(), std::byte{0});
+  std::memcpy(dst.data(), "FQ28STOR", 8);
+  const uint32_t n = narrow_cast<uint32_t>(src.size());
+  std::memcpy(dst.data() + 8, &n, 4);
+  if (!src.empty()) std::memcpy(dst.data() + STORED_HEADER, src.data(), src.size());
+  return dst;
+}
+inline std::vector<std::byte> memdecompress(const std::vector<std::byte> &src, std::size_t original) {
+  if (src.size() != STORED_HEADER + original || std::memcmp(src.data(), "FQ28STOR", 8) != 0)
+    throw std::runtime_error("misc buffer is not a FQ28STOR container (archive written by a libbsc build?)");
+  return std::vector<std::byte>(src.begin() + STORED_HEADER, src.end());
+}
+
+// ---------------------------------------------------------------- archive
+struct BlockInfo {  // src/archive.h:17-26
+  int64_t offset;
+  uint32_t idx;
+};
+static_assert(sizeof(BlockInfo) == 16);
+
+class Archive {
+public:
+  static constexpr std::streamoff OFFSET_META = 4;  // src/archive.h:29
+  std::fstream fs;
+  DatasetMeta meta;
+  headers::Format fmt;
+  std::vector<headers::field_t> first_fields;
+  std::vector<BlockInfo> index;
+
+  template <typename T> void writeInteger(T v) { fs.write(reinterpret_cast<const char *>(&v), sizeof(v)); }
+  template <typename T> T readInteger() { T v{}; fs.read(reinterpret_cast<char *>(&v), sizeof(v)); return v; }
+  void writeBytes(const std::vector<std::byte> &b) {  // src/archive.cpp:165-169
+    writeInteger(narrow_cast<uint32_t>(b.size()));
+    fs.write(reinterpret_cast<const char *>(b.data()), static_cast<std::streamsize>(b.size()));
+  }
+  void readBytes(std::vector<std::byte> &b) {  // src/archive.cpp:171-175
+    b.resize(readInteger<uint32_t>());
+    fs.read(reinterpret_cast<char *>(b.data()), static_cast<std::streamsize>(b.size()));
+  }
+  void setMeta(DatasetMeta &&m) {
+    meta = std::move(m);
+    fmt = headers::Format::fromHeader(meta.first_header);
+    first_fields = headers::fieldsOf(meta.first_header, fmt);
+  }
+  void writeMeta() {  // src/archive.cpp:22-25, src/prepare.cpp:12-21
+    std::vector<char> bytes;
+    DatasetMeta::storeToBytes(meta, bytes);
+    fs.seekp(OFFSET_META);
+    fs.write(bytes.data(), static_cast<std::streamsize>(bytes.size()));
+  }
+  /** src/archive.cpp:57-106 */
+  void writeBlock(const CompressedBuffersDst &cb, const std::vector<headers::FieldStorage> &fields) {
+    BlockInfo bi{};
+    bi.idx = cb.chunk_idx;
+    bi.offset = static_cast<int64_t>(fs.tellp());
+    writeInteger(cb.original_size.total);
+    writeInteger(cb.original_size.n_records);
+    writeInteger(cb.original_size.readlens);
+    writeBytes(memcompress(cb.readlens));
+    writeInteger(cb.original_size.n_count);
+    writeBytes(memcompress(cb.n_count));
+    writeInteger(cb.original_size.n_pos);
+    writeBytes(memcompress(cb.n_pos));
+    writeBytes(cb.seq);
+    writeBytes(cb.qual);
+    for (std::size_t i = 0; i < fmt.n_fields(); ++i) {
+      const auto &f = fields[i];
+      if (fmt.field_types[i] == headers::FieldType::STRING) {
+        writeInteger(narrow_cast<uint32_t>(f.isDifferentFlag.size()));
+        writeBytes(memcompress(f.isDifferentFlag));
+        writeInteger(narrow_cast<uint32_t>(f.content.size()));
+        writeBytes(memcompress(f.content));
+        writeInteger(narrow_cast<uint32_t>(f.contentLength.size()));
+        writeBytes(memcompress(f.contentLength));
+      } else {
+        writeInteger(narrow_cast<uint32_t>(f.content.size()));
+        writeBytes(memcompress(f.content));
+      }
+    }
+    index.push_back(bi);
+  }
+  /** src/archive.cpp:45-55 */
+  void writeIndex() {
+    const std::streamoff end = fs.tellp();
+    fs.seekp(0);
+    writeInteger(narrow_cast<uint32_t>(index.size()));
+    fs.seekp(end);
+    fs.write(reinterpret_cast<const char *>(index.data()), static_cast<std::streamsize>(index.size() * sizeof(BlockInfo)));
+  }
+  /** src/archive.cpp:27-43 */
+  void readHeader() {
+    const uint32_t n_blocks = readInteger<uint32_t>();
+    readlen_t hlen = readInteger<readlen_t>();
+    std::vector<char> m(sizeof(hlen) + hlen + sizeof(SeqFreqTable) + sizeof(QualFreqTable));
+    std::memcpy(m.data(), &hlen, sizeof(hlen));
+    fs.read(m.data() + sizeof(hlen), static_cast<std::streamsize>(m.size() - sizeof(hlen)));
+    setMeta(DatasetMeta::loadFromBytes(m.data(), m.size()));
+    const auto data_start = fs.tellg();
+    fs.seekg(-static_cast<std::streamoff>(n_blocks * sizeof(BlockInfo)), std::ios_base::end);
+    index.resize(n_blocks);
+    fs.read(reinterpret_cast<char *>(index.data()), static_cast<std::streamsize>(n_blocks * sizeof(BlockInfo)));
+    fs.seekg(data_start);
+    std::sort(index.begin(), index.end(), [](const BlockInfo &a, const BlockInfo &b) { return a.idx < b.idx; });
+    if (!fs) throw std::runtime_error("truncated archive");
+  }
+  /** src/archive.cpp:108-163 */
+  void readBlock(const BlockInfo &bi, CompressedBuffersSrc &cb, std::vector<headers::FieldStorage> &fields) {
+    cb.clear();
+    fs.seekg(bi.offset);
+    cb.chunk_idx = bi.idx;
+    cb.original_size.total = readInteger<uint32_t>();
+    cb.original_size.n_records = readInteger<uint32_t>();
+    std::vector<std::byte> tmp;
+    cb.original_size.readlens = readInteger<uint32_t>();
+    readBytes(tmp);
+    cb.readlens = memdecompress(tmp, cb.original_size.readlens);
+    cb.original_size.n_count = readInteger<uint32_t>();
+    readBytes(tmp);
+    cb.n_count = memdecompress(tmp, cb.original_size.n_count);
+    cb.original_size.n_pos = readInteger<uint32_t>();
+    readBytes(tmp);
+    cb.n_pos = memdecompress(tmp, cb.original_size.n_pos);
+    readBytes(cb.seq);
+    readBytes(cb.qual);
+    fields.assign(fmt.n_fields(), {});
+    for (std::size_t i = 0; i < fmt.n_fields(); ++i) {
+      auto &f = fields[i];
+      if (fmt.field_types[i] == headers::FieldType::STRING) {
+        uint32_t o = readInteger<uint32_t>();
+        readBytes(tmp);
+        f.isDifferentFlag = memdecompress(tmp, o);
+        o = readInteger<uint32_t>();
+        readBytes(tmp);
+        f.content = memdecompress(tmp, o);
+        o = readInteger<uint32_t>();
+        readBytes(tmp);
+        f.contentLength = memdecompress(tmp, o);
+      } else {
+        const uint32_t o = readInteger<uint32_t>();
+        readBytes(tmp);
+        f.content = memdecompress(tmp, o);
+      }
+    }
+    if (!fs) throw std::runtime_error("truncated block");
+  }
+};
+
+static double now_s() {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+// ---------------------------------------------------------------- c
+/** processReads, src/process.cpp:32-82 */
+static int compress(const Settings &set) {
+  std::ifstream in(set.mates1, std::ios::binary);
+  if (!in) throw std::system_error(errno, std::generic_category(), set.mates1);
+  in.seekg(0, std::ios::end);
+  const std::size_t file_size = static_cast<std::size_t>(in.tellg());
+  in.seekg(0);
+  const std::size_t R = static_cast<std::size_t>(set.reading_mb) << 20, S = static_cast<std::size_t>(set.sample_mb) << 20;
+  const std::size_t slab_cap = std::max(set.slab_mb << 20, 2 * R);
+  auto ctx = GpuContext::shared();
+  Archive ar;
+  ar.fs.open(set.archive, std::ios::binary | std::ios::out | std::ios::trunc);
+  if (!ar.fs) throw std::system_error(errno, std::generic_category(), set.archive);
+
+  std::vector<char> slab;
+  std::size_t file_pos = 0, carry = 0;
+  double t_gpu = 0, t_host = 0;
+  uint32_t next_idx = 0;
+  std::size_t tot_seq = 0, tot_qual = 0, n_records = 0;
+  bool have_meta = false;
+  std::unique_ptr<CompressionWorkspace> wksp;
+  while (file_pos < file_size || carry) {
+    const std::size_t want = std::min(slab_cap - carry, file_size - file_pos);
+    slab.resize(carry + want);
+    in.read(slab.data() + carry, static_cast<std::streamsize>(want));
+    file_pos += want;
+    const bool eof = file_pos == file_size;
+    if (!have_meta) {
+      // analyzeDataset (src/prepare.cpp:42-47): first chunk of a reader with reading size S
+      if (slab.size() < std::min(S, file_size)) throw std::runtime_error("slab smaller than the sample window; raise --slab-mb");
+      FastqChunk sample;
+      const std::size_t win = std::min(S, slab.size());
+      sample.raw_data.assign(slab.begin(), slab.begin() + static_cast<std::ptrdiff_t>(win));
+      const std::size_t used = FastqReader::parseRecords(sample, *ctx);
+      sample.raw_data.resize(used);
+      if (sample.records.empty()) throw std::invalid_argument("no complete FASTQ record in the sample window");
+      ar.setMeta(DatasetMeta(sample, *ctx));
+      ar.writeMeta();
+      wksp = std::make_unique<CompressionWorkspace>(&ar.meta, ctx);
+      have_meta = true;
+    }
+    std::vector<CompressedBuffersDst> blocks;
+    std::size_t consumed = 0;
+    double t0 = now_s();
+    wksp->encodeChunks(slab.data(), slab.size(), R, eof, blocks, &consumed);
+    t_gpu += now_s() - t0;
+    t0 = now_s();
+    std::vector<headers::FieldStorage> fields;
+    for (auto &cb : blocks) {
+      cb.chunk_idx = next_idx++;
+      headers::tokenize(cb.raw_headers, cb.header_lengths, ar.fmt, ar.first_fields, fields);
+      ar.writeBlock(cb, fields);
+      tot_seq += cb.seq.size();
+      tot_qual += cb.qual.size();
+      n_records += cb.original_size.n_records;
+    }
+    t_host += now_s() - t0;
+    if (eof) break;  // a trailing partial record is dropped, like the reference (src/fastq_io.cpp:31-32)
+    if (consumed == 0) throw std::runtime_error("no whole chunk fits the slab; raise --slab-mb");
+    carry = slab.size() - consumed;
+    std::memmove(slab.data(), slab.data() + consumed, carry);
+  }
+  ar.writeIndex();
+  ar.fs.flush();
+  if (set.verbose || true) {
+    std::fprintf(stderr, "fqcomp28 (B200 path): %zu records, %u blocks, seq %zu B, qual %zu B; codec %.3f s, host (headers + archive) %.3f s\n",
+                 n_records, next_idx, tot_seq, tot_qual, t_gpu, t_host);
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------- d
+/** processArchiveParts, src/process.cpp:84-105 */
+static int decompress(const Settings &set) {
+  Archive ar;
+  ar.fs.open(set.archive, std::ios::binary | std::ios::in);
+  if (!ar.fs) throw std::system_error(errno, std::generic_category(), set.archive);
+  ar.readHeader();
+  std::ofstream out(set.mates1, std::ios::binary | std::ios::trunc);
+  if (!out) throw std::system_error(errno, std::generic_category(), set.mates1);
+  auto ctx = GpuContext::shared();
+  DecompressionWorkspace wksp(&ar.meta, ctx);
+  const std::size_t batch_bytes = set.slab_mb << 20;
+  std::size_t i = 0;
+  while (i < ar.index.size()) {
+    std::vector<CompressedBuffersSrc> srcs;
+    std::vector<headers::FieldStorage> fields;
+    std::size_t bytes = 0;
+    while (i < ar.index.size() && (srcs.empty() || bytes < batch_bytes)) {
+      srcs.emplace_back();
+      ar.readBlock(ar.index[i++], srcs.back(), fields);
+      auto &cb = srcs.back();
+      headers::detokenize(fields, ar.fmt, ar.first_fields, cb.original_size.n_records, cb.raw_headers, cb.header_lengths);
+      bytes += cb.original_size.total;
+    }
+    std::vector<CompressedBuffersSrc *> ps;
+    std::vector<FastqChunk> chunks(srcs.size());
+    std::vector<FastqChunk *> pc;
+    for (std::size_t k = 0; k < srcs.size(); ++k) { ps.push_back(&srcs[k]); pc.push_back(&chunks[k]); }
+    wksp.decodeChunks(ps, pc);
+    for (auto &c : chunks) out.write(c.raw_data.data(), static_cast<std::streamsize>(c.raw_data.size()));  // idx order
+  }
+  out.flush();
+  return out ? 0 : 1;
+}
+
+}  // namespace fqcomp28
+
+// ---------------------------------------------------------------- CLI (src/app.cpp:27-80, without CLI11)
+static void usage() {
+  std::fprintf(stderr,
+               "fqcomp28 (B200 codec path)\n"
+               "  fqcomp28 c --i1|--input1 FILE -o|--output ARCHIVE [-S|--sample-size-Mb N=128] [-R|--reading-size-Mb N=256]\n"
+               "             [-t|--threads N] [--verbose] [--slab-mb N=1024]\n"
+               "  fqcomp28 d -i|--input ARCHIVE --o1|--output1 FILE [-t|--threads N] [--verbose] [--slab-mb N=1024]\n");
+}
+
+int main(int argc, char **argv) {
+  using namespace fqcomp28;
+  if (argc < 2) { usage(); return 106; }
+  const std::string cmd = argv[1];
+  Settings set;
+  auto need = [&](int &i) -> std::string {
+    if (i + 1 >= argc) { usage(); std::exit(106); }
+    return argv[++i];
+  };
+  auto mb = [&](const std::string &v) {  // NonNegativeNumber in the reference; 0 is UB there
+    const long x = std::strtol(v.c_str(), nullptr, 10);
+    if (x < 1) { std::fprintf(stderr, "size options must be >= 1 MB\n"); std::exit(105); }
+    return static_cast<unsigned>(x);
+  };
+  for (int i = 2; i < argc; ++i) {
+    const std::string a = argv[i];
+    if (cmd == "c" && (a == "--i1" || a == "--input1")) set.mates1 = need(i);
+    else if (cmd == "c" && (a == "-o" || a == "--output")) set.archive = need(i);
+    else if (cmd == "c" && (a == "-S" || a == "--sample-size-Mb")) set.sample_mb = mb(need(i));
+    else if (cmd == "c" && (a == "-R" || a == "--reading-size-Mb")) set.reading_mb = mb(need(i));
+    else if (cmd == "d" && (a == "-i" || a == "--input")) set.archive = need(i);
+    else if (cmd == "d" && (a == "--o1" || a == "--output1")) set.mates1 = need(i);
+    else if (a == "-t" || a == "--threads") set.n_threads = mb(need(i));  // accepted; the GPU path has one worker per GPU
+    else if (a == "--slab-mb") set.slab_mb = mb(need(i));
+    else if (a == "--verbose") set.verbose = true;
+    else { std::fprintf(stderr, "unknown option %s\n", a.c_str()); usage(); return 109; }
+  }
+  if ((cmd != "c" && cmd != "d") || set.mates1.empty() || set.archive.empty()) { usage(); return 106; }
+  try {
+    return cmd == "c" ? compress(set) : decompress(set);
+  } catch (const std::exception &e) {
+    std::fprintf(stderr, "fqcomp28: %s\n", e.what());
+    return 1;
+  }
+}

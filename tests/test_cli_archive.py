@@ -1,0 +1,111 @@
+"""Row N1: the drop-in `fqcomp28 c|d` CLI (fqcomp28_b200/host/fqcomp28_cli.cpp).
+
+* `c` then `d` restores the input (scripts/check_compression_integrity.sh:21-24);
+* the archive follows the reference's framing (src/archive.cpp:22-163,
+  src/archive.h:10-29): u32 n_blocks | meta (u16 hlen, first header, raw
+  FreqTable images) | blocks | index of {i64 offset; u32 idx; pad}; the meta
+  tables and every block's seq / qual streams equal the CPU oracle's.
+"""
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import DATA, FIXTURES, ROOT, load_fixture
+
+CLI = os.path.join(ROOT, "fqcomp28_b200", "fqcomp28")
+
+
+def build_cli():
+    pkg = os.path.join(ROOT, "fqcomp28_b200")
+    subprocess.check_call(["g++", "-std=c++20", "-O2", "-Wall", "-Wextra", "-o", CLI, os.path.join(pkg, "host", "fqcomp28_cli.cpp"),
+                           "-L", pkg, "-lfq28", "-Wl,-rpath,$ORIGIN"])
+
+
+def test_cli_builds():
+    build_cli()
+    r = subprocess.run([CLI], capture_output=True, text=True)
+    assert r.returncode == 106 and "fqcomp28 c" in r.stderr  # usage, like CLI11's RequiredError exit
+
+
+def parse_archive(buf: bytes, n_fields_types):
+    """-> (first_header, ft_seq, ft_qual, [blocks sorted by idx])"""
+    (n_blocks,) = struct.unpack_from("<I", buf, 0)
+    (hlen,) = struct.unpack_from("<H", buf, 4)
+    pos = 6
+    first = buf[pos : pos + hlen].decode()
+    pos += hlen
+    ft_seq = np.frombuffer(buf, np.uint8, 3076, pos); pos += 3076
+    ft_qual = np.frombuffer(buf, np.uint8, 1081348, pos); pos += 1081348
+    index = [struct.unpack_from("<qI4x", buf, len(buf) - 16 * n_blocks + 16 * i) for i in range(n_blocks)]
+    blocks = []
+    for off, idx in sorted(index, key=lambda t: t[1]):
+        p = off
+        total, n_rec = struct.unpack_from("<II", buf, p); p += 8
+        side = []
+        for _ in range(3):  # readlens, n_count, n_pos: u32 original, u32 size, bytes
+            orig, sz = struct.unpack_from("<II", buf, p); p += 8
+            side.append((orig, buf[p : p + sz])); p += sz
+        (sz,) = struct.unpack_from("<I", buf, p); p += 4
+        seq = buf[p : p + sz]; p += sz
+        (sz,) = struct.unpack_from("<I", buf, p); p += 4
+        qual = buf[p : p + sz]; p += sz
+        blocks.append(dict(idx=idx, total=total, n_rec=n_rec, side=side, seq=seq, qual=qual))
+    return first, ft_seq, ft_qual, blocks
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", FIXTURES)
+def test_cli_roundtrip_fixture(tmp_path, oracle, name):
+    build_cli()
+    src = os.path.join(DATA, name + ".fastq")
+    arc, out = str(tmp_path / "a.fqz"), str(tmp_path / "o.fastq")
+    subprocess.check_call([CLI, "c", "--input1", src, "-o", arc, "--threads", "4"])
+    subprocess.check_call([CLI, "d", "--input", arc, "--o1", out, "--threads", "4"])
+    assert open(out, "rb").read() == open(src, "rb").read()
+    # archive framing + streams vs the oracle (default -S 128 -R 256: one chunk, sample = whole file)
+    O = oracle
+    d = load_fixture(name)
+    recs, _ = O.parse_records(d)
+    fs, fq = O.make_ft(*O.hist(d, recs))
+    enc = O.Codec(fs, fq).encode_chunk(d, recs)
+    first, a_fs, a_fq, blocks = parse_archive(open(arc, "rb").read(), None)
+    assert first == bytes(d[: recs["hdr_len"][0]]).decode()
+    assert np.array_equal(a_fs, fs) and np.array_equal(a_fq, fq)
+    assert len(blocks) == 1 and blocks[0]["idx"] == 0
+    b = blocks[0]
+    assert (b["total"], b["n_rec"]) == (d.size, len(recs))
+    assert b["seq"] == enc["seq"].tobytes() and b["qual"] == enc["qual"].tobytes()
+    assert [s[0] for s in b["side"]] == [2 * len(recs), 2 * len(recs), 2 * enc["n_pos"].size]
+    # STORED container: 28-byte header then the raw buffer
+    assert b["side"][0][1][:8] == b"FQ28STOR" and b["side"][0][1][28:] == enc["readlens"].tobytes()
+    assert b["side"][2][1][28:] == enc["n_pos"].tobytes()
+
+
+@pytest.mark.gpu
+def test_cli_multichunk_synthetic(tmp_path, oracle):
+    import synth
+
+    build_cli()
+    d = synth.illumina(0, 12000, seed=30).numpy()  # ~4.2 MB
+    src, arc, out = str(tmp_path / "s.fastq"), str(tmp_path / "s.fqz"), str(tmp_path / "s.out")
+    d.tofile(src)
+    subprocess.check_call([CLI, "c", "--i1", src, "--output", arc, "-R", "1", "-S", "2", "--slab-mb", "3"])
+    subprocess.check_call([CLI, "d", "-i", arc, "--output1", out])
+    assert np.array_equal(np.fromfile(out, dtype=np.uint8), d)
+    O = oracle
+    offs = O.split_chunks(d, 1 << 20)
+    sample = d[: int(O.split_chunks(d, 2 << 20)[1])]
+    recs, _ = O.parse_records(sample)
+    fs, fq = O.make_ft(*O.hist(sample, recs))
+    first, a_fs, a_fq, blocks = parse_archive(open(arc, "rb").read(), None)
+    assert np.array_equal(a_fs, fs) and np.array_equal(a_fq, fq)
+    assert [b["idx"] for b in blocks] == list(range(len(offs) - 1))
+    cod = O.Codec(fs, fq)
+    for k, b in enumerate(blocks):
+        sub = d[int(offs[k]) : int(offs[k + 1])]
+        r, _ = O.parse_records(sub)
+        e = cod.encode_chunk(sub, r)
+        assert b["total"] == sub.size and b["seq"] == e["seq"].tobytes() and b["qual"] == e["qual"].tobytes()
