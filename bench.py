@@ -452,8 +452,10 @@ def run_ours(args):
                 "value": vc if args.mode == "compress" else vd, "unit": "MB/s", "cores": threads, "kind": "port",
                 "sample": f"leading {host.size} bytes of the rank-0 slab ({res.n_chunks} chunks), one pass",
                 "compress_MBps": vc, "decompress_MBps": vd, "roundtrip_ok": bool(res.roundtrip_ok),
-                "streams_match_gpu": bool(host.size == n_bytes and res.seq_bytes == int(summ.seq_bytes)
-                                          and res.qual_bytes == int(summ.qual_bytes) and res.checksum == gpu_fnv(O)),
+                "streams_match_gpu": bool(host.size == n_bytes
+                                          and res.seq_bytes == sum(int(state["dec_infos"][kk].seq_len) for kk in range(int(summ.n_chunks)))
+                                          and res.qual_bytes == sum(int(state["dec_infos"][kk].qual_len) for kk in range(int(summ.n_chunks)))
+                                          and res.checksum == gpu_fnv(O)),
             }
         except Exception as e:  # the oracle is a checker, never a dependency of the product arm
             cpu_baseline = {"error": repr(e)}

@@ -89,9 +89,9 @@ print("wrote", f"{tag}_launches.md", f"{tag}_ncu_summary.md")
 import json
 
 stage_of = [
-    ("k_chain<Kind<unsigned int", "chain_qual"), ("k_chain<Kind<unsigned short", "chain_seq"),
+    ("k_chain<Kind<unsigned int", "chain_qual"), ("k_chain_dom<Kind<unsigned int", "chain_qual"), ("k_chain<Kind<unsigned short", "chain_seq"),
     ("k_decode_seq", "decode_seq"), ("k_decode_qual", "decode_qual"), ("k_tile_part_small", "part_seq"),
-    ("k_tile_rank<Kind<unsigned int", "part_qual"), ("k_pack_write<8192>", "pack"), ("k_extract", "extract"),
+    ("k_tile_rank<Kind<unsigned int", "part_qual"), ("k_tile_hist<Kind<unsigned int", "part_qual"), ("k_pack_write<8192>", "pack"), ("k_extract", "extract"),
 ]
 nsym = None
 try:
@@ -100,18 +100,20 @@ try:
 except Exception:
     pass
 traffic = {}
-seen = set()
+done = set()
+scale = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}
 for r in rr[2:]:
     name = r[h.index("Kernel Name")]
+    short = name.split("(")[0]
     for pat, stage in stage_of:
-        if pat in name and stage not in seen:
-            seen.add(stage)
-            rd = float(r[h.index("dram__bytes_read.sum")].replace(",", ""))
-            wr = float(r[h.index("dram__bytes_write.sum")].replace(",", ""))
-            scale = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}
-            rd *= scale.get(units[h.index("dram__bytes_read.sum")], 1.0)
-            wr *= scale.get(units[h.index("dram__bytes_write.sum")], 1.0)
-            traffic[stage] = {"dram_bytes_per_launch": rd + wr, "nsym_of_capture": nsym,
-                              "dram_bytes_per_symbol": (rd + wr) / nsym if nsym else None}
+        if pat in name and (stage, short) not in done:  # one launch of every kernel of the stage
+            done.add((stage, short))
+            rd = float(r[h.index("dram__bytes_read.sum")].replace(",", "")) * scale.get(units[h.index("dram__bytes_read.sum")], 1.0)
+            wr = float(r[h.index("dram__bytes_write.sum")].replace(",", "")) * scale.get(units[h.index("dram__bytes_write.sum")], 1.0)
+            t = traffic.setdefault(stage, {"dram_bytes_per_launch": 0.0, "nsym_of_capture": nsym, "kernels": []})
+            t["dram_bytes_per_launch"] += rd + wr
+            t["kernels"].append(short)
+for t in traffic.values():
+    t["dram_bytes_per_symbol"] = t["dram_bytes_per_launch"] / nsym if nsym else None
 json.dump(traffic, open(os.path.join(out, f"traffic_{tag}.json"), "w"), indent=1)
 print("wrote", f"traffic_{tag}.json", traffic.get("chain_qual"))
