@@ -180,7 +180,7 @@ def run_reference(args):
                                  "oracle/ port with the reference threading model (one chunk per worker thread)"},
         "e2e": {"value": head, "unit": "MB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
     return 0
 
 
@@ -473,7 +473,7 @@ def run_ours(args):
             "stats": {"n_chunks": int(summ.n_chunks), "n_records": int(summ.n_records), "seq_bytes": int(summ.seq_bytes),
                       "qual_bytes": int(summ.qual_bytes), "ratio_seq_qual": n_bytes / max(1, int(summ.seq_bytes) + int(summ.qual_bytes))},
         }
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     h.close()
     if world > 1:
         dist.destroy_process_group()

@@ -337,3 +337,36 @@ def test_synthetic_illumina_32mb_roundtrip_and_checksum(oracle, H):
         enc = cod.encode_chunk(sub, recs)
         assert np.array_equal(ar["seq"][ci.seq_off : ci.seq_off + ci.seq_len], enc["seq"])
         assert np.array_equal(ar["qual"][ci.qual_off : ci.qual_off + ci.qual_len], enc["qual"])
+
+
+@pytest.mark.parametrize("profile", ["hiseq", "novaseq"])
+def test_synthetic_profiles_chunk_parity(oracle, H, profile):
+    """BASELINE config-2 data shapes (4-bin NovaSeq / 41-level HiSeq qualities)
+    at a size the oracle handles in seconds: every chunk's streams are
+    byte-identical, with tables from a leading sample only."""
+    import synth
+
+    d = synth.illumina(0, 9000, seed=30, profile=profile).numpy()
+    sample = d[: int(oracle.split_chunks(d, 1 << 20)[1])]
+    recs, _ = oracle.parse_records(sample)
+    fs, fq = oracle.make_ft(*oracle.hist(sample, recs))
+    ft = (np.zeros(3076, np.uint8), np.zeros(1081348, np.uint8))
+    infos, summ, ar = H.compress(d, 1 << 20, sample_bytes=1 << 20, ft_out=ft)
+    assert np.array_equal(ft[0], fs) and np.array_equal(ft[1], fq)  # analyzeDataset inside fq28_compress
+    check_chunks(oracle, H, d, 1 << 20, fs, fq)
+
+
+def test_long_reads_ont_like(oracle, H):
+    """BASELINE config 4: variable-length long reads (1-50 kb), ONT-like
+    qualities (thousands of live quality contexts)."""
+    import synth
+
+    d = synth.ont(0, 120, seed=32).numpy()
+    recs, cs, cq, fs, fq = oracle_tables(oracle, d)
+    assert int(recs["len"].max()) > 20000 and int((cq.sum(1) > 0).sum()) > 1500
+    gcs, gcq = H.hist(d)
+    assert np.array_equal(gcs, cs) and np.array_equal(gcq, cq)
+    gfs, gfq = H.build_tables(gcs, gcq)
+    assert np.array_equal(gfs, fs) and np.array_equal(gfq, fq)
+    check_chunks(oracle, H, d, 1 << 20, fs, fq)
+    check_chunks(oracle, H, d, 256 << 20, fs, fq)
