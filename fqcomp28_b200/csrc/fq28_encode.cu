@@ -1069,7 +1069,7 @@ int encode_slab(fq28_handle *h, fq28_chunk_info *infos, size_t infos_cap, fq28_e
     // quality partition first with the whole GPU; its chain is latency-bound on a
     // few SMs, so the complete sequence pipeline runs underneath it
     FQ28_TRY((run_kind<QualKind, QUAL_A, QUAL_TILE, QUAL_STRIDE, 1>(h, h->qual, h->key_qual.as<uint32_t>(), bq, true, h->ev_join)));
-    if (getenv("FQ28_SEQ_AFTER_QPART")) FQ28_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_join, 0));
+    if (!getenv("FQ28_FULL_OVERLAP")) FQ28_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_join, 0));
     FQ28_TRY((run_kind<SeqKind, SEQ_A, SEQ_TILE, SEQ_STRIDE, 4>(h, h->seq, h->key_seq.as<uint16_t>(), bs, false)));
     FQ28_TRY(side_join(h));
   } else {

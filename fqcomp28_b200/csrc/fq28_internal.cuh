@@ -27,7 +27,7 @@ constexpr unsigned SEQ_N = FQ28_SEQ_MODELS, SEQ_A = FQ28_SEQ_ALPHABET;
 constexpr unsigned QUAL_N = FQ28_QUAL_MODELS, QUAL_A = FQ28_QUAL_ALPHABET;
 
 // ---- partition / pack tiling ------------------------------------------------
-constexpr unsigned SEQ_TILE = 16384;    // symbols per context-partition tile (seq)
+constexpr unsigned SEQ_TILE = 8192;     // symbols per context-partition tile (seq)
 constexpr unsigned QUAL_TILE = 131072;  // symbols per context-partition tile (qual)
 // slots per tile region: every non-empty context run is padded to a multiple of 16
 constexpr unsigned SEQ_STRIDE = SEQ_TILE + 16 * SEQ_N;
