@@ -189,11 +189,25 @@ k_tile_hist(const typename K::key_t *__restrict__ key, const uint32_t *__restric
   for (unsigned i = threadIdx.x; i < N; i += 256) hist[i] = 0;
   __syncthreads();
   const unsigned lane = threadIdx.x & 31;
-  for (unsigned j = threadIdx.x; j < ((tr.cnt + 255u) & ~255u); j += 256) {
-    unsigned ctx = 0xFFFFFFFFu;
-    if (j < tr.cnt) ctx = (unsigned)key[tr.g0 + j] >> K::shift;
-    const unsigned peers = __match_any_sync(0xffffffffu, ctx);
-    if (ctx != 0xFFFFFFFFu && lane == (unsigned)(__ffs(peers) - 1)) atomicAdd(&hist[ctx], (unsigned)__popc(peers));
+  // every thread walks 8 consecutive keys and issues one shared-memory atomic
+  // per RUN of equal contexts (quality contexts come in runs), the loads of a
+  // step are independent and in flight together
+  const typename K::key_t *kp = key + tr.g0;
+  for (unsigned j0 = threadIdx.x * 8; j0 < tr.cnt; j0 += 256 * 8) {
+    unsigned c[8];
+#pragma unroll
+    for (unsigned u = 0; u < 8; u++) c[u] = j0 + u < tr.cnt ? (unsigned)kp[j0 + u] >> K::shift : 0xFFFFFFFFu;
+    unsigned cur = c[0], n = 1;
+#pragma unroll
+    for (unsigned u = 1; u < 8; u++) {
+      if (c[u] == cur) { n++; }
+      else {
+        if (cur != 0xFFFFFFFFu) atomicAdd(&hist[cur], n);
+        cur = c[u];
+        n = 1;
+      }
+    }
+    if (cur != 0xFFFFFFFFu) atomicAdd(&hist[cur], n);
   }
   __syncthreads();
   // exclusive scan of hist[N]; thread i owns N/256 consecutive entries
@@ -240,11 +254,17 @@ k_tile_rank(const typename K::key_t *__restrict__ key, const uint32_t *__restric
   for (unsigned i = lane; i < N; i += 32) run[i] = tb[i] & ~15u;
   __syncwarp();
   const typename K::key_t *kp = key + tr.g0;
-  unsigned nxt = lane < tr.cnt ? (unsigned)kp[lane] : 0u;
+  // keys are prefetched four steps (128 symbols) ahead: a step takes a few
+  // hundred cycles, DRAM latency is several steps
+  unsigned q0 = lane < tr.cnt ? (unsigned)kp[lane] : 0u;
+  unsigned q1 = 32 + lane < tr.cnt ? (unsigned)kp[32 + lane] : 0u;
+  unsigned q2 = 64 + lane < tr.cnt ? (unsigned)kp[64 + lane] : 0u;
+  unsigned q3 = 96 + lane < tr.cnt ? (unsigned)kp[96 + lane] : 0u;
   for (unsigned j = 0; j < tr.cnt; j += 32) {
-    const unsigned kv = nxt;
-    const unsigned jn = j + 32 + lane;
-    nxt = jn < tr.cnt ? (unsigned)kp[jn] : 0u;
+    const unsigned kv = q0;
+    q0 = q1; q1 = q2; q2 = q3;
+    const unsigned jn = j + 128 + lane;
+    q3 = jn < tr.cnt ? (unsigned)kp[jn] : 0u;
     const bool live = j + lane < tr.cnt;
     const unsigned ctx = live ? kv >> K::shift : 0xFFFFFFFFu;
     const unsigned peers = __match_any_sync(0xffffffffu, ctx);
@@ -516,19 +536,25 @@ k_chain(const uint8_t *__restrict__ ssym, const uint32_t *__restrict__ tile0, un
 }
 
 // ---------------------------------------------------------------------------
-// Long chains in contexts with a DOMINANT symbol (norm > T/2, so every step
-// with it emits 0 or 1 bit): binned qualities put > 80 % of a chunk's symbols
-// into one such chain, and its length bounds the whole encoder.  One warp per
-// (chunk, context) pair:
-//   * P8[x] = effect of 8 consecutive dominant symbols on state x: next state
-//     (11 bits) | nbBits of the 8 steps (8 bits) | emitted bits (8 bits),
-//     built in shared memory from the CTable;
-//   * per block of 32 groups (512 symbols): every lane loads one group and
-//     tests its two 8-symbol halves against the dominant pattern (parallel),
-//     the warp then walks the 64 halves serially -- ONE table lookup for an
-//     all-dominant half, 8 ordinary steps otherwise -- and finally every lane
-//     expands and stores the 16 fields of its group (parallel).
+// Long chains in contexts with a DOMINANT symbol (norm > T/2): binned qualities
+// put > 80 % of a chunk's symbols into one such chain, and its length bounds
+// the whole encoder.  The state recurrence x' = f_s(x) is split in two:
+//   * a serial WALK that only tracks the state.  Composed step tables in shared
+//     memory -- R_r = r consecutive dominant symbols (r = 1..16), S_j = one step
+//     with the j-th most frequent other symbol -- turn a 16-symbol group into
+//     ~2 table lookups (one per run of dominant symbols, one per other symbol);
+//   * a parallel EXPANSION: given the state at the start of its group, every
+//     lane replays its 16 symbols with the ordinary FSE_encodeSymbol step and
+//     stores the 16 fields.
+// CTA = 8 warps = one context x 8 consecutive chunks (the tables depend on the
+// context only); a warp processes its chain in blocks of 32 groups.
 // ---------------------------------------------------------------------------
+constexpr unsigned DOM_WARPS = 8;
+constexpr unsigned DOM_NS = 3;                     // other symbols with a step table of their own
+constexpr unsigned DOM_TABLES = 16 + DOM_NS;
+constexpr unsigned DOM_GENERIC = 0x100;            // op code: ordinary step with symbol (op & 0xFF)
+constexpr size_t DOM_SMEM = (size_t)DOM_TABLES * 4096 + 4096 + 64 * 8 + (size_t)DOM_WARPS * 512 * 2 * 2;
+
 template <class K>
 __global__ void k_dom_list(const uint32_t *__restrict__ tile0, unsigned n_chunks, const uint32_t *__restrict__ tbase,
                            const int8_t *__restrict__ dom_sym, uint32_t *__restrict__ list, unsigned cap,
@@ -537,69 +563,95 @@ __global__ void k_dom_list(const uint32_t *__restrict__ tile0, unsigned n_chunks
   const unsigned c = blockIdx.x;
   if (dom_sym[c] < 0) return;
   const unsigned k = blockIdx.y * blockDim.x + threadIdx.x;
-  if (k >= n_chunks) return;
   unsigned total = 0;
-  for (unsigned t = tile0[k]; t < tile0[k + 1]; t++) total += run_count(tbase + (size_t)t * (N + 1) + c);
-  if (total >= DOM_MIN) {
+  if (k < n_chunks)
+    for (unsigned t = tile0[k]; t < tile0[k + 1]; t++) total += run_count(tbase + (size_t)t * (N + 1) + c);
+  // one entry per block of DOM_WARPS consecutive chunks with at least one long chain
+  const unsigned any = __ballot_sync(0xffffffffu, total >= DOM_MIN);
+  const unsigned lane = threadIdx.x & 31;
+  if ((lane % DOM_WARPS) == 0 && ((any >> lane) & ((1u << DOM_WARPS) - 1u))) {
     const unsigned long long i = atomicAdd(count, 1ULL);
-    if (i < cap) list[i] = c | (k << 13);
+    if (i < cap) list[i] = c | ((k / DOM_WARPS) << 13);
   }
 }
 
 template <class K, unsigned A, unsigned STRIDE>
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(DOM_WARPS * 32)
 k_chain_dom(const uint32_t *__restrict__ list, const unsigned long long *__restrict__ count,
-            const uint8_t *__restrict__ ssym, const uint32_t *__restrict__ tile0, const uint32_t *__restrict__ tbase,
-            const uint32_t *__restrict__ logs, const uint32_t *__restrict__ toff, const uint16_t *__restrict__ ctab,
-            const int2 *__restrict__ symtt, const int8_t *__restrict__ dom_sym, uint16_t *__restrict__ field,
-            uint16_t *__restrict__ fstate) {
+            const uint8_t *__restrict__ ssym, const uint32_t *__restrict__ tile0, unsigned n_chunks,
+            const uint32_t *__restrict__ tbase, const uint32_t *__restrict__ logs, const uint32_t *__restrict__ toff,
+            const uint16_t *__restrict__ ctab, const int2 *__restrict__ symtt, const int16_t *__restrict__ norm,
+            const int8_t *__restrict__ dom_sym, uint16_t *__restrict__ field, uint16_t *__restrict__ fstate) {
   constexpr unsigned N = K::n_models;
-  constexpr unsigned SLOW = 0xFFFFFFFFu;
-  __shared__ uint16_t st[1u << FSE_MAX_TABLELOG];
-  __shared__ int2 tt[A];
-  __shared__ uint32_t P8[1u << FIX_LOG];
-  __shared__ uint32_t E[64];
-  __shared__ uint16_t F[512];
+  static_assert(A <= 64, "symbol transform table sized for the quality alphabet");
+  extern __shared__ __align__(16) unsigned char dsm[];
+  unsigned char *tbl = dsm;                                                  // [DOM_TABLES][2048] u16: 2 * (x' - T)
+  uint16_t *st = reinterpret_cast<uint16_t *>(dsm + (size_t)DOM_TABLES * 4096);  // [2048]
+  int2 *tt = reinterpret_cast<int2 *>(st + 2048);                            // [64]
+  uint16_t *ops_all = reinterpret_cast<uint16_t *>(tt + 64);                 // [DOM_WARPS][512]
+  uint16_t *xs_all = ops_all + DOM_WARPS * 512;                              // [DOM_WARPS][512]
+  __shared__ unsigned nsym[DOM_NS];
   if (blockIdx.x >= *count) return;
-  const unsigned lane = threadIdx.x;
+  const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const unsigned ent = list[blockIdx.x];
-  const unsigned c = ent & 0x1FFFu, k = ent >> 13;
+  const unsigned c = ent & 0x1FFFu, k = (ent >> 13) * DOM_WARPS + warp;
   const unsigned t_log = logs[c], T = 1u << t_log;
   const unsigned sdom = (unsigned)dom_sym[c];
   {
     const uint16_t *gs = ctab + toff[c];
-    for (unsigned i = lane; i < T; i += 32) st[i] = gs[i];
-    for (unsigned i = lane; i < A; i += 32) tt[i] = symtt[(size_t)c * A + i];
-  }
-  __syncwarp();
-  {
-    const int2 a = tt[sdom];
-    for (unsigned x0 = T + lane; x0 < 2 * T; x0 += 32) {
-      unsigned x = x0, nbm = 0, vm = 0;
-#pragma unroll
-      for (unsigned i = 0; i < 8; i++) {
-        const unsigned nb = (x + (unsigned)a.y) >> 16;  // 0 or 1
-        nbm |= nb << i;
-        vm |= (x & nb) << i;
-        x = st[(int)(x >> nb) + a.x];
+    for (unsigned i = tid; i < T; i += DOM_WARPS * 32) st[i] = gs[i];
+    for (unsigned i = tid; i < A; i += DOM_WARPS * 32) tt[i] = symtt[(size_t)c * A + i];
+    if (tid == 0) {  // the DOM_NS most frequent symbols besides the dominant one
+      unsigned best[DOM_NS];
+      int bn[DOM_NS];
+      for (unsigned j = 0; j < DOM_NS; j++) { best[j] = 0xFFu; bn[j] = 0; }
+      for (unsigned s = 0; s < A; s++) {
+        int v = norm[(size_t)c * A + s];
+        if (v < 0) v = 1;
+        if (s == sdom || v == 0) continue;
+        unsigned cs = s;
+        for (unsigned j = 0; j < DOM_NS; j++)
+          if (v > bn[j]) { const int tv = bn[j]; const unsigned ts = best[j]; bn[j] = v; best[j] = cs; v = tv; cs = ts; }
       }
-      P8[x0 - T] = (x - T) | (nbm << 11) | (vm << 19);
+      for (unsigned j = 0; j < DOM_NS; j++) nsym[j] = best[j];
     }
   }
-  __syncwarp();
-  const unsigned pat = sdom * 0x01010101u;
-  unsigned x = T;  // FSE_initCState
-  auto slow_half = [&](unsigned wa, unsigned wb, unsigned cnt, unsigned fbase) {
-    // cnt ordinary FSE_encodeSymbol steps over the bytes of (wa, wb); uniform across the warp
-    for (unsigned i = 0; i < cnt; i++) {
-      const unsigned s = ((i < 4 ? wa >> (8 * i) : wb >> (8 * (i - 4))) & 0xFFu) & (A - 1);
-      const int2 a = tt[s];
-      const unsigned nb = (x + (unsigned)a.y) >> 16;
-      if (lane == 0) F[fbase + i] = (uint16_t)((nb << 12) | (x & ((1u << nb) - 1u)));
-      x = st[(int)(x >> nb) + a.x];
-    }
+  __syncthreads();
+  auto step_from = [&](unsigned x, unsigned s) -> unsigned {  // FSE_encodeSymbol state update
+    const int2 a = tt[s];
+    const unsigned nb = (x + (unsigned)a.y) >> 16;
+    return st[(int)(x >> nb) + a.x];
   };
-  for (unsigned t = tile0[k]; t < tile0[k + 1]; t++) {
+  {
+    uint16_t *R1 = reinterpret_cast<uint16_t *>(tbl);
+    for (unsigned i = tid; i < T; i += DOM_WARPS * 32) {
+      R1[i] = (uint16_t)((step_from(T + i, sdom) - T) * 2);
+      for (unsigned j = 0; j < DOM_NS; j++)
+        if (nsym[j] != 0xFFu)
+          reinterpret_cast<uint16_t *>(tbl + (size_t)(16 + j) * 4096)[i] = (uint16_t)((step_from(T + i, nsym[j]) - T) * 2);
+    }
+    __syncthreads();
+    for (unsigned r = 1; r < 16; r++) {  // R_{r+1} = R_1 o R_r
+      const uint16_t *prev = reinterpret_cast<const uint16_t *>(tbl + (size_t)(r - 1) * 4096);
+      uint16_t *cur = reinterpret_cast<uint16_t *>(tbl + (size_t)r * 4096);
+      for (unsigned i = tid; i < T; i += DOM_WARPS * 32) cur[i] = R1[prev[i] >> 1];
+      __syncthreads();
+    }
+  }
+  // only chains k_chain left out are walked here (same criterion)
+  if (k >= n_chunks) return;
+  const unsigned t_begin = tile0[k], t_end = tile0[k + 1];
+  {
+    unsigned total = 0;
+    for (unsigned t = t_begin; t < t_end; t++) total += run_count(tbase + (size_t)t * (N + 1) + c);
+    if (total < DOM_MIN) return;
+  }
+  uint16_t *ops = ops_all + warp * 512;
+  uint16_t *xs = xs_all + warp * 512;
+  const unsigned pat = sdom * 0x01010101u;
+  const unsigned ns0 = nsym[0], ns1 = nsym[1], ns2 = nsym[2];
+  unsigned xo = 0;  // 2 * (x - T); FSE_initCState: x = T
+  for (unsigned t = t_begin; t < t_end; t++) {
     const uint32_t *tb = tbase + (size_t)t * (N + 1) + c;
     const unsigned a0 = tb[0], a1 = tb[1];
     const unsigned b0 = a0 & ~15u, padded = (a1 & ~15u) - b0;
@@ -607,55 +659,75 @@ k_chain_dom(const uint32_t *__restrict__ list, const unsigned long long *__restr
     const unsigned groups = padded >> 4;
     const unsigned last_valid = (a0 & 15u) ? (a0 & 15u) : 16u;
     const size_t slot0 = (size_t)t * STRIDE + b0;
+    uint4 wn = make_uint4(0, 0, 0, 0);
+    if (lane < groups) wn = __ldg(reinterpret_cast<const uint4 *>(ssym + slot0 + (size_t)lane * 16));
     for (unsigned blk0 = 0; blk0 < groups; blk0 += 32) {
       const unsigned g = blk0 + lane;
       const bool have = g < groups;
-      uint4 w = make_uint4(0, 0, 0, 0);
-      if (have) w = __ldg(reinterpret_cast<const uint4 *>(ssym + slot0 + (size_t)g * 16));
-      const unsigned valid_g = have ? (g == groups - 1 ? last_valid : 16u) : 0u;
-      const unsigned m0 = __ballot_sync(0xffffffffu, valid_g >= 8 && w.x == pat && w.y == pat);
-      const unsigned m1 = __ballot_sync(0xffffffffu, valid_g == 16 && w.z == pat && w.w == pat);
-      const unsigned nb_groups = groups - blk0 < 32 ? groups - blk0 : 32;
-      for (unsigned j = 0; j < nb_groups; j++) {
-        const unsigned vj = __shfl_sync(0xffffffffu, valid_g, j);
-        if ((m0 >> j) & 1u) {
-          const unsigned e = P8[x - T];
-          if (lane == 0) E[2 * j] = e;
-          x = T + (e & 0x7FFu);
-        } else {
-          const unsigned wa = __shfl_sync(0xffffffffu, w.x, j), wb = __shfl_sync(0xffffffffu, w.y, j);
-          slow_half(wa, wb, vj < 8 ? vj : 8u, j * 16);
-          if (lane == 0) E[2 * j] = SLOW;
-        }
-        if ((m1 >> j) & 1u) {
-          const unsigned e = P8[x - T];
-          if (lane == 0) E[2 * j + 1] = e;
-          x = T + (e & 0x7FFu);
-        } else {
-          const unsigned wa = __shfl_sync(0xffffffffu, w.z, j), wb = __shfl_sync(0xffffffffu, w.w, j);
-          slow_half(wa, wb, vj > 8 ? vj - 8 : 0u, j * 16 + 8);
-          if (lane == 0) E[2 * j + 1] = SLOW;
+      const uint4 w = wn;
+      if (g + 32 < groups)  // next block's group: in flight during this block's walk
+        wn = __ldg(reinterpret_cast<const uint4 *>(ssym + slot0 + (size_t)(g + 32) * 16));
+      const unsigned valid = have ? (g == groups - 1 ? last_valid : 16u) : 0u;
+      // dominance mask of the group's valid symbols
+      unsigned m = 0;
+      {
+        const unsigned ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (unsigned q = 0; q < 4; q++)
+          m |= (((__vcmpeq4(ww[q], pat) & 0x08040201u) * 0x01010101u) >> 24) << (4 * q);
+        m &= (1u << valid) - 1u;
+      }
+      // ops of the group: one per run of dominant symbols, one per other symbol
+      const unsigned n_ops = (valid - __popc(m)) + __popc(m & ~(m << 1));
+      unsigned ofs = n_ops;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const unsigned o = __shfl_up_sync(0xffffffffu, ofs, d);
+        if (lane >= (unsigned)d) ofs += o;
+      }
+      const unsigned total_ops = __shfl_sync(0xffffffffu, ofs, 31);
+      ofs -= n_ops;
+      {
+        unsigned o = ofs;
+        for (unsigned i = 0; i < valid;) {
+          if ((m >> i) & 1u) {
+            const unsigned r = __ffs(~(m >> i)) - 1;  // run length, ends at `valid` at the latest
+            ops[o++] = (uint16_t)(r - 1);
+            i += r;
+          } else {
+            const unsigned word = i < 8 ? (i < 4 ? w.x : w.y) : (i < 12 ? w.z : w.w);
+            const unsigned sy = (word >> (8 * (i & 3))) & (A - 1);
+            ops[o++] = (uint16_t)(sy == ns0 ? 16u : sy == ns1 ? 17u : sy == ns2 ? 18u : (DOM_GENERIC | sy));
+            i++;
+          }
         }
       }
       __syncwarp();
+      // serial walk over the block's ops (all lanes in lockstep), state after op i -> xs[i]
+      const unsigned xo_in = xo;
+      for (unsigned i = 0; i < total_ops; i++) {
+        const unsigned op = ops[i];
+        if (op < DOM_GENERIC) {
+          xo = *reinterpret_cast<const uint16_t *>(tbl + op * 4096u + xo);
+        } else {
+          xo = (step_from(T + (xo >> 1), op & 0xFFu) - T) * 2;
+        }
+        if (lane == 0) xs[i] = (uint16_t)xo;
+      }
+      __syncwarp();
       if (have) {
+        unsigned x = T + ((ofs ? (unsigned)xs[ofs - 1] : xo_in) >> 1);
+        const unsigned ww[4] = {w.x, w.y, w.z, w.w};
         unsigned f[8];
 #pragma unroll
-        for (unsigned hh = 0; hh < 2; hh++) {
-          const unsigned e = E[2 * lane + hh];
-          if (e != SLOW) {
-            const unsigned nbm = (e >> 11) & 0xFFu, vm = (e >> 19) & 0xFFu;
-#pragma unroll
-            for (unsigned i = 0; i < 8; i += 2) {
-              const unsigned n0 = (nbm >> i) & 1u, n1 = (nbm >> (i + 1)) & 1u;
-              const unsigned f0 = (n0 << 12) | (n0 & (vm >> i)), f1 = (n1 << 12) | (n1 & (vm >> (i + 1)));
-              f[hh * 4 + (i >> 1)] = f0 | (f1 << 16);
-            }
-          } else {
-#pragma unroll
-            for (unsigned i = 0; i < 8; i += 2)
-              f[hh * 4 + (i >> 1)] = (unsigned)F[lane * 16 + hh * 8 + i] | ((unsigned)F[lane * 16 + hh * 8 + i + 1] << 16);
-          }
+        for (unsigned i = 0; i < 16; i++) {
+          const unsigned sy = (ww[i >> 2] >> (8 * (i & 3))) & (A - 1);
+          const int2 a = tt[sy];
+          const unsigned nb = (x + (unsigned)a.y) >> 16;
+          const unsigned fv = (nb << 12) | (x & ((1u << nb) - 1u));
+          const unsigned xn = st[(int)(x >> nb) + a.x];
+          if (i < valid) x = xn;
+          if (i & 1) f[i >> 1] |= fv << 16; else f[i >> 1] = fv;
         }
         uint4 *fp = reinterpret_cast<uint4 *>(field + slot0 + (size_t)g * 16);
         fp[0] = make_uint4(f[0], f[1], f[2], f[3]);
@@ -664,7 +736,7 @@ k_chain_dom(const uint32_t *__restrict__ list, const unsigned long long *__restr
       __syncwarp();
     }
   }
-  if (lane == 0) fstate[(size_t)k * N + c] = (uint16_t)x;
+  if (lane == 0) fstate[(size_t)k * N + c] = (uint16_t)(T + (xo >> 1));
 }
 
 // ---------------------------------------------------------------------------
@@ -966,10 +1038,16 @@ static int run_kind(fq28_handle *h, const DevTables &tab, const typename K::key_
                                                       use_dom ? tab.dom_sym : nullptr);
     FQ28_LAUNCH_CHECK(h);
     if (use_dom) {
-      k_chain_dom<K, A, STRIDE><<<b.dom_cap, 32, 0, strm>>>(h->dom_list.as<uint32_t>(), dom_count, b.ssym.as<uint8_t>(),
-                                                           b.tile0.as<uint32_t>(), b.tbase.as<uint32_t>(), tab.logs, tab.toff,
-                                                           tab.ctab, tab.symtt, tab.dom_sym, b.field.as<uint16_t>(),
-                                                           b.fstate.as<uint16_t>());
+      static bool dom_attr = false;
+      if (!dom_attr) {
+        FQ28_CUDA(h, cudaFuncSetAttribute(k_chain_dom<K, A, STRIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)DOM_SMEM));
+        dom_attr = true;
+      }
+      k_chain_dom<K, A, STRIDE><<<b.dom_cap, DOM_WARPS * 32, DOM_SMEM, strm>>>(
+          h->dom_list.as<uint32_t>(), dom_count, b.ssym.as<uint8_t>(), b.tile0.as<uint32_t>(), n_chunks,
+          b.tbase.as<uint32_t>(), tab.logs, tab.toff, tab.ctab, tab.symtt, tab.norm, tab.dom_sym,
+          b.field.as<uint16_t>(), b.fstate.as<uint16_t>());
       FQ28_LAUNCH_CHECK(h);
     }
   }
