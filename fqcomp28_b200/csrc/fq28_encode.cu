@@ -551,9 +551,17 @@ k_chain(const uint8_t *__restrict__ ssym, const uint32_t *__restrict__ tile0, un
 // ---------------------------------------------------------------------------
 constexpr unsigned DOM_WARPS = 8;
 constexpr unsigned DOM_NS = 3;                     // other symbols with a step table of their own
-constexpr unsigned DOM_TABLES = 16 + DOM_NS;
+constexpr unsigned DOM_IDENT = 16 + DOM_NS;          // op code of the identity table (pads the op list)
+constexpr unsigned DOM_TABLES = 16 + DOM_NS + 1;
 constexpr unsigned DOM_GENERIC = 0x100;            // op code: ordinary step with symbol (op & 0xFF)
-constexpr size_t DOM_SMEM = (size_t)DOM_TABLES * 4096 + 4096 + 64 * 8 + (size_t)DOM_WARPS * 512 * 2 * 2;
+constexpr unsigned DOM_OPS = 512 + 16;             // ops per block + padding to 8 + look-ahead
+constexpr size_t DOM_SMEM = (size_t)DOM_TABLES * 4096 + 4096 + 64 * 8 + (size_t)DOM_WARPS * DOM_OPS * 2 * 2;
+
+__device__ __forceinline__ unsigned lds_u16(unsigned saddr) {  // tables are read-only while they are walked
+  unsigned short v;
+  asm("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(saddr));
+  return v;
+}
 
 template <class K>
 __global__ void k_dom_list(const uint32_t *__restrict__ tile0, unsigned n_chunks, const uint32_t *__restrict__ tbase,
@@ -588,8 +596,8 @@ k_chain_dom(const uint32_t *__restrict__ list, const unsigned long long *__restr
   unsigned char *tbl = dsm;                                                  // [DOM_TABLES][2048] u16: 2 * (x' - T)
   uint16_t *st = reinterpret_cast<uint16_t *>(dsm + (size_t)DOM_TABLES * 4096);  // [2048]
   int2 *tt = reinterpret_cast<int2 *>(st + 2048);                            // [64]
-  uint16_t *ops_all = reinterpret_cast<uint16_t *>(tt + 64);                 // [DOM_WARPS][512]
-  uint16_t *xs_all = ops_all + DOM_WARPS * 512;                              // [DOM_WARPS][512]
+  uint16_t *ops_all = reinterpret_cast<uint16_t *>(tt + 64);                 // [DOM_WARPS][DOM_OPS]
+  uint16_t *xs_all = ops_all + DOM_WARPS * DOM_OPS;                          // [DOM_WARPS][DOM_OPS]
   __shared__ unsigned nsym[DOM_NS];
   if (blockIdx.x >= *count) return;
   const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -626,6 +634,7 @@ k_chain_dom(const uint32_t *__restrict__ list, const unsigned long long *__restr
     uint16_t *R1 = reinterpret_cast<uint16_t *>(tbl);
     for (unsigned i = tid; i < T; i += DOM_WARPS * 32) {
       R1[i] = (uint16_t)((step_from(T + i, sdom) - T) * 2);
+      reinterpret_cast<uint16_t *>(tbl + (size_t)DOM_IDENT * 4096)[i] = (uint16_t)(i * 2);
       for (unsigned j = 0; j < DOM_NS; j++)
         if (nsym[j] != 0xFFu)
           reinterpret_cast<uint16_t *>(tbl + (size_t)(16 + j) * 4096)[i] = (uint16_t)((step_from(T + i, nsym[j]) - T) * 2);
@@ -646,8 +655,13 @@ k_chain_dom(const uint32_t *__restrict__ list, const unsigned long long *__restr
     for (unsigned t = t_begin; t < t_end; t++) total += run_count(tbase + (size_t)t * (N + 1) + c);
     if (total < DOM_MIN) return;
   }
-  uint16_t *ops = ops_all + warp * 512;
-  uint16_t *xs = xs_all + warp * 512;
+  uint16_t *ops = ops_all + warp * DOM_OPS;
+  uint16_t *xs = xs_all + warp * DOM_OPS;
+  unsigned tbl_s;  // shared-window address of the tables, pinned in a register (not rematerialised per use)
+  {
+    const unsigned t0 = (unsigned)__cvta_generic_to_shared(tbl);
+    asm volatile("mov.u32 %0, %1;" : "=r"(tbl_s) : "r"(t0));
+  }
   const unsigned pat = sdom * 0x01010101u;
   const unsigned ns0 = nsym[0], ns1 = nsym[1], ns2 = nsym[2];
   unsigned xo = 0;  // 2 * (x - T); FSE_initCState: x = T
@@ -689,30 +703,55 @@ k_chain_dom(const uint32_t *__restrict__ list, const unsigned long long *__restr
       ofs -= n_ops;
       {
         unsigned o = ofs;
-        for (unsigned i = 0; i < valid;) {
+        // op starts: every other symbol, and the first symbol of every dominant run
+        for (unsigned starts = (~m & ((1u << valid) - 1u)) | (m & ~(m << 1)); starts; starts &= starts - 1) {
+          const unsigned i = __ffs(starts) - 1;
+          unsigned code;
           if ((m >> i) & 1u) {
-            const unsigned r = __ffs(~(m >> i)) - 1;  // run length, ends at `valid` at the latest
-            ops[o++] = (uint16_t)(r - 1);
-            i += r;
+            code = __ffs(~(m >> i)) - 2;  // run length - 1; the run ends at `valid` at the latest
           } else {
             const unsigned word = i < 8 ? (i < 4 ? w.x : w.y) : (i < 12 ? w.z : w.w);
             const unsigned sy = (word >> (8 * (i & 3))) & (A - 1);
-            ops[o++] = (uint16_t)(sy == ns0 ? 16u : sy == ns1 ? 17u : sy == ns2 ? 18u : (DOM_GENERIC | sy));
-            i++;
+            code = sy == ns0 ? 16u : sy == ns1 ? 17u : sy == ns2 ? 18u : (DOM_GENERIC | sy);
           }
+          ops[o++] = (uint16_t)code;
         }
+        if (lane < 8) ops[total_ops + lane] = (uint16_t)DOM_IDENT;  // pad to a multiple of 8
       }
       __syncwarp();
       // serial walk over the block's ops (all lanes in lockstep), state after op i -> xs[i]
       const unsigned xo_in = xo;
-      for (unsigned i = 0; i < total_ops; i++) {
-        const unsigned op = ops[i];
-        if (op < DOM_GENERIC) {
-          xo = *reinterpret_cast<const uint16_t *>(tbl + op * 4096u + xo);
-        } else {
-          xo = (step_from(T + (xo >> 1), op & 0xFFu) - T) * 2;
+      {
+        // eight ops per iteration; the op codes of the next half are loaded
+        // before the current lookups, so the only dependent latency per op is
+        // one address add + one shared-memory load
+        auto quad = [&](const uint2 cq, unsigned i) {
+          if (((cq.x | cq.y) & (DOM_GENERIC * 0x00010001u)) == 0) {
+            const unsigned o0 = tbl_s + ((cq.x & 0xFFFFu) << 12), o1 = tbl_s + ((cq.x >> 16) << 12);
+            const unsigned o2 = tbl_s + ((cq.y & 0xFFFFu) << 12), o3 = tbl_s + ((cq.y >> 16) << 12);
+            const unsigned x0 = lds_u16(o0 + xo);
+            const unsigned x1 = lds_u16(o1 + x0);
+            const unsigned x2 = lds_u16(o2 + x1);
+            const unsigned x3 = lds_u16(o3 + x2);
+            if (lane == 0) *reinterpret_cast<uint2 *>(xs + i) = make_uint2(x0 | (x1 << 16), x2 | (x3 << 16));
+            xo = x3;
+          } else {
+#pragma unroll 1
+            for (unsigned j = 0; j < 4; j++) {
+              const unsigned op = ((j < 2 ? cq.x : cq.y) >> (16 * (j & 1))) & 0xFFFFu;
+              if (op < DOM_GENERIC) xo = lds_u16(tbl_s + op * 4096u + xo);
+              else xo = (step_from(T + (xo >> 1), op & 0xFFu) - T) * 2;
+              if (lane == 0) xs[i + j] = (uint16_t)xo;
+            }
+          }
+        };
+        uint2 qa = *reinterpret_cast<const uint2 *>(ops);
+        for (unsigned i = 0; i < total_ops; i += 8) {
+          const uint2 qb = *reinterpret_cast<const uint2 *>(ops + i + 4);
+          quad(qa, i);
+          qa = *reinterpret_cast<const uint2 *>(ops + i + 8);  // may be past the block's ops: never used then
+          quad(qb, i + 4);
         }
-        if (lane == 0) xs[i] = (uint16_t)xo;
       }
       __syncwarp();
       if (have) {
