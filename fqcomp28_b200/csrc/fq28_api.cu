@@ -134,7 +134,7 @@ static void free_buf(DevBuf &b) {
 static void free_tables(DevTables &t) {
   cudaFree(t.counts); cudaFree(t.norm); cudaFree(t.logs); cudaFree(t.max_log); cudaFree(t.toff);
   cudaFree(t.ctab); cudaFree(t.symtt); cudaFree(t.dtab); cudaFree(t.dtab_fix);
-  cudaFree(t.logsuf); cudaFree(t.seqdec); cudaFree(t.cid); cudaFree(t.n_touched); cudaFree(t.dom_sym);
+  cudaFree(t.logsuf); cudaFree(t.seqdec); cudaFree(t.cid); cudaFree(t.n_touched); cudaFree(t.dom_sym); cudaFree(t.zrun); cudaFree(t.zinfo);
   t = DevTables();
 }
 

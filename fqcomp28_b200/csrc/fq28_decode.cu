@@ -212,34 +212,46 @@ __device__ __forceinline__ RecMeta load_meta(const uint16_t *__restrict__ readle
 }
 
 // ---------------------------------------------------------------------------
-// sequence decoder: CTA = one warp = 32 streams, one CTA per SM
-// (shared memory: compressed tables 210 KB + states u16[256][32] 16 KB + ring)
+// sequence decoder: one CTA per SM (shared memory: compressed tables 210 KB +
+// states u16[256][32] 16 KB + ring); `warps` warps x `lanes` streams per warp,
+// at most 32 streams per CTA.
+//
+// The loop is software-pipelined.  Per symbol there are two dependent chains:
+//   A  symbol -> next context -> its state (shared) -> its table words (shared)
+//   B  table words -> rank -> nbBits -> bit read -> new state -> store
+// Only A is a recurrence between symbols (B feeds back only when the next
+// context equals the current one, i.e. inside homopolymers), so the loads of
+// chain A for symbol i+1 are issued before chain B of symbol i and both run
+// in flight together.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(32, 1)
-k_decode_seq(const DecChunk *__restrict__ ch, unsigned n_chunks, const uint8_t *__restrict__ arena,
+__global__ void __launch_bounds__(1024, 1)
+k_decode_seq(const DecChunk *__restrict__ ch, unsigned n_chunks, unsigned lanes, const uint8_t *__restrict__ arena,
              const SeqDecTables *__restrict__ gtab, const uint32_t *__restrict__ logsuf,
              const uint32_t *__restrict__ recscan, const uint16_t *__restrict__ readlens,
              const uint16_t *__restrict__ hdr_lens, char *__restrict__ out, DevStatus *st) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const unsigned char *tb = smem_raw;
-  uint16_t *S = reinterpret_cast<uint16_t *>(smem_raw + SEQ_TAB_BYTES);  // S[ctx * 32 + lane]
+  uint16_t *S = reinterpret_cast<uint16_t *>(smem_raw + SEQ_TAB_BYTES);  // S[ctx * 32 + slot]
   uint32_t *ring = reinterpret_cast<uint32_t *>(smem_raw + SEQ_TAB_BYTES + (size_t)SEQ_N * 32 * sizeof(uint16_t));
   {  // cooperative copy of the compressed tables (uint4 granularity)
     const uint4 *src = reinterpret_cast<const uint4 *>(gtab);
     uint4 *dst = reinterpret_cast<uint4 *>(smem_raw);
-    for (unsigned i = threadIdx.x; i < sizeof(SeqDecTables) / 16; i += 32) dst[i] = __ldg(src + i);
+    for (unsigned i = threadIdx.x; i < sizeof(SeqDecTables) / 16; i += blockDim.x) dst[i] = __ldg(src + i);
   }
-  __syncwarp();
-  const unsigned lane = threadIdx.x;
-  const unsigned k = blockIdx.x * 32 + lane;
-  const bool live = k < n_chunks;
+  __syncthreads();
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned per_cta = lanes * (blockDim.x >> 5);
+  const unsigned slot = warp * lanes + lane;  // stream slot inside the CTA
+  const unsigned k = blockIdx.x * per_cta + slot;
+  const bool live = lane < lanes && k < n_chunks;
   DecChunk c;
   c.n_rec = 0; c.rec0 = 0; c.out_off = 0; c.seq_off = 0; c.seq_len = 0;
   if (live) c = ch[k];
   LaneBitReader br;
   bool ok = true;
+  uint16_t *Sl = S + (live ? slot : 0);
   if (live) {
-    ok = br.init(arena + c.seq_off, c.seq_len, ring + lane * 2);
+    ok = br.init(arena + c.seq_off, c.seq_len, ring + slot * 2);
     // FSE_Decoder::startChunk (src/fse_common.hpp:134-138): states for ctx N-1 .. 0
     if (!ok || br.top_bit - br.floor_ < (long long)logsuf[SEQ_N]) {
       ok = false;
@@ -247,7 +259,7 @@ k_decode_seq(const DecChunk *__restrict__ ch, unsigned n_chunks, const uint8_t *
     } else {
       for (unsigned cc = SEQ_N; cc > 0; --cc) {
         const unsigned lg = *reinterpret_cast<const uint16_t *>(tb + offsetof(SeqDecTables, snext) + (cc - 1) * 8) >> 12;
-        S[(cc - 1) * 32 + lane] = (uint16_t)br.read(lg);
+        Sl[(cc - 1) * 32] = (uint16_t)br.read(lg);
       }
     }
   }
@@ -258,44 +270,72 @@ k_decode_seq(const DecChunk *__restrict__ ch, unsigned n_chunks, const uint8_t *
   if (rr > 1) nxt = load_meta(readlens, hdr_lens, recscan, c.rec0 + rr - 2);
   char *dst = out + c.out_off + (cur.scan - scan0) + cur.hl + 1;
   unsigned i = 0, ctx = SEQ_INITIAL_CTX;
+  // chain A results of the symbol about to be decoded
+  unsigned s0, fr;
+  uint2 nx, wv, cr;
+  auto load_nx = [&](unsigned cx) {
+    return *reinterpret_cast<const uint2 *>(tb + offsetof(SeqDecTables, snext) + cx * 8);
+  };
+  auto load_cell = [&](unsigned cx, unsigned sx, uint2 &w_, unsigned &f_, uint2 &c_) {
+    const unsigned blk = sx >> 5;  // 32-cell block of the state
+    w_ = *reinterpret_cast<const uint2 *>(tb + offsetof(SeqDecTables, symtab) + cx * 512 + blk * 8);
+    f_ = *reinterpret_cast<const unsigned *>(tb + offsetof(SeqDecTables, fine) + cx * 256 + blk * 4);
+    c_ = *reinterpret_cast<const uint2 *>(tb + offsetof(SeqDecTables, coarse) + cx * 64 + (sx >> 8) * 8);
+  };
+  s0 = Sl[ctx * 32];
+  nx = load_nx(ctx);
+  load_cell(ctx, s0, wv, fr, cr);
   for (;;) {
     // uniform trip count: symbols until the first lane reaches a record end
     const unsigned n = __reduce_min_sync(0xffffffffu, rr > 0 ? cur.L - i : 0xFFFFFFFFu);
     if (n == 0xFFFFFFFFu) break;
     if (rr > 0) {
       for (unsigned t = 0; t < n; t++) {
-        const unsigned s0 = S[ctx * 32 + lane];
-        // independent of the state
-        const uint2 nx = *reinterpret_cast<const uint2 *>(tb + offsetof(SeqDecTables, snext) + ctx * 8);
-        // 32-cell block of the state
-        const unsigned blk = s0 >> 5, p = s0 & 31;
-        const uint2 wv = *reinterpret_cast<const uint2 *>(tb + offsetof(SeqDecTables, symtab) + ctx * 512 + blk * 8);
-        const unsigned fr = *reinterpret_cast<const unsigned *>(tb + offsetof(SeqDecTables, fine) + ctx * 256 + blk * 4);
-        const uint2 cr = *reinterpret_cast<const uint2 *>(tb + offsetof(SeqDecTables, coarse) + ctx * 64 + (s0 >> 8) * 8);
-        const unsigned lg = (nx.x >> 12) & 15u;
-        // masks of the cells below p in each word: depend on p only
-        const unsigned m0 = p >= 16 ? 0xFFFFFFFFu : ((1u << (2 * p)) - 1u);
-        const unsigned m1 = p > 16 ? ((1u << (2 * (p - 16))) - 1u) : 0u;
+        const unsigned p = s0 & 31;
         const unsigned wsel = (p & 16) ? wv.y : wv.x;
         const unsigned sym = (wsel >> ((p & 15) * 2)) & 3u;
-        const unsigned pat = sym * 0x55555555u;
-        const unsigned x0 = wv.x ^ pat, x1 = wv.y ^ pat;
-        const unsigned e0 = ~(x0 | (x0 >> 1)) & 0x55555555u & m0;
-        const unsigned e1 = ~(x1 | (x1 >> 1)) & 0x55555555u & m1;
-        const unsigned rank = __popc(e0) + __popc(e1) + ((fr >> (8 * sym)) & 0xFFu) + pick_u16x4(cr, sym);
-        const unsigned xs = (pick_u16x4(nx, sym) & 0xFFFu) + rank;  // symbolNext + rank
-        const unsigned nb = lg - (31u - (unsigned)__clz(xs));       // Appendix A.6
-        const unsigned ns = (xs << nb) - (1u << lg);
-        S[ctx * 32 + lane] = (uint16_t)(ns + br.read(nb));
-        dst[i + t] = (char)((0x54474341u >> (8 * sym)) & 0xFFu);    // "ACGT"
-        ctx = (ctx >> 2) + (sym << 6);                              // addSymUpper
+        // the first symbol of the next record starts from the initial context
+        const unsigned ctx1 = (i + t + 1 == cur.L) ? SEQ_INITIAL_CTX : (ctx >> 2) + (sym << 6);  // addSymUpper
+        // chain B up to the new-state base: (symbol, rank) -> cell (Appendix A.6)
+        auto cell_base = [&](unsigned &nb) -> unsigned {
+          const unsigned lg = (nx.x >> 12) & 15u;
+          // masks of the cells below p in each word: depend on p only
+          const unsigned m0 = p >= 16 ? 0xFFFFFFFFu : ((1u << (2 * p)) - 1u);
+          const unsigned m1 = p > 16 ? ((1u << (2 * (p - 16))) - 1u) : 0u;
+          const unsigned pat = sym * 0x55555555u;
+          const unsigned x0 = wv.x ^ pat, x1 = wv.y ^ pat;
+          const unsigned e0 = ~(x0 | (x0 >> 1)) & 0x55555555u & m0;
+          const unsigned e1 = ~(x1 | (x1 >> 1)) & 0x55555555u & m1;
+          const unsigned rank = __popc(e0) + __popc(e1) + ((fr >> (8 * sym)) & 0xFFu) + pick_u16x4(cr, sym);
+          const unsigned xs = (pick_u16x4(nx, sym) & 0xFFFu) + rank;  // symbolNext + rank
+          nb = lg - (31u - (unsigned)__clz(xs));
+          return (xs << nb) - (1u << lg);
+        };
+        unsigned s1, fr1;
+        uint2 nx1, wv1, cr1;
+        if (ctx1 != ctx) {
+          s1 = Sl[ctx1 * 32];
+          nx1 = load_nx(ctx1);
+          load_cell(ctx1, s1, wv1, fr1, cr1);
+          unsigned nb;
+          const unsigned ns = cell_base(nb);
+          Sl[ctx * 32] = (uint16_t)(ns + br.read(nb));
+        } else {  // homopolymer: the next symbol needs the state written by this one
+          unsigned nb;
+          const unsigned ns = cell_base(nb);
+          s1 = ns + br.read(nb);
+          Sl[ctx * 32] = (uint16_t)s1;
+          nx1 = nx;
+          load_cell(ctx1, s1, wv1, fr1, cr1);
+        }
+        dst[i + t] = (char)((0x54474341u >> (8 * sym)) & 0xFFu);  // "ACGT"
+        ctx = ctx1; s0 = s1; nx = nx1; wv = wv1; fr = fr1; cr = cr1;
       }
       i += n;
-      if (i >= cur.L) {  // record done
+      if (i >= cur.L) {  // record done (ctx is already the initial context)
         --rr;
         cur = nxt;
         i = 0;
-        ctx = SEQ_INITIAL_CTX;
         dst = out + c.out_off + (cur.scan - scan0) + cur.hl + 1;
         if (rr > 1) nxt = load_meta(readlens, hdr_lens, recscan, c.rec0 + rr - 2);
       }
@@ -305,27 +345,36 @@ k_decode_seq(const DecChunk *__restrict__ ch, unsigned n_chunks, const uint8_t *
 }
 
 // ---------------------------------------------------------------------------
-// quality decoder: CTA = one warp = up to 32 streams
-// smem: cid map u16[8192] + ring + compact states u16[n_touched][lanes].
+// quality decoder: CTA = `warps` warps x `lanes` streams per warp (<= 32 streams)
+// smem: cid map u16[8192] + ring + zero-bit run tables + compact states
+// u16[n_touched][streams]; the maps are shared by the CTA's streams, which
+// leaves most of the SM's L1 to the DTable cells.
 // Contexts without a compact id (prior-only tables: never seen in the sample)
 // keep their state in a global fallback array.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(1024)
 k_decode_qual(const DecChunk *__restrict__ ch, unsigned n_chunks, unsigned lanes, const uint8_t *__restrict__ arena,
               const uint32_t *__restrict__ logs, const uint32_t *__restrict__ logsuf,
               const uint32_t *__restrict__ dtab_fix, const uint16_t *__restrict__ gcid, unsigned n_touched,
-              uint16_t *cold_states /*[n_chunks][8192]*/, const uint32_t *__restrict__ recscan,
+              const uint16_t *__restrict__ gzrun, unsigned n_z, uint4 zctx, uint16_t *cold_states /*[n_chunks][8192]*/, const uint32_t *__restrict__ recscan,
               const uint16_t *__restrict__ readlens, const uint16_t *__restrict__ hdr_lens, char *__restrict__ out,
               DevStatus *st) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint16_t *cid = reinterpret_cast<uint16_t *>(smem_raw);
   uint32_t *ring = reinterpret_cast<uint32_t *>(cid + QUAL_N);
-  uint16_t *S = reinterpret_cast<uint16_t *>(ring + RING_WORDS);  // S[id * lanes + lane]
-  for (unsigned i = threadIdx.x; i < QUAL_N; i += 32) cid[i] = gcid[i];
-  __syncwarp();
-  const unsigned lane = threadIdx.x;
-  const unsigned k = blockIdx.x * lanes + lane;
+  uint16_t *zt = reinterpret_cast<uint16_t *>(ring + RING_WORDS);  // [n_z][2][2048] zero-bit run tables
+  uint16_t *S = zt + (size_t)n_z * 2 * (1u << FIX_LOG);             // S[id * per_cta + slot]
+  for (unsigned i = threadIdx.x; i < QUAL_N; i += blockDim.x) cid[i] = gcid[i];
+  for (unsigned i = threadIdx.x; i < n_z * (1u << FIX_LOG); i += blockDim.x)  // u32 copies of the u16 tables
+    reinterpret_cast<uint32_t *>(zt)[i] = reinterpret_cast<const uint32_t *>(gzrun)[i];
+  __syncthreads();
+  const unsigned lane = threadIdx.x & 31;
+  const unsigned per_cta = lanes * (blockDim.x >> 5);
+  const unsigned slot = (threadIdx.x >> 5) * lanes + lane;  // stream slot inside the CTA
+  const unsigned k = blockIdx.x * per_cta + slot;
   const bool live = lane < lanes && k < n_chunks;
+  const unsigned nt_pad = (n_touched + 1u) & ~1u;
+  uint16_t *Sl = S + (size_t)slot * nt_pad;  // this stream's states
   DecChunk c;
   c.n_rec = 0; c.rec0 = 0; c.out_off = 0; c.qual_off = 0; c.qual_len = 0;
   if (live) c = ch[k];
@@ -333,7 +382,7 @@ k_decode_qual(const DecChunk *__restrict__ ch, unsigned n_chunks, unsigned lanes
   LaneBitReader br;
   bool ok = true;
   if (live) {
-    ok = br.init(arena + c.qual_off, c.qual_len, ring + lane * 2);
+    ok = br.init(arena + c.qual_off, c.qual_len, ring + slot * 2);
     if (!ok || br.top_bit - br.floor_ < (long long)logsuf[QUAL_N]) {
       ok = false;
       c.n_rec = 0;
@@ -341,7 +390,7 @@ k_decode_qual(const DecChunk *__restrict__ ch, unsigned n_chunks, unsigned lanes
       for (unsigned cc = QUAL_N; cc > 0; --cc) {
         const uint16_t v = (uint16_t)br.read(logs[cc - 1]);
         const unsigned id = cid[cc - 1];
-        if (id != 0xFFFFu) S[id * lanes + lane] = v; else cold[cc - 1] = v;
+        if (id != 0xFFFFu) Sl[id & 0x1FFFu] = v; else cold[cc - 1] = v;
       }
     }
   }
@@ -352,24 +401,84 @@ k_decode_qual(const DecChunk *__restrict__ ch, unsigned n_chunks, unsigned lanes
   if (rr > 1) nxt = load_meta(readlens, hdr_lens, recscan, c.rec0 + rr - 2);
   char *dst = out + c.out_off + (cur.scan - scan0) + cur.hl + 1 + cur.L + 3;
   unsigned i = 0, ctx = qual_ctx(0, 0, 0), q1 = 0, q2 = 0;
+  // shared-window addresses and the table base pinned in registers: the hot
+  // loop is bound by its instruction count
+  unsigned cid_s, zt_s, sl_s;
+  const uint32_t *dt;
+  {
+    const unsigned a0 = (unsigned)__cvta_generic_to_shared(cid), a1 = (unsigned)__cvta_generic_to_shared(zt),
+                   a2 = (unsigned)__cvta_generic_to_shared(Sl);
+    asm volatile("mov.u32 %0, %1;" : "=r"(cid_s) : "r"(a0));
+    asm volatile("mov.u32 %0, %1;" : "=r"(zt_s) : "r"(a1));
+    asm volatile("mov.u32 %0, %1;" : "=r"(sl_s) : "r"(a2));
+    asm volatile("mov.u64 %0, %1;" : "=l"(dt) : "l"(dtab_fix));
+  }
+  auto lds16 = [](unsigned a) -> unsigned {  // read-only tables
+    unsigned short v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a));
+    return v;
+  };
+  auto lds16_state = [](unsigned a) -> unsigned {  // ordered with the state stores
+    unsigned short v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a));
+    return v;
+  };
+  auto sts16_state = [](unsigned a, unsigned v) {
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((unsigned short)v));
+  };
   for (;;) {
     const unsigned n = __reduce_min_sync(0xffffffffu, rr > 0 ? cur.L - i : 0xFFFFFFFFu);
     if (n == 0xFFFFFFFFu) break;
     if (rr > 0) {
-      for (unsigned t = 0; t < n; t++) {
-        const unsigned id = cid[ctx];
-        const bool hot = id != 0xFFFFu;
-        const unsigned s0 = hot ? S[id * lanes + lane] : cold[ctx];
-        const unsigned e = __ldg(&dtab_fix[(ctx << FIX_LOG) + s0]);
+      char *o = dst + i;
+      for (unsigned t = 0; t < n;) {
+        // compact id in bits 0..12, zero-bit run slot + 1 in bits 13..15 (k_qual_zrun)
+        const unsigned cv = lds16(cid_s + ctx * 2);
+        if (cv == 0xFFFFu) {  // context without a compact id: state in global memory (rare)
+          const unsigned e = __ldg(dt + (ctx << FIX_LOG) + cold[ctx]);
+          const unsigned q = (e >> 16) & 63u;
+          cold[ctx] = (uint16_t)((e & 0xFFFFu) + br.read(e >> 24));
+          *o++ = (char)(q + QUAL_OFFSET);
+          const unsigned mx = q1 > q2 ? q1 : q2;
+          ctx = (((mx << 6) + q) & 0xFFFu) + ((unsigned)(q1 == q2) << 12);
+          q2 = q1;
+          q1 = q;
+          t++;
+          continue;
+        }
+        const unsigned sa = sl_s + (cv & 0x1FFFu) * 2;
+        const unsigned s0 = lds16_state(sa);
+        // zero-bit run (QZ_MAX in fq28_internal.cuh): the last three symbols equal d
+        // and d is dominant in ctx(d,d,d) -- up to 15 symbols from one table lookup
+        if (n_z && (cv >> 13)) {
+          const unsigned zb = zt_s + ((cv >> 13) - 1u) * (4u << FIX_LOG);
+          const unsigned z = lds16(zb + s0 * 2);
+          unsigned kz = z >> 11;
+          if (kz) {
+            unsigned x = z & 0x7FFu;
+            if (kz > n - t) {  // record ends inside the run: single steps
+              kz = n - t;
+              x = s0;
+              for (unsigned u = 0; u < kz; u++) x = lds16(zb + (2u << FIX_LOG) + x * 2);
+            }
+            sts16_state(sa, x);
+            const char dc = (char)((ctx & 63u) + QUAL_OFFSET);
+            for (unsigned u = 0; u < kz; u++) o[u] = dc;
+            o += kz;
+            t += kz;
+            continue;  // q1 == q2 == d, context unchanged
+          }
+        }
+        const unsigned e = __ldg(dt + (ctx << FIX_LOG) + s0);
         const unsigned q = (e >> 16) & 63u;
-        const unsigned nv = (e & 0xFFFFu) + br.read(e >> 24);
-        if (hot) S[id * lanes + lane] = (uint16_t)nv; else cold[ctx] = (uint16_t)nv;
-        dst[i + t] = (char)(q + QUAL_OFFSET);
+        sts16_state(sa, (e & 0xFFFFu) + br.read(e >> 24));
+        *o++ = (char)(q + QUAL_OFFSET);
         // calcContext(q, q1, q2), src/fse_quality.h:40-44
         const unsigned mx = q1 > q2 ? q1 : q2;
         ctx = (((mx << 6) + q) & 0xFFFu) + ((unsigned)(q1 == q2) << 12);
         q2 = q1;
         q1 = q;
+        t++;
       }
       i += n;
       if (i >= cur.L) {
@@ -476,9 +585,20 @@ int decode_batch(fq28_handle *h, const fq28_dec_arenas *in, const fq28_chunk_inf
       FQ28_CUDA(h, cudaFuncSetAttribute(k_decode_seq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SEQ_DEC_SMEM));
       attr_set = true;
     }
-    k_decode_seq<<<(unsigned)((n_chunks + 31) / 32), 32, SEQ_DEC_SMEM, h->stream>>>(
-        ch, (unsigned)n_chunks, in->seq, reinterpret_cast<const SeqDecTables *>(h->seq.seqdec), h->seq.logsuf, recscan,
-        in->readlens, in->hdr_lens, d_out, h->d_status);
+    // streams per CTA (= per SM): few per warp keeps the homopolymer path from
+    // stalling the other streams of a warp; big batches fill 32 slots per SM
+    unsigned s_lanes = 1, s_warps = 4;
+    if (n_chunks > 148 * 4) { s_lanes = 1; s_warps = 8; }
+    if (n_chunks > 148 * 8) { s_lanes = 2; s_warps = 8; }
+    if (n_chunks > 148 * 16) { s_lanes = 4; s_warps = 8; }
+    if (const char *e = getenv("FQ28_SEQ_LANES")) s_lanes = (unsigned)atoi(e) ? (unsigned)atoi(e) : s_lanes;
+    if (const char *e = getenv("FQ28_SEQ_WARPS")) s_warps = (unsigned)atoi(e) ? (unsigned)atoi(e) : s_warps;
+    if (s_lanes > 32) s_lanes = 32;
+    while (s_lanes * s_warps > 32) s_warps >>= 1;
+    const unsigned per_cta = s_lanes * s_warps;
+    k_decode_seq<<<(unsigned)((n_chunks + per_cta - 1) / per_cta), s_warps * 32, SEQ_DEC_SMEM, h->stream>>>(
+        ch, (unsigned)n_chunks, s_lanes, in->seq, reinterpret_cast<const SeqDecTables *>(h->seq.seqdec), h->seq.logsuf,
+        recscan, in->readlens, in->hdr_lens, d_out, h->d_status);
     FQ28_LAUNCH_CHECK(h);
   }
   stage_end(h, ST_DECODE_SEQ);
@@ -488,21 +608,33 @@ int decode_batch(fq28_handle *h, const fq28_dec_arenas *in, const fq28_chunk_inf
     // a warp wait for the slowest lane: pack only as many streams per warp as
     // are needed to keep ~2 warps per scheduler busy (about 1000 warps per
     // GPU), up to 32 for big batches; the compact state arrays must fit ~160 KB.
-    unsigned lanes = 1;
-    while (lanes < 32 && n_chunks / lanes > 1024) lanes <<= 1;
+    unsigned lanes = 1, q_warps = 8;
+    while (lanes < 4 && n_chunks / (lanes * q_warps) > 148) lanes <<= 1;
     if (const char *e = getenv("FQ28_QUAL_LANES")) lanes = (unsigned)atoi(e) ? (unsigned)atoi(e) : lanes;
+    if (const char *e = getenv("FQ28_QUAL_WARPS")) q_warps = (unsigned)atoi(e) ? (unsigned)atoi(e) : q_warps;
     if (lanes > 32) lanes = 32;
-    while (lanes > 1 && (size_t)nt * lanes * sizeof(uint16_t) > 160 * 1024) lanes >>= 1;
-    const size_t smem = (size_t)QUAL_N * sizeof(uint16_t) + RING_WORDS * sizeof(uint32_t) + (size_t)nt * lanes * sizeof(uint16_t) + 16;
+    while (lanes * q_warps > 32) q_warps >>= 1;
+    while (lanes * q_warps > 1 && (size_t)nt * lanes * q_warps * sizeof(uint16_t) > 160 * 1024) {
+      if (q_warps > 1) q_warps >>= 1; else lanes >>= 1;
+    }
+    const unsigned q_per_cta = lanes * q_warps;
+    const unsigned nz = getenv("FQ28_NO_ZRUN") ? 0u : h->qual.h_n_z;
+    const size_t zbytes = (size_t)nz * 2 * (1u << FIX_LOG) * sizeof(uint16_t);
+    const size_t smem = (size_t)QUAL_N * sizeof(uint16_t) + RING_WORDS * sizeof(uint32_t) + zbytes + (size_t)((nt + 1u) & ~1u) * q_per_cta * sizeof(uint16_t) + 16;
+    uint4 zctx = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+    if (nz > 0) zctx.x = h->qual.h_zctx[0];
+    if (nz > 1) zctx.y = h->qual.h_zctx[1];
+    if (nz > 2) zctx.z = h->qual.h_zctx[2];
+    if (nz > 3) zctx.w = h->qual.h_zctx[3];
     static size_t attr_smem = 0;
     if (smem > attr_smem) {
       FQ28_CUDA(h, cudaFuncSetAttribute(k_decode_qual, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       attr_smem = smem;
     }
     side_stage_begin(h, ST_DECODE_QUAL);
-    k_decode_qual<<<(unsigned)((n_chunks + lanes - 1) / lanes), 32, smem, h->side>>>(
+    k_decode_qual<<<(unsigned)((n_chunks + q_per_cta - 1) / q_per_cta), q_warps * 32, smem, h->side>>>(
         ch, (unsigned)n_chunks, lanes, in->qual, h->qual.logs, h->qual.logsuf, h->qual.dtab_fix, h->qual.cid, nt,
-        h->dec_cold.as<uint16_t>(), recscan, in->readlens, in->hdr_lens, d_out, h->d_status);
+        h->qual.zrun, nz, zctx, h->dec_cold.as<uint16_t>(), recscan, in->readlens, in->hdr_lens, d_out, h->d_status);
     FQ28_LAUNCH_CHECK(h);
     side_stage_end(h, ST_DECODE_QUAL);
   }

@@ -50,6 +50,17 @@ struct SeqDecTables {
                                   // bits 12..15 of snext[ctx][0] hold the context's table log
 };
 
+// ---- zero-bit runs in the quality decoder -----------------------------------
+// In a context whose dominant symbol d has norm > T/2, most cells decode d with
+// nbBits == 0: the step reads no bits and its next state is a function of the
+// state alone.  When the context maps to itself under d (ctx(d,d,d)), such
+// steps chain: run table Z[x] = (k << 11) | state after the k <= 15 zero-bit
+// steps that start at x; J1[x] = state after one such step (0xFFFF if the cell
+// at x is not a zero-bit d cell), used when fewer than k symbols are left in
+// the record.
+constexpr unsigned QZ_MAX = 4;
+constexpr unsigned QZ_CAP = 15;
+
 // ---- error record written by kernels ----------------------------------------
 struct DevStatus {
   int code;          // first (lowest) FQ28_ERR_* seen, 0 if none
@@ -84,6 +95,12 @@ struct DevTables {
                                 // untouched (prior-only) pattern, 0xFFFF otherwise
   uint32_t *n_touched = nullptr;   // quality only: [1] number of compact ids
   uint32_t h_n_touched = 0;
+  // quality only: zero-bit run tables of the self-loop contexts ctx(d,d,d) whose
+  // symbol d is dominant (QualZrun), copied to shared memory by the decoder
+  uint16_t *zrun = nullptr;        // [QZ_MAX][2][1 << FIX_LOG]
+  uint32_t *zinfo = nullptr;       // [0] = number of slots, [1 + j] = context of slot j
+  uint32_t h_n_z = 0;
+  uint32_t h_zctx[4] = {0, 0, 0, 0};
   size_t cells_cap = 0;
   bool ready = false;
 };

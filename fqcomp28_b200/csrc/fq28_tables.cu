@@ -395,6 +395,46 @@ k_qual_cid(const short *__restrict__ norm, const uint32_t *__restrict__ logs, ui
   }
 }
 
+// Zero-bit run tables (see QZ_MAX in fq28_internal.cuh).  Single CTA.
+__global__ void __launch_bounds__(1024)
+k_qual_zrun(const uint32_t *__restrict__ logs, const uint32_t *__restrict__ dtab_fix, const int8_t *__restrict__ dom_sym,
+            uint16_t *__restrict__ cid, uint16_t *__restrict__ zrun, uint32_t *__restrict__ zinfo) {
+  __shared__ unsigned slot_sym[QZ_MAX];
+  __shared__ unsigned n_slots;
+  if (threadIdx.x == 0) {
+    unsigned n = 0;
+    for (int d = (int)QUAL_A - 1; d >= 0 && n < QZ_MAX; --d) {  // high qualities first
+      const unsigned cx = qual_ctx((unsigned)d, (unsigned)d, (unsigned)d);
+      if (dom_sym[cx] == d && cid[cx] != 0xFFFFu) {
+        cid[cx] = (uint16_t)(cid[cx] | ((n + 1) << 13));  // run slot + 1 above the 13-bit compact id
+        slot_sym[n++] = (unsigned)d;
+      }
+    }
+    n_slots = n;
+    zinfo[0] = n;
+    for (unsigned j = 0; j < QZ_MAX; j++)
+      zinfo[1 + j] = j < n ? qual_ctx(slot_sym[j], slot_sym[j], slot_sym[j]) : 0xFFFFFFFFu;
+  }
+  __syncthreads();
+  for (unsigned j = 0; j < n_slots; j++) {
+    const unsigned d = slot_sym[j], cx = qual_ctx(d, d, d);
+    const unsigned T = 1u << logs[cx];
+    uint16_t *Z = zrun + (size_t)j * 2 * (1u << FIX_LOG), *J1 = Z + (1u << FIX_LOG);
+    for (unsigned x = threadIdx.x; x < (1u << FIX_LOG); x += blockDim.x) {
+      unsigned k = 0, y = x, j1 = 0xFFFFu;
+      while (x < T && k < QZ_CAP) {
+        const unsigned e = dtab_fix[((size_t)cx << FIX_LOG) + y];
+        if (((e >> 16) & 63u) != d || (e >> 24) != 0) break;
+        y = e & 0xFFFFu;
+        if (k == 0) j1 = y;
+        k++;
+      }
+      Z[x] = (uint16_t)((k << 11) | y);
+      J1[x] = (uint16_t)j1;
+    }
+  }
+}
+
 int tables_alloc(fq28_handle *h, DevTables &t, unsigned n_models, unsigned alphabet) {
   if (t.norm) return FQ28_OK;
   t.n_models = n_models;
@@ -419,6 +459,8 @@ int tables_alloc(fq28_handle *h, DevTables &t, unsigned n_models, unsigned alpha
   } else {
     FQ28_CUDA(h, cudaMalloc(&t.cid, n_models * sizeof(uint16_t)));
     FQ28_CUDA(h, cudaMalloc(&t.n_touched, sizeof(uint32_t)));
+    FQ28_CUDA(h, cudaMalloc(&t.zrun, (size_t)QZ_MAX * 2 * (1u << FIX_LOG) * sizeof(uint16_t)));
+    FQ28_CUDA(h, cudaMalloc(&t.zinfo, (QZ_MAX + 1) * sizeof(uint32_t)));
   }
   return FQ28_OK;
 }
@@ -440,8 +482,14 @@ int tables_from_norm(fq28_handle *h, DevTables &t) {
   } else {
     k_qual_cid<<<1, 1024, 0, h->stream>>>(t.norm, t.logs, t.cid, t.n_touched);
     FQ28_LAUNCH_CHECK(h);
+    k_qual_zrun<<<1, 1024, 0, h->stream>>>(t.logs, t.dtab_fix, t.dom_sym, t.cid, t.zrun, t.zinfo);
+    FQ28_LAUNCH_CHECK(h);
+    uint32_t zi[QZ_MAX + 1];
     FQ28_CUDA(h, cudaMemcpyAsync(&t.h_n_touched, t.n_touched, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    FQ28_CUDA(h, cudaMemcpyAsync(zi, t.zinfo, sizeof(zi), cudaMemcpyDeviceToHost, h->stream));
     FQ28_CUDA(h, cudaStreamSynchronize(h->stream));
+    t.h_n_z = zi[0];
+    for (unsigned j = 0; j < QZ_MAX; j++) t.h_zctx[j] = zi[1 + j];
   }
   t.ready = true;
   return FQ28_OK;
