@@ -587,10 +587,9 @@ int decode_batch(fq28_handle *h, const fq28_dec_arenas *in, const fq28_chunk_inf
     }
     // streams per CTA (= per SM): few per warp keeps the homopolymer path from
     // stalling the other streams of a warp; big batches fill 32 slots per SM
-    unsigned s_lanes = 1, s_warps = 4;
-    if (n_chunks > 148 * 4) { s_lanes = 1; s_warps = 8; }
-    if (n_chunks > 148 * 8) { s_lanes = 2; s_warps = 8; }
-    if (n_chunks > 148 * 16) { s_lanes = 4; s_warps = 8; }
+    unsigned s_lanes = 1, s_warps = 8;
+    if (n_chunks > 74 * 8) s_lanes = 2;    // leave about half of the SMs to the quality decoder
+    if (n_chunks > 74 * 16) s_lanes = 4;
     if (const char *e = getenv("FQ28_SEQ_LANES")) s_lanes = (unsigned)atoi(e) ? (unsigned)atoi(e) : s_lanes;
     if (const char *e = getenv("FQ28_SEQ_WARPS")) s_warps = (unsigned)atoi(e) ? (unsigned)atoi(e) : s_warps;
     if (s_lanes > 32) s_lanes = 32;
