@@ -222,7 +222,7 @@ void fq28_destroy(fq28_handle *h) {
                     &h->perm_seq, &h->perm_qual, &h->ssym_seq, &h->ssym_qual, &h->out_seq, &h->out_qual, &h->tile0_seq,
                     &h->tile0_qual, &h->tbase_seq, &h->tbase_qual, &h->fstate_seq, &h->fstate_qual, &h->ptile0_seq,
                     &h->ptile0_qual, &h->pbits_seq, &h->pbits_qual, &h->pscan_seq, &h->pscan_qual, &h->arena_seq,
-                    &h->arena_qual, &h->d_infos, &h->scan_tmp, &h->scan_tmp_side, &h->dom_list, &h->hdrscan, &h->hdr_arena, &h->dec_out, &h->dec_recout, &h->dec_hdrin,
+                    &h->arena_qual, &h->d_infos, &h->scan_tmp, &h->scan_tmp_side, &h->dom_list, &h->present, &h->hdrscan, &h->hdr_arena, &h->dec_out, &h->dec_recout, &h->dec_hdrin,
                     &h->dec_npos_off, &h->dec_meta, &h->dec_cold};
   for (DevBuf *b : bufs) free_buf(*b);
   for (DevBuf &b : h->dec_in) free_buf(b);

@@ -181,7 +181,8 @@ __device__ __forceinline__ TileRef tile_ref(unsigned t, const uint32_t *__restri
 template <class K, unsigned TILE>
 __global__ void __launch_bounds__(256)
 k_tile_hist(const typename K::key_t *__restrict__ key, const uint32_t *__restrict__ tile0,
-            const uint32_t *__restrict__ chunk_sym, unsigned n_chunks, uint32_t *__restrict__ tbase) {
+            const uint32_t *__restrict__ chunk_sym, unsigned n_chunks, uint32_t *__restrict__ tbase,
+            uint32_t *__restrict__ present /*[N] flags of the contexts seen in the slab, or null*/) {
   constexpr unsigned N = K::n_models;
   __shared__ uint32_t hist[N];
   __shared__ uint32_t wsum[9];
@@ -216,6 +217,11 @@ k_tile_hist(const typename K::key_t *__restrict__ key, const uint32_t *__restric
   unsigned s = 0;
 #pragma unroll
   for (unsigned i = 0; i < PER; i++) { local[i] = hist[threadIdx.x * PER + i]; s += (local[i] + 15u) & ~15u; }
+  if (present) {
+#pragma unroll
+    for (unsigned i = 0; i < PER; i++)
+      if (local[i]) present[threadIdx.x * PER + i] = 1u;  // same value from every tile: plain stores
+  }
   unsigned inc = s;
 #pragma unroll
   for (int dd = 1; dd < 32; dd <<= 1) {
@@ -234,6 +240,8 @@ k_tile_hist(const typename K::key_t *__restrict__ key, const uint32_t *__restric
   if (threadIdx.x == 255) out[N] = ex;
 }
 
+constexpr unsigned RANKC_CAP = 1024, RANKC_WARPS = 8;  // k_tile_rank_compact
+
 // Stable rank: one warp per tile walks the tile in encode order, 32 symbols a
 // step; run[c] is the next free slot of context c.  Emits
 //   ssym[t * STRIDE + slot] = symbol    (partitioned symbols, chain input)
@@ -242,9 +250,11 @@ template <class K, unsigned TILE, unsigned STRIDE, unsigned WARPS>
 __global__ void __launch_bounds__(WARPS * 32)
 k_tile_rank(const typename K::key_t *__restrict__ key, const uint32_t *__restrict__ tile0,
             const uint32_t *__restrict__ chunk_sym, unsigned n_chunks, unsigned n_tiles,
-            const uint32_t *__restrict__ tbase, uint8_t *__restrict__ ssym, uint32_t *__restrict__ perm) {
+            const uint32_t *__restrict__ tbase, uint8_t *__restrict__ ssym, uint32_t *__restrict__ perm,
+            const uint32_t *__restrict__ n_present /*null, or: skip when k_tile_rank_compact covers the slab*/) {
   constexpr unsigned N = K::n_models;
   __shared__ uint32_t run_s[WARPS][N];
+  if (n_present && *n_present <= RANKC_CAP) return;
   const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned t = blockIdx.x * WARPS + warp;
   if (t >= n_tiles) return;
@@ -273,6 +283,100 @@ k_tile_rank(const typename K::key_t *__restrict__ key, const uint32_t *__restric
     __syncwarp();
     const unsigned below = peers & ((1u << lane) - 1u);
     if (live && below == 0) run[ctx] = slot + (unsigned)__popc(peers);
+    __syncwarp();
+    if (live) {
+      const unsigned dst = t * STRIDE + slot + (unsigned)__popc(below);
+      ssym[dst] = (uint8_t)(kv & K::sym_mask);
+      perm[tr.g0 + j + lane] = dst;
+    }
+  }
+}
+
+// Compact ids of the contexts present in the slab (flags from k_tile_hist):
+// map[c] = id or 0xFFFF, inv[id] = c, *n_present = number of ids.  Single CTA.
+template <unsigned N>
+__global__ void __launch_bounds__(1024)
+k_present_compact(const uint32_t *__restrict__ present, uint16_t *__restrict__ map, uint16_t *__restrict__ inv,
+                  uint32_t *__restrict__ n_present) {
+  constexpr unsigned PER = N / 1024;
+  static_assert(N % 1024 == 0, "contexts per thread");
+  __shared__ unsigned wsum[32];
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned f[PER], s = 0;
+#pragma unroll
+  for (unsigned i = 0; i < PER; i++) { f[i] = present[threadIdx.x * PER + i] ? 1u : 0u; s += f[i]; }
+  unsigned inc = s;
+#pragma unroll
+  for (int dd = 1; dd < 32; dd <<= 1) {
+    const unsigned o = __shfl_up_sync(0xffffffffu, inc, dd);
+    if (lane >= (unsigned)dd) inc += o;
+  }
+  if (lane == 31) wsum[warp] = inc;
+  __syncthreads();
+  unsigned woff = 0;
+  for (unsigned i = 0; i < warp; i++) woff += wsum[i];
+  unsigned id = woff + inc - s;
+#pragma unroll
+  for (unsigned i = 0; i < PER; i++) {
+    const unsigned c = threadIdx.x * PER + i;
+    if (f[i]) { map[c] = (uint16_t)id; inv[id] = (uint16_t)c; id++; } else map[c] = 0xFFFFu;
+  }
+  if (threadIdx.x == 1023) *n_present = id;
+}
+
+// Stable rank with compact cursors: as k_tile_rank, but the next-free-slot
+// cursors are indexed by the compact id of the context, so a warp needs
+// 4 B x RANKC_CAP of shared memory instead of 4 B x N and every SM holds
+// 32 tiles in flight instead of 7 (the pass is bound by the per-step latency).
+// Runs when at most RANKC_CAP contexts are present; k_tile_rank covers the rest.
+template <class K>
+constexpr size_t rankc_smem() { return (size_t)K::n_models * 2 + (size_t)RANKC_WARPS * RANKC_CAP * 4; }
+
+template <class K, unsigned TILE, unsigned STRIDE>
+__global__ void __launch_bounds__(RANKC_WARPS * 32)
+k_tile_rank_compact(const typename K::key_t *__restrict__ key, const uint32_t *__restrict__ tile0,
+                    const uint32_t *__restrict__ chunk_sym, unsigned n_chunks, unsigned n_tiles,
+                    const uint32_t *__restrict__ tbase, const uint16_t *__restrict__ gmap,
+                    const uint16_t *__restrict__ inv, const uint32_t *__restrict__ n_present,
+                    uint8_t *__restrict__ ssym, uint32_t *__restrict__ perm) {
+  constexpr unsigned N = K::n_models;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint16_t *map = reinterpret_cast<uint16_t *>(smem_raw);                 // [N]
+  uint32_t *run_all = reinterpret_cast<uint32_t *>(smem_raw + N * 2);     // [RANKC_WARPS][RANKC_CAP]
+  const unsigned ne = *n_present;
+  if (ne > RANKC_CAP) return;
+  for (unsigned i = threadIdx.x; i < N / 2; i += RANKC_WARPS * 32)
+    reinterpret_cast<uint32_t *>(map)[i] = reinterpret_cast<const uint32_t *>(gmap)[i];
+  __syncthreads();
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned t = blockIdx.x * RANKC_WARPS + warp;
+  if (t >= n_tiles) return;
+  uint32_t *run = run_all + warp * RANKC_CAP;
+  const TileRef tr = tile_ref(t, tile0, chunk_sym, n_chunks, TILE);
+  const uint32_t *tb = tbase + (size_t)t * (N + 1);
+  for (unsigned i = lane; i < ne; i += 32) run[i] = tb[inv[i]] & ~15u;
+  __syncwarp();
+  const typename K::key_t *kp = key + tr.g0;
+  // keys are prefetched four steps (128 symbols) ahead, the compact id of a
+  // key is looked up one step ahead
+  unsigned q0 = lane < tr.cnt ? (unsigned)kp[lane] : 0u;
+  unsigned q1 = 32 + lane < tr.cnt ? (unsigned)kp[32 + lane] : 0u;
+  unsigned q2 = 64 + lane < tr.cnt ? (unsigned)kp[64 + lane] : 0u;
+  unsigned q3 = 96 + lane < tr.cnt ? (unsigned)kp[96 + lane] : 0u;
+  unsigned idn = lane < tr.cnt ? map[q0 >> K::shift] : 0xFFFFu;
+  for (unsigned j = 0; j < tr.cnt; j += 32) {
+    const unsigned kv = q0, id = idn;
+    q0 = q1; q1 = q2; q2 = q3;
+    const unsigned jn = j + 128 + lane;
+    q3 = jn < tr.cnt ? (unsigned)kp[jn] : 0u;
+    idn = j + 32 + lane < tr.cnt ? map[q0 >> K::shift] : 0xFFFFu;
+    const bool live = j + lane < tr.cnt;
+    const unsigned peers = __match_any_sync(0xffffffffu, id);
+    unsigned slot = 0;
+    if (live) slot = run[id];
+    __syncwarp();
+    const unsigned below = peers & ((1u << lane) - 1u);
+    if (live && below == 0) run[id] = slot + (unsigned)__popc(peers);
     __syncwarp();
     if (live) {
       const unsigned dst = t * STRIDE + slot + (unsigned)__popc(below);
@@ -1018,6 +1122,7 @@ static int prep_kind(fq28_handle *h, KindBufs &b, size_t G) {
     b.dom_cap = n_chunks * (max_syms / DOM_MIN + 1);
     if (getenv("FQ28_NO_DOM")) b.dom_cap = 0;
     FQ28_TRY(ensure(h, h->dom_list, (size_t)b.dom_cap * 4 + 16));
+    FQ28_TRY(ensure(h, h->present, (size_t)N * 8 + 64));
   }
   // scan scratch of the side stream must exist before the pipelines fork
   FQ28_TRY(ensure(h, h->scan_tmp, ((size_t)b.n_ptiles / 4096 + 8) * 8));
@@ -1035,7 +1140,8 @@ static int run_kind(fq28_handle *h, const DevTables &tab, const typename K::key_
   const unsigned n_tiles = b.n_tiles, n_ptiles = b.n_ptiles;
 
   int slot = stage_open(h, N == SEQ_N ? ST_PART_SEQ : ST_PART_QUAL, strm);
-  if (n_tiles && N == SEQ_N) {
+  if constexpr (N == SEQ_N) {
+    if (n_tiles) {
     using P = PartSmall<SeqKind, SEQ_TILE, SEQ_STRIDE>;
     static bool attr_set = false;
     if (!attr_set) {
@@ -1047,13 +1153,31 @@ static int run_kind(fq28_handle *h, const DevTables &tab, const typename K::key_
         reinterpret_cast<const uint16_t *>(key), b.tile0.as<uint32_t>(), chunk_sym, n_chunks, n_tiles,
         b.tbase.as<uint32_t>(), b.ssym.as<uint8_t>(), b.perm.as<uint32_t>());
     FQ28_LAUNCH_CHECK(h);
+    }
   } else if (n_tiles) {
+    // presence flags [N] u32 | map [N] u16 | inv [N] u16 | n_present
+    uint32_t *present = h->present.as<uint32_t>();
+    uint16_t *cmap = reinterpret_cast<uint16_t *>(present + N), *cinv = cmap + N;
+    uint32_t *n_present = reinterpret_cast<uint32_t *>(cinv + N);
+    FQ28_CUDA(h, cudaMemsetAsync(present, 0, N * sizeof(uint32_t), strm));
     k_tile_hist<K, TILE><<<n_tiles, 256, 0, strm>>>(key, b.tile0.as<uint32_t>(), chunk_sym, n_chunks,
-                                                   b.tbase.as<uint32_t>());
+                                                   b.tbase.as<uint32_t>(), present);
+    FQ28_LAUNCH_CHECK(h);
+    k_present_compact<N><<<1, 1024, 0, strm>>>(present, cmap, cinv, n_present);
+    FQ28_LAUNCH_CHECK(h);
+    static bool rc_attr = false;
+    if (!rc_attr) {
+      FQ28_CUDA(h, cudaFuncSetAttribute(k_tile_rank_compact<K, TILE, STRIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)rankc_smem<K>()));
+      rc_attr = true;
+    }
+    k_tile_rank_compact<K, TILE, STRIDE><<<(n_tiles + RANKC_WARPS - 1) / RANKC_WARPS, RANKC_WARPS * 32, rankc_smem<K>(), strm>>>(
+        key, b.tile0.as<uint32_t>(), chunk_sym, n_chunks, n_tiles, b.tbase.as<uint32_t>(), cmap, cinv, n_present,
+        b.ssym.as<uint8_t>(), b.perm.as<uint32_t>());
     FQ28_LAUNCH_CHECK(h);
     k_tile_rank<K, TILE, STRIDE, RANK_WARPS><<<(n_tiles + RANK_WARPS - 1) / RANK_WARPS, RANK_WARPS * 32, 0, strm>>>(
         key, b.tile0.as<uint32_t>(), chunk_sym, n_chunks, n_tiles, b.tbase.as<uint32_t>(), b.ssym.as<uint8_t>(),
-        b.perm.as<uint32_t>());
+        b.perm.as<uint32_t>(), getenv("FQ28_NO_RANKC") ? nullptr : n_present);
     FQ28_LAUNCH_CHECK(h);
   }
   stage_close(h, slot, strm);

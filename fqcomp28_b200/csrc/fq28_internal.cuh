@@ -155,7 +155,7 @@ struct fq28_handle {
   fq28::DevBuf key_seq, key_qual, perm_seq, perm_qual, ssym_seq, ssym_qual, out_seq, out_qual;
   fq28::DevBuf tile0_seq, tile0_qual, tbase_seq, tbase_qual, fstate_seq, fstate_qual;
   fq28::DevBuf ptile0_seq, ptile0_qual, pbits_seq, pbits_qual, pscan_seq, pscan_qual;
-  fq28::DevBuf arena_seq, arena_qual, d_infos, scan_tmp, scan_tmp_side, dom_list;
+  fq28::DevBuf arena_seq, arena_qual, d_infos, scan_tmp, scan_tmp_side, dom_list, present;
   std::vector<fq28_chunk_info> h_infos;
   fq28_enc_summary last_summary{};
   bool have_result = false;
