@@ -432,16 +432,29 @@ k_tile_part_small(const typename K::key_t *__restrict__ key, const uint32_t *__r
   const TileRef tr = tile_ref(t, tile0, chunk_sym, n_chunks, TILE);
   for (unsigned i = lane; i < N * 16; i += 32) reinterpret_cast<uint32_t *>(cnt)[i] = 0u;
   const typename K::key_t *kp = key + tr.g0;
-  {  // coalesced key load, 8 loads in flight per lane
-    unsigned j = lane;
-    for (; j + 7 * 32 < tr.cnt; j += 8 * 32) {
-      uint16_t v[8];
+  {  // key load: 128-bit vectors from the 16-byte boundary at or below the tile's first key, 8 in flight per lane
+    const unsigned o = (unsigned)((reinterpret_cast<uintptr_t>(kp) >> 1) & 7u);
+    const uint4 *vp = reinterpret_cast<const uint4 *>(kp - o);
+    const unsigned nvec = (o + tr.cnt + 7u) >> 3;
+    for (unsigned v0 = 0; v0 < nvec; v0 += 8 * 32) {
+      uint4 x[8];
 #pragma unroll
-      for (unsigned u = 0; u < 8; u++) v[u] = (uint16_t)kp[j + u * 32];
+      for (unsigned u = 0; u < 8; u++) {
+        const unsigned idx = v0 + u * 32 + lane;
+        x[u] = idx < nvec ? __ldg(vp + idx) : make_uint4(0, 0, 0, 0);
+      }
 #pragma unroll
-      for (unsigned u = 0; u < 8; u++) { const unsigned jj = j + u * 32; keys[(jj / SEG) * ROW + (jj % SEG)] = v[u]; }
+      for (unsigned u = 0; u < 8; u++) {
+        const unsigned w[4] = {x[u].x, x[u].y, x[u].z, x[u].w};
+        const int jb = (int)((v0 + u * 32 + lane) * 8) - (int)o;
+#pragma unroll
+        for (unsigned e = 0; e < 8; e++) {
+          const int jj = jb + (int)e;
+          if (jj >= 0 && jj < (int)tr.cnt)
+            keys[((unsigned)jj / SEG) * ROW + ((unsigned)jj % SEG)] = (uint16_t)(w[e >> 1] >> (16 * (e & 1)));
+        }
+      }
     }
-    for (; j < tr.cnt; j += 32) keys[(j / SEG) * ROW + (j % SEG)] = (uint16_t)kp[j];
   }
   __syncwarp();
   const unsigned j0 = lane * SEG < tr.cnt ? lane * SEG : tr.cnt;
@@ -529,8 +542,19 @@ k_tile_part_small(const typename K::key_t *__restrict__ key, const uint32_t *__r
   __syncwarp();
   const unsigned t_slot0 = t * STRIDE;
   uint32_t *pp = perm + tr.g0;
-#pragma unroll 8
-  for (unsigned j = lane; j < tr.cnt; j += 32) pp[j] = t_slot0 + keys[(j / SEG) * ROW + (j % SEG)];
+  for (unsigned j = lane; j < tr.cnt; j += 8 * 32) {  // slots -> perm, eight shared loads in flight
+    unsigned v[8];
+#pragma unroll
+    for (unsigned u = 0; u < 8; u++) {
+      const unsigned jj = j + u * 32;
+      v[u] = jj < tr.cnt ? keys[(jj / SEG) * ROW + (jj % SEG)] : 0u;
+    }
+#pragma unroll
+    for (unsigned u = 0; u < 8; u++) {
+      const unsigned jj = j + u * 32;
+      if (jj < tr.cnt) pp[jj] = t_slot0 + v[u];
+    }
+  }
   // carry = padded size of the tile's region (multiple of 16)
   const uint4 *rsrc = reinterpret_cast<const uint4 *>(region);
   uint4 *rdst = reinterpret_cast<uint4 *>(ssym + (size_t)t_slot0);
