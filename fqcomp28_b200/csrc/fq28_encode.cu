@@ -65,39 +65,47 @@ k_extract(const char *__restrict__ d, const uint32_t *__restrict__ seq_off, cons
   }
   unsigned n_cnt = 0;
   bool bad = false;
+  // Every lane loads its own base and quality once; the neighbours come from
+  // warp votes / shuffles.  Sequence: the two bit planes of the 32 bases of a
+  // step are ballots, (p, m) = planes of the previous and the current step, so
+  // the four bases before position i are four consecutive bits of (m:p).  The
+  // virtual prefix b[-4..-1] = T,C,C,T (0xD7) seeds the top bits of p.
+  unsigned p0 = 0xF0000000u, p1 = 0x90000000u, prevq = 0;
+  auto spread4 = [](unsigned x) {  // bit j -> bit 2j
+    unsigned t = (x | (x << 2)) & 0x33u;
+    return (t | (t << 1)) & 0x55u;
+  };
   for (unsigned base = 0; base < L; base += 32) {
     const unsigned i = base + lane;
-    bool is_n = false;
-    if (i < L) {
-      // ---- sequence: ctx = b[i-1]<<6 | b[i-2]<<4 | b[i-3]<<2 | b[i-4] over
-      // the virtual prefix b[-1..-4] = T,C,C,T (0xD7)
-      unsigned ctx = 0;
-#pragma unroll
-      for (unsigned k = 1; k <= 4; k++) {
-        unsigned b;
-        if (i >= k) {
-          const unsigned char c = sp[i - k];
-          const int v = (c == 'N') ? 0 : base2bits(c);
-          b = (unsigned)(v & 3);
-        } else {
-          b = (SEQ_INITIAL_CTX >> (2 * (4 - (k - i)))) & 3u;
-        }
-        ctx |= b << (2 * (4 - k));
-      }
-      const unsigned char c = sp[i];
-      is_n = (c == 'N');
-      const int sv = is_n ? 0 : base2bits(c);
-      if (sv < 0) bad = true;
-      key_seq[g_last - i] = (uint16_t)((ctx << 2) | (unsigned)(sv & 3));
-      // ---- quality: ctx = calcContext(q[i-1], q[i-2], q[i-3]), q[<0] = 0
-      const unsigned q = (unsigned)qp[i] - QUAL_OFFSET;
-      const unsigned q0 = i >= 1 ? ((unsigned)qp[i - 1] - QUAL_OFFSET) & 63u : 0u;
-      const unsigned q1 = i >= 2 ? ((unsigned)qp[i - 2] - QUAL_OFFSET) & 63u : 0u;
-      const unsigned q2 = i >= 3 ? ((unsigned)qp[i - 3] - QUAL_OFFSET) & 63u : 0u;
-      if (q > 63u) bad = true;
+    const bool in = i < L;
+    const unsigned c = in ? sp[i] : (unsigned)'A';
+    const unsigned qc = in ? qp[i] : QUAL_OFFSET;
+    const bool is_n = c == 'N';
+    const unsigned dl = c - 'A';
+    if (!(dl < 26u && ((0x82045u >> dl) & 1u))) bad = true;   // A C G N T
+    const unsigned bits = is_n ? 0u : ((c >> 1) ^ (c >> 2)) & 3u;  // A C G T -> 0 1 2 3, N coded as A
+    const unsigned m0 = __ballot_sync(0xffffffffu, bits & 1u), m1 = __ballot_sync(0xffffffffu, bits >> 1);
+    const unsigned x0 = (lane >= 4 ? m0 >> (lane - 4) : __funnelshift_r(p0, m0, 28 + lane)) & 15u;
+    const unsigned x1 = (lane >= 4 ? m1 >> (lane - 4) : __funnelshift_r(p1, m1, 28 + lane)) & 15u;
+    const unsigned ctx = spread4(x0) | (spread4(x1) << 1);  // b[i-1]<<6 | b[i-2]<<4 | b[i-3]<<2 | b[i-4]
+    p0 = m0;
+    p1 = m1;
+    // quality: ctx = calcContext(q[i-1], q[i-2], q[i-3]), q[<0] = 0
+    const unsigned q = qc - QUAL_OFFSET;
+    if (q > 63u) bad = true;
+    const unsigned pk = (prevq << 8) | (q & 63u);
+    const unsigned s1 = __shfl_sync(0xffffffffu, pk, (lane - 1) & 31);
+    const unsigned s2 = __shfl_sync(0xffffffffu, pk, (lane - 2) & 31);
+    const unsigned s3 = __shfl_sync(0xffffffffu, pk, (lane - 3) & 31);
+    const unsigned q0 = (lane >= 1 ? s1 : s1 >> 8) & 63u;
+    const unsigned q1 = (lane >= 2 ? s2 : s2 >> 8) & 63u;
+    const unsigned q2 = (lane >= 3 ? s3 : s3 >> 8) & 63u;
+    prevq = q & 63u;
+    if (in) {
+      key_seq[g_last - i] = (uint16_t)((ctx << 2) | bits);
       key_qual[g_last - i] = (qual_ctx(q0, q1, q2) << 6) | (q & 63u);
     }
-    n_cnt += __popc(__ballot_sync(0xffffffffu, is_n));
+    n_cnt += __popc(__ballot_sync(0xffffffffu, in && is_n));
   }
   if (__any_sync(0xffffffffu, bad) && lane == 0) set_error(st, FQ28_ERR_ALPHABET, (unsigned)r);
   if (lane == 0) n_count[r] = (uint16_t)n_cnt;
