@@ -138,6 +138,15 @@ k_chunk_walk(const uint32_t *__restrict__ hdr_off, const uint32_t *__restrict__ 
              size_t n_bytes, size_t R, int eof, size_t cap, uint32_t *__restrict__ chunk_rec,
              uint32_t *__restrict__ chunk_sym, uint32_t *__restrict__ chunk_byte,
              uint64_t *__restrict__ n_chunks_out, DevStatus *st) {
+  // Speculation: the walk is a chain of dependent loads (one per chunk).  The
+  // record index where chunk j ends is predictable from the average record
+  // size, so the 32-record windows around the predicted ends of the next 32
+  // chunks are fetched together (one memory latency for 32 chunks) and the
+  // chunks are then resolved from shared memory; a window that does not
+  // bracket the answer falls back to the search below.
+  __shared__ uint32_t win[32][32];
+  __shared__ unsigned long long wp0[32];
+  unsigned spec_i = 32;
   const unsigned lane = threadIdx.x;
   size_t s_rec = 0, k = 0;
   if (lane == 0) { chunk_rec[0] = 0; chunk_sym[0] = 0; chunk_byte[0] = 0; }
@@ -145,6 +154,7 @@ k_chunk_walk(const uint32_t *__restrict__ hdr_off, const uint32_t *__restrict__ 
   // answer, which settles fixed-length data in ONE dependent load per chunk
   const size_t avg = n_rec ? ((size_t)hdr_off[n_rec] - hdr_off[0] + n_rec - 1) / n_rec : 1;
   size_t s = n_rec ? hdr_off[0] : 0;  // byte start of the current chunk (carried, never re-loaded)
+  size_t last_recs = n_rec ? n_rec : 1, last_bytes = n_rec ? (size_t)hdr_off[n_rec] - hdr_off[0] : 1;
   for (;;) {
     if (s_rec >= n_rec) {
       // bytes left but no complete record: in the reference this is a
@@ -159,7 +169,41 @@ k_chunk_walk(const uint32_t *__restrict__ hdr_off, const uint32_t *__restrict__ 
     size_t hi = s_rec + R / 12 + 1;  // a record is at least 12 bytes
     if (hi > n_rec) hi = n_rec;
     size_t lo_val = s;               // hdr_off[lo]
-    {  // bracket probe: 32 consecutive records around the estimate
+    bool resolved = false;
+    if (spec_i >= 32 && avg) {       // fetch the windows of the next 32 chunks
+      // records per chunk, 8 fractional bits, from the record size of the last chunk (record
+      // sizes drift along a file: read ids grow), of the whole slab before the first chunk
+      const size_t rpc256 = (size_t)((double)R * 256.0 * (double)last_recs / (double)last_bytes);
+#pragma unroll 8
+      for (unsigned j = 0; j < 32; j++) {
+        // chunk j ends about (j+1) chunks of records ahead, minus half a record of slack per chunk
+        size_t est = s_rec + (((size_t)(j + 1) * rpc256 - (size_t)j * 128) >> 8);
+        if (est > n_rec) est = n_rec;
+        const size_t p0 = est >= 16 ? est - 16 : 0;
+        size_t p = p0 + lane;
+        if (p > n_rec) p = n_rec;
+        win[j][lane] = hdr_off[p];
+        if (lane == 0) wp0[j] = p0;
+      }
+      spec_i = 0;
+      __syncwarp();
+    }
+    if (spec_i < 32 && !reaches_eof) {
+      const size_t p0 = (size_t)wp0[spec_i];
+      const size_t v = win[spec_i][lane];
+      ++spec_i;
+      const unsigned m = __ballot_sync(0xffffffffu, v <= L);
+      const unsigned c = __popc(m);
+      // valid when the window starts at or below the answer and ends above it
+      if ((m & 1u) && c < 32 && p0 + c - 1 <= hi && p0 + c - 1 > s_rec) {
+        lo = p0 + c - 1;
+        lo_val = __shfl_sync(0xffffffffu, v, c - 1);
+        resolved = true;
+      } else {
+        spec_i = 32;                 // mis-predicted: search, then predict again from the next chunk
+      }
+    }
+    if (!resolved) {  // bracket probe: 32 consecutive records around the estimate
       size_t est = s_rec + (L - s) / (avg ? avg : 1);
       if (est > hi) est = hi;
       size_t p0 = est >= s_rec + 16 ? est - 16 : s_rec;
@@ -178,7 +222,7 @@ k_chunk_walk(const uint32_t *__restrict__ hdr_off, const uint32_t *__restrict__ 
         hi = p0 - 1;                 // answer is below the bracket (p0 > s_rec here)
       }
     }
-    while (lo < hi) {
+    while (!resolved && lo < hi) {
       const size_t step = (hi - lo + 31) / 32;
       size_t p = lo + (size_t)(lane + 1) * step;
       if (p > hi) p = hi;
@@ -207,14 +251,19 @@ k_chunk_walk(const uint32_t *__restrict__ hdr_off, const uint32_t *__restrict__ 
     }
     if (lane == 0) {
       chunk_rec[k] = (uint32_t)lo;
-      chunk_sym[k] = symoff ? symoff[lo] : 0u;
       chunk_byte[k] = (uint32_t)lo_val;
     }
+    last_recs = lo - s_rec;
+    last_bytes = lo_val - s;
     s_rec = lo;
     s = lo_val;
     if (reaches_eof) break;
   }
   if (lane == 0) *n_chunks_out = k;
+  // symbol offsets of the chunk starts: gathered after the walk so that the
+  // loads do not sit in its dependent chain
+  __syncwarp();
+  for (size_t kk = 1 + lane; kk <= k; kk += 32) chunk_sym[kk] = symoff ? symoff[chunk_rec[kk]] : 0u;
 }
 
 int parse_slab(fq28_handle *h, const char *d_fastq, size_t n_bytes, bool need_symoff) {
