@@ -336,14 +336,42 @@ __global__ void k_build_tables(const short *__restrict__ norm_in, const uint32_t
 // logsuf[c] = sum of logs[c'] for c' > c: FSE_Decoder::startChunk reads the
 // initial states for ctx N-1 .. 0 (src/fse_common.hpp:134-138), so the state
 // of context c starts logsuf[c] bits below the end mark.  Single thread.
-__global__ void k_logsuf(const uint32_t *__restrict__ logs, unsigned n_models, uint32_t *__restrict__ logsuf) {
-  unsigned acc = 0;
-  logsuf[n_models] = 0;
-  for (unsigned c = n_models; c > 0; --c) {
-    logsuf[c - 1] = acc;
-    acc += logs[c - 1];
+__global__ void __launch_bounds__(1024)
+k_logsuf(const uint32_t *__restrict__ logs, unsigned n_models, uint32_t *__restrict__ logsuf) {
+  // single CTA: thread i owns a block of consecutive contexts; suffix sums via
+  // an inclusive prefix scan of the block totals
+  __shared__ unsigned wsum[33];
+  const unsigned per = (n_models + 1023) / 1024;
+  const unsigned c0 = threadIdx.x * per, c1 = min(c0 + per, n_models);
+  unsigned s = 0;
+  for (unsigned c = c0; c < c1; c++) s += logs[c];
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned inc = s;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const unsigned o = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= (unsigned)d) inc += o;
   }
-  logsuf[n_models] = acc;  // total bits of the state block
+  if (lane == 31) wsum[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    unsigned v = wsum[lane], w = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const unsigned o = __shfl_up_sync(0xffffffffu, w, d);
+      if (lane >= (unsigned)d) w += o;
+    }
+    wsum[lane] = w - v;
+    if (lane == 31) wsum[32] = w;
+  }
+  __syncthreads();
+  const unsigned total = wsum[32];
+  unsigned before = wsum[warp] + inc - s;  // sum of logs[c] for c < c0
+  for (unsigned c = c0; c < c1; c++) {
+    before += logs[c];
+    logsuf[c] = total - before;             // sum of logs[c'] for c' > c
+  }
+  if (threadIdx.x == 0) logsuf[n_models] = total;  // total bits of the state block
 }
 
 // Compressed sequence DTables (SeqDecTables), one thread per context.
@@ -388,11 +416,39 @@ k_qual_cid(const short *__restrict__ norm, const uint32_t *__restrict__ logs, ui
     flags[c] = touched ? 1u : 0u;
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    unsigned n = 0;
-    for (unsigned c = 0; c < QUAL_N; c++) cid[c] = flags[c] ? (uint16_t)(n++) : (uint16_t)0xFFFF;
-    *n_touched = n;
+  // in-order prefix: thread i owns QUAL_N / 1024 consecutive contexts
+  __shared__ unsigned wsum[33];
+  constexpr unsigned PER = QUAL_N / 1024;
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned s = 0;
+#pragma unroll
+  for (unsigned i = 0; i < PER; i++) s += flags[threadIdx.x * PER + i];
+  unsigned inc = s;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const unsigned o = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= (unsigned)d) inc += o;
   }
+  if (lane == 31) wsum[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    unsigned v = wsum[lane], w = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const unsigned o = __shfl_up_sync(0xffffffffu, w, d);
+      if (lane >= (unsigned)d) w += o;
+    }
+    wsum[lane] = w - v;
+    if (lane == 31) wsum[32] = w;
+  }
+  __syncthreads();
+  unsigned n = wsum[warp] + inc - s;
+#pragma unroll
+  for (unsigned i = 0; i < PER; i++) {
+    const unsigned c = threadIdx.x * PER + i;
+    cid[c] = flags[c] ? (uint16_t)(n++) : (uint16_t)0xFFFF;
+  }
+  if (threadIdx.x == 0) *n_touched = wsum[32];
 }
 
 // Zero-bit run tables (see QZ_MAX in fq28_internal.cuh).  Single CTA.
@@ -474,7 +530,7 @@ int tables_from_norm(fq28_handle *h, DevTables &t) {
   else
     k_build_tables<QUAL_A><<<blocks, threads, 0, h->stream>>>(t.norm, t.logs, t.toff, t.n_models, t.ctab, t.symtt, t.dtab, t.dtab_fix, t.dom_sym);
   FQ28_LAUNCH_CHECK(h);
-  k_logsuf<<<1, 1, 0, h->stream>>>(t.logs, t.n_models, t.logsuf);
+  k_logsuf<<<1, 1024, 0, h->stream>>>(t.logs, t.n_models, t.logsuf);
   FQ28_LAUNCH_CHECK(h);
   if (t.alphabet == SEQ_A) {
     k_build_seqdec<<<(SEQ_N + 63) / 64, 64, 0, h->stream>>>(t.norm, t.logs, t.dtab_fix, reinterpret_cast<SeqDecTables *>(t.seqdec));
