@@ -282,55 +282,63 @@ k_decode_seq(const DecChunk *__restrict__ ch, unsigned n_chunks, unsigned lanes,
     f_ = *reinterpret_cast<const unsigned *>(tb + offsetof(SeqDecTables, fine) + cx * 256 + blk * 4);
     c_ = *reinterpret_cast<const uint2 *>(tb + offsetof(SeqDecTables, coarse) + cx * 64 + (sx >> 8) * 8);
   };
-  s0 = Sl[ctx * 32];
+  uint16_t *scur = Sl + ctx * 32;  // state slot of the current context
+  s0 = *scur;
   nx = load_nx(ctx);
   load_cell(ctx, s0, wv, fr, cr);
+  // one symbol; `last` = this may be the last symbol of the lane's record
+  auto step = [&](unsigned t, bool last) {
+    const unsigned p = s0 & 31;
+    const bool upper = (p & 16) != 0;
+    const unsigned wsel = upper ? wv.y : wv.x;
+    const unsigned sym = (wsel >> ((p & 15) * 2)) & 3u;
+    // the first symbol of the next record starts from the initial context
+    unsigned ctx1 = (ctx >> 2) + (sym << 6);  // addSymUpper
+    if (last && i + t + 1 == cur.L) ctx1 = SEQ_INITIAL_CTX;
+    // chain B up to the new-state base: (symbol, rank) -> cell (Appendix A.6)
+    auto cell_base = [&](unsigned &nb) -> unsigned {
+      const unsigned lg = (nx.x >> 12) & 15u;
+      // masks of the cells below p in the two words of the block: one shift serves both
+      const unsigned msk = (1u << ((2 * p) & 31)) - 1u;
+      const unsigned m0 = upper ? 0xFFFFFFFFu : msk;
+      const unsigned m1 = upper ? msk : 0u;
+      const unsigned pat = sym * 0x55555555u;
+      const unsigned x0 = wv.x ^ pat, x1 = wv.y ^ pat;
+      const unsigned e0 = ~(x0 | (x0 >> 1)) & 0x55555555u & m0;
+      const unsigned e1 = ~(x1 | (x1 >> 1)) & 0x55555555u & m1;
+      const unsigned rank = __popc(e0) + __popc(e1) + ((fr >> (8 * sym)) & 0xFFu) + pick_u16x4(cr, sym);
+      const unsigned xs = (pick_u16x4(nx, sym) & 0xFFFu) + rank;  // symbolNext + rank
+      nb = lg - (31u - (unsigned)__clz(xs));
+      return (xs << nb) - (1u << lg);
+    };
+    unsigned s1, fr1;
+    uint2 nx1, wv1, cr1;
+    uint16_t *snext = Sl + ctx1 * 32;
+    if (ctx1 != ctx) {
+      s1 = *snext;
+      nx1 = load_nx(ctx1);
+      load_cell(ctx1, s1, wv1, fr1, cr1);
+      unsigned nb;
+      const unsigned ns = cell_base(nb);
+      *scur = (uint16_t)(ns + br.read(nb));
+    } else {  // homopolymer: the next symbol needs the state written by this one
+      unsigned nb;
+      const unsigned ns = cell_base(nb);
+      s1 = ns + br.read(nb);
+      *scur = (uint16_t)s1;
+      nx1 = nx;
+      load_cell(ctx1, s1, wv1, fr1, cr1);
+    }
+    dst[i + t] = (char)((0x54474341u >> (8 * sym)) & 0xFFu);  // "ACGT"
+    ctx = ctx1; scur = snext; s0 = s1; nx = nx1; wv = wv1; fr = fr1; cr = cr1;
+  };
   for (;;) {
     // uniform trip count: symbols until the first lane reaches a record end
     const unsigned n = __reduce_min_sync(0xffffffffu, rr > 0 ? cur.L - i : 0xFFFFFFFFu);
     if (n == 0xFFFFFFFFu) break;
     if (rr > 0) {
-      for (unsigned t = 0; t < n; t++) {
-        const unsigned p = s0 & 31;
-        const unsigned wsel = (p & 16) ? wv.y : wv.x;
-        const unsigned sym = (wsel >> ((p & 15) * 2)) & 3u;
-        // the first symbol of the next record starts from the initial context
-        const unsigned ctx1 = (i + t + 1 == cur.L) ? SEQ_INITIAL_CTX : (ctx >> 2) + (sym << 6);  // addSymUpper
-        // chain B up to the new-state base: (symbol, rank) -> cell (Appendix A.6)
-        auto cell_base = [&](unsigned &nb) -> unsigned {
-          const unsigned lg = (nx.x >> 12) & 15u;
-          // masks of the cells below p in each word: depend on p only
-          const unsigned m0 = p >= 16 ? 0xFFFFFFFFu : ((1u << (2 * p)) - 1u);
-          const unsigned m1 = p > 16 ? ((1u << (2 * (p - 16))) - 1u) : 0u;
-          const unsigned pat = sym * 0x55555555u;
-          const unsigned x0 = wv.x ^ pat, x1 = wv.y ^ pat;
-          const unsigned e0 = ~(x0 | (x0 >> 1)) & 0x55555555u & m0;
-          const unsigned e1 = ~(x1 | (x1 >> 1)) & 0x55555555u & m1;
-          const unsigned rank = __popc(e0) + __popc(e1) + ((fr >> (8 * sym)) & 0xFFu) + pick_u16x4(cr, sym);
-          const unsigned xs = (pick_u16x4(nx, sym) & 0xFFFu) + rank;  // symbolNext + rank
-          nb = lg - (31u - (unsigned)__clz(xs));
-          return (xs << nb) - (1u << lg);
-        };
-        unsigned s1, fr1;
-        uint2 nx1, wv1, cr1;
-        if (ctx1 != ctx) {
-          s1 = Sl[ctx1 * 32];
-          nx1 = load_nx(ctx1);
-          load_cell(ctx1, s1, wv1, fr1, cr1);
-          unsigned nb;
-          const unsigned ns = cell_base(nb);
-          Sl[ctx * 32] = (uint16_t)(ns + br.read(nb));
-        } else {  // homopolymer: the next symbol needs the state written by this one
-          unsigned nb;
-          const unsigned ns = cell_base(nb);
-          s1 = ns + br.read(nb);
-          Sl[ctx * 32] = (uint16_t)s1;
-          nx1 = nx;
-          load_cell(ctx1, s1, wv1, fr1, cr1);
-        }
-        dst[i + t] = (char)((0x54474341u >> (8 * sym)) & 0xFFu);  // "ACGT"
-        ctx = ctx1; s0 = s1; nx = nx1; wv = wv1; fr = fr1; cr = cr1;
-      }
+      for (unsigned t = 0; t + 1 < n; t++) step(t, false);
+      step(n - 1, true);
       i += n;
       if (i >= cur.L) {  // record done (ctx is already the initial context)
         --rr;
