@@ -934,6 +934,54 @@ __device__ __forceinline__ unsigned entry_value(unsigned e, unsigned n_sym, unsi
   return 0;
 }
 
+// PACK_EPT (8) consecutive u32 starting at p[idx] (idx arbitrary): three aligned
+// 128-bit loads and a uniform-per-CTA rotation instead of eight strided 32-bit loads.
+__device__ __forceinline__ void load8_u32(const uint32_t *__restrict__ p, size_t idx, unsigned (&out)[8]) {
+  const size_t a = idx & ~(size_t)3;
+  const unsigned off = (unsigned)(idx & 3);
+  const uint4 *v = reinterpret_cast<const uint4 *>(p + a);
+  const uint4 x0 = __ldg(v), x1 = __ldg(v + 1);
+  uint4 x2 = make_uint4(0, 0, 0, 0);
+  if (off) x2 = __ldg(v + 2);
+  const unsigned w[12] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w, x2.x, x2.y, x2.z, x2.w};
+  switch (off) {  // sym0 is a per-chunk constant: the branch is uniform
+    case 0:
+#pragma unroll
+      for (int i = 0; i < 8; i++) out[i] = w[i];
+      break;
+    case 1:
+#pragma unroll
+      for (int i = 0; i < 8; i++) out[i] = w[i + 1];
+      break;
+    case 2:
+#pragma unroll
+      for (int i = 0; i < 8; i++) out[i] = w[i + 2];
+      break;
+    default:
+#pragma unroll
+      for (int i = 0; i < 8; i++) out[i] = w[i + 3];
+      break;
+  }
+}
+
+// Values of PACK_EPT consecutive stream entries starting at e0 (a multiple of PACK_EPT).
+template <unsigned N>
+__device__ __forceinline__ void entry_values(unsigned e0, unsigned n_sym, unsigned sym0, unsigned k,
+                                             const uint32_t *__restrict__ perm, const uint16_t *__restrict__ field,
+                                             const uint32_t *__restrict__ logs, const uint16_t *__restrict__ fstate,
+                                             unsigned (&v)[PACK_EPT]) {
+  static_assert(PACK_EPT == 8, "load8_u32");
+  if (e0 + PACK_EPT <= n_sym) {  // all symbols: vector perm load, then the field gather
+    unsigned slot[8];
+    load8_u32(perm, (size_t)sym0 + e0, slot);
+#pragma unroll
+    for (unsigned i = 0; i < PACK_EPT; i++) v[i] = field[slot[i]];
+  } else {
+#pragma unroll
+    for (unsigned i = 0; i < PACK_EPT; i++) v[i] = entry_value<N>(e0 + i, n_sym, sym0, k, perm, field, logs, fstate);
+  }
+}
+
 template <unsigned N>
 __global__ void __launch_bounds__(PACK_THREADS)
 k_pack_count(const uint32_t *__restrict__ ptile0, const uint32_t *__restrict__ chunk_sym, unsigned n_chunks,
@@ -944,9 +992,10 @@ k_pack_count(const uint32_t *__restrict__ ptile0, const uint32_t *__restrict__ c
   const unsigned sym0 = chunk_sym[k], n_sym = chunk_sym[k + 1] - sym0;
   const unsigned e0 = (blockIdx.x - ptile0[k]) * PACK_TILE + threadIdx.x * PACK_EPT;
   unsigned bits = 0;
+  unsigned ev[PACK_EPT];
+  entry_values<N>(e0, n_sym, sym0, k, perm, field, logs, fstate, ev);
 #pragma unroll
-  for (unsigned i = 0; i < PACK_EPT; i++)
-    bits += entry_value<N>(e0 + i, n_sym, sym0, k, perm, field, logs, fstate) >> 12;
+  for (unsigned i = 0; i < PACK_EPT; i++) bits += ev[i] >> 12;
   bits = __reduce_add_sync(0xffffffffu, bits);
   if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = bits;
   __syncthreads();
@@ -1058,11 +1107,9 @@ k_pack_write(const uint32_t *__restrict__ ptile0, const uint32_t *__restrict__ c
   for (unsigned i = threadIdx.x; i < SW; i += PACK_THREADS) sw[i] = 0;
   unsigned v[PACK_EPT];
   unsigned bits = 0;
+  entry_values<N>(e0, n_sym, sym0, k, perm, field, logs, fstate, v);
 #pragma unroll
-  for (unsigned i = 0; i < PACK_EPT; i++) {
-    v[i] = entry_value<N>(e0 + i, n_sym, sym0, k, perm, field, logs, fstate);
-    bits += v[i] >> 12;
-  }
+  for (unsigned i = 0; i < PACK_EPT; i++) bits += v[i] >> 12;
   const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   unsigned inc = bits;
 #pragma unroll
@@ -1143,7 +1190,7 @@ static int prep_kind(fq28_handle *h, KindBufs &b, size_t G) {
   FQ28_CUDA(h, cudaStreamSynchronize(h->stream));  // host vectors go out of scope
   FQ28_TRY(ensure(h, b.tbase, (size_t)(b.n_tiles + 1) * (N + 1) * 4));
   FQ28_TRY(ensure(h, b.ssym, (size_t)b.n_tiles * STRIDE + 64));
-  FQ28_TRY(ensure(h, b.perm, (G + 4) * 4));
+  FQ28_TRY(ensure(h, b.perm, (G + 16) * 4));
   FQ28_TRY(ensure(h, b.field, ((size_t)b.n_tiles * STRIDE + 64) * 2));
   FQ28_TRY(ensure(h, b.fstate, (size_t)n_chunks * N * 2 + 16));
   FQ28_TRY(ensure(h, b.pbits, (size_t)(b.n_ptiles + 1) * 4));
