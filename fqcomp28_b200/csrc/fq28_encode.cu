@@ -569,6 +569,124 @@ k_tile_part_small(const typename K::key_t *__restrict__ key, const uint32_t *__r
   for (unsigned i = lane; i < (carry >> 4); i += 32) rdst[i] = rsrc[i];
 }
 
+// Cooperative fused partition for a small context space (sequence): CTA = 16
+// warps = one tile; warp w ranks the tile's w-th sixteenth in steps of 32
+// consecutive symbols.  A step ranks its symbols with match_any against the
+// warp's private context counters (u16[N] in shared memory); afterwards a
+// scan over (context, warp) turns the counters into bases, and every symbol's
+// slot is base + rank.  Same outputs as k_tile_hist + k_tile_rank, stable in
+// encode order: (warp, step, lane) is ascending g.  The symbols of the tile
+// are staged in shared memory and stored with 128-bit writes.
+constexpr unsigned PART8_WARPS = 16;
+template <class K, unsigned TILE, unsigned STRIDE>
+struct Part8 {
+  static constexpr unsigned N = K::n_models;
+  static constexpr unsigned PER_WARP = TILE / PART8_WARPS;
+  static constexpr unsigned STEPS = PER_WARP / 32;
+  static_assert(N <= PART8_WARPS * 32 && N % 32 == 0 && TILE % (PART8_WARPS * 32) == 0 && STRIDE % 16 == 0 && STRIDE < 65536, "layout");
+  static constexpr size_t SMEM = (size_t)PART8_WARPS * N * 2 + (size_t)N * 4 + STRIDE + 64;
+};
+
+template <class K, unsigned TILE, unsigned STRIDE>
+__global__ void __launch_bounds__(PART8_WARPS * 32, 2)
+k_tile_part8(const typename K::key_t *__restrict__ key, const uint32_t *__restrict__ tile0,
+             const uint32_t *__restrict__ chunk_sym, unsigned n_chunks, unsigned n_tiles,
+             uint32_t *__restrict__ tbase, uint8_t *__restrict__ ssym, uint32_t *__restrict__ perm) {
+  using P = Part8<K, TILE, STRIDE>;
+  constexpr unsigned N = P::N, STEPS = P::STEPS;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint16_t *cnt = reinterpret_cast<uint16_t *>(smem_raw);                          // [8][N]
+  uint32_t *cbase = reinterpret_cast<uint32_t *>(smem_raw + PART8_WARPS * N * 2);  // [N]
+  uint8_t *region = smem_raw + PART8_WARPS * N * 2 + N * 4;                        // [STRIDE]
+  __shared__ unsigned wsum[PART8_WARPS + 1];
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned t = blockIdx.x;
+  const TileRef tr = tile_ref(t, tile0, chunk_sym, n_chunks, TILE);
+  for (unsigned i = threadIdx.x; i < PART8_WARPS * N / 2; i += PART8_WARPS * 32) reinterpret_cast<uint32_t *>(cnt)[i] = 0u;
+  // the warp's keys, one per step and lane, all loads in flight together
+  const typename K::key_t *kp = key + tr.g0;
+  const unsigned j0 = warp * P::PER_WARP + lane;
+  unsigned kr[STEPS];  // key | rank << 16
+#pragma unroll
+  for (unsigned i = 0; i < STEPS; i++) {
+    const unsigned j = j0 + i * 32;
+    kr[i] = j < tr.cnt ? (unsigned)kp[j] : 0xFFFFu;
+  }
+  __syncthreads();
+  uint16_t *mycnt = cnt + warp * N;
+  const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+  for (unsigned i = 0; i < STEPS; i++) {
+    const unsigned kv = kr[i];
+    const bool live = kv != 0xFFFFu;
+    const unsigned ctx = live ? kv >> K::shift : 0u;
+    // lanes with the same context: one vote per context bit (cheaper than match_any)
+    unsigned peers = __ballot_sync(0xffffffffu, live);
+#pragma unroll
+    for (unsigned bit = 0; (1u << bit) < N; bit++) {
+      const unsigned vote = __ballot_sync(0xffffffffu, (ctx >> bit) & 1u);
+      peers &= ((ctx >> bit) & 1u) ? vote : ~vote;
+    }
+    unsigned old = 0;
+    if (live) old = mycnt[ctx];
+    __syncwarp();
+    const unsigned below = peers & lt;
+    if (live && below == 0) mycnt[ctx] = (uint16_t)(old + (unsigned)__popc(peers));
+    __syncwarp();
+    kr[i] = kv | ((old + (unsigned)__popc(below)) << 16);
+  }
+  __syncthreads();
+  {  // thread c < N: exclusive scan of context c's counts over the warps, then of the padded totals over the contexts
+    const unsigned c = threadIdx.x;
+    unsigned run = 0;
+    if (c < N) {
+#pragma unroll
+      for (unsigned w = 0; w < PART8_WARPS; w++) {
+        const unsigned v = cnt[w * N + c];
+        cnt[w * N + c] = (uint16_t)run;
+        run += v;
+      }
+    }
+    const unsigned padded = (run + 15u) & ~15u;
+    unsigned inc = padded;
+#pragma unroll
+    for (int dd = 1; dd < 32; dd <<= 1) {
+      const unsigned o = __shfl_up_sync(0xffffffffu, inc, dd);
+      if (lane >= (unsigned)dd) inc += o;
+    }
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    unsigned woff = 0;
+#pragma unroll
+    for (unsigned w = 0; w < N / 32; w++) woff += (w < warp) ? wsum[w] : 0u;
+    const unsigned base = woff + inc - padded;
+    if (c < N) {
+      cbase[c] = base;
+      uint32_t *tb = tbase + (size_t)t * (N + 1);
+      tb[c] = base | (run & 15u);
+      if (c == N - 1) { tb[N] = base + padded; wsum[PART8_WARPS] = base + padded; }
+    }
+  }
+  __syncthreads();
+  const unsigned t_slot0 = t * STRIDE;
+  uint32_t *pp = perm + tr.g0;
+#pragma unroll
+  for (unsigned i = 0; i < STEPS; i++) {
+    const unsigned kv = kr[i] & 0xFFFFu;
+    if (kv != 0xFFFFu) {
+      const unsigned ctx = kv >> K::shift;
+      const unsigned slot = cbase[ctx] + mycnt[ctx] + (kr[i] >> 16);
+      region[slot] = (uint8_t)(kv & K::sym_mask);
+      pp[j0 + i * 32] = t_slot0 + slot;
+    }
+  }
+  __syncthreads();
+  const unsigned carry = wsum[PART8_WARPS];  // padded size of the tile's region (multiple of 16)
+  const uint4 *rsrc = reinterpret_cast<const uint4 *>(region);
+  uint4 *rdst = reinterpret_cast<uint4 *>(ssym + (size_t)t_slot0);
+  for (unsigned i = threadIdx.x; i < (carry >> 4); i += PART8_WARPS * 32) rdst[i] = rsrc[i];
+}
+
 // symbols of a context inside a tile, from the packed tbase entries
 __device__ __forceinline__ unsigned run_count(const uint32_t *__restrict__ tb) {
   const unsigned a0 = tb[0], a1 = tb[1];
@@ -1221,14 +1339,14 @@ static int run_kind(fq28_handle *h, const DevTables &tab, const typename K::key_
   int slot = stage_open(h, N == SEQ_N ? ST_PART_SEQ : ST_PART_QUAL, strm);
   if constexpr (N == SEQ_N) {
     if (n_tiles) {
-    using P = PartSmall<SeqKind, SEQ_TILE, SEQ_STRIDE>;
+    using P = Part8<SeqKind, SEQ_TILE, SEQ_STRIDE>;
     static bool attr_set = false;
     if (!attr_set) {
-      FQ28_CUDA(h, cudaFuncSetAttribute(k_tile_part_small<SeqKind, SEQ_TILE, SEQ_STRIDE>,
+      FQ28_CUDA(h, cudaFuncSetAttribute(k_tile_part8<SeqKind, SEQ_TILE, SEQ_STRIDE>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P::SMEM));
       attr_set = true;
     }
-    k_tile_part_small<SeqKind, SEQ_TILE, SEQ_STRIDE><<<n_tiles, 32, P::SMEM, strm>>>(
+    k_tile_part8<SeqKind, SEQ_TILE, SEQ_STRIDE><<<n_tiles, PART8_WARPS * 32, P::SMEM, strm>>>(
         reinterpret_cast<const uint16_t *>(key), b.tile0.as<uint32_t>(), chunk_sym, n_chunks, n_tiles,
         b.tbase.as<uint32_t>(), b.ssym.as<uint8_t>(), b.perm.as<uint32_t>());
     FQ28_LAUNCH_CHECK(h);
