@@ -394,181 +394,6 @@ k_tile_rank_compact(const typename K::key_t *__restrict__ key, const uint32_t *_
   }
 }
 
-// Fused histogram + stable rank for a small context space (sequence, 256
-// contexts).  One warp per tile; lane l owns the l-th contiguous 1/32 of the
-// tile, so the order inside a context is (lane, position in the lane's
-// segment) and no two lanes ever touch the same counter:
-//   load    keys -> shared memory, coalesced (segment rows padded to an odd
-//           word stride so that the per-lane walks are bank-conflict free)
-//   pass 1  cnt[ctx][lane]++                       (u16, lane-private column)
-//   scan    per context: exclusive scan over the lanes -> each lane's first
-//           slot inside the context's run; per tile: exclusive scan over the
-//           contexts of the 16-padded totals -> tbase (same format as
-//           k_tile_hist)
-//   pass 2  slot = cbase[ctx] + cnt[ctx][lane]++; the symbol goes to
-//           region[slot] in shared memory, the slot replaces the key
-//   store   region -> ssym and slots -> perm, coalesced
-// No match_any, no cross-lane dependency inside the passes, and every global
-// access is a full-width coalesced transaction.
-template <class K, unsigned TILE, unsigned STRIDE>
-struct PartSmall {
-  static constexpr unsigned N = K::n_models;
-  static constexpr unsigned SEG = TILE / 32;           // keys per lane
-  static constexpr unsigned ROW = SEG + 2;             // u16 per padded row: (SEG + 2) / 2 words is odd
-  static_assert(N % 32 == 0 && TILE % 64 == 0 && STRIDE < 65536 && ((ROW / 2) & 1) == 1, "layout");
-  static constexpr size_t KEYS_BYTES = (size_t)32 * ROW * 2;
-  static constexpr size_t CNT_BYTES = (size_t)N * 32 * 2;
-  static constexpr size_t CBASE_BYTES = (size_t)N * 4;
-  static constexpr size_t SMEM = KEYS_BYTES + CNT_BYTES + CBASE_BYTES + STRIDE;
-};
-
-template <class K, unsigned TILE, unsigned STRIDE>
-__global__ void __launch_bounds__(32)
-k_tile_part_small(const typename K::key_t *__restrict__ key, const uint32_t *__restrict__ tile0,
-                  const uint32_t *__restrict__ chunk_sym, unsigned n_chunks, unsigned n_tiles,
-                  uint32_t *__restrict__ tbase, uint8_t *__restrict__ ssym, uint32_t *__restrict__ perm) {
-  using P = PartSmall<K, TILE, STRIDE>;
-  constexpr unsigned N = P::N, SEG = P::SEG, ROW = P::ROW;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  uint16_t *keys = reinterpret_cast<uint16_t *>(smem_raw);                      // [32][ROW]
-  uint16_t *cnt = reinterpret_cast<uint16_t *>(smem_raw + P::KEYS_BYTES);       // [N][32]
-  uint32_t *cbase = reinterpret_cast<uint32_t *>(smem_raw + P::KEYS_BYTES + P::CNT_BYTES);
-  uint8_t *region = smem_raw + P::KEYS_BYTES + P::CNT_BYTES + P::CBASE_BYTES;   // [STRIDE]
-  const unsigned lane = threadIdx.x;
-  const unsigned t = blockIdx.x;
-  if (t >= n_tiles) return;
-  const TileRef tr = tile_ref(t, tile0, chunk_sym, n_chunks, TILE);
-  for (unsigned i = lane; i < N * 16; i += 32) reinterpret_cast<uint32_t *>(cnt)[i] = 0u;
-  const typename K::key_t *kp = key + tr.g0;
-  {  // key load: 128-bit vectors from the 16-byte boundary at or below the tile's first key, 8 in flight per lane
-    const unsigned o = (unsigned)((reinterpret_cast<uintptr_t>(kp) >> 1) & 7u);
-    const uint4 *vp = reinterpret_cast<const uint4 *>(kp - o);
-    const unsigned nvec = (o + tr.cnt + 7u) >> 3;
-    for (unsigned v0 = 0; v0 < nvec; v0 += 8 * 32) {
-      uint4 x[8];
-#pragma unroll
-      for (unsigned u = 0; u < 8; u++) {
-        const unsigned idx = v0 + u * 32 + lane;
-        x[u] = idx < nvec ? __ldg(vp + idx) : make_uint4(0, 0, 0, 0);
-      }
-#pragma unroll
-      for (unsigned u = 0; u < 8; u++) {
-        const unsigned w[4] = {x[u].x, x[u].y, x[u].z, x[u].w};
-        const int jb = (int)((v0 + u * 32 + lane) * 8) - (int)o;
-#pragma unroll
-        for (unsigned e = 0; e < 8; e++) {
-          const int jj = jb + (int)e;
-          if (jj >= 0 && jj < (int)tr.cnt)
-            keys[((unsigned)jj / SEG) * ROW + ((unsigned)jj % SEG)] = (uint16_t)(w[e >> 1] >> (16 * (e & 1)));
-        }
-      }
-    }
-  }
-  __syncwarp();
-  const unsigned j0 = lane * SEG < tr.cnt ? lane * SEG : tr.cnt;
-  const unsigned j1 = (lane + 1) * SEG < tr.cnt ? (lane + 1) * SEG : tr.cnt;
-  uint16_t *myk = keys + lane * ROW;
-  const unsigned nk = j1 - j0;
-  {
-    unsigned j = 0;
-    for (; j + 4 <= nk; j += 4) {  // key loads hoisted: only the counter updates are ordered
-      const unsigned c0 = (unsigned)myk[j] >> K::shift, c1 = (unsigned)myk[j + 1] >> K::shift;
-      const unsigned c2 = (unsigned)myk[j + 2] >> K::shift, c3 = (unsigned)myk[j + 3] >> K::shift;
-      cnt[c0 * 32 + lane]++;
-      cnt[c1 * 32 + lane]++;
-      cnt[c2 * 32 + lane]++;
-      cnt[c3 * 32 + lane]++;
-    }
-    for (; j < nk; j++) cnt[((unsigned)myk[j] >> K::shift) * 32 + lane]++;
-  }
-  __syncwarp();
-  // per context: exclusive scan over lanes; lane (c & 31) keeps the total of context c
-  unsigned tot[N / 32];
-#pragma unroll
-  for (unsigned i = 0; i < N / 32; i++) {
-#pragma unroll 1
-    for (unsigned cl = 0; cl < 32; cl += 4) {  // four independent rows per step: the shuffle latencies overlap
-      unsigned v[4], inc[4];
-#pragma unroll
-      for (unsigned u = 0; u < 4; u++) { v[u] = cnt[(32 * i + cl + u) * 32 + lane]; inc[u] = v[u]; }
-#pragma unroll
-      for (int dd = 1; dd < 32; dd <<= 1) {
-#pragma unroll
-        for (unsigned u = 0; u < 4; u++) {
-          const unsigned o = __shfl_up_sync(0xffffffffu, inc[u], dd);
-          if (lane >= (unsigned)dd) inc[u] += o;
-        }
-      }
-#pragma unroll
-      for (unsigned u = 0; u < 4; u++) {
-        cnt[(32 * i + cl + u) * 32 + lane] = (uint16_t)(inc[u] - v[u]);
-        const unsigned total = __shfl_sync(0xffffffffu, inc[u], 31);
-        if (lane == cl + u) tot[i] = total;
-      }
-    }
-  }
-  // context bases in context order c = 32 i + lane: scan over lanes, carry over i
-  uint32_t *tb = tbase + (size_t)t * (N + 1);
-  unsigned carry = 0;
-#pragma unroll
-  for (unsigned i = 0; i < N / 32; i++) {
-    const unsigned v = (tot[i] + 15u) & ~15u;
-    unsigned inc = v;
-#pragma unroll
-    for (int dd = 1; dd < 32; dd <<= 1) {
-      const unsigned o = __shfl_up_sync(0xffffffffu, inc, dd);
-      if (lane >= (unsigned)dd) inc += o;
-    }
-    const unsigned base = carry + inc - v;
-    cbase[32 * i + lane] = base;
-    tb[32 * i + lane] = base | (tot[i] & 15u);
-    carry += __shfl_sync(0xffffffffu, inc, 31);
-  }
-  if (lane == 0) tb[N] = carry;
-  __syncwarp();
-  {
-    auto place = [&](unsigned j, unsigned kv, unsigned cb) {
-      const unsigned ctx = kv >> K::shift;
-      const unsigned o = cnt[ctx * 32 + lane];
-      cnt[ctx * 32 + lane] = (uint16_t)(o + 1);
-      const unsigned slot = cb + o;
-      region[slot] = (uint8_t)(kv & K::sym_mask);
-      myk[j] = (uint16_t)slot;
-    };
-    unsigned j = 0;
-    for (; j + 4 <= nk; j += 4) {
-      const unsigned k0 = myk[j], k1 = myk[j + 1], k2 = myk[j + 2], k3 = myk[j + 3];
-      const unsigned b0 = cbase[k0 >> K::shift], b1 = cbase[k1 >> K::shift];
-      const unsigned b2 = cbase[k2 >> K::shift], b3 = cbase[k3 >> K::shift];
-      place(j, k0, b0);
-      place(j + 1, k1, b1);
-      place(j + 2, k2, b2);
-      place(j + 3, k3, b3);
-    }
-    for (; j < nk; j++) { const unsigned kv = myk[j]; place(j, kv, cbase[kv >> K::shift]); }
-  }
-  __syncwarp();
-  const unsigned t_slot0 = t * STRIDE;
-  uint32_t *pp = perm + tr.g0;
-  for (unsigned j = lane; j < tr.cnt; j += 8 * 32) {  // slots -> perm, eight shared loads in flight
-    unsigned v[8];
-#pragma unroll
-    for (unsigned u = 0; u < 8; u++) {
-      const unsigned jj = j + u * 32;
-      v[u] = jj < tr.cnt ? keys[(jj / SEG) * ROW + (jj % SEG)] : 0u;
-    }
-#pragma unroll
-    for (unsigned u = 0; u < 8; u++) {
-      const unsigned jj = j + u * 32;
-      if (jj < tr.cnt) pp[jj] = t_slot0 + v[u];
-    }
-  }
-  // carry = padded size of the tile's region (multiple of 16)
-  const uint4 *rsrc = reinterpret_cast<const uint4 *>(region);
-  uint4 *rdst = reinterpret_cast<uint4 *>(ssym + (size_t)t_slot0);
-  for (unsigned i = lane; i < (carry >> 4); i += 32) rdst[i] = rsrc[i];
-}
-
 // Cooperative fused partition for a small context space (sequence): CTA = 16
 // warps = one tile; warp w ranks the tile's w-th sixteenth in steps of 32
 // consecutive symbols.  A step ranks its symbols with match_any against the
@@ -588,7 +413,7 @@ struct Part8 {
 };
 
 template <class K, unsigned TILE, unsigned STRIDE>
-__global__ void __launch_bounds__(PART8_WARPS * 32, 2)
+__global__ void __launch_bounds__(PART8_WARPS * 32, 3)
 k_tile_part8(const typename K::key_t *__restrict__ key, const uint32_t *__restrict__ tile0,
              const uint32_t *__restrict__ chunk_sym, unsigned n_chunks, unsigned n_tiles,
              uint32_t *__restrict__ tbase, uint8_t *__restrict__ ssym, uint32_t *__restrict__ perm) {
