@@ -215,6 +215,7 @@ int fq28_create(int device, fq28_handle **out) {
 
 void fq28_destroy(fq28_handle *h) {
   if (!h) return;
+  if (h->sibling) { fq28_destroy(h->sibling); h->sibling = nullptr; }
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   DevBuf *bufs[] = {&h->in_fastq, &h->tile_cnt, &h->nl, &h->hdr_off, &h->seq_off, &h->qual_off, &h->len, &h->hdr_len,
@@ -222,7 +223,7 @@ void fq28_destroy(fq28_handle *h) {
                     &h->perm_seq, &h->perm_qual, &h->ssym_seq, &h->ssym_qual, &h->out_seq, &h->out_qual, &h->tile0_seq,
                     &h->tile0_qual, &h->tbase_seq, &h->tbase_qual, &h->fstate_seq, &h->fstate_qual, &h->ptile0_seq,
                     &h->ptile0_qual, &h->pbits_seq, &h->pbits_qual, &h->pscan_seq, &h->pscan_qual, &h->arena_seq,
-                    &h->arena_qual, &h->d_infos, &h->scan_tmp, &h->scan_tmp_side, &h->dom_list, &h->present, &h->hdrscan, &h->hdr_arena, &h->dec_out, &h->dec_recout, &h->dec_hdrin,
+                    &h->arena_qual, &h->d_infos, &h->scan_tmp, &h->scan_tmp_side, &h->dom_list, &h->present, &h->in_raw, &h->hdrscan, &h->hdr_arena, &h->dec_out, &h->dec_recout, &h->dec_hdrin,
                     &h->dec_npos_off, &h->dec_meta, &h->dec_cold};
   for (DevBuf *b : bufs) free_buf(*b);
   for (DevBuf &b : h->dec_in) free_buf(b);
@@ -234,6 +235,7 @@ void fq28_destroy(fq28_handle *h) {
   if (h->h_scalars) cudaFreeHost(h->h_scalars);
   for (auto &r : h->ev_pool) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   if (h->side) { cudaStreamSynchronize(h->side); cudaStreamDestroy(h->side); }
+  if (h->ev_copy) cudaEventDestroy(h->ev_copy);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
@@ -357,6 +359,8 @@ int fq28_load_tables(fq28_handle *h, const void *ft_seq, const void *ft_qual) {
   stage_reset(h);
   FQ28_TRY(ft_image_in(h, h->seq, ft_seq));
   FQ28_TRY(ft_image_in(h, h->qual, ft_qual));
+  h->ft_img_seq.assign(static_cast<const uint8_t *>(ft_seq), static_cast<const uint8_t *>(ft_seq) + FQ28_FT_SEQ_BYTES);
+  h->ft_img_qual.assign(static_cast<const uint8_t *>(ft_qual), static_cast<const uint8_t *>(ft_qual) + FQ28_FT_QUAL_BYTES);
   stage_begin(h, ST_TABLES);
   FQ28_TRY(tables_from_norm(h, h->seq));
   FQ28_TRY(tables_from_norm(h, h->qual));
@@ -406,11 +410,19 @@ int fq28_compress_dev(fq28_handle *h, const char *d_fastq, size_t n_bytes, size_
   FQ28_TRY(parse_slab(h, d_fastq, n_bytes, true));
   FQ28_TRY(split_slab(h, reading_size, eof != 0, 0));
   stage_end(h, ST_PARSE);
-  return encode_slab(h, infos, infos_cap, summary);
+  FQ28_TRY(encode_slab(h, infos, infos_cap, summary));
+  if (sample_bytes > 0 && ft_seq_out && ft_qual_out && ft_seq_out != h->ft_img_seq.data()) {
+    // keep the images: a later host-buffer call with sample_bytes == 0 may hand them to the sibling handle
+    h->ft_img_seq.assign(static_cast<const uint8_t *>(ft_seq_out), static_cast<const uint8_t *>(ft_seq_out) + FQ28_FT_SEQ_BYTES);
+    h->ft_img_qual.assign(static_cast<const uint8_t *>(ft_qual_out), static_cast<const uint8_t *>(ft_qual_out) + FQ28_FT_QUAL_BYTES);
+  } else if (sample_bytes > 0 && !(ft_seq_out && ft_qual_out)) {
+    h->ft_img_seq.clear();
+    h->ft_img_qual.clear();
+  }
+  return FQ28_OK;
 }
 
-int fq28_compress_fetch(fq28_handle *h, const fq28_enc_arenas *out) {
-  if (!h || !out) return FQ28_ERR_ARG;
+static int fetch_async(fq28_handle *h, const fq28_enc_arenas *out) {
   if (!h->have_result) return fail(h, FQ28_ERR_ARG, "no compress result to fetch");
   FQ28_TRY(bind(h));
   const fq28_enc_summary &s = h->last_summary;
@@ -431,7 +443,102 @@ int fq28_compress_fetch(fq28_handle *h, const fq28_enc_arenas *out) {
     FQ28_CUDA(h, cudaMemcpyAsync(out->hdr_lens, h->hdr_len.p, s.n_records * 2, cudaMemcpyDeviceToHost, h->stream));
   if (out->headers && s.hdr_bytes)
     FQ28_CUDA(h, cudaMemcpyAsync(out->headers, h->hdr_arena.p, s.hdr_bytes, cudaMemcpyDeviceToHost, h->stream));
+  return FQ28_OK;
+}
+
+int fq28_compress_fetch(fq28_handle *h, const fq28_enc_arenas *out) {
+  if (!h || !out) return FQ28_ERR_ARG;
+  FQ28_TRY(fetch_async(h, out));
   FQ28_CUDA(h, cudaStreamSynchronize(h->stream));
+  return FQ28_OK;
+}
+
+// Host-buffer compress of a large slab as two overlapped halves.  The chunk
+// walk of the first half (eof = 0) stops at a chunk boundary `consumed`; the
+// second half [consumed, n) is encoded by the sibling handle with the same
+// tables, and its chunk infos are shifted behind the first half's.  Overlap:
+// H2D of the second half with the first half's kernels, D2H of the first
+// half's result with the second half's kernels.  Same bytes as the one-pass
+// path (the walk is deterministic from its start offset).
+static size_t pipe_min_bytes() {
+  if (const char *e = getenv("FQ28_PIPE_MIN_MB")) return (size_t)atoll(e) << 20;
+  return (size_t)256 << 20;
+}
+
+static int compress_two_stage(fq28_handle *h, const char *fastq, size_t n_bytes, size_t h1, size_t sample_bytes,
+                              size_t reading_size, int eof, void *ft_seq_out, void *ft_qual_out,
+                              const fq28_enc_arenas *out, fq28_chunk_info *infos, size_t infos_cap,
+                              fq28_enc_summary *summary) {
+  if (!h->sibling) {
+    FQ28_TRY(fq28_create(h->device, &h->sibling));
+    FQ28_TRY(bind(h));
+  }
+  fq28_handle *s = h->sibling;
+  if (!h->ev_copy) FQ28_CUDA(h, cudaEventCreateWithFlags(&h->ev_copy, cudaEventDisableTiming));
+  FQ28_TRY(ensure(h, h->in_fastq, h1 + 64));
+  FQ28_TRY(ensure(s, s->in_raw, n_bytes - h1 + 64));
+  FQ28_TRY(ensure(s, s->in_fastq, n_bytes + 64));
+  // both host->device copies are queued now; the second one starts when the first is done
+  FQ28_CUDA(h, cudaMemcpyAsync(h->in_fastq.p, fastq, h1, cudaMemcpyHostToDevice, h->stream));
+  FQ28_CUDA(h, cudaEventRecord(h->ev_copy, h->stream));
+  FQ28_CUDA(h, cudaStreamWaitEvent(s->stream, h->ev_copy, 0));
+  FQ28_CUDA(h, cudaMemcpyAsync(s->in_raw.p, fastq + h1, n_bytes - h1, cudaMemcpyHostToDevice, s->stream));
+  // first half
+  h->ft_img_seq.resize(FQ28_FT_SEQ_BYTES);
+  h->ft_img_qual.resize(FQ28_FT_QUAL_BYTES);
+  fq28_enc_summary sa;
+  FQ28_TRY(fq28_compress_dev(h, h->in_fastq.as<char>(), h1, sample_bytes, reading_size, 0,
+                             sample_bytes ? h->ft_img_seq.data() : nullptr, sample_bytes ? h->ft_img_qual.data() : nullptr,
+                             infos, infos_cap, &sa));
+  if (sample_bytes) {
+    if (ft_seq_out) memcpy(ft_seq_out, h->ft_img_seq.data(), FQ28_FT_SEQ_BYTES);
+    if (ft_qual_out) memcpy(ft_qual_out, h->ft_img_qual.data(), FQ28_FT_QUAL_BYTES);
+  }
+  FQ28_TRY(fetch_async(h, out));  // device->host of the first half overlaps the second half's kernels
+  // second half: same tables, FASTQ = [consumed, n) moved to an aligned buffer
+  if (!(s->seq.ready && s->qual.ready && s->ft_img_seq == h->ft_img_seq && s->ft_img_qual == h->ft_img_qual)) {
+    const int rc = fq28_load_tables(s, h->ft_img_seq.data(), h->ft_img_qual.data());
+    if (rc != FQ28_OK) return fail(h, rc, "second half: %s", fq28_last_error(s));
+  }
+  const size_t ca = (size_t)sa.consumed;
+  FQ28_CUDA(h, cudaMemcpyAsync(s->in_fastq.p, h->in_fastq.as<char>() + ca, h1 - ca, cudaMemcpyDeviceToDevice, s->stream));
+  FQ28_CUDA(h, cudaMemcpyAsync(s->in_fastq.as<char>() + (h1 - ca), s->in_raw.p, n_bytes - h1, cudaMemcpyDeviceToDevice, s->stream));
+  fq28_enc_arenas ob = *out;
+  ob.seq += sa.seq_bytes; ob.seq_cap -= sa.seq_bytes;
+  ob.qual += sa.qual_bytes; ob.qual_cap -= sa.qual_bytes;
+  ob.readlens += sa.n_records; ob.readlens_cap -= sa.n_records;
+  ob.n_count += sa.n_records; ob.n_count_cap -= sa.n_records;
+  ob.n_pos += sa.n_pos_entries; ob.n_pos_cap -= sa.n_pos_entries;
+  if (ob.hdr_lens) { ob.hdr_lens += sa.n_records; ob.hdr_lens_cap -= sa.n_records; }
+  if (ob.headers) { ob.headers += sa.hdr_bytes; ob.headers_cap -= sa.hdr_bytes; }
+  fq28_chunk_info *ib = infos + sa.n_chunks;
+  fq28_enc_summary sb;
+  {
+    int rc = fq28_compress_dev(s, s->in_fastq.as<char>(), n_bytes - ca, 0, reading_size, eof, nullptr, nullptr, ib,
+                               infos_cap - (size_t)sa.n_chunks, &sb);
+    if (rc == FQ28_OK) rc = fq28_compress_fetch(s, &ob);
+    if (rc != FQ28_OK) {
+      cudaStreamSynchronize(h->stream);
+      return fail(h, rc, "second half: %s", fq28_last_error(s));
+    }
+  }
+  FQ28_TRY(bind(h));
+  FQ28_CUDA(h, cudaStreamSynchronize(h->stream));
+  for (uint64_t k = 0; k < sb.n_chunks; k++) {
+    fq28_chunk_info &ci = ib[k];
+    ci.fastq_off += ca;
+    ci.rec_off += sa.n_records;
+    ci.seq_off += sa.seq_bytes;
+    ci.qual_off += sa.qual_bytes;
+    ci.n_pos_off += sa.n_pos_entries;
+    ci.hdr_off += sa.hdr_bytes;
+  }
+  fq28_enc_summary m = sa;
+  m.n_chunks += sb.n_chunks; m.n_records += sb.n_records; m.n_symbols += sb.n_symbols;
+  m.seq_bytes += sb.seq_bytes; m.qual_bytes += sb.qual_bytes; m.n_pos_entries += sb.n_pos_entries;
+  m.consumed = ca + sb.consumed; m.hdr_bytes += sb.hdr_bytes;
+  if (summary) *summary = m;
+  h->have_result = false;  // the device-resident result is split over two handles: not fetchable again
   return FQ28_OK;
 }
 
@@ -440,6 +547,16 @@ int fq28_compress(fq28_handle *h, const char *fastq, size_t n_bytes, size_t samp
                   size_t infos_cap, fq28_enc_summary *summary) {
   if (!h || !out || !infos) return FQ28_ERR_ARG;
   FQ28_TRY(bind(h));
+  {
+    // two overlapped halves for large slabs; the sample window must lie inside the first half
+    const size_t win = sample_bytes < n_bytes ? sample_bytes : n_bytes;
+    size_t h1 = (n_bytes / 2) & ~(size_t)15;
+    if (win > h1) h1 = (win + 15) & ~(size_t)15;
+    const bool tables_ok = sample_bytes > 0 || (h->ft_img_seq.size() == FQ28_FT_SEQ_BYTES && h->ft_img_qual.size() == FQ28_FT_QUAL_BYTES);
+    if (n_bytes >= pipe_min_bytes() && h1 + ((size_t)16 << 20) <= n_bytes && tables_ok)
+      return compress_two_stage(h, fastq, n_bytes, h1, sample_bytes, reading_size, eof, ft_seq_out, ft_qual_out, out, infos,
+                                infos_cap, summary);
+  }
   FQ28_TRY(stage_in(h, fastq, n_bytes));
   FQ28_TRY(fq28_compress_dev(h, h->in_fastq.as<char>(), n_bytes, sample_bytes, reading_size, eof, ft_seq_out, ft_qual_out,
                              infos, infos_cap, summary));

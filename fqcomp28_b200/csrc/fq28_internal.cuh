@@ -166,6 +166,12 @@ struct fq28_handle {
   // side stream: the sequence and quality pipelines are independent
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  // host-buffer compress of a large slab runs as two overlapped halves: the second half is
+  // staged and encoded by a sibling handle (own streams and buffers) while the first one computes
+  fq28_handle *sibling = nullptr;
+  fq28::DevBuf in_raw;                   // sibling: second half as copied from the host (before alignment)
+  cudaEvent_t ev_copy = nullptr;
+  std::vector<uint8_t> ft_img_seq, ft_img_qual;   // host copies of the FreqTable images (for the sibling)
 
   // timings
   struct EvRec { int stage; cudaEvent_t a, b; };

@@ -356,6 +356,43 @@ def test_synthetic_profiles_chunk_parity(oracle, H, profile):
     check_chunks(oracle, H, d, 1 << 20, fs, fq)
 
 
+@pytest.mark.parametrize("eof", [True, False])
+def test_two_stage_host_compress(oracle, H, monkeypatch, eof):
+    """Large host slabs are compressed as two overlapped halves (second half on
+    a sibling handle): same chunks, streams and side arrays as the one-pass
+    walk, with the tables from the sample inside fq28_compress and with
+    pre-loaded tables."""
+    import synth
+
+    monkeypatch.setenv("FQ28_PIPE_MIN_MB", "1")
+    d = synth.illumina_bytes(40 << 20, seed=31)[0].numpy()
+    S, R = 4 << 20, 1 << 20
+    sample = d[: int(oracle.split_chunks(d, S)[1])]
+    recs, _ = oracle.parse_records(sample)
+    fs, fq = oracle.make_ft(*oracle.hist(sample, recs))
+    ft = (np.zeros(3076, np.uint8), np.zeros(1081348, np.uint8))
+    infos, summ, ar = H.compress(d, R, eof=eof, sample_bytes=S, ft_out=ft)
+    assert np.array_equal(ft[0], fs) and np.array_equal(ft[1], fq)
+    assert int(summ.n_chunks) >= 38
+    seq_a = ar["seq"][: int(summ.seq_bytes)].copy()
+    # pre-loaded tables (sample_bytes == 0), chunk by chunk against the oracle + decode
+    H.load_tables(fs, fq)
+    infos2, summ2, ar2 = check_chunks(oracle, H, d, R, fs, fq, eof=eof)
+    assert int(summ2.n_chunks) == int(summ.n_chunks) and int(summ2.consumed) == int(summ.consumed)
+    assert np.array_equal(ar2["seq"][: int(summ2.seq_bytes)], seq_a)
+    # and identical to the one-pass path
+    monkeypatch.setenv("FQ28_PIPE_MIN_MB", "100000")
+    infos1, summ1, ar1 = H.compress(d, R, eof=eof)
+    assert int(summ1.n_chunks) == int(summ.n_chunks)
+    for k in range(int(summ1.n_chunks)):
+        for f in ("fastq_off", "total", "n_records", "rec_off", "seq_off", "qual_off", "seq_len", "qual_len",
+                  "n_pos_off", "n_pos_len", "hdr_bytes", "hdr_off"):
+            assert getattr(infos1[k], f) == getattr(infos2[k], f), (k, f)
+    for key in ("seq", "qual"):
+        nb = int(getattr(summ1, key + "_bytes"))
+        assert np.array_equal(ar1[key][:nb], ar2[key][:nb]), key
+
+
 def test_long_reads_ont_like(oracle, H):
     """BASELINE config 4: variable-length long reads (1-50 kb), ONT-like
     qualities (thousands of live quality contexts)."""
