@@ -638,6 +638,21 @@ int decode_batch(fq28_handle *h, const fq28_dec_arenas *in, const fq28_chunk_inf
       FQ28_CUDA(h, cudaFuncSetAttribute(k_decode_qual, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       attr_smem = smem;
     }
+    {
+      // Few CTAs land on an SM (the batch has ~n_chunks / q_per_cta of them), but the default
+      // carve-out reserves shared memory for a full SM of them and shrinks the L1 that holds
+      // the DTable cells: ask for just what the resident CTAs need.
+      static int carve_set = -1;
+      const unsigned n_ctas = (unsigned)((n_chunks + q_per_cta - 1) / q_per_cta);
+      const unsigned per_sm = (n_ctas + 83) / 84 + 1;  // quality shares the GPU with the sequence decoder
+      int pct = (int)((per_sm * (smem + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024));
+      if (const char *e = getenv("FQ28_QUAL_CARVEOUT")) pct = atoi(e);
+      if (pct > 100) pct = 100;
+      if (pct != carve_set) {
+        FQ28_CUDA(h, cudaFuncSetAttribute(k_decode_qual, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+        carve_set = pct;
+      }
+    }
     side_stage_begin(h, ST_DECODE_QUAL);
     k_decode_qual<<<(unsigned)((n_chunks + q_per_cta - 1) / q_per_cta), q_warps * 32, smem, h->side>>>(
         ch, (unsigned)n_chunks, lanes, in->qual, h->qual.logs, h->qual.logsuf, h->qual.dtab_fix, h->qual.cid, nt,

@@ -90,8 +90,11 @@ import json
 
 stage_of = [
     ("k_chain<Kind<unsigned int", "chain_qual"), ("k_chain_dom<Kind<unsigned int", "chain_qual"), ("k_chain<Kind<unsigned short", "chain_seq"),
-    ("k_decode_seq", "decode_seq"), ("k_decode_qual", "decode_qual"), ("k_tile_part_small", "part_seq"),
-    ("k_tile_rank<Kind<unsigned int", "part_qual"), ("k_tile_hist<Kind<unsigned int", "part_qual"), ("k_pack_write<8192>", "pack"), ("k_extract", "extract"),
+    ("k_decode_seq", "decode_seq"), ("k_decode_qual", "decode_qual"), ("k_tile_part8", "part_seq"),
+    ("k_tile_rank_compact<Kind<unsigned int", "part_qual"), ("k_tile_hist<Kind<unsigned int", "part_qual"),
+    ("k_pack_write<256>", "pack_seq"), ("k_pack_count<256>", "pack_seq"), ("k_pack_write<8192>", "pack_qual"), ("k_pack_count<8192>", "pack_qual"),
+    ("k_extract", "extract"), ("k_gather_headers", "extract"), ("k_npos", "extract"),
+    ("k_count_nl", "parse"), ("k_fill_nl", "parse"), ("k_records", "parse"), ("k_chunk_walk", "parse"),
 ]
 nsym = None
 try:
