@@ -142,17 +142,18 @@ k_npos(const char *__restrict__ d, const uint32_t *__restrict__ seq_off, const u
 }
 
 // Header lines ('@'.., without '\n') back to back: the input of the host-side
-// header tokeniser (src/workspace.cpp:95-125, out of path).  One warp per record.
+// header tokeniser (src/workspace.cpp:95-125, out of path).  Half a warp per
+// record (Illumina headers are 40-70 bytes).
 __global__ void __launch_bounds__(EX_WARPS * 32)
 k_gather_headers(const char *__restrict__ d, const uint32_t *__restrict__ hdr_off, const uint16_t *__restrict__ hdr_len,
                  const uint32_t *__restrict__ hdrscan, size_t n_rec, uint8_t *__restrict__ out) {
-  const unsigned lane = threadIdx.x & 31;
-  const size_t r = (size_t)blockIdx.x * EX_WARPS + (threadIdx.x >> 5);
+  const unsigned sub = threadIdx.x & 15;
+  const size_t r = ((size_t)blockIdx.x * EX_WARPS * 32 + threadIdx.x) >> 4;
   if (r >= n_rec) return;
   const unsigned hl = hdr_len[r];
   const char *src = d + hdr_off[r];
   uint8_t *dst = out + hdrscan[r];
-  for (unsigned i = lane; i < hl; i += 32) dst[i] = (uint8_t)src[i];
+  for (unsigned i = sub; i < hl; i += 16) dst[i] = (uint8_t)src[i];
 }
 
 // ---------------------------------------------------------------------------
@@ -181,6 +182,36 @@ __device__ __forceinline__ TileRef tile_ref(unsigned t, const uint32_t *__restri
   return tr;
 }
 
+// Eight consecutive u32 starting at p[idx] (idx arbitrary): three aligned
+// 128-bit loads and a uniform-per-CTA rotation instead of eight strided 32-bit loads.
+__device__ __forceinline__ void load8_u32(const uint32_t *__restrict__ p, size_t idx, unsigned (&out)[8]) {
+  const size_t a = idx & ~(size_t)3;
+  const unsigned off = (unsigned)(idx & 3);
+  const uint4 *v = reinterpret_cast<const uint4 *>(p + a);
+  const uint4 x0 = __ldg(v), x1 = __ldg(v + 1);
+  uint4 x2 = make_uint4(0, 0, 0, 0);
+  if (off) x2 = __ldg(v + 2);
+  const unsigned w[12] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w, x2.x, x2.y, x2.z, x2.w};
+  switch (off) {  // sym0 is a per-chunk constant: the branch is uniform
+    case 0:
+#pragma unroll
+      for (int i = 0; i < 8; i++) out[i] = w[i];
+      break;
+    case 1:
+#pragma unroll
+      for (int i = 0; i < 8; i++) out[i] = w[i + 1];
+      break;
+    case 2:
+#pragma unroll
+      for (int i = 0; i < 8; i++) out[i] = w[i + 2];
+      break;
+    default:
+#pragma unroll
+      for (int i = 0; i < 8; i++) out[i] = w[i + 3];
+      break;
+  }
+}
+
 // Per tile: context histogram, then exclusive scan over contexts of the counts
 // rounded up to 16 (every context's run starts 16-byte aligned so that the
 // chain kernel can move it with 128-bit loads):
@@ -204,8 +235,19 @@ k_tile_hist(const typename K::key_t *__restrict__ key, const uint32_t *__restric
   const typename K::key_t *kp = key + tr.g0;
   for (unsigned j0 = threadIdx.x * 8; j0 < tr.cnt; j0 += 256 * 8) {
     unsigned c[8];
+    if constexpr (sizeof(typename K::key_t) == 4) {
+      if (j0 + 8 <= tr.cnt) {
+        load8_u32(reinterpret_cast<const uint32_t *>(key), (size_t)tr.g0 + j0, c);
 #pragma unroll
-    for (unsigned u = 0; u < 8; u++) c[u] = j0 + u < tr.cnt ? (unsigned)kp[j0 + u] >> K::shift : 0xFFFFFFFFu;
+        for (unsigned u = 0; u < 8; u++) c[u] >>= K::shift;
+      } else {
+#pragma unroll
+        for (unsigned u = 0; u < 8; u++) c[u] = j0 + u < tr.cnt ? (unsigned)kp[j0 + u] >> K::shift : 0xFFFFFFFFu;
+      }
+    } else {
+#pragma unroll
+      for (unsigned u = 0; u < 8; u++) c[u] = j0 + u < tr.cnt ? (unsigned)kp[j0 + u] >> K::shift : 0xFFFFFFFFu;
+    }
     unsigned cur = c[0], n = 1;
 #pragma unroll
     for (unsigned u = 1; u < 8; u++) {
@@ -877,36 +919,6 @@ __device__ __forceinline__ unsigned entry_value(unsigned e, unsigned n_sym, unsi
   return 0;
 }
 
-// PACK_EPT (8) consecutive u32 starting at p[idx] (idx arbitrary): three aligned
-// 128-bit loads and a uniform-per-CTA rotation instead of eight strided 32-bit loads.
-__device__ __forceinline__ void load8_u32(const uint32_t *__restrict__ p, size_t idx, unsigned (&out)[8]) {
-  const size_t a = idx & ~(size_t)3;
-  const unsigned off = (unsigned)(idx & 3);
-  const uint4 *v = reinterpret_cast<const uint4 *>(p + a);
-  const uint4 x0 = __ldg(v), x1 = __ldg(v + 1);
-  uint4 x2 = make_uint4(0, 0, 0, 0);
-  if (off) x2 = __ldg(v + 2);
-  const unsigned w[12] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w, x2.x, x2.y, x2.z, x2.w};
-  switch (off) {  // sym0 is a per-chunk constant: the branch is uniform
-    case 0:
-#pragma unroll
-      for (int i = 0; i < 8; i++) out[i] = w[i];
-      break;
-    case 1:
-#pragma unroll
-      for (int i = 0; i < 8; i++) out[i] = w[i + 1];
-      break;
-    case 2:
-#pragma unroll
-      for (int i = 0; i < 8; i++) out[i] = w[i + 2];
-      break;
-    default:
-#pragma unroll
-      for (int i = 0; i < 8; i++) out[i] = w[i + 3];
-      break;
-  }
-}
-
 // Values of PACK_EPT consecutive stream entries starting at e0 (a multiple of PACK_EPT).
 template <unsigned N>
 __device__ __forceinline__ void entry_values(unsigned e0, unsigned n_sym, unsigned sym0, unsigned k,
@@ -1285,7 +1297,7 @@ int encode_slab(fq28_handle *h, fq28_chunk_info *infos, size_t infos_cap, fq28_e
   const uint32_t *chunk_sym = chunk_rec + stride, *chunk_byte = chunk_rec + 2 * stride;
 
   FQ28_TRY(ensure(h, h->key_seq, (G + 8) * 2));
-  FQ28_TRY(ensure(h, h->key_qual, (G + 4) * 4));
+  FQ28_TRY(ensure(h, h->key_qual, (G + 16) * 4));
   FQ28_TRY(ensure(h, h->n_count, (n_rec + 2) * 2));
   FQ28_TRY(ensure(h, h->npos_off, (n_rec + 2) * 4));
 
@@ -1308,7 +1320,7 @@ int encode_slab(fq28_handle *h, fq28_chunk_info *infos, size_t infos_cap, fq28_e
     h->last_summary.n_pos_entries = total_n;
     h->last_summary.hdr_bytes = total_h;
     FQ28_TRY(ensure(h, h->hdr_arena, (size_t)total_h + 64));
-    k_gather_headers<<<blocks, EX_WARPS * 32, 0, h->stream>>>(h->d_fastq, h->hdr_off.as<uint32_t>(),
+    k_gather_headers<<<(unsigned)((n_rec + EX_WARPS * 2 - 1) / (EX_WARPS * 2)), EX_WARPS * 32, 0, h->stream>>>(h->d_fastq, h->hdr_off.as<uint32_t>(),
                                                              h->hdr_len.as<uint16_t>(), h->hdrscan.as<uint32_t>(), n_rec,
                                                              h->hdr_arena.as<uint8_t>());
     FQ28_LAUNCH_CHECK(h);

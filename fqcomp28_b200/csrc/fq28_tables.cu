@@ -78,8 +78,16 @@ k_hist(const char *__restrict__ d, const uint32_t *__restrict__ seq_off, const u
       }
       // warp-aggregate equal (ctx, sym) pairs: the hottest pair carries most of
       // the symbols, so one RED per distinct key instead of one per lane
-      const unsigned peers = __match_any_sync(0xffffffffu, key);
-      if (key != 0xFFFFFFFFu && lane == (unsigned)(__ffs(peers) - 1)) atomicAdd(&g_qual[key], (unsigned)__popc(peers));
+      // (one RED per distinct key: vote on the key of the first lane still unserved;
+      // binned qualities settle in 2-4 votes, and a vote is far cheaper than match_any)
+      unsigned todo = __ballot_sync(0xffffffffu, key != 0xFFFFFFFFu);
+      while (todo) {
+        const unsigned leader = (unsigned)__ffs(todo) - 1u;
+        const unsigned lk = __shfl_sync(0xffffffffu, key, leader);
+        const unsigned same = __ballot_sync(0xffffffffu, key == lk);
+        if (lane == leader) atomicAdd(&g_qual[lk], (unsigned)__popc(same));
+        todo &= ~same;
+      }
     }
   }
   __syncthreads();
