@@ -340,6 +340,132 @@ __global__ void k_build_tables(const short *__restrict__ norm_in, const uint32_t
   }
 }
 
+// Sequence tables (4 symbols): one WARP per context.  Without low-probability
+// symbols (norm == -1) the spread visits cell (v * step) & mask at visit v and
+// symbol s owns visits [cumul[s], cumul[s+1]), so the cells are filled in
+// parallel; the ascending-u pass ranks the 32 cells of a step with one vote
+// per symbol.  Contexts with a -1 entry take the serial path of
+// k_build_tables (lane 0).  Also fills the compressed decoder tables
+// (SeqDecTables), replacing k_build_seqdec.
+__global__ void __launch_bounds__(128)
+k_build_tables_seq(const short *__restrict__ norm_in, const uint32_t *__restrict__ logs, const uint32_t *__restrict__ toff,
+                   uint16_t *__restrict__ ctab, int2 *__restrict__ symtt, uint32_t *__restrict__ dtab,
+                   uint32_t *__restrict__ dtab_fix, int8_t *__restrict__ dom_sym, SeqDecTables *__restrict__ dec) {
+  constexpr int A = SEQ_A;
+  const unsigned lane = threadIdx.x & 31;
+  const unsigned ctx = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (ctx >= SEQ_N) return;
+  short norm[A];
+#pragma unroll
+  for (int s = 0; s < A; s++) norm[s] = norm_in[(size_t)ctx * A + s];
+  const unsigned t = logs[ctx], T = 1u << t, mask = T - 1;
+  const unsigned step = (T >> 1) + (T >> 3) + 3;
+  uint32_t *cells = dtab + toff[ctx];
+  uint16_t *st = ctab + toff[ctx];
+  bool lowprob = false;
+  unsigned cumul[A + 1];
+  cumul[0] = 0;
+#pragma unroll
+  for (int s = 0; s < A; s++) {
+    lowprob |= norm[s] == -1;
+    cumul[s + 1] = cumul[s] + (norm[s] == -1 ? 1u : (unsigned)norm[s]);
+  }
+  // ---- spread (A.3): cells[u] = symbol
+  if (!lowprob) {
+    for (unsigned v = lane; v < T; v += 32) {
+      const unsigned s = (v >= cumul[1]) + (v >= cumul[2]) + (v >= cumul[3]);
+      cells[(v * step) & mask] = s;
+    }
+  } else if (lane == 0) {
+    unsigned high = T - 1;
+    for (int s = 0; s < A; s++)
+      if (norm[s] == -1) cells[high--] = (unsigned)s;
+    unsigned pos = 0;
+    for (int s = 0; s < A; s++)
+      for (int i = 0; i < norm[s]; i++) {
+        cells[pos] = (unsigned)s;
+        pos = (pos + step) & mask;
+        while (pos > high) pos = (pos + step) & mask;
+      }
+  }
+  // ---- symbol transforms (A.4), dominant symbol
+  if (lane == 0) {
+    unsigned total = 0;
+    int d = -1;
+    for (int s = 0; s < A; s++) {
+      int2 tt;
+      if (norm[s] == 0) {
+        tt.x = 0;
+        tt.y = (int)(((t + 1) << 16) - T);
+      } else if (norm[s] == -1 || norm[s] == 1) {
+        tt.y = (int)((t << 16) - T);
+        tt.x = (int)(total - 1);
+        total++;
+      } else {
+        const unsigned max_bits_out = t - hb32((unsigned)norm[s] - 1);
+        const unsigned min_state_plus = (unsigned)norm[s] << max_bits_out;
+        tt.y = (int)((max_bits_out << 16) - min_state_plus);
+        tt.x = (int)(total - (unsigned)norm[s]);
+        total += (unsigned)norm[s];
+      }
+      symtt[(size_t)ctx * A + s] = tt;
+      if (norm[s] > (int)(T >> 1)) d = s;
+      dec->snext[ctx][s] = (uint16_t)((norm[s] == -1 ? 1 : norm[s]) | (s == 0 ? (t << 12) : 0u));
+    }
+    dom_sym[ctx] = (int8_t)d;
+  }
+  __syncwarp();
+  // ---- next-state table + decode cells + compressed decoder tables, ascending u, 32 cells a step
+  unsigned run[A];  // cells of symbol s below the current step (uniform across the warp)
+#pragma unroll
+  for (int s = 0; s < A; s++) run[s] = 0;
+  unsigned coarse_base[A] = {0, 0, 0, 0};
+  const unsigned lt = (1u << lane) - 1u;
+  for (unsigned u0 = 0; u0 < (1u << FIX_LOG); u0 += 32) {
+    const unsigned u = u0 + lane;
+    const bool in = u < T;
+    const unsigned s = in ? cells[u] & 3u : 0u;
+    unsigned votes[A];
+#pragma unroll
+    for (int q = 0; q < A; q++) votes[q] = __ballot_sync(0xffffffffu, in && s == (unsigned)q);
+    if ((u0 & 255) == 0) {
+#pragma unroll
+      for (int q = 0; q < A; q++) {
+        coarse_base[q] = run[q];
+        if (lane == 0) dec->coarse[ctx][u0 >> 8][q] = (uint16_t)run[q];
+      }
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int q = 0; q < A; q++) dec->fine[ctx][u0 >> 5][q] = (uint8_t)(run[q] - coarse_base[q]);
+    }
+    // 16 two-bit symbols per word: lanes 0 and 16 assemble the two words of the step
+    {
+      unsigned w = s << (2 * (lane & 15));
+#pragma unroll
+      for (int d2 = 8; d2 >= 1; d2 >>= 1) w |= __shfl_xor_sync(0xffffffffu, w, d2);
+      if ((lane & 15) == 0) dec->symtab[ctx][(u0 >> 4) + (lane >> 4)] = w;
+    }
+    if (in) {
+      const unsigned myrun = s == 0 ? run[0] : s == 1 ? run[1] : s == 2 ? run[2] : run[3];
+      const unsigned myvote = s == 0 ? votes[0] : s == 1 ? votes[1] : s == 2 ? votes[2] : votes[3];
+      const unsigned r = myrun + (unsigned)__popc(myvote & lt);  // rank of the cell among the symbol's cells
+      const unsigned cs = s == 0 ? cumul[0] : s == 1 ? cumul[1] : s == 2 ? cumul[2] : cumul[3];
+      const unsigned w_ = s == 0 ? (norm[0] == -1 ? 1u : (unsigned)norm[0]) : s == 1 ? (norm[1] == -1 ? 1u : (unsigned)norm[1])
+                        : s == 2 ? (norm[2] == -1 ? 1u : (unsigned)norm[2]) : (norm[3] == -1 ? 1u : (unsigned)norm[3]);
+      st[cs + r] = (uint16_t)(T + u);
+      const unsigned x = w_ + r;
+      const unsigned nb = t - hb32(x);
+      const unsigned nst = (x << nb) - T;
+      const unsigned cell = (nst & 0xFFFFu) | (s << 16) | (nb << 24);
+      cells[u] = cell;
+      if (t <= FIX_LOG) dtab_fix[((size_t)ctx << FIX_LOG) + u] = cell;
+    }
+#pragma unroll
+    for (int q = 0; q < A; q++) run[q] += (unsigned)__popc(votes[q]);
+  }
+}
+
 // ---- decoder-side structures ----------------------------------------------
 // logsuf[c] = sum of logs[c'] for c' > c: FSE_Decoder::startChunk reads the
 // initial states for ctx N-1 .. 0 (src/fse_common.hpp:134-138), so the state
@@ -380,35 +506,6 @@ k_logsuf(const uint32_t *__restrict__ logs, unsigned n_models, uint32_t *__restr
     logsuf[c] = total - before;             // sum of logs[c'] for c' > c
   }
   if (threadIdx.x == 0) logsuf[n_models] = total;  // total bits of the state block
-}
-
-// Compressed sequence DTables (SeqDecTables), one thread per context.
-__global__ void k_build_seqdec(const short *__restrict__ norm, const uint32_t *__restrict__ logs,
-                               const uint32_t *__restrict__ dtab_fix, SeqDecTables *__restrict__ out) {
-  const unsigned ctx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (ctx >= SEQ_N) return;
-  const unsigned t = logs[ctx], T = 1u << t;
-  unsigned run[4] = {0, 0, 0, 0}, coarse_base[4] = {0, 0, 0, 0};
-  unsigned word = 0;
-  for (unsigned u = 0; u < (1u << FIX_LOG); u++) {
-    if ((u & 255) == 0) {
-      for (int s = 0; s < 4; s++) { out->coarse[ctx][u >> 8][s] = (uint16_t)run[s]; coarse_base[s] = run[s]; }
-    }
-    if ((u & 31) == 0) {
-      for (int s = 0; s < 4; s++) out->fine[ctx][u >> 5][s] = (uint8_t)(run[s] - coarse_base[s]);
-    }
-    unsigned sym = 0;
-    if (u < T) {
-      sym = (dtab_fix[((size_t)ctx << FIX_LOG) + u] >> 16) & 3u;
-      run[sym]++;
-    }
-    word |= sym << (2 * (u & 15));
-    if ((u & 15) == 15) { out->symtab[ctx][u >> 4] = word; word = 0; }
-  }
-  for (int s = 0; s < 4; s++) {
-    const short n = norm[ctx * 4 + s];
-    out->snext[ctx][s] = (uint16_t)((n == -1 ? 1 : n) | (s == 0 ? (t << 12) : 0u));
-  }
 }
 
 // Quality: compact ids for the contexts whose table is not the untouched
@@ -534,16 +631,14 @@ int tables_from_norm(fq28_handle *h, DevTables &t) {
   FQ28_LAUNCH_CHECK(h);
   const unsigned threads = 64, blocks = (t.n_models + threads - 1) / threads;
   if (t.alphabet == SEQ_A)
-    k_build_tables<SEQ_A><<<blocks, threads, 0, h->stream>>>(t.norm, t.logs, t.toff, t.n_models, t.ctab, t.symtt, t.dtab, t.dtab_fix, t.dom_sym);
+    k_build_tables_seq<<<SEQ_N / 4, 128, 0, h->stream>>>(t.norm, t.logs, t.toff, t.ctab, t.symtt, t.dtab, t.dtab_fix, t.dom_sym,
+                                                        reinterpret_cast<SeqDecTables *>(t.seqdec));
   else
     k_build_tables<QUAL_A><<<blocks, threads, 0, h->stream>>>(t.norm, t.logs, t.toff, t.n_models, t.ctab, t.symtt, t.dtab, t.dtab_fix, t.dom_sym);
   FQ28_LAUNCH_CHECK(h);
   k_logsuf<<<1, 1024, 0, h->stream>>>(t.logs, t.n_models, t.logsuf);
   FQ28_LAUNCH_CHECK(h);
-  if (t.alphabet == SEQ_A) {
-    k_build_seqdec<<<(SEQ_N + 63) / 64, 64, 0, h->stream>>>(t.norm, t.logs, t.dtab_fix, reinterpret_cast<SeqDecTables *>(t.seqdec));
-    FQ28_LAUNCH_CHECK(h);
-  } else {
+  if (t.alphabet != SEQ_A) {
     k_qual_cid<<<1, 1024, 0, h->stream>>>(t.norm, t.logs, t.cid, t.n_touched);
     FQ28_LAUNCH_CHECK(h);
     k_qual_zrun<<<1, 1024, 0, h->stream>>>(t.logs, t.dtab_fix, t.dom_sym, t.cid, t.zrun, t.zinfo);
