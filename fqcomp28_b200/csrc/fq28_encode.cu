@@ -601,17 +601,30 @@ k_chain(const uint8_t *__restrict__ ssym, const uint32_t *__restrict__ tile0, un
   uint4 nxtv = make_uint4(0, 0, 0, 0);   // the group loaded in the previous round
   unsigned nxt_valid = 0;
   size_t nxt_slot = 0;
+  // tbase entries of the next tile to open, requested one tile ahead: the lanes of a warp
+  // change tiles at different rounds, an unprefetched pair of loads would stall every round
+  unsigned na0 = 0, na1 = 0;
+  if (t < t_end) {
+    const uint32_t *tb = tbase + (size_t)t * (N + 1) + c;
+    na0 = tb[0];
+    na1 = tb[1];
+  }
   auto fetch = [&]() {                   // advance to the next non-empty run if needed, load one group
     while (grp_left == 0 && t < t_end) {
-      const uint32_t *tb = tbase + (size_t)t * (N + 1) + c;
-      const unsigned a0 = tb[0], a1 = tb[1];
+      const unsigned a0 = na0, a1 = na1;
+      const unsigned tcur = t;
+      ++t;
+      if (t < t_end) {
+        const uint32_t *tb = tbase + (size_t)t * (N + 1) + c;
+        na0 = tb[0];
+        na1 = tb[1];
+      }
       const unsigned b0 = a0 & ~15u, padded = (a1 & ~15u) - b0;
       if (padded) {
         grp_left = padded >> 4;
         last_valid = (a0 & 15u) ? (a0 & 15u) : 16u;
-        slot = (size_t)t * STRIDE + b0;
+        slot = (size_t)tcur * STRIDE + b0;
       }
-      ++t;
     }
     nxt_valid = 0;
     if (grp_left) {
