@@ -648,6 +648,7 @@ int decode_batch(fq28_handle *h, const fq28_dec_arenas *in, const fq28_chunk_inf
       int pct = (int)((per_sm * (smem + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024));
       if (const char *e = getenv("FQ28_QUAL_CARVEOUT")) pct = atoi(e);
       if (pct > 100) pct = 100;
+      if (pct < 0) pct = cudaSharedmemCarveoutDefault;
       if (pct != carve_set) {
         FQ28_CUDA(h, cudaFuncSetAttribute(k_decode_qual, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
         carve_set = pct;
