@@ -483,9 +483,18 @@ def run_ours(args):
 
 def main():
     args = parse_args()
-    if args.impl == "reference":
-        return run_reference(args)
-    return run_ours(args)
+    # stdout carries exactly one JSON line: libraries that write to fd 1 (NCCL's
+    # version banner) go to stderr, the line itself is written to the saved fd
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(saved, "w")
+    try:
+        if args.impl == "reference":
+            return run_reference(args)
+        return run_ours(args)
+    finally:
+        sys.stdout.flush()
 
 
 if __name__ == "__main__":
