@@ -393,6 +393,47 @@ def test_two_stage_host_compress(oracle, H, monkeypatch, eof):
         assert np.array_equal(ar1[key][:nb], ar2[key][:nb]), key
 
 
+def _runny_fastq(n_records, seed, levels, p_stay, min_len=40, max_len=260):
+    """Qualities with long runs of several dominant levels (two-state chains per
+    level) and a tail of rare levels: every dominant-chain / zero-bit-run path."""
+    rng = np.random.default_rng(seed)
+    out = bytearray()
+    rare = np.array([2, 7, 11, 14, 19, 23, 25, 29, 33], dtype=np.uint8)
+    for i in range(n_records):
+        L = int(rng.integers(min_len, max_len + 1))
+        seq = rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), L)
+        q = np.empty(L, np.uint8)
+        cur = levels[int(rng.integers(0, len(levels)))]
+        for j in range(L):
+            u = rng.random()
+            if u > p_stay:
+                cur = levels[int(rng.integers(0, len(levels)))] if u > p_stay + (1 - p_stay) * 0.5 else cur
+                q[j] = rare[int(rng.integers(0, len(rare)))] if u <= p_stay + (1 - p_stay) * 0.5 else cur
+            else:
+                q[j] = cur
+        out += b"@x%d r:%d\n" % (i, int(rng.integers(0, 999)))
+        out += seq.tobytes() + b"\n+\n" + (q + 33).tobytes() + b"\n"
+    return np.frombuffer(bytes(out), dtype=np.uint8)
+
+
+@pytest.mark.parametrize("levels,p_stay", [((37,), 0.93), ((37, 2), 0.95), ((37, 25, 11, 2, 30), 0.97)])
+def test_dominant_runs_many_levels(oracle, H, levels, p_stay):
+    """Long dominant-symbol chains whose other symbols go beyond the three with a
+    step table of their own (generic ops of k_chain_dom), several self-loop
+    contexts with zero-bit run tables, variable read lengths (runs cut by record
+    ends): chunk streams identical to the oracle, exact round trip."""
+    d = _runny_fastq(9000, 41 + len(levels), levels, p_stay)
+    recs, cs, cq, fs, fq = oracle_tables(oracle, d)
+    gcs, gcq = H.hist(d)
+    assert np.array_equal(gcs, cs) and np.array_equal(gcq, cq)
+    H.build_tables(gcs, gcq)
+    norm, logs = oracle.ft_norm(fq), oracle.ft_logs(fq)
+    dom_ctx = [c for c in range(8192) if norm[c].max() > (1 << int(logs[c])) // 2]
+    assert len(dom_ctx) >= len(levels)  # at least ctx(d,d,d) of every run level is dominant
+    check_chunks(oracle, H, d, 1 << 20, fs, fq)
+    check_chunks(oracle, H, d, 300000, fs, fq, eof=False)
+
+
 def test_long_reads_ont_like(oracle, H):
     """BASELINE config 4: variable-length long reads (1-50 kb), ONT-like
     qualities (thousands of live quality contexts)."""
