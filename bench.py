@@ -44,7 +44,8 @@ def parse_args():
     ap.add_argument("--size-mb", type=int, default=1024, help="FASTQ MB per GPU")
     ap.add_argument("--reading-mb", type=int, default=1, help="-R, chunk size in MB")
     ap.add_argument("--sample-mb", type=int, default=128, help="-S, sample size in MB")
-    ap.add_argument("--profile", default="novaseq", choices=["novaseq", "hiseq"])
+    ap.add_argument("--profile", default="novaseq", choices=["novaseq", "hiseq", "ont"],
+                    help="quality model of the synthetic reads; ont = BASELINE config 4 (1-50 kb reads)")
     ap.add_argument("--cpu-mb", type=int, default=2048, help="bounded sample (MB of the slab) for the CPU legs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--threads", type=int, default=0, help="CPU threads (0 = all)")
@@ -129,6 +130,12 @@ def make_data(args, rank: int, device: str):
     """Rank r's slab: records [r*M, (r+1)*M) of the virtual global file."""
     import synth
 
+    if args.profile == "ont":  # variable-length long reads, ~24.5 kB per record on average
+        import torch
+
+        m = max(1, (args.size_mb << 20) // 24500)
+        parts = [synth.ont(rank * m + a, min(1024, m - a), seed=32, device=device) for a in range(0, m, 1024)]
+        return torch.cat(parts), m
     per = 150 * 2 + 52
     m = (args.size_mb << 20) // per
     t = synth.illumina(rank * m, m, seed=30, profile=args.profile, device=device)
@@ -186,7 +193,8 @@ def run_reference(args):
 
 def workload_config(args, n_bytes):
     return {
-        "workload": f"synthetic Illumina 150bp single-end FASTQ ({args.profile} qualities), {args.size_mb} MB per GPU, "
+        "workload": ("synthetic variable-length long reads (1-50 kb, ONT-like qualities)" if args.profile == "ont"
+                     else f"synthetic Illumina 150bp single-end FASTQ ({args.profile} qualities)") + f", {args.size_mb} MB per GPU, "
                     f"static tables from the leading -S {args.sample_mb} MB (the reference's only mode), -R {args.reading_mb} MB chunks",
         "fastq_bytes_per_gpu": int(n_bytes), "reading_size_mb": args.reading_mb, "sample_size_mb": args.sample_mb,
         "cache": "inputs (>= 1 GB per GPU) are larger than the 126 MB L2; no explicit flush",
@@ -227,7 +235,8 @@ def run_ours(args):
         dist.broadcast(k, 0)
         K = int(k.item())
         a, b = MG.shard_range(K, rank, world)
-        d_sample = synth.illumina(a, b - a, seed=30, profile=args.profile, device=str(dev))
+        d_sample = (synth.ont(a, b - a, seed=32, device=str(dev)) if args.profile == "ont"
+                    else synth.illumina(a, b - a, seed=30, profile=args.profile, device=str(dev)))
         sample_window = d_sample.numel()
     else:
         d_sample = d_fastq
