@@ -10,21 +10,25 @@
 // (#chunks x 2 stream types) and the time of a batch is
 //     symbols per stream  x  latency of one symbol
 // until the machine runs out of issue slots.  Design:
-//  * one THREAD per stream, 32 streams per warp: a decoded symbol costs 1/32 of
-//    a warp instruction, so the kernels stay latency-bound (not issue-bound)
-//    up to tens of thousands of streams per GPU;
-//  * lockstep across the 32 streams of a warp is only harmless if every step
-//    has the same latency, so the per-symbol table lookups must not go to L2:
+//  * one THREAD per stream.  A stream is one in-order dependent instruction
+//    chain, so the kernels are latency-bound: few streams per warp for small
+//    batches (a slow lane stalls its warp), up to 32 per warp for big ones;
+//  * the per-symbol table lookups must not go to L2:
 //      - sequence: all 256 DTables live in shared memory in compressed form
-//        (SeqDecTables, 832 B per context) -- a cell is rebuilt from its 2-bit
-//        symbol plus a two-level rank directory, in 32-bit integer ops;
+//        (SeqDecTables, 840 B per context) -- a cell is rebuilt from its 2-bit
+//        symbol plus a two-level rank directory, in 32-bit integer ops; the
+//        loop is software-pipelined (next symbol's loads before the current
+//        symbol's rank / bit-read chain);
 //      - quality: decoder states sit in shared memory under compact ids of the
-//        contexts that have a real table (a few hundred of 8192), which leaves
-//        most of the SM's 256 KB as L1 for the hot DTable cells;
+//        contexts that have a real table (a few hundred of 8192), the maps are
+//        shared by the streams of a CTA, which leaves most of the SM's 256 KB
+//        as L1 for the hot DTable cells; runs of a dominant symbol in its
+//        self-loop context are decoded up to 15 symbols per lookup (QZ_MAX);
 //  * the bit reader keeps the next <= 64 stream bits left-aligned in two 32-bit
 //    registers: taking nbBits is ONE funnel shift on the critical path, and the
 //    next stream word is always prefetched one refill ahead;
-//  * the two stream types run concurrently on two CUDA streams.
+//  * the two stream types run concurrently on two CUDA streams, on disjoint
+//    sets of SMs (a sequence CTA takes a whole SM's shared memory).
 #include <stdlib.h>
 
 #include "fq28_internal.cuh"

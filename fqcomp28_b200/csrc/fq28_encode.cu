@@ -12,9 +12,12 @@
 // c only evolves over the symbols coded in c, so the work splits into
 //   extract   : key[g] = (ctx, sym) for every symbol, g = encode-order index
 //   partition : per tile, stable counting sort of the symbols by context
+//               (k_tile_part8 for the 256 sequence contexts; histogram +
+//               compact-cursor rank for the 8192 quality contexts)
 //   chain     : one thread per (chunk, context) walks its symbols in order
 //               through the context's CTable held in shared memory and emits
-//               (nbBits, bits) per symbol
+//               (nbBits, bits) per symbol; long chains of contexts with a
+//               dominant symbol go through composed step tables (k_chain_dom)
 //   pack      : gather the fields back into encode order, prefix-sum nbBits,
 //               OR the fields into the output words
 #include <stdlib.h>
