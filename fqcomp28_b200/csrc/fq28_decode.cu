@@ -599,9 +599,14 @@ int decode_batch(fq28_handle *h, const fq28_dec_arenas *in, const fq28_chunk_inf
     }
     // streams per CTA (= per SM): few per warp keeps the homopolymer path from
     // stalling the other streams of a warp; big batches fill 32 slots per SM
-    unsigned s_lanes = 1, s_warps = 8;
-    if (n_chunks > 74 * 8) s_lanes = 2;    // leave about half of the SMs to the quality decoder
-    if (n_chunks > 74 * 16) s_lanes = 4;
+    // One warp per SM sub-partition: a stream is a chain of dependent instructions that wants an
+    // issue slot every ~4.5 cycles, two warps on one scheduler already slow each other down
+    // (measured: 4 warps x 3 streams 62 ms, 8 x 2 71 ms, 16 x 1 104 ms).  Streams per warp are
+    // chosen so that the sequence CTAs take about 86 SMs and leave the rest to the quality decoder.
+    unsigned s_warps = 4;
+    unsigned s_lanes = (unsigned)((n_chunks + 4 * 86 - 1) / (4 * 86));
+    if (s_lanes < 1) s_lanes = 1;
+    if (s_lanes > 8) s_lanes = 8;
     if (const char *e = getenv("FQ28_SEQ_LANES")) s_lanes = (unsigned)atoi(e) ? (unsigned)atoi(e) : s_lanes;
     if (const char *e = getenv("FQ28_SEQ_WARPS")) s_warps = (unsigned)atoi(e) ? (unsigned)atoi(e) : s_warps;
     if (s_lanes > 32) s_lanes = 32;
