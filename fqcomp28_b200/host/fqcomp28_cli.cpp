@@ -25,6 +25,7 @@
 #include <cstdlib>
 #include <fstream>
 #include <iostream>
+#include <numeric>
 #include <variant>
 
 #include "fqcomp28_gpu.hpp"
@@ -187,6 +188,27 @@ inline std::vector<std::byte> memdecompress(const std::vector<std::byte> &src, s
   return std::vector<std::byte>(src.begin() + STORED_HEADER, src.end());
 }
 
+// ---------------------------------------------------------------- report (row N4)
+// InputStats / CompressedStats of src/report.h:10-69: what the stderr table of
+// `fqcomp28 c` is computed from.
+struct InputStats {
+  std::size_t seq = 0, header = 0, n_records = 0;
+  std::size_t total() const { return header + 2 * seq + n_records * 5; }  // 4 newlines and a '+' per record
+};
+struct CompressedStats {
+  std::size_t readlens = 0, qual = 0, seq = 0, n_count = 0, n_pos = 0, n_blocks = 0;
+  std::vector<std::size_t> header_fields;
+  std::size_t sequence() const { return seq + readlens + n_count + n_pos; }
+  std::size_t quality() const { return qual; }
+  std::size_t headers() const { return std::accumulate(header_fields.begin(), header_fields.end(), std::size_t{0}); }
+  /** src/report.cpp:104-125: payload + the u32 size words of every block */
+  std::size_t data_section_size(std::size_t n_string_fields) const {
+    std::size_t block_meta = 4 + 4 + 2 * 4 + 2 * 4 + 2 * 4 + 2 * 4;
+    block_meta += n_string_fields * 3 * 2 * 4 + (header_fields.size() - n_string_fields) * 2 * 4;
+    return sequence() + quality() + headers() + n_blocks * block_meta;
+  }
+};
+
 // ---------------------------------------------------------------- archive
 struct BlockInfo {  // src/archive.h:17-26
   int64_t offset;
@@ -202,12 +224,14 @@ public:
   headers::Format fmt;
   std::vector<headers::field_t> first_fields;
   std::vector<BlockInfo> index;
+  CompressedStats cstats;  // sizes of what writeBlock stores (the reference counts them in the workspace)
 
   template <typename T> void writeInteger(T v) { fs.write(reinterpret_cast<const char *>(&v), sizeof(v)); }
   template <typename T> T readInteger() { T v{}; fs.read(reinterpret_cast<char *>(&v), sizeof(v)); return v; }
-  void writeBytes(const std::vector<std::byte> &b) {  // src/archive.cpp:165-169
+  std::size_t writeBytes(const std::vector<std::byte> &b) {  // src/archive.cpp:165-169
     writeInteger(narrow_cast<uint32_t>(b.size()));
     fs.write(reinterpret_cast<const char *>(b.data()), static_cast<std::streamsize>(b.size()));
+    return b.size();
   }
   void readBytes(std::vector<std::byte> &b) {  // src/archive.cpp:171-175
     b.resize(readInteger<uint32_t>());
@@ -232,25 +256,27 @@ public:
     writeInteger(cb.original_size.total);
     writeInteger(cb.original_size.n_records);
     writeInteger(cb.original_size.readlens);
-    writeBytes(memcompress(cb.readlens));
+    cstats.readlens += writeBytes(memcompress(cb.readlens));
     writeInteger(cb.original_size.n_count);
-    writeBytes(memcompress(cb.n_count));
+    cstats.n_count += writeBytes(memcompress(cb.n_count));
     writeInteger(cb.original_size.n_pos);
-    writeBytes(memcompress(cb.n_pos));
-    writeBytes(cb.seq);
-    writeBytes(cb.qual);
+    cstats.n_pos += writeBytes(memcompress(cb.n_pos));
+    cstats.seq += writeBytes(cb.seq);
+    cstats.qual += writeBytes(cb.qual);
+    cstats.header_fields.resize(fmt.n_fields());
+    cstats.n_blocks++;
     for (std::size_t i = 0; i < fmt.n_fields(); ++i) {
       const auto &f = fields[i];
       if (fmt.field_types[i] == headers::FieldType::STRING) {
         writeInteger(narrow_cast<uint32_t>(f.isDifferentFlag.size()));
-        writeBytes(memcompress(f.isDifferentFlag));
+        cstats.header_fields[i] += writeBytes(memcompress(f.isDifferentFlag));
         writeInteger(narrow_cast<uint32_t>(f.content.size()));
-        writeBytes(memcompress(f.content));
+        cstats.header_fields[i] += writeBytes(memcompress(f.content));
         writeInteger(narrow_cast<uint32_t>(f.contentLength.size()));
-        writeBytes(memcompress(f.contentLength));
+        cstats.header_fields[i] += writeBytes(memcompress(f.contentLength));
       } else {
         writeInteger(narrow_cast<uint32_t>(f.content.size()));
-        writeBytes(memcompress(f.content));
+        cstats.header_fields[i] += writeBytes(memcompress(f.content));
       }
     }
     index.push_back(bi);
@@ -327,6 +353,47 @@ static double now_s() {
 
 // ---------------------------------------------------------------- c
 /** processReads, src/process.cpp:32-82 */
+/** The stderr table of the reference (src/report.cpp:37-102): input sizes, stored
+ *  stream sizes with their share of the archive, compression ratios, block count.
+ *  Returns the archive size the table is based on (index + data section + meta),
+ *  which the reference asserts to equal the file size. */
+static std::size_t printReport(const InputStats &inp, const Archive &ar, std::FILE *os) {
+  const CompressedStats &comp = ar.cstats;
+  const char *sep = "*****************************\n";
+  const std::size_t n_string = static_cast<std::size_t>(
+      std::count(ar.fmt.field_types.begin(), ar.fmt.field_types.end(), headers::FieldType::STRING));
+  const std::size_t meta_headers = sizeof(readlen_t) + ar.meta.first_header.size();
+  const std::size_t meta_seq = sizeof(SeqFreqTable), meta_qual = sizeof(QualFreqTable);
+  const std::size_t index_bytes = sizeof(uint32_t) + ar.index.size() * sizeof(BlockInfo);
+  const std::size_t archive_size = index_bytes + comp.data_section_size(n_string) + meta_headers + meta_seq + meta_qual;
+  auto ratio = [](std::size_t a, std::size_t b) { return static_cast<double>(a) / static_cast<double>(b); };
+  std::fputs(sep, os);
+  std::fputs("Input sizes:\n", os);
+  std::fprintf(os, "Sequence\t%zu\t\nQuality\t%zu\t\nHeaders\t%zu\t\n", inp.seq, inp.seq, inp.header);
+  std::fputs(sep, os);
+  std::fputs("Compressed stream sizes:\n", os);
+  auto cstream = [&](const std::string &name, std::size_t bytes) {
+    std::fprintf(os, "%s\t%zu\t%.3f\t\n", name.c_str(), bytes, ratio(bytes, archive_size));
+  };
+  cstream("seq", comp.seq);
+  cstream("readlens", comp.readlens);
+  cstream("n_count", comp.n_count);
+  cstream("n_pos", comp.n_pos);
+  cstream("qual", comp.qual);
+  for (std::size_t i = 0; i < comp.header_fields.size(); ++i) cstream("header_field_" + std::to_string(i + 1), comp.header_fields[i]);
+  cstream("meta_seq", meta_seq);
+  cstream("meta_qual", meta_qual);
+  std::fputs(sep, os);
+  std::fputs("CR\n", os);
+  std::fprintf(os, "Sequence\t%.3f\t\n", ratio(inp.seq, comp.sequence() + meta_seq));
+  std::fprintf(os, "Quality\t%.3f\t\n", ratio(inp.seq, comp.quality() + meta_qual));
+  std::fprintf(os, "Headers\t%.3f\t\n", ratio(inp.header, comp.headers() + meta_headers));
+  std::fprintf(os, "Total\t%.3f\t\n", ratio(inp.total(), archive_size));
+  std::fputs(sep, os);
+  std::fprintf(os, "# blocks: \t%zu\t\n", comp.n_blocks);
+  return archive_size;
+}
+
 static int compress(const Settings &set) {
   std::ifstream in(set.mates1, std::ios::binary);
   if (!in) throw std::system_error(errno, std::generic_category(), set.mates1);
@@ -345,6 +412,7 @@ static int compress(const Settings &set) {
   double t_gpu = 0, t_host = 0;
   uint32_t next_idx = 0;
   std::size_t tot_seq = 0, tot_qual = 0, n_records = 0;
+  InputStats istats;
   bool have_meta = false;
   std::unique_ptr<CompressionWorkspace> wksp;
   while (file_pos < file_size || carry) {
@@ -381,6 +449,10 @@ static int compress(const Settings &set) {
       tot_seq += cb.seq.size();
       tot_qual += cb.qual.size();
       n_records += cb.original_size.n_records;
+      istats.n_records += cb.original_size.n_records;
+      istats.header += cb.raw_headers.size();
+      for (std::size_t q = 0; q + 1 < cb.readlens.size(); q += 2)  // readlens: u16 LE per record
+        istats.seq += std::to_integer<std::size_t>(cb.readlens[q]) | (std::to_integer<std::size_t>(cb.readlens[q + 1]) << 8);
     }
     t_host += now_s() - t0;
     if (eof) break;  // a trailing partial record is dropped, like the reference (src/fastq_io.cpp:31-32)
@@ -390,6 +462,13 @@ static int compress(const Settings &set) {
   }
   ar.writeIndex();
   ar.fs.flush();
+  {  // src/process.cpp:80-81: flush, then the report; the reference asserts archive_size == file size
+    const std::size_t archive_size = printReport(istats, ar, stderr);
+    ar.fs.seekp(0, std::ios::end);
+    const std::size_t on_disk = static_cast<std::size_t>(ar.fs.tellp());
+    if (archive_size != on_disk)
+      std::fprintf(stderr, "warning: report assumes an archive of %zu bytes, the file has %zu\n", archive_size, on_disk);
+  }
   if (set.verbose || true) {
     std::fprintf(stderr, "fqcomp28 (B200 path): %zu records, %u blocks, seq %zu B, qual %zu B; codec %.3f s, host (headers + archive) %.3f s\n",
                  n_records, next_idx, tot_seq, tot_qual, t_gpu, t_host);

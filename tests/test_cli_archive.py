@@ -109,3 +109,39 @@ def test_cli_multichunk_synthetic(tmp_path, oracle):
         r, _ = O.parse_records(sub)
         e = cod.encode_chunk(sub, r)
         assert b["total"] == sub.size and b["seq"] == e["seq"].tobytes() and b["qual"] == e["qual"].tobytes()
+
+
+@pytest.mark.gpu
+def test_cli_report(tmp_path, oracle):
+    """Row N4: the stderr table of `fqcomp28 c` (src/report.cpp:37-102) -- input
+    sizes, stored stream sizes, ratios, block count -- and its invariant
+    archive_size == file size (the reference's assert at :94-96)."""
+    import synth
+
+    build_cli()
+    d = synth.illumina(0, 12000, seed=30).numpy()
+    src, arc = str(tmp_path / "s.fastq"), str(tmp_path / "s.fqz")
+    d.tofile(src)
+    r = subprocess.run([CLI, "c", "--i1", src, "--output", arc, "-R", "1", "-S", "2", "--slab-mb", "3"],
+                       capture_output=True, text=True, check=True)
+    err = r.stderr
+    assert "warning" not in err
+    rows = {}
+    for line in err.splitlines():
+        f = line.split("\t")
+        if len(f) >= 2 and f[0] not in rows:
+            rows[f[0]] = f[1:]
+    recs, _ = oracle.parse_records(d)
+    n_sym = int(recs["len"].sum())
+    assert int(rows["Sequence"][0]) == n_sym and int(rows["Headers"][0]) == int(recs["hdr_len"].sum())
+    first, _, _, blocks = parse_archive(open(arc, "rb").read(), None)
+    assert int(rows["# blocks: "][0]) == len(blocks)
+    assert int(rows["seq"][0]) == sum(len(b["seq"]) for b in blocks)
+    assert int(rows["qual"][0]) == sum(len(b["qual"]) for b in blocks)
+    assert int(rows["readlens"][0]) == sum(len(b["side"][0][1]) for b in blocks)
+    assert int(rows["meta_seq"][0]) == 3076 and int(rows["meta_qual"][0]) == 1081348
+    size = os.path.getsize(arc)
+    total_in = int(recs["hdr_len"].sum()) + 2 * n_sym + 5 * len(recs)
+    # CR section comes after the stream table: the last "Total" row
+    total_cr = [l.split("\t")[1] for l in err.splitlines() if l.startswith("Total\t")][-1]
+    assert total_cr == f"{total_in / size:.3f}"
