@@ -37,6 +37,24 @@ class Fq28Error(RuntimeError):
         self.code = code
 
 
+HDR_MAX_FIELDS = 32
+
+
+class HdrFormat(C.Structure):  # fq28_hdr_format
+    _fields_ = [
+        ("n_fields", C.c_uint32),
+        ("is_string", C.c_uint8 * HDR_MAX_FIELDS),
+        ("separators", C.c_uint8 * HDR_MAX_FIELDS),
+        ("first_numeric", C.c_int32 * HDR_MAX_FIELDS),
+        ("first_str_off", C.c_uint32 * (HDR_MAX_FIELDS + 1)),
+        ("first_strings", C.c_char_p),
+    ]
+
+
+class HdrFieldInfo(C.Structure):  # fq28_hdr_field_info
+    _fields_ = [(n, C.c_uint64) for n in ("flag_off", "flag_len", "content_off", "content_len", "clen_off", "clen_len")]
+
+
 class ChunkInfo(C.Structure):
     _fields_ = [
         ("fastq_off", C.c_uint64),
@@ -94,7 +112,7 @@ SYMBOLS = [
     "fq28_build_tables_dev", "fq28_load_tables", "fq28_compress", "fq28_compress_dev",
     "fq28_compress_fetch", "fq28_bound_seq", "fq28_bound_qual", "fq28_decompress",
     "fq28_decompress_dev", "fq28_get_ctable", "fq28_get_dtable", "fq28_compress_dev_arenas",
-    "fq28_last_timings", "fq28_stage_name",
+    "fq28_last_timings", "fq28_stage_name", "fq28_tokenize_headers",
 ]
 
 _lib = None
@@ -143,6 +161,7 @@ def load() -> C.CDLL:
     L.fq28_last_timings.argtypes = [vp, vp, sz, psz]
     L.fq28_stage_name.argtypes = [sz]
     L.fq28_stage_name.restype = C.c_char_p
+    L.fq28_tokenize_headers.argtypes = [vp, vp, sz, vp, sz, vp, sz, C.POINTER(HdrFormat), vp, sz, C.POINTER(HdrFieldInfo), psz]
     _lib = L
     return L
 
@@ -187,6 +206,60 @@ class Handle:
     @property
     def launches(self) -> int:
         return int(self.L.fq28_launch_count(self.h))
+
+    def tokenize_headers(self, headers: np.ndarray, hdr_lens: np.ndarray, chunk_rec, first_header: bytes):
+        """fq28_tokenize_headers: header lines back to back + lengths + first record of every chunk
+        (n_chunks + 1 entries) -> (format dict, [[{flag, content, clen} per field] per chunk]).
+        The format is derived from `first_header` like HeaderFormatSpeciciation::fromHeader."""
+        headers = np.ascontiguousarray(headers, dtype=np.uint8)
+        hdr_lens = np.ascontiguousarray(hdr_lens, dtype=np.uint16)
+        cr = np.ascontiguousarray(chunk_rec, dtype=np.uint64)
+        fmt, types, seps, first = HdrFormat(), [], [], []
+        body, pos = first_header[1:], 0
+        while True:  # src/headers.cpp:43-73
+            end = pos
+            while end < len(body) and chr(body[end]).isalnum() and body[end] < 128:
+                end += 1
+            fld = body[pos:end]
+            types.append(0 if fld.isdigit() or len(fld) == 0 else 1)
+            first.append(fld)
+            if end == len(body):
+                break
+            seps.append(body[end])
+            pos = end + 1
+        F = len(types)
+        fmt.n_fields = F
+        strings, off = b"", [0]
+        for i in range(F):
+            fmt.is_string[i] = types[i]
+            if i < len(seps):
+                fmt.separators[i] = seps[i]
+            if types[i]:
+                strings += first[i]
+            else:
+                fmt.first_numeric[i] = int(first[i]) if first[i] else 0
+            off.append(len(strings))
+        for i, o in enumerate(off):
+            fmt.first_str_off[i] = o
+        fmt.first_strings = strings
+        n_chunks = len(cr) - 1
+        arena = np.zeros(headers.size + 6 * hdr_lens.size * F + 64, np.uint8)
+        infos = (HdrFieldInfo * (n_chunks * F))()
+        used = C.c_size_t(0)
+        self._ck(self.L.fq28_tokenize_headers(self.h, _ptr(headers), headers.size, _ptr(hdr_lens), hdr_lens.size, _ptr(cr),
+                                              n_chunks, C.byref(fmt), _ptr(arena), arena.size, infos, C.byref(used)))
+        out = []
+        for k in range(n_chunks):
+            row = []
+            for i in range(F):
+                fi = infos[k * F + i]
+                row.append({
+                    "flag": arena[fi.flag_off : fi.flag_off + fi.flag_len].tobytes(),
+                    "content": arena[fi.content_off : fi.content_off + fi.content_len].tobytes(),
+                    "clen": arena[fi.clen_off : fi.clen_off + fi.clen_len].tobytes(),
+                })
+            out.append(row)
+        return {"types": types, "separators": bytes(seps), "first": first}, out
 
     def timings(self) -> dict:
         ms = (C.c_float * 16)()

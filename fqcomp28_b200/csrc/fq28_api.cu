@@ -620,6 +620,17 @@ int fq28_decompress(fq28_handle *h, const fq28_dec_arenas *in, const fq28_chunk_
   return FQ28_OK;
 }
 
+// ---------------------------------------------------------------- headers
+int fq28_tokenize_headers(fq28_handle *h, const uint8_t *headers, size_t headers_bytes, const uint16_t *hdr_lens,
+                          size_t n_records, const uint64_t *chunk_rec, size_t n_chunks, const fq28_hdr_format *fmt,
+                          uint8_t *arena, size_t arena_cap, fq28_hdr_field_info *infos, size_t *arena_bytes) {
+  if (!h || !headers || !hdr_lens || !chunk_rec || !fmt || !arena || !infos) return FQ28_ERR_ARG;
+  FQ28_TRY(bind(h));
+  stage_reset(h);
+  return tokenize_headers(h, headers, headers_bytes, hdr_lens, n_records, chunk_rec, n_chunks, fmt, arena, arena_cap, infos,
+                          arena_bytes);
+}
+
 // ---------------------------------------------------------------- introspection
 int fq28_get_ctable(fq28_handle *h, int kind, unsigned ctx, uint16_t *state_table, int32_t *dfs, uint32_t *dnb,
                     unsigned *table_log) {

@@ -38,6 +38,7 @@ struct Settings {  // src/settings.h:15-39
   unsigned sample_mb = 128, reading_mb = 256, n_threads = 1;
   bool verbose = false;
   std::size_t slab_mb = 1024;  // FASTQ bytes handed to the GPU per pass
+  bool host_headers = false;   // tokenise headers on the host instead of the GPU (row N2)
 };
 
 // ---------------------------------------------------------------- headers
@@ -168,6 +169,52 @@ inline void detokenize(const std::vector<FieldStorage> &in, const Format &fmt, c
                reinterpret_cast<const std::byte *>(line.data()) + line.size());
     lens.push_back(narrow_cast<readlen_t>(line.size()));
   }
+}
+
+/** encodeHeader for every header of a batch of blocks on the GPU (fq28_tokenize_headers);
+ *  same field streams as tokenize() above, block by block. */
+inline void tokenizeOnGpu(GpuContext &ctx, const std::vector<CompressedBuffersDst> &blocks, const Format &fmt,
+                          const std::vector<field_t> &first, std::vector<std::vector<FieldStorage>> &out) {
+  out.assign(blocks.size(), std::vector<FieldStorage>(fmt.n_fields()));
+  if (blocks.empty()) return;
+  if (fmt.n_fields() > FQ28_HDR_MAX_FIELDS) throw std::invalid_argument("more header fields than the GPU tokeniser supports");
+  std::vector<uint8_t> raw;
+  std::vector<uint16_t> lens;
+  std::vector<uint64_t> chunk_rec{0};
+  for (const auto &cb : blocks) {
+    const auto *p = reinterpret_cast<const uint8_t *>(cb.raw_headers.data());
+    raw.insert(raw.end(), p, p + cb.raw_headers.size());
+    lens.insert(lens.end(), cb.header_lengths.begin(), cb.header_lengths.end());
+    chunk_rec.push_back(lens.size());
+  }
+  fq28_hdr_format f{};
+  f.n_fields = static_cast<uint32_t>(fmt.n_fields());
+  std::string strings;
+  for (std::size_t i = 0; i < fmt.n_fields(); ++i) {
+    f.is_string[i] = fmt.field_types[i] == FieldType::STRING;
+    if (i + 1 < fmt.n_fields()) f.separators[i] = fmt.separators[i];
+    f.first_str_off[i] = static_cast<uint32_t>(strings.size());
+    if (f.is_string[i]) strings += std::get<std::string>(first[i]);
+    else f.first_numeric[i] = std::get<numeric_t>(first[i]);
+  }
+  f.first_str_off[fmt.n_fields()] = static_cast<uint32_t>(strings.size());
+  f.first_strings = strings.data();
+  std::vector<uint8_t> arena(raw.size() + 6 * lens.size() * fmt.n_fields() + 64);
+  std::vector<fq28_hdr_field_info> infos(blocks.size() * fmt.n_fields());
+  std::size_t used = 0;
+  ctx.check(fq28_tokenize_headers(ctx.handle(), raw.data(), raw.size(), lens.data(), lens.size(), chunk_rec.data(),
+                                  blocks.size(), &f, arena.data(), arena.size(), infos.data(), &used));
+  auto take = [&arena](std::vector<std::byte> &dst, uint64_t off, uint64_t len) {
+    const auto *p = reinterpret_cast<const std::byte *>(arena.data() + off);
+    dst.assign(p, p + len);
+  };
+  for (std::size_t k = 0; k < blocks.size(); ++k)
+    for (std::size_t i = 0; i < fmt.n_fields(); ++i) {
+      const auto &fi = infos[k * fmt.n_fields() + i];
+      take(out[k][i].isDifferentFlag, fi.flag_off, fi.flag_len);
+      take(out[k][i].content, fi.content_off, fi.content_len);
+      take(out[k][i].contentLength, fi.clen_off, fi.clen_len);
+    }
 }
 }  // namespace headers
 
@@ -442,10 +489,14 @@ static int compress(const Settings &set) {
     t_gpu += now_s() - t0;
     t0 = now_s();
     std::vector<headers::FieldStorage> fields;
+    std::vector<std::vector<headers::FieldStorage>> gpu_fields;
+    if (!set.host_headers) headers::tokenizeOnGpu(*ctx, blocks, ar.fmt, ar.first_fields, gpu_fields);
+    std::size_t bi = 0;
     for (auto &cb : blocks) {
       cb.chunk_idx = next_idx++;
-      headers::tokenize(cb.raw_headers, cb.header_lengths, ar.fmt, ar.first_fields, fields);
-      ar.writeBlock(cb, fields);
+      if (set.host_headers) headers::tokenize(cb.raw_headers, cb.header_lengths, ar.fmt, ar.first_fields, fields);
+      ar.writeBlock(cb, set.host_headers ? fields : gpu_fields[bi]);
+      ++bi;
       tot_seq += cb.seq.size();
       tot_qual += cb.qual.size();
       n_records += cb.original_size.n_records;
@@ -518,7 +569,7 @@ static void usage() {
   std::fprintf(stderr,
                "fqcomp28 (B200 codec path)\n"
                "  fqcomp28 c --i1|--input1 FILE -o|--output ARCHIVE [-S|--sample-size-Mb N=128] [-R|--reading-size-Mb N=256]\n"
-               "             [-t|--threads N] [--verbose] [--slab-mb N=1024]\n"
+               "             [-t|--threads N] [--verbose] [--slab-mb N=1024] [--host-headers]\n"
                "  fqcomp28 d -i|--input ARCHIVE --o1|--output1 FILE [-t|--threads N] [--verbose] [--slab-mb N=1024]\n");
 }
 
@@ -547,6 +598,7 @@ int main(int argc, char **argv) {
     else if (a == "-t" || a == "--threads") set.n_threads = mb(need(i));  // accepted; the GPU path has one worker per GPU
     else if (a == "--slab-mb") set.slab_mb = mb(need(i));
     else if (a == "--verbose") set.verbose = true;
+    else if (a == "--host-headers") set.host_headers = true;
     else { std::fprintf(stderr, "unknown option %s\n", a.c_str()); usage(); return 109; }
   }
   if ((cmd != "c" && cmd != "d") || set.mates1.empty() || set.archive.empty()) { usage(); return 106; }

@@ -199,6 +199,43 @@ int fq28_decompress_dev(fq28_handle *h, const fq28_dec_arenas *in,
                         const fq28_chunk_info *infos, size_t n_chunks,
                         char *d_fastq_out, size_t out_cap, size_t *out_bytes);
 
+/* -- header tokeniser (row N2, encode side) ----------------------------------
+ * encodeHeader for every header of a batch of chunks: src/workspace.cpp:95-125
+ * with storeString / storeNumeric of src/headers.cpp:75-89,108-118.  A header is
+ * '@' field sep field ... field; the format (field types, separators) and the
+ * field values of the archive's first header come from the host
+ * (HeaderFormatSpeciciation::fromHeader, src/headers.cpp:43-73).  Every chunk
+ * starts from the first header's fields (startNewChunk, src/workspace.cpp:90-93).
+ * NUMERIC field: content = int32 delta to the previous record's value, 4 bytes per
+ * record.  STRING field: isDifferentFlag = one byte per record; when the value
+ * differs from the previous record's, its bytes go to content and its length
+ * (one byte, < 255) to contentLength. */
+#define FQ28_HDR_MAX_FIELDS 32
+typedef struct {
+  uint32_t n_fields;
+  uint8_t is_string[FQ28_HDR_MAX_FIELDS];      /* headers::FieldType of field i          */
+  char separators[FQ28_HDR_MAX_FIELDS];        /* separators[i] follows field i          */
+  int32_t first_numeric[FQ28_HDR_MAX_FIELDS];  /* first header's value (NUMERIC fields)  */
+  uint32_t first_str_off[FQ28_HDR_MAX_FIELDS + 1]; /* first_strings[off[i], off[i+1]) = first
+                                                  header's value of STRING field i        */
+  const char *first_strings;                   /* host pointer                           */
+} fq28_hdr_format;
+typedef struct {                               /* one per (chunk, field), offsets into the arena */
+  uint64_t flag_off, flag_len;                 /* isDifferentFlag (STRING only)          */
+  uint64_t content_off, content_len;           /* content                                */
+  uint64_t clen_off, clen_len;                 /* contentLength (STRING only)            */
+} fq28_hdr_field_info;
+/* headers: header lines back to back (as in fq28_enc_arenas.headers), hdr_lens
+ * per record, chunk_rec[k] = first record of chunk k (n_chunks + 1 entries).
+ * infos: n_chunks * n_fields entries, chunk-major.  arena_cap >= headers_bytes +
+ * 6 * n_records * n_fields is always enough.  A STRING value of 255 bytes or more
+ * -> FQ28_ERR_FORMAT (std::invalid_argument in the reference). */
+int fq28_tokenize_headers(fq28_handle *h, const uint8_t *headers, size_t headers_bytes,
+                          const uint16_t *hdr_lens, size_t n_records,
+                          const uint64_t *chunk_rec, size_t n_chunks,
+                          const fq28_hdr_format *fmt, uint8_t *arena, size_t arena_cap,
+                          fq28_hdr_field_info *infos, size_t *arena_bytes);
+
 /* -- introspection for tests (device tables copied out) --------------------- */
 /* CTable next-state cells / DTable cells of one context (T = 1<<log entries);
  * kind 0 = seq, 1 = qual. */

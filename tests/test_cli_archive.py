@@ -145,3 +145,26 @@ def test_cli_report(tmp_path, oracle):
     # CR section comes after the stream table: the last "Total" row
     total_cr = [l.split("\t")[1] for l in err.splitlines() if l.startswith("Total\t")][-1]
     assert total_cr == f"{total_in / size:.3f}"
+
+
+@pytest.mark.gpu
+def test_cli_gpu_header_tokeniser_same_archive(tmp_path):
+    """Row N2 (encode side): the archive written with the GPU header tokeniser is
+    byte-identical to the one written with the host tokeniser."""
+    import synth
+
+    build_cli()
+    d = synth.illumina(0, 12000, seed=33).numpy()
+    src = str(tmp_path / "s.fastq")
+    d.tofile(src)
+    a1, a2, out = str(tmp_path / "gpu.fqz"), str(tmp_path / "host.fqz"), str(tmp_path / "o.fastq")
+    subprocess.check_call([CLI, "c", "--i1", src, "-o", a1, "-R", "1", "-S", "2", "--slab-mb", "3"])
+    subprocess.check_call([CLI, "c", "--i1", src, "-o", a2, "-R", "1", "-S", "2", "--slab-mb", "3", "--host-headers"])
+    assert open(a1, "rb").read() == open(a2, "rb").read()
+    subprocess.check_call([CLI, "d", "-i", a1, "--o1", out])
+    assert np.array_equal(np.fromfile(out, dtype=np.uint8), d)
+    for name in FIXTURES:
+        f = os.path.join(DATA, name + ".fastq")
+        subprocess.check_call([CLI, "c", "--i1", f, "-o", a1])
+        subprocess.check_call([CLI, "c", "--i1", f, "-o", a2, "--host-headers"])
+        assert open(a1, "rb").read() == open(a2, "rb").read(), name
