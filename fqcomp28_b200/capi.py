@@ -112,7 +112,7 @@ SYMBOLS = [
     "fq28_build_tables_dev", "fq28_load_tables", "fq28_compress", "fq28_compress_dev",
     "fq28_compress_fetch", "fq28_bound_seq", "fq28_bound_qual", "fq28_decompress",
     "fq28_decompress_dev", "fq28_get_ctable", "fq28_get_dtable", "fq28_compress_dev_arenas",
-    "fq28_last_timings", "fq28_stage_name", "fq28_tokenize_headers",
+    "fq28_last_timings", "fq28_stage_name", "fq28_tokenize_headers", "fq28_detokenize_headers",
 ]
 
 _lib = None
@@ -162,6 +162,7 @@ def load() -> C.CDLL:
     L.fq28_stage_name.argtypes = [sz]
     L.fq28_stage_name.restype = C.c_char_p
     L.fq28_tokenize_headers.argtypes = [vp, vp, sz, vp, sz, vp, sz, C.POINTER(HdrFormat), vp, sz, C.POINTER(HdrFieldInfo), psz]
+    L.fq28_detokenize_headers.argtypes = [vp, vp, sz, C.POINTER(HdrFieldInfo), vp, sz, C.POINTER(HdrFormat), vp, sz, vp, psz]
     _lib = L
     return L
 
@@ -259,7 +260,25 @@ class Handle:
                     "clen": arena[fi.clen_off : fi.clen_off + fi.clen_len].tobytes(),
                 })
             out.append(row)
+        self._hdr_raw = (fmt, strings, arena[: used.value].copy(), infos, cr)  # for detokenize_headers
         return {"types": types, "separators": bytes(seps), "first": first}, out
+
+    def detokenize_headers(self, raw=None):
+        """fq28_detokenize_headers on the streams of the last tokenize_headers call (or `raw` =
+        (fmt, strings, arena, infos, chunk_rec)) -> (header bytes, hdr_lens)."""
+        fmt, strings, arena, infos, cr = raw if raw is not None else self._hdr_raw
+        n_rec = int(cr[-1])
+        lens = np.zeros(n_rec, np.uint16)
+        used = C.c_size_t(0)
+        out = np.zeros(64 * n_rec + 4096, np.uint8)
+        rc = self.L.fq28_detokenize_headers(self.h, _ptr(arena), arena.size, infos, _ptr(cr), len(cr) - 1, C.byref(fmt),
+                                            _ptr(out), out.size, _ptr(lens), C.byref(used))
+        if rc == -6 and used.value > out.size:  # FQ28_ERR_CAP: the call reports the size it needs
+            out = np.zeros(used.value, np.uint8)
+            rc = self.L.fq28_detokenize_headers(self.h, _ptr(arena), arena.size, infos, _ptr(cr), len(cr) - 1, C.byref(fmt),
+                                                _ptr(out), out.size, _ptr(lens), C.byref(used))
+        self._ck(rc)
+        return out[: used.value].copy(), lens
 
     def timings(self) -> dict:
         ms = (C.c_float * 16)()

@@ -631,6 +631,16 @@ int fq28_tokenize_headers(fq28_handle *h, const uint8_t *headers, size_t headers
                           arena_bytes);
 }
 
+int fq28_detokenize_headers(fq28_handle *h, const uint8_t *arena, size_t arena_bytes, const fq28_hdr_field_info *infos,
+                            const uint64_t *chunk_rec, size_t n_chunks, const fq28_hdr_format *fmt, uint8_t *headers_out,
+                            size_t headers_cap, uint16_t *hdr_lens_out, size_t *headers_bytes) {
+  if (!h || !arena || !infos || !chunk_rec || !fmt || !headers_out || !hdr_lens_out) return FQ28_ERR_ARG;
+  FQ28_TRY(bind(h));
+  stage_reset(h);
+  return detokenize_headers(h, arena, arena_bytes, infos, chunk_rec, n_chunks, fmt, headers_out, headers_cap, hdr_lens_out,
+                            headers_bytes);
+}
+
 // ---------------------------------------------------------------- introspection
 int fq28_get_ctable(fq28_handle *h, int kind, unsigned ctx, uint16_t *state_table, int32_t *dfs, uint32_t *dnb,
                     unsigned *table_log) {

@@ -235,6 +235,9 @@ int split_slab(fq28_handle *h, size_t reading_size, bool eof, size_t max_chunks)
 int tokenize_headers(fq28_handle *h, const uint8_t *headers, size_t headers_bytes, const uint16_t *hdr_lens, size_t n_rec,
                      const uint64_t *chunk_rec, size_t n_chunks, const fq28_hdr_format *fmt, uint8_t *arena, size_t arena_cap,
                      fq28_hdr_field_info *infos, size_t *arena_bytes);
+int detokenize_headers(fq28_handle *h, const uint8_t *arena, size_t arena_bytes, const fq28_hdr_field_info *infos,
+                       const uint64_t *chunk_rec, size_t n_chunks, const fq28_hdr_format *fmt, uint8_t *headers_out,
+                       size_t headers_cap, uint16_t *hdr_lens_out, size_t *headers_bytes);
 int hist_slab(fq28_handle *h, uint32_t *d_seq_counts, uint32_t *d_qual_counts);
 int tables_alloc(fq28_handle *h, DevTables &t, unsigned n_models, unsigned alphabet);
 int tables_from_counts(fq28_handle *h, DevTables &t, const uint32_t *d_counts);

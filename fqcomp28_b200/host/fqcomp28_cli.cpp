@@ -216,6 +216,69 @@ inline void tokenizeOnGpu(GpuContext &ctx, const std::vector<CompressedBuffersDs
       take(out[k][i].contentLength, fi.clen_off, fi.clen_len);
     }
 }
+
+/** decodeHeader for every record of a batch of blocks on the GPU (fq28_detokenize_headers) */
+inline void detokenizeOnGpu(GpuContext &ctx, const std::vector<std::vector<FieldStorage>> &fields,
+                            const std::vector<std::size_t> &n_records, const Format &fmt, const std::vector<field_t> &first,
+                            std::vector<CompressedBuffersSrc> &blocks) {
+  if (fields.empty()) return;
+  if (fmt.n_fields() > FQ28_HDR_MAX_FIELDS) throw std::invalid_argument("more header fields than the GPU tokeniser supports");
+  const std::size_t F = fmt.n_fields();
+  std::vector<uint8_t> arena;
+  std::vector<fq28_hdr_field_info> infos(fields.size() * F);
+  std::vector<uint64_t> chunk_rec{0};
+  auto put = [&arena](const std::vector<std::byte> &b, uint64_t &off, uint64_t &len) {
+    off = arena.size();
+    len = b.size();
+    const auto *p = reinterpret_cast<const uint8_t *>(b.data());
+    arena.insert(arena.end(), p, p + b.size());
+  };
+  for (std::size_t k = 0; k < fields.size(); ++k) {
+    for (std::size_t i = 0; i < F; ++i) {
+      auto &fi = infos[k * F + i];
+      put(fields[k][i].isDifferentFlag, fi.flag_off, fi.flag_len);
+      put(fields[k][i].content, fi.content_off, fi.content_len);
+      put(fields[k][i].contentLength, fi.clen_off, fi.clen_len);
+    }
+    chunk_rec.push_back(chunk_rec.back() + n_records[k]);
+  }
+  fq28_hdr_format f{};
+  f.n_fields = static_cast<uint32_t>(F);
+  std::string strings;
+  for (std::size_t i = 0; i < F; ++i) {
+    f.is_string[i] = fmt.field_types[i] == FieldType::STRING;
+    if (i + 1 < F) f.separators[i] = fmt.separators[i];
+    f.first_str_off[i] = static_cast<uint32_t>(strings.size());
+    if (f.is_string[i]) strings += std::get<std::string>(first[i]);
+    else f.first_numeric[i] = std::get<numeric_t>(first[i]);
+  }
+  f.first_str_off[F] = static_cast<uint32_t>(strings.size());
+  f.first_strings = strings.data();
+  const std::size_t n_rec = static_cast<std::size_t>(chunk_rec.back());
+  std::vector<uint8_t> out(64 * n_rec + 4096);
+  std::vector<uint16_t> lens(n_rec);
+  std::size_t used = 0;
+  if (arena.empty()) arena.push_back(0);
+  int rc = fq28_detokenize_headers(ctx.handle(), arena.data(), arena.size(), infos.data(), chunk_rec.data(), fields.size(), &f,
+                                   out.data(), out.size(), lens.data(), &used);
+  if (rc == FQ28_ERR_CAP && used > out.size()) {  // the call reports the size it needs
+    out.resize(used);
+    rc = fq28_detokenize_headers(ctx.handle(), arena.data(), arena.size(), infos.data(), chunk_rec.data(), fields.size(), &f,
+                                 out.data(), out.size(), lens.data(), &used);
+  }
+  ctx.check(rc);
+  std::size_t pos = 0;
+  for (std::size_t k = 0; k < fields.size(); ++k) {
+    auto &cb = blocks[k];
+    cb.header_lengths.assign(lens.begin() + static_cast<std::ptrdiff_t>(chunk_rec[k]),
+                             lens.begin() + static_cast<std::ptrdiff_t>(chunk_rec[k + 1]));
+    std::size_t bytes = 0;
+    for (auto l : cb.header_lengths) bytes += l;
+    const auto *p = reinterpret_cast<const std::byte *>(out.data() + pos);
+    cb.raw_headers.assign(p, p + bytes);
+    pos += bytes;
+  }
+}
 }  // namespace headers
 
 // ---------------------------------------------------------------- misc buffer container
@@ -543,14 +606,22 @@ static int decompress(const Settings &set) {
   while (i < ar.index.size()) {
     std::vector<CompressedBuffersSrc> srcs;
     std::vector<headers::FieldStorage> fields;
+    std::vector<std::vector<headers::FieldStorage>> batch_fields;
+    std::vector<std::size_t> batch_records;
     std::size_t bytes = 0;
     while (i < ar.index.size() && (srcs.empty() || bytes < batch_bytes)) {
       srcs.emplace_back();
       ar.readBlock(ar.index[i++], srcs.back(), fields);
       auto &cb = srcs.back();
-      headers::detokenize(fields, ar.fmt, ar.first_fields, cb.original_size.n_records, cb.raw_headers, cb.header_lengths);
+      if (set.host_headers) {
+        headers::detokenize(fields, ar.fmt, ar.first_fields, cb.original_size.n_records, cb.raw_headers, cb.header_lengths);
+      } else {
+        batch_fields.push_back(fields);
+        batch_records.push_back(cb.original_size.n_records);
+      }
       bytes += cb.original_size.total;
     }
+    if (!set.host_headers) headers::detokenizeOnGpu(*ctx, batch_fields, batch_records, ar.fmt, ar.first_fields, srcs);
     std::vector<CompressedBuffersSrc *> ps;
     std::vector<FastqChunk> chunks(srcs.size());
     std::vector<FastqChunk *> pc;
@@ -570,7 +641,7 @@ static void usage() {
                "fqcomp28 (B200 codec path)\n"
                "  fqcomp28 c --i1|--input1 FILE -o|--output ARCHIVE [-S|--sample-size-Mb N=128] [-R|--reading-size-Mb N=256]\n"
                "             [-t|--threads N] [--verbose] [--slab-mb N=1024] [--host-headers]\n"
-               "  fqcomp28 d -i|--input ARCHIVE --o1|--output1 FILE [-t|--threads N] [--verbose] [--slab-mb N=1024]\n");
+               "  fqcomp28 d -i|--input ARCHIVE --o1|--output1 FILE [-t|--threads N] [--verbose] [--slab-mb N=1024] [--host-headers]\n");
 }
 
 int main(int argc, char **argv) {

@@ -236,6 +236,19 @@ int fq28_tokenize_headers(fq28_handle *h, const uint8_t *headers, size_t headers
                           const fq28_hdr_format *fmt, uint8_t *arena, size_t arena_cap,
                           fq28_hdr_field_info *infos, size_t *arena_bytes);
 
+/* decodeHeader for every record of a batch of chunks (row N2, decode side):
+ * src/workspace.cpp:127-157 with loadNextString / loadNextNumeric of
+ * src/headers.cpp:91-106,120-133.  Input = the field streams as produced by
+ * fq28_tokenize_headers (arena + infos); output = header lines back to back
+ * ('@' field sep ... field, numeric fields printed with std::to_chars) and their
+ * lengths.  Streams that do not fit their chunk's record count -> FQ28_ERR_STREAM;
+ * headers_cap too small -> FQ28_ERR_CAP with the needed size in *headers_bytes. */
+int fq28_detokenize_headers(fq28_handle *h, const uint8_t *arena, size_t arena_bytes,
+                            const fq28_hdr_field_info *infos, const uint64_t *chunk_rec,
+                            size_t n_chunks, const fq28_hdr_format *fmt,
+                            uint8_t *headers_out, size_t headers_cap, uint16_t *hdr_lens_out,
+                            size_t *headers_bytes);
+
 /* -- introspection for tests (device tables copied out) --------------------- */
 /* CTable next-state cells / DTable cells of one context (T = 1<<log entries);
  * kind 0 = seq, 1 = qual. */

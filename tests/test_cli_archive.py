@@ -163,8 +163,12 @@ def test_cli_gpu_header_tokeniser_same_archive(tmp_path):
     assert open(a1, "rb").read() == open(a2, "rb").read()
     subprocess.check_call([CLI, "d", "-i", a1, "--o1", out])
     assert np.array_equal(np.fromfile(out, dtype=np.uint8), d)
+    subprocess.check_call([CLI, "d", "-i", a1, "--o1", out, "--host-headers", "--slab-mb", "1"])
+    assert np.array_equal(np.fromfile(out, dtype=np.uint8), d)
     for name in FIXTURES:
         f = os.path.join(DATA, name + ".fastq")
         subprocess.check_call([CLI, "c", "--i1", f, "-o", a1])
         subprocess.check_call([CLI, "c", "--i1", f, "-o", a2, "--host-headers"])
         assert open(a1, "rb").read() == open(a2, "rb").read(), name
+        subprocess.check_call([CLI, "d", "-i", a1, "--o1", out])
+        assert open(out, "rb").read() == open(f, "rb").read(), name

@@ -1,6 +1,7 @@
-"""Row N2 (encode side): the GPU header tokeniser (fq28_tokenize_headers) against a
-Python restatement of CompressionWorkspace::encodeHeader (src/workspace.cpp:95-125)
-with storeString / storeNumeric (src/headers.cpp:75-89,108-118)."""
+"""Row N2: the GPU header tokeniser / detokeniser (fq28_tokenize_headers,
+fq28_detokenize_headers) against Python restatements of encodeHeader / decodeHeader
+(src/workspace.cpp:95-157) with storeString / storeNumeric / loadNextString /
+loadNextNumeric (src/headers.cpp:75-133)."""
 import struct
 
 import numpy as np
@@ -70,7 +71,39 @@ def ref_tokenize(lines, chunk_rec, types, seps, first):
     return out
 
 
-def run_case(H, lines, chunk_rec):
+def ref_detokenize(streams, n_per_chunk, types, seps, first):
+    """decodeHeader (src/workspace.cpp:127-157) -> list of header lines"""
+    F = len(types)
+    first_vals = [f if types[i] else from_chars_i32(f) for i, f in enumerate(first)]
+    lines = []
+    for k, n in enumerate(n_per_chunk):
+        prev = list(first_vals)
+        dpos, cpos, lpos = [0] * F, [0] * F, [0] * F
+        for _ in range(n):
+            line = b"@"
+            for i in range(F):
+                st = streams[k][i]
+                if types[i]:
+                    if st["flag"][dpos[i]]:
+                        ln = st["clen"][lpos[i]]
+                        lpos[i] += 1
+                        prev[i] = st["content"][cpos[i] : cpos[i] + ln]
+                        cpos[i] += ln
+                    dpos[i] += 1
+                    line += prev[i]
+                else:
+                    (delta,) = struct.unpack_from("<i", st["content"], cpos[i])
+                    cpos[i] += 4
+                    v = (prev[i] + delta + (1 << 31)) % (1 << 32) - (1 << 31)
+                    prev[i] = v
+                    line += str(v).encode()
+                if i + 1 < F:
+                    line += bytes([seps[i]])
+            lines.append(line)
+    return lines
+
+
+def run_case(H, lines, chunk_rec, canonical=False):
     raw = np.frombuffer(b"".join(lines), dtype=np.uint8)
     lens = np.array([len(l) for l in lines], dtype=np.uint16)
     fmt, got = H.tokenize_headers(raw, lens, chunk_rec, lines[0])
@@ -80,6 +113,14 @@ def run_case(H, lines, chunk_rec):
         for i, (gf, wf) in enumerate(zip(g, w)):
             for name in ("flag", "content", "clen"):
                 assert gf[name] == wf[name], (k, i, name)
+    # decode side: GPU detokeniser == restated decodeHeader on the same streams
+    back, blens = H.detokenize_headers()
+    n_per_chunk = [chunk_rec[k + 1] - chunk_rec[k] for k in range(len(chunk_rec) - 1)]
+    ref_lines = ref_detokenize(want, n_per_chunk, fmt["types"], fmt["separators"], fmt["first"])
+    assert [int(x) for x in blens] == [len(l) for l in ref_lines]
+    assert back.tobytes() == b"".join(ref_lines)
+    if canonical:  # well-formed headers survive the round trip
+        assert ref_lines == lines
     return fmt
 
 
@@ -103,7 +144,7 @@ def test_synthetic_illumina_headers(oracle, H):
     offs = oracle.split_chunks(d, 1 << 20)
     ends = recs["hdr_off"].astype(np.int64)
     chunk_rec = [int(np.searchsorted(ends, int(o), side="left")) for o in offs[:-1]] + [len(lines)]
-    fmt = run_case(H, lines, chunk_rec)
+    fmt = run_case(H, lines, chunk_rec, canonical=True)
     assert len(fmt["types"]) >= 8 and 0 in fmt["types"] and 1 in fmt["types"]
 
 
@@ -150,3 +191,17 @@ def test_string_value_too_long(H):
     with pytest.raises(fqcomp28_b200.Fq28Error) as e:
         H.tokenize_headers(raw, lens, [0, 2], lines[0])
     assert e.value.code == -2  # FQ28_ERR_FORMAT
+
+
+def test_detokenize_rejects_short_streams(H):
+    import fqcomp28_b200
+
+    lines = [b"@ab.1", b"@ab.2", b"@cd.3"]
+    raw = np.frombuffer(b"".join(lines), dtype=np.uint8)
+    lens = np.array([len(l) for l in lines], dtype=np.uint16)
+    H.tokenize_headers(raw, lens, [0, 3], lines[0])
+    fmt, strings, arena, infos, cr = H._hdr_raw
+    infos[1].content_len -= 4  # numeric field one record short
+    with pytest.raises(fqcomp28_b200.Fq28Error) as e:
+        H.detokenize_headers((fmt, strings, arena, infos, cr))
+    assert e.value.code == -8  # FQ28_ERR_STREAM
