@@ -171,3 +171,32 @@ def test_bad_alphabet_rejected(oracle):
     recs, _ = O.parse_records(d)
     with pytest.raises(O.OracleError):
         O.hist(d, recs)
+
+
+def test_random_fastq_roundtrip_and_stream_invariants(oracle):
+    """Property checks on adversarial random FASTQ (variable lengths from 3, N
+    runs, every quality level): the oracle's chunk streams decode back to the
+    chunk bytes at several chunk sizes, every stream ends with a non-zero byte
+    (BIT_closeCStream's end mark), and side arrays have one entry per record."""
+    import synth
+
+    for seed, levels in ((3, 64), (4, 8), (5, 41)):
+        d = synth.random_fastq(400, seed=seed, min_len=3, max_len=260, qual_levels=levels)
+        recs, used = oracle.parse_records(d)
+        assert used == d.size
+        fs, fq = oracle.make_ft(*oracle.hist(d, recs))
+        cod = oracle.Codec(fs, fq)
+        for R in (d.size, 20000, 3000):
+            offs = oracle.split_chunks(d, R)
+            assert int(offs[0]) == 0 and int(offs[-1]) == d.size and np.all(np.diff(offs.astype(np.int64)) > 0)
+            for a, b in zip(offs[:-1], offs[1:]):
+                sub = d[int(a) : int(b)]
+                r, u = oracle.parse_records(sub)
+                assert u == sub.size
+                enc = cod.encode_chunk(sub, r)
+                assert enc["seq"][-1] != 0 and enc["qual"][-1] != 0
+                assert enc["readlens"].size == len(r) and enc["n_count"].size == len(r)
+                assert int(enc["n_count"].astype(np.int64).sum()) == enc["n_pos"].size
+                hdr, hl = oracle.gather_headers(sub, r)
+                out = cod.decode_chunk(enc, hdr, hl, sub.size)
+                assert np.array_equal(out, sub)
