@@ -1,6 +1,7 @@
 // fq28_api.cu -- the C ABI of include/fq28.h: handle lifetime, error plumbing,
 // host<->device staging for the host-buffer entry points, stage timers.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "fq28_internal.cuh"
 
@@ -134,6 +135,7 @@ static void free_buf(DevBuf &b) {
 static void free_tables(DevTables &t) {
   cudaFree(t.counts); cudaFree(t.norm); cudaFree(t.logs); cudaFree(t.max_log); cudaFree(t.toff);
   cudaFree(t.ctab); cudaFree(t.symtt); cudaFree(t.dtab); cudaFree(t.dtab_fix);
+  cudaFree(t.wtab); cudaFree(t.qrk); cudaFree(t.qdinfo);
   cudaFree(t.logsuf); cudaFree(t.seqdec); cudaFree(t.cid); cudaFree(t.n_touched); cudaFree(t.dom_sym); cudaFree(t.zrun); cudaFree(t.zinfo);
   t = DevTables();
 }
@@ -204,6 +206,24 @@ int fq28_create(int device, fq28_handle **out) {
     if (cudaMalloc(&h->d_scalars, 64 * sizeof(uint64_t)) != cudaSuccess) { rc = FQ28_ERR_CUDA; break; }
     if (cudaMallocHost(&h->h_scalars, 64 * sizeof(uint64_t)) != cudaSuccess) { rc = FQ28_ERR_CUDA; break; }
     cudaMemset(h->d_status, 0, sizeof(DevStatus));
+    {  // diagnostic knobs: read once here, never on the per-call paths
+      auto env_u = [](const char *n) -> unsigned { const char *e = getenv(n); return e ? (unsigned)atoi(e) : 0u; };
+      h->cfg.dec_v1 = getenv("FQ28_DEC_V1") != nullptr;
+      h->cfg.seq_lanes = env_u("FQ28_SEQ_LANES"); h->cfg.seq_warps = env_u("FQ28_SEQ_WARPS");
+      h->cfg.qual_lanes = env_u("FQ28_QUAL_LANES"); h->cfg.qual_warps = env_u("FQ28_QUAL_WARPS");
+      if (const char *e = getenv("FQ28_QUAL_CARVEOUT")) h->cfg.qual_carveout = atoi(e);
+      h->cfg.no_zrun = getenv("FQ28_NO_ZRUN") != nullptr;
+      h->cfg.no_dom = getenv("FQ28_NO_DOM") != nullptr;
+      h->cfg.no_rankc = getenv("FQ28_NO_RANKC") != nullptr;
+      h->cfg.serial = getenv("FQ28_SERIAL") != nullptr;
+      h->cfg.full_overlap = getenv("FQ28_FULL_OVERLAP") != nullptr;
+      if (const char *e = getenv("FQ28_PIPE_MIN_MB")) h->cfg.pipe_min_bytes = (size_t)atoll(e) << 20;
+    }
+    // kernel attributes are per device: set them for this handle's device (not once per process)
+    rc = encode_init_device(h);
+    if (rc) break;
+    rc = decode_init_device(h);
+    if (rc) break;
     rc = tables_alloc(h, h->seq, SEQ_N, SEQ_A);
     if (rc) break;
     rc = tables_alloc(h, h->qual, QUAL_N, QUAL_A);
@@ -460,11 +480,6 @@ int fq28_compress_fetch(fq28_handle *h, const fq28_enc_arenas *out) {
 // H2D of the second half with the first half's kernels, D2H of the first
 // half's result with the second half's kernels.  Same bytes as the one-pass
 // path (the walk is deterministic from its start offset).
-static size_t pipe_min_bytes() {
-  if (const char *e = getenv("FQ28_PIPE_MIN_MB")) return (size_t)atoll(e) << 20;
-  return (size_t)256 << 20;
-}
-
 static int compress_two_stage(fq28_handle *h, const char *fastq, size_t n_bytes, size_t h1, size_t sample_bytes,
                               size_t reading_size, int eof, void *ft_seq_out, void *ft_qual_out,
                               const fq28_enc_arenas *out, fq28_chunk_info *infos, size_t infos_cap,
@@ -553,7 +568,7 @@ int fq28_compress(fq28_handle *h, const char *fastq, size_t n_bytes, size_t samp
     size_t h1 = (n_bytes / 2) & ~(size_t)15;
     if (win > h1) h1 = (win + 15) & ~(size_t)15;
     const bool tables_ok = sample_bytes > 0 || (h->ft_img_seq.size() == FQ28_FT_SEQ_BYTES && h->ft_img_qual.size() == FQ28_FT_QUAL_BYTES);
-    if (n_bytes >= pipe_min_bytes() && h1 + ((size_t)16 << 20) <= n_bytes && tables_ok)
+    if (n_bytes >= h->cfg.pipe_min_bytes && h1 + ((size_t)16 << 20) <= n_bytes && tables_ok)
       return compress_two_stage(h, fastq, n_bytes, h1, sample_bytes, reading_size, eof, ft_seq_out, ft_qual_out, out, infos,
                                 infos_cap, summary);
   }

@@ -32,6 +32,7 @@
 #include <stdlib.h>
 
 #include "fq28_internal.cuh"
+#include "fq28_dec2.cuh"
 
 namespace fq28 {
 
@@ -507,6 +508,113 @@ k_decode_qual(const DecChunk *__restrict__ ch, unsigned n_chunks, unsigned lanes
   if (live && (!ok || !br.finished())) set_error(st, FQ28_ERR_STREAM, k);
 }
 
+// ---------------------------------------------------------------------------
+// Decoder v2 (fq28_dec2.cuh): every context caches the cell of its current state
+// in shared memory, the table fetch of the next cell is deferred (8 in flight).
+// One thread per stream, `lanes` streams per warp in lockstep (few for small
+// batches: one warp per SM sub-partition is the sweet spot of a latency chain;
+// 32 for big ones).  Shared memory per CTA:
+//   sequence: 4 homopolymer tables (32 KB) | ring | scratch | S (1 KB per stream)
+//   quality : rk | zc | run tables (4 + 8 KB per slot) | ring | scratch | S (|V| * 512 B per stream)
+// ---------------------------------------------------------------------------
+constexpr unsigned D2_HT_BYTES = 4u * (4u << FIX_LOG);
+__host__ __device__ inline size_t d2_seq_smem(unsigned per_cta) {
+  return D2_HT_BYTES + (size_t)per_cta * 16 + (size_t)per_cta * 4 + 1024 /*alignment slack*/ + (size_t)per_cta * 1024;
+}
+__host__ __device__ inline size_t d2_qual_fixed(unsigned nz) { return 128 + (size_t)nz * ((2u << FIX_LOG) + (4u << FIX_LOG)); }
+__host__ __device__ inline size_t d2_qual_smem(unsigned per_cta, unsigned nz, unsigned nv) {
+  return d2_qual_fixed(nz) + (size_t)per_cta * 16 + (size_t)per_cta * 4 + 256 + (size_t)per_cta * nv * 2 * dec2::QROW_BYTES;
+}
+
+__device__ __forceinline__ void d2_args(dec2::StreamArgs &a, const DecChunk &c, bool live, const uint8_t *stream, uint32_t len,
+                                        const uint32_t *recscan, const uint16_t *readlens, const uint16_t *hdr_lens, char *out,
+                                        const uint32_t *logs, const uint32_t *logsuf, const uint32_t *wtab, void *ring) {
+  a.src = stream; a.len = len; a.rec0 = c.rec0; a.n_rec = c.n_rec;
+  a.readlens = readlens; a.hdr_lens = hdr_lens; a.recscan = recscan;
+  a.out = out + c.out_off; a.logs = logs; a.logsuf = logsuf; a.wtab = wtab; a.ring = ring; a.live = live;
+}
+
+__global__ void __launch_bounds__(256)
+k_dec2_seq(const DecChunk *__restrict__ ch, unsigned n_chunks, unsigned lanes, const uint8_t *__restrict__ arena,
+           const uint32_t *__restrict__ wtab, const uint32_t *__restrict__ logs, const uint32_t *__restrict__ logsuf,
+           const uint32_t *__restrict__ recscan, const uint16_t *__restrict__ readlens,
+           const uint16_t *__restrict__ hdr_lens, char *__restrict__ out, DevStatus *st) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const unsigned per_cta = lanes * (blockDim.x >> 5);
+  {  // homopolymer contexts AAAA, CCCC, GGGG, TTTT = 0x00, 0x55, 0xAA, 0xFF
+    uint4 *dst = reinterpret_cast<uint4 *>(smem_raw);
+    for (unsigned i = threadIdx.x; i < D2_HT_BYTES / 16; i += blockDim.x) {
+      const unsigned j = i >> (FIX_LOG - 2), u = i & ((1u << (FIX_LOG - 2)) - 1u);
+      dst[i] = __ldg(reinterpret_cast<const uint4 *>(wtab + ((size_t)(j * 0x55u) << FIX_LOG)) + u);
+    }
+  }
+  __syncthreads();
+  const uint32_t base = (uint32_t)__cvta_generic_to_shared(smem_raw);
+  const uint32_t ring0 = base + D2_HT_BYTES, scr0 = ring0 + per_cta * 16;
+  const uint32_t s0 = (scr0 + per_cta * 4 + 1023u) & ~1023u;
+  const unsigned lane = threadIdx.x & 31;
+  const unsigned slot = (threadIdx.x >> 5) * lanes + lane;
+  const unsigned k = blockIdx.x * per_cta + slot;
+  const bool live = lane < lanes && k < n_chunks;
+  DecChunk c;
+  c.n_rec = 0; c.rec0 = 0; c.out_off = 0; c.seq_off = 0; c.seq_len = 0;
+  if (live) c = ch[k];
+  const unsigned sl = live ? slot : 0;
+  dec2::StreamArgs a;
+  d2_args(a, c, live, arena + c.seq_off, c.seq_len, recscan, readlens, hdr_lens, out, logs, logsuf, wtab,
+          smem_raw + (ring0 - base) + sl * 16);
+  const bool ok = dec2::decode_seq_stream(a, s0 + sl * 1024, base, scr0 + sl * 4);
+  if (live && !ok) set_error(st, FQ28_ERR_STREAM, k);  // BIT_endOfDStream, src/fse_common.hpp:141
+}
+
+__global__ void __launch_bounds__(256)
+k_dec2_qual(const DecChunk *__restrict__ ch, unsigned n_chunks, unsigned lanes, const uint8_t *__restrict__ arena,
+            const uint32_t *__restrict__ wtab, const uint32_t *__restrict__ logs, const uint32_t *__restrict__ logsuf,
+            const uint32_t *__restrict__ dtab_fix, const uint16_t *__restrict__ cid, const uint8_t *__restrict__ qrk,
+            unsigned nv, const uint16_t *__restrict__ gzrun, unsigned nz, uint4 zctx, uint16_t *cold_states,
+            const uint32_t *__restrict__ recscan, const uint16_t *__restrict__ readlens,
+            const uint16_t *__restrict__ hdr_lens, char *__restrict__ out, DevStatus *st) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const unsigned per_cta = lanes * (blockDim.x >> 5);
+  const uint32_t base = (uint32_t)__cvta_generic_to_shared(smem_raw);
+  dec2::QualShared qs;
+  qs.rk_a = base; qs.zc_a = base + 64; qs.zt_a = base + 128; qs.hz_a = qs.zt_a + nz * (2u << FIX_LOG);
+  {
+    if (threadIdx.x < 64) smem_raw[threadIdx.x] = qrk[threadIdx.x];
+    const unsigned zc[4] = {zctx.x, zctx.y, zctx.z, zctx.w};
+    for (unsigned j = 0; j < nz; j++) {
+      const unsigned d = zc[j] & 63u;        // run context = ctx(d, d, d)
+      const unsigned r = qrk[d];
+      if (threadIdx.x == 0) reinterpret_cast<uint32_t *>(smem_raw + 64)[j] = d + QUAL_OFFSET;
+      // Z part of the run tables ((k << 11) | state after k zero-bit steps); u32 copies of the u16 table
+      const uint32_t *zsrc = reinterpret_cast<const uint32_t *>(gzrun + (size_t)j * 2 * (1u << FIX_LOG));
+      uint32_t *zdst = reinterpret_cast<uint32_t *>(smem_raw + 128 + j * (2u << FIX_LOG));
+      for (unsigned i = threadIdx.x; i < (1u << (FIX_LOG - 1)); i += blockDim.x) zdst[i] = zsrc[i];
+      const uint32_t *hsrc = wtab + ((size_t)dec2::qual_dense_id(r, 1, r) << FIX_LOG);
+      uint32_t *hdst = reinterpret_cast<uint32_t *>(smem_raw + 128 + nz * (2u << FIX_LOG) + j * (4u << FIX_LOG));
+      for (unsigned i = threadIdx.x; i < (1u << FIX_LOG); i += blockDim.x) hdst[i] = hsrc[i];
+    }
+  }
+  __syncthreads();
+  const uint32_t ring0 = qs.hz_a + nz * (4u << FIX_LOG), scr0 = ring0 + per_cta * 16;
+  const uint32_t s0 = (scr0 + per_cta * 4 + 255u) & ~255u;
+  const unsigned s_bytes = nv * 2 * dec2::QROW_BYTES;
+  const unsigned lane = threadIdx.x & 31;
+  const unsigned slot = (threadIdx.x >> 5) * lanes + lane;
+  const unsigned k = blockIdx.x * per_cta + slot;
+  const bool live = lane < lanes && k < n_chunks;
+  DecChunk c;
+  c.n_rec = 0; c.rec0 = 0; c.out_off = 0; c.qual_off = 0; c.qual_len = 0;
+  if (live) c = ch[k];
+  const unsigned sl = live ? slot : 0;
+  dec2::StreamArgs a;
+  d2_args(a, c, live, arena + c.qual_off, c.qual_len, recscan, readlens, hdr_lens, out, logs, logsuf, wtab,
+          smem_raw + (ring0 - base) + sl * 16);
+  const bool ok = dec2::decode_qual_stream(a, qs, s0 + sl * s_bytes, scr0 + sl * 4, dtab_fix, cid,
+                                          cold_states + (size_t)(live ? k : 0) * QUAL_N);
+  if (live && !ok) set_error(st, FQ28_ERR_STREAM, k);
+}
+
 // N re-insertion (src/fse_sequence.cpp:115-126,138-142): cumulative deltas.
 __global__ void k_ninsert(const DecChunk *__restrict__ ch, unsigned n_chunks, const uint32_t *__restrict__ recscan,
                           const uint32_t *__restrict__ nscan, const uint16_t *__restrict__ readlens,
@@ -527,6 +635,45 @@ __global__ void k_ninsert(const DecChunk *__restrict__ ch, unsigned n_chunks, co
     p = (p + np[i]) & 0xFFFFu;  // readlen_t arithmetic
     if (p >= L) { set_error(st, FQ28_ERR_STREAM, k); return; }
     dst[p] = 'N';
+  }
+}
+
+// Side-information checks that must hold BEFORE any kernel writes through offsets derived from
+// it (a corrupt archive must produce an error code, not an out-of-bounds write): per chunk, the
+// records' laid-out size (u64, no wrap) fits `total`, every read length is >= 1, the chunk's
+// header bytes stay inside `headers`.  One CTA per chunk.
+__global__ void __launch_bounds__(256)
+k_validate_chunks(const DecChunk *__restrict__ ch, unsigned n_chunks, const uint16_t *__restrict__ readlens,
+                  const uint16_t *__restrict__ hdr_lens, const uint16_t *__restrict__ n_count, size_t headers_bytes,
+                  const uint32_t *__restrict__ hdrscan, size_t n_rec_total, DevStatus *st) {
+  __shared__ unsigned long long s_bytes[8], s_np[8];
+  __shared__ unsigned s_bad;
+  const unsigned k = blockIdx.x;
+  if (threadIdx.x == 0) s_bad = 0;
+  __syncthreads();
+  const DecChunk c = ch[k];
+  unsigned long long bytes = 0, np = 0;
+  unsigned bad = 0;
+  for (unsigned r = threadIdx.x; r < c.n_rec; r += blockDim.x) {
+    const unsigned L = readlens[c.rec0 + r];
+    bytes += (unsigned long long)hdr_lens[c.rec0 + r] + 2ull * L + 5ull;
+    np += n_count[c.rec0 + r];
+    bad |= L == 0;
+  }
+  for (int d = 16; d >= 1; d >>= 1) {
+    bytes += __shfl_xor_sync(0xffffffffu, bytes, d);
+    np += __shfl_xor_sync(0xffffffffu, np, d);
+  }
+  if ((threadIdx.x & 31) == 0) { s_bytes[threadIdx.x >> 5] = bytes; s_np[threadIdx.x >> 5] = np; }
+  if (bad) atomicOr(&s_bad, 1u);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long tb = 0, tn = 0;
+    for (int w = 0; w < 8; w++) { tb += s_bytes[w]; tn += s_np[w]; }
+    if (s_bad) set_error(st, FQ28_ERR_SHORT, k);
+    else if (tb > c.total) set_error(st, FQ28_ERR_FORMAT, k);
+    else if (tn > c.npos_len) set_error(st, FQ28_ERR_STREAM, k);
+    if (k == n_chunks - 1 && (size_t)hdrscan[n_rec_total] > headers_bytes) set_error(st, FQ28_ERR_FORMAT, k);
   }
 }
 
@@ -557,6 +704,10 @@ int decode_batch(fq28_handle *h, const fq28_dec_arenas *in, const fq28_chunk_inf
     out_off += ci.total;
   }
   if (infos[0].rec_off != 0) return fail(h, FQ28_ERR_ARG, "first chunk must start at record 0");
+  if (infos[n_chunks - 1].rec_off + infos[n_chunks - 1].n_records != n_rec)
+    return fail(h, FQ28_ERR_ARG, "chunks cover %llu records, arenas hold %zu",
+                (unsigned long long)(infos[n_chunks - 1].rec_off + infos[n_chunks - 1].n_records), n_rec);
+  if (n_rec >= 0xFFFFFFF0u) return fail(h, FQ28_ERR_ARG, "too many records in one batch");
   if (out_off > out_cap) return fail(h, FQ28_ERR_CAP, "output needs %llu bytes, cap %zu", (unsigned long long)out_off, out_cap);
   if (out_off > FQ28_MAX_SLAB) return fail(h, FQ28_ERR_ARG, "batch output exceeds FQ28_MAX_SLAB");
   FQ28_TRY(ensure(h, h->dec_meta, n_chunks * sizeof(DecChunk)));
@@ -579,6 +730,11 @@ int decode_batch(fq28_handle *h, const fq28_dec_arenas *in, const fq28_chunk_inf
   FQ28_TRY(scan_exclusive_u32(h, recscan, recscan, n_rec));
   FQ28_TRY(scan_exclusive_u16_to_u32(h, in->hdr_lens, hdrscan, n_rec));
   FQ28_TRY(scan_exclusive_u16_to_u32(h, in->n_count, nscan, n_rec));
+  // no kernel below may write before the side information has been validated
+  k_validate_chunks<<<(unsigned)n_chunks, 256, 0, h->stream>>>(ch, (unsigned)n_chunks, in->readlens, in->hdr_lens, in->n_count,
+                                                              in->headers_bytes, hdrscan, n_rec, h->d_status);
+  FQ28_LAUNCH_CHECK(h);
+  FQ28_TRY(check_status(h, "decodeChunk side information"));
   if (n_rec) {
     k_layout<<<(unsigned)((n_rec + LAY_WARPS - 1) / LAY_WARPS), LAY_WARPS * 32, 0, h->stream>>>(
         ch, (unsigned)n_chunks, recscan, hdrscan, in->readlens, in->hdr_lens, in->headers, n_rec, d_out);
@@ -590,13 +746,49 @@ int decode_batch(fq28_handle *h, const fq28_dec_arenas *in, const fq28_chunk_inf
 
   // the two stream types are independent: quality runs on the side stream
   FQ28_TRY(side_fork(h));
+  if (!h->cfg.dec_v1) {
+    // Lanes (streams per warp): a stream is one latency chain, and one warp per SM sub-partition
+    // (592 on the GPU) runs it without issue contention; beyond that, lockstep lanes are cheaper
+    // than more warps.  Both stream types run at the same time, hence 2 * n_chunks streams.
+    unsigned lanes = (unsigned)((2 * n_chunks + 591) / 592);
+    lanes = lanes < 1 ? 1 : lanes > 32 ? 32 : lanes;
+    auto shape = [&](unsigned want_lanes, unsigned want_warps, unsigned &l, unsigned &w) {
+      l = want_lanes ? (want_lanes > 32 ? 32 : want_lanes) : lanes;
+      w = want_warps ? (want_warps > 8 ? 8 : want_warps) : 4;
+    };
+    stage_begin(h, ST_DECODE_SEQ);
+    {
+      unsigned l, w;
+      shape(h->cfg.seq_lanes, h->cfg.seq_warps, l, w);
+      while (d2_seq_smem(l * w) > 200 * 1024 && w > 1) w >>= 1;
+      const unsigned per_cta = l * w;
+      k_dec2_seq<<<(unsigned)((n_chunks + per_cta - 1) / per_cta), w * 32, d2_seq_smem(per_cta), h->stream>>>(
+          ch, (unsigned)n_chunks, l, in->seq, h->seq.wtab, h->seq.logs, h->seq.logsuf, recscan, in->readlens, in->hdr_lens,
+          d_out, h->d_status);
+      FQ28_LAUNCH_CHECK(h);
+    }
+    stage_end(h, ST_DECODE_SEQ);
+    {
+      unsigned l, w;
+      shape(h->cfg.qual_lanes, h->cfg.qual_warps, l, w);
+      const unsigned nz = h->cfg.no_zrun ? 0u : h->qual.h_n_z, nv = h->qual.h_n_v;
+      // the per-stream context arrays (|V| * 512 B) must fit: fewer warps first, then fewer lanes
+      while (d2_qual_smem(l * w, nz, nv) > 200 * 1024 && l * w > 1) {
+        if (w > 1) w >>= 1; else l = (l + 1) / 2;
+      }
+      const unsigned per_cta = l * w;
+      uint4 zctx = make_uint4(h->qual.h_zctx[0], h->qual.h_zctx[1], h->qual.h_zctx[2], h->qual.h_zctx[3]);
+      side_stage_begin(h, ST_DECODE_QUAL);
+      k_dec2_qual<<<(unsigned)((n_chunks + per_cta - 1) / per_cta), w * 32, d2_qual_smem(per_cta, nz, nv), h->side>>>(
+          ch, (unsigned)n_chunks, l, in->qual, h->qual.wtab, h->qual.logs, h->qual.logsuf, h->qual.dtab_fix, h->qual.cid,
+          h->qual.qrk, nv, h->qual.zrun, nz, zctx, h->dec_cold.as<uint16_t>(), recscan, in->readlens, in->hdr_lens, d_out,
+          h->d_status);
+      FQ28_LAUNCH_CHECK(h);
+      side_stage_end(h, ST_DECODE_QUAL);
+    }
+  } else {
   stage_begin(h, ST_DECODE_SEQ);
   {
-    static bool attr_set = false;
-    if (!attr_set) {
-      FQ28_CUDA(h, cudaFuncSetAttribute(k_decode_seq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SEQ_DEC_SMEM));
-      attr_set = true;
-    }
     // streams per CTA (= per SM): few per warp keeps the homopolymer path from
     // stalling the other streams of a warp; big batches fill 32 slots per SM
     // One warp per SM sub-partition: a stream is a chain of dependent instructions that wants an
@@ -607,8 +799,8 @@ int decode_batch(fq28_handle *h, const fq28_dec_arenas *in, const fq28_chunk_inf
     unsigned s_lanes = (unsigned)((n_chunks + 4 * 86 - 1) / (4 * 86));
     if (s_lanes < 1) s_lanes = 1;
     if (s_lanes > 8) s_lanes = 8;
-    if (const char *e = getenv("FQ28_SEQ_LANES")) s_lanes = (unsigned)atoi(e) ? (unsigned)atoi(e) : s_lanes;
-    if (const char *e = getenv("FQ28_SEQ_WARPS")) s_warps = (unsigned)atoi(e) ? (unsigned)atoi(e) : s_warps;
+    if (h->cfg.seq_lanes) s_lanes = h->cfg.seq_lanes;
+    if (h->cfg.seq_warps) s_warps = h->cfg.seq_warps;
     if (s_lanes > 32) s_lanes = 32;
     while (s_lanes * s_warps > 32) s_warps >>= 1;
     const unsigned per_cta = s_lanes * s_warps;
@@ -626,15 +818,15 @@ int decode_batch(fq28_handle *h, const fq28_dec_arenas *in, const fq28_chunk_inf
     // GPU), up to 32 for big batches; the compact state arrays must fit ~160 KB.
     unsigned lanes = 1, q_warps = 8;
     while (lanes < 4 && n_chunks / (lanes * q_warps) > 148) lanes <<= 1;
-    if (const char *e = getenv("FQ28_QUAL_LANES")) lanes = (unsigned)atoi(e) ? (unsigned)atoi(e) : lanes;
-    if (const char *e = getenv("FQ28_QUAL_WARPS")) q_warps = (unsigned)atoi(e) ? (unsigned)atoi(e) : q_warps;
+    if (h->cfg.qual_lanes) lanes = h->cfg.qual_lanes;
+    if (h->cfg.qual_warps) q_warps = h->cfg.qual_warps;
     if (lanes > 32) lanes = 32;
     while (lanes * q_warps > 32) q_warps >>= 1;
     while (lanes * q_warps > 1 && (size_t)nt * lanes * q_warps * sizeof(uint16_t) > 160 * 1024) {
       if (q_warps > 1) q_warps >>= 1; else lanes >>= 1;
     }
     const unsigned q_per_cta = lanes * q_warps;
-    const unsigned nz = getenv("FQ28_NO_ZRUN") ? 0u : h->qual.h_n_z;
+    const unsigned nz = h->cfg.no_zrun ? 0u : h->qual.h_n_z;
     const size_t zbytes = (size_t)nz * 2 * (1u << FIX_LOG) * sizeof(uint16_t);
     const size_t smem = (size_t)QUAL_N * sizeof(uint16_t) + RING_WORDS * sizeof(uint32_t) + zbytes + (size_t)((nt + 1u) & ~1u) * q_per_cta * sizeof(uint16_t) + 16;
     uint4 zctx = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
@@ -642,25 +834,19 @@ int decode_batch(fq28_handle *h, const fq28_dec_arenas *in, const fq28_chunk_inf
     if (nz > 1) zctx.y = h->qual.h_zctx[1];
     if (nz > 2) zctx.z = h->qual.h_zctx[2];
     if (nz > 3) zctx.w = h->qual.h_zctx[3];
-    static size_t attr_smem = 0;
-    if (smem > attr_smem) {
-      FQ28_CUDA(h, cudaFuncSetAttribute(k_decode_qual, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attr_smem = smem;
-    }
     {
       // Few CTAs land on an SM (the batch has ~n_chunks / q_per_cta of them), but the default
       // carve-out reserves shared memory for a full SM of them and shrinks the L1 that holds
       // the DTable cells: ask for just what the resident CTAs need.
-      static int carve_set = -1;
       const unsigned n_ctas = (unsigned)((n_chunks + q_per_cta - 1) / q_per_cta);
       const unsigned per_sm = (n_ctas + 83) / 84 + 1;  // quality shares the GPU with the sequence decoder
       int pct = (int)((per_sm * (smem + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024));
-      if (const char *e = getenv("FQ28_QUAL_CARVEOUT")) pct = atoi(e);
+      if (h->cfg.qual_carveout != -2) pct = h->cfg.qual_carveout;
       if (pct > 100) pct = 100;
       if (pct < 0) pct = cudaSharedmemCarveoutDefault;
-      if (pct != carve_set) {
+      if (pct != h->qual_carve_set) {
         FQ28_CUDA(h, cudaFuncSetAttribute(k_decode_qual, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
-        carve_set = pct;
+        h->qual_carve_set = pct;
       }
     }
     side_stage_begin(h, ST_DECODE_QUAL);
@@ -669,6 +855,7 @@ int decode_batch(fq28_handle *h, const fq28_dec_arenas *in, const fq28_chunk_inf
         h->qual.zrun, nz, zctx, h->dec_cold.as<uint16_t>(), recscan, in->readlens, in->hdr_lens, d_out, h->d_status);
     FQ28_LAUNCH_CHECK(h);
     side_stage_end(h, ST_DECODE_QUAL);
+  }
   }
   FQ28_TRY(side_join(h));
 
@@ -682,6 +869,16 @@ int decode_batch(fq28_handle *h, const fq28_dec_arenas *in, const fq28_chunk_inf
   stage_end(h, ST_NINSERT);
   FQ28_TRY(check_status(h, "decode"));
   if (out_bytes) *out_bytes = (size_t)out_off;
+  return FQ28_OK;
+}
+
+// Dynamic shared memory opt-ins, per device (fq28_create).
+int decode_init_device(fq28_handle *h) {
+  const int big = 227 * 1024;
+  FQ28_CUDA(h, cudaFuncSetAttribute(k_decode_seq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SEQ_DEC_SMEM));
+  FQ28_CUDA(h, cudaFuncSetAttribute(k_decode_qual, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  FQ28_CUDA(h, cudaFuncSetAttribute(k_dec2_seq, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  FQ28_CUDA(h, cudaFuncSetAttribute(k_dec2_qual, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   return FQ28_OK;
 }
 

@@ -1170,7 +1170,7 @@ static int prep_kind(fq28_handle *h, KindBufs &b, size_t G) {
     uint32_t max_syms = 0;
     for (unsigned k = 0; k < n_chunks; k++) max_syms = std::max(max_syms, h->h_chunk_sym[k + 1] - h->h_chunk_sym[k]);
     b.dom_cap = n_chunks * (max_syms / DOM_MIN + 1);
-    if (getenv("FQ28_NO_DOM")) b.dom_cap = 0;
+    if (h->cfg.no_dom) b.dom_cap = 0;
     FQ28_TRY(ensure(h, h->dom_list, (size_t)b.dom_cap * 4 + 16));
     FQ28_TRY(ensure(h, h->present, (size_t)N * 8 + 64));
   }
@@ -1193,12 +1193,6 @@ static int run_kind(fq28_handle *h, const DevTables &tab, const typename K::key_
   if constexpr (N == SEQ_N) {
     if (n_tiles) {
     using P = Part8<SeqKind, SEQ_TILE, SEQ_STRIDE>;
-    static bool attr_set = false;
-    if (!attr_set) {
-      FQ28_CUDA(h, cudaFuncSetAttribute(k_tile_part8<SeqKind, SEQ_TILE, SEQ_STRIDE>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P::SMEM));
-      attr_set = true;
-    }
     k_tile_part8<SeqKind, SEQ_TILE, SEQ_STRIDE><<<n_tiles, PART8_WARPS * 32, P::SMEM, strm>>>(
         reinterpret_cast<const uint16_t *>(key), b.tile0.as<uint32_t>(), chunk_sym, n_chunks, n_tiles,
         b.tbase.as<uint32_t>(), b.ssym.as<uint8_t>(), b.perm.as<uint32_t>());
@@ -1215,19 +1209,13 @@ static int run_kind(fq28_handle *h, const DevTables &tab, const typename K::key_
     FQ28_LAUNCH_CHECK(h);
     k_present_compact<N><<<1, 1024, 0, strm>>>(present, cmap, cinv, n_present);
     FQ28_LAUNCH_CHECK(h);
-    static bool rc_attr = false;
-    if (!rc_attr) {
-      FQ28_CUDA(h, cudaFuncSetAttribute(k_tile_rank_compact<K, TILE, STRIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)rankc_smem<K>()));
-      rc_attr = true;
-    }
     k_tile_rank_compact<K, TILE, STRIDE><<<(n_tiles + RANKC_WARPS - 1) / RANKC_WARPS, RANKC_WARPS * 32, rankc_smem<K>(), strm>>>(
         key, b.tile0.as<uint32_t>(), chunk_sym, n_chunks, n_tiles, b.tbase.as<uint32_t>(), cmap, cinv, n_present,
         b.ssym.as<uint8_t>(), b.perm.as<uint32_t>());
     FQ28_LAUNCH_CHECK(h);
     k_tile_rank<K, TILE, STRIDE, RANK_WARPS><<<(n_tiles + RANK_WARPS - 1) / RANK_WARPS, RANK_WARPS * 32, 0, strm>>>(
         key, b.tile0.as<uint32_t>(), chunk_sym, n_chunks, n_tiles, b.tbase.as<uint32_t>(), b.ssym.as<uint8_t>(),
-        b.perm.as<uint32_t>(), getenv("FQ28_NO_RANKC") ? nullptr : n_present);
+        b.perm.as<uint32_t>(), h->cfg.no_rankc ? nullptr : n_present);
     FQ28_LAUNCH_CHECK(h);
   }
   stage_close(h, slot, strm);
@@ -1251,12 +1239,6 @@ static int run_kind(fq28_handle *h, const DevTables &tab, const typename K::key_
                                                       use_dom ? tab.dom_sym : nullptr);
     FQ28_LAUNCH_CHECK(h);
     if (use_dom) {
-      static bool dom_attr = false;
-      if (!dom_attr) {
-        FQ28_CUDA(h, cudaFuncSetAttribute(k_chain_dom<K, A, STRIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)DOM_SMEM));
-        dom_attr = true;
-      }
       k_chain_dom<K, A, STRIDE><<<b.dom_cap, DOM_WARPS * 32, DOM_SMEM, strm>>>(
           h->dom_list.as<uint32_t>(), dom_count, b.ssym.as<uint8_t>(), b.tile0.as<uint32_t>(), n_chunks,
           b.tbase.as<uint32_t>(), tab.logs, tab.toff, tab.ctab, tab.symtt, tab.norm, tab.dom_sym,
@@ -1354,13 +1336,13 @@ int encode_slab(fq28_handle *h, fq28_chunk_info *infos, size_t infos_cap, fq28_e
   FQ28_TRY((prep_kind<SeqKind, SEQ_TILE, SEQ_STRIDE>(h, bs, G)));
   FQ28_TRY((prep_kind<QualKind, QUAL_TILE, QUAL_STRIDE>(h, bq, G)));
   FQ28_TRY(ensure(h, h->d_infos, (size_t)(n_chunks + 1) * sizeof(fq28_chunk_info)));
-  const bool overlap = getenv("FQ28_SERIAL") == nullptr;
+  const bool overlap = !h->cfg.serial;
   if (overlap) {
     FQ28_TRY(side_fork(h));
     // quality partition first with the whole GPU; its chain is latency-bound on a
     // few SMs, so the complete sequence pipeline runs underneath it
     FQ28_TRY((run_kind<QualKind, QUAL_A, QUAL_TILE, QUAL_STRIDE, 1>(h, h->qual, h->key_qual.as<uint32_t>(), bq, true, h->ev_join)));
-    if (!getenv("FQ28_FULL_OVERLAP")) FQ28_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_join, 0));
+    if (!h->cfg.full_overlap) FQ28_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_join, 0));
     FQ28_TRY((run_kind<SeqKind, SEQ_A, SEQ_TILE, SEQ_STRIDE, 4>(h, h->seq, h->key_seq.as<uint16_t>(), bs, false)));
     FQ28_TRY(side_join(h));
   } else {
@@ -1395,6 +1377,21 @@ int encode_slab(fq28_handle *h, fq28_chunk_info *infos, size_t infos_cap, fq28_e
   memcpy(infos, h->h_infos.data(), (size_t)n_chunks * sizeof(fq28_chunk_info));
   if (summary) *summary = h->last_summary;
   h->have_result = true;
+  return FQ28_OK;
+}
+
+// Dynamic shared memory opt-ins.  The attribute is per device, so this runs for every handle
+// (fq28_create, after cudaSetDevice) instead of once per process.
+int encode_init_device(fq28_handle *h) {
+  using P = Part8<SeqKind, SEQ_TILE, SEQ_STRIDE>;
+  FQ28_CUDA(h, cudaFuncSetAttribute(k_tile_part8<SeqKind, SEQ_TILE, SEQ_STRIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)P::SMEM));
+  FQ28_CUDA(h, cudaFuncSetAttribute(k_tile_rank_compact<QualKind, QUAL_TILE, QUAL_STRIDE>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rankc_smem<QualKind>()));
+  FQ28_CUDA(h, cudaFuncSetAttribute(k_chain_dom<QualKind, QUAL_A, QUAL_STRIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)DOM_SMEM));
+  FQ28_CUDA(h, cudaFuncSetAttribute(k_chain_dom<SeqKind, SEQ_A, SEQ_STRIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)DOM_SMEM));
   return FQ28_OK;
 }
 

@@ -101,6 +101,12 @@ struct DevTables {
   uint32_t *zinfo = nullptr;       // [0] = number of slots, [1 + j] = context of slot j
   uint32_t h_n_z = 0;
   uint32_t h_zctx[4] = {0, 0, 0, 0};
+  // decoder v2 (fq28_dec2.cuh): W tables = DTable cells repacked for the cached-cell decoder.
+  // sequence: [256 << 11]; quality: rows of the dense contexts only, [2 * n_v * 64 << 11]
+  uint32_t *wtab = nullptr;
+  uint8_t *qrk = nullptr;          // quality only: rk[64] (q -> rank in V, 0xFF outside) then vq[64] (rank -> q)
+  uint32_t *qdinfo = nullptr;      // quality only: [0] = |V|
+  uint32_t h_n_v = 0;
   size_t cells_cap = 0;
   bool ready = false;
 };
@@ -173,6 +179,16 @@ struct fq28_handle {
   cudaEvent_t ev_copy = nullptr;
   std::vector<uint8_t> ft_img_seq, ft_img_qual;   // host copies of the FreqTable images (for the sibling)
 
+  // policy knobs, read from the environment once at fq28_create (diagnostics)
+  struct Cfg {
+    bool dec_v1 = false;           // FQ28_DEC_V1: round-1 decoders (thread per stream over state tables)
+    unsigned seq_lanes = 0, seq_warps = 0, qual_lanes = 0, qual_warps = 0;  // 0 = automatic
+    int qual_carveout = -2;        // -2 = automatic
+    bool no_zrun = false, no_dom = false, no_rankc = false, serial = false, full_overlap = false;
+    size_t pipe_min_bytes = (size_t)256 << 20;
+  } cfg;
+  int qual_carve_set = -1;         // last shared-memory carve-out set for k_decode_qual on this device
+
   // timings
   struct EvRec { int stage; cudaEvent_t a, b; };
   std::vector<EvRec> ev_pool;
@@ -244,6 +260,9 @@ int tables_from_counts(fq28_handle *h, DevTables &t, const uint32_t *d_counts);
 int tables_from_norm(fq28_handle *h, DevTables &t);
 // fq28_encode.cu: K2 + K5
 int encode_slab(fq28_handle *h, fq28_chunk_info *infos, size_t infos_cap, fq28_enc_summary *summary);
+// per-device kernel attributes (dynamic shared memory opt-in); called by fq28_create
+int encode_init_device(fq28_handle *h);
+int decode_init_device(fq28_handle *h);
 // fq28_decode.cu: K6 + K7
 int decode_batch(fq28_handle *h, const fq28_dec_arenas *d_in, const fq28_chunk_info *infos,
                  size_t n_chunks, char *d_out, size_t out_cap, size_t *out_bytes);

@@ -10,6 +10,7 @@
 // zstd's FSE_optimalTableLog / FSE_normalizeCount / FSE_buildCTable_wksp /
 // FSE_buildDTable_wksp as specified in SURVEY.md Appendix A.
 #include "fq28_internal.cuh"
+#include "fq28_dec2.cuh"
 
 namespace fq28 {
 
@@ -596,6 +597,58 @@ k_qual_zrun(const uint32_t *__restrict__ logs, const uint32_t *__restrict__ dtab
   }
 }
 
+
+// ---- decoder v2 tables (fq28_dec2.cuh) ---------------------------------------
+// Sequence W table: the DTable cells repacked (char, symbol, nbBits, base, inline flag).
+__global__ void k_seq_wtab(const uint32_t *__restrict__ logs, const uint32_t *__restrict__ dtab_fix,
+                           uint32_t *__restrict__ wtab) {
+  const unsigned ctx = blockIdx.x;
+  const unsigned T = 1u << logs[ctx];
+  for (unsigned u = threadIdx.x; u < (1u << FIX_LOG); u += blockDim.x) {
+    const size_t i = ((size_t)ctx << FIX_LOG) + u;
+    wtab[i] = u < T ? dec2::make_w_seq(dtab_fix[i], ctx) : 0u;
+  }
+}
+
+// Quality: dense alphabet V = {0} + every value that is the last symbol of a touched
+// context (cid != 0xFFFF).  rk[q] = rank of q in V (0xFF outside), vq[rank] = q.  Single CTA.
+__global__ void __launch_bounds__(64)
+k_qual_dense(const uint16_t *__restrict__ cid, uint8_t *__restrict__ qrk, uint32_t *__restrict__ qdinfo) {
+  __shared__ unsigned inv[64];
+  const unsigned q = threadIdx.x;
+  unsigned seen = q == 0;
+  for (unsigned c = q; c < QUAL_N && !seen; c += 64) seen = cid[c] != 0xFFFFu;  // contexts with (c & 63) == q
+  inv[q] = seen;
+  __syncthreads();
+  unsigned rank = 0, nv = 0;
+  for (unsigned j = 0; j < 64; j++) {
+    if (j < q) rank += inv[j];
+    nv += inv[j];
+  }
+  qrk[q] = seen ? (uint8_t)rank : (uint8_t)0xFF;
+  qrk[64 + q] = 0;
+  __syncthreads();
+  if (seen) qrk[64 + rank] = (uint8_t)q;
+  if (q == 0) qdinfo[0] = nv;
+}
+
+// Quality W table: one CTA per dense context (row = rank(max) * 2 + eq, column = rank(q)).
+__global__ void k_qual_wtab(const uint32_t *__restrict__ logs, const uint32_t *__restrict__ dtab_fix,
+                            const uint8_t *__restrict__ qrk, const uint32_t *__restrict__ qdinfo,
+                            uint32_t *__restrict__ wtab) {
+  __shared__ uint8_t rk[64];
+  const unsigned nv = qdinfo[0];
+  const unsigned rq = blockIdx.x & 63u, eq = (blockIdx.x >> 6) & 1u, rm = blockIdx.x >> 7;
+  if (rq >= nv || rm >= nv) return;
+  if (threadIdx.x < 64) rk[threadIdx.x] = qrk[threadIdx.x];
+  __syncthreads();
+  const unsigned cx = ((unsigned)qrk[64 + rm] << 6) + qrk[64 + rq] + (eq << 12);
+  const unsigned d = dec2::qual_dense_id(rm, eq, rq);
+  const unsigned T = 1u << logs[cx];
+  for (unsigned u = threadIdx.x; u < (1u << FIX_LOG); u += blockDim.x)
+    wtab[((size_t)d << FIX_LOG) + u] = u < T ? dec2::make_w_qual(dtab_fix[((size_t)cx << FIX_LOG) + u], rk) : 0u;
+}
+
 int tables_alloc(fq28_handle *h, DevTables &t, unsigned n_models, unsigned alphabet) {
   if (t.norm) return FQ28_OK;
   t.n_models = n_models;
@@ -615,9 +668,13 @@ int tables_alloc(fq28_handle *h, DevTables &t, unsigned n_models, unsigned alpha
   FQ28_CUDA(h, cudaMalloc(&t.dtab, t.cells_cap * sizeof(uint32_t)));
   FQ28_CUDA(h, cudaMalloc(&t.dtab_fix, ((size_t)n_models << FIX_LOG) * sizeof(uint32_t)));
   FQ28_CUDA(h, cudaMalloc(&t.logsuf, (n_models + 1) * sizeof(uint32_t)));
+  // W tables of the v2 decoder: all contexts (sequence) / the largest dense set (quality: 2 * 64 * 64 rows)
+  FQ28_CUDA(h, cudaMalloc(&t.wtab, ((size_t)n_models << FIX_LOG) * sizeof(uint32_t)));
   if (alphabet == SEQ_A) {
     FQ28_CUDA(h, cudaMalloc(&t.seqdec, sizeof(SeqDecTables)));
   } else {
+    FQ28_CUDA(h, cudaMalloc(&t.qrk, 128));
+    FQ28_CUDA(h, cudaMalloc(&t.qdinfo, 4 * sizeof(uint32_t)));
     FQ28_CUDA(h, cudaMalloc(&t.cid, n_models * sizeof(uint16_t)));
     FQ28_CUDA(h, cudaMalloc(&t.n_touched, sizeof(uint32_t)));
     FQ28_CUDA(h, cudaMalloc(&t.zrun, (size_t)QZ_MAX * 2 * (1u << FIX_LOG) * sizeof(uint16_t)));
@@ -638,13 +695,21 @@ int tables_from_norm(fq28_handle *h, DevTables &t) {
   FQ28_LAUNCH_CHECK(h);
   k_logsuf<<<1, 1024, 0, h->stream>>>(t.logs, t.n_models, t.logsuf);
   FQ28_LAUNCH_CHECK(h);
-  if (t.alphabet != SEQ_A) {
+  if (t.alphabet == SEQ_A) {
+    k_seq_wtab<<<SEQ_N, 256, 0, h->stream>>>(t.logs, t.dtab_fix, t.wtab);
+    FQ28_LAUNCH_CHECK(h);
+  } else {
     k_qual_cid<<<1, 1024, 0, h->stream>>>(t.norm, t.logs, t.cid, t.n_touched);
+    FQ28_LAUNCH_CHECK(h);
+    k_qual_dense<<<1, 64, 0, h->stream>>>(t.cid, t.qrk, t.qdinfo);  // before k_qual_zrun tags cid with run slots
+    FQ28_LAUNCH_CHECK(h);
+    k_qual_wtab<<<2 * 64 * 64, 256, 0, h->stream>>>(t.logs, t.dtab_fix, t.qrk, t.qdinfo, t.wtab);
     FQ28_LAUNCH_CHECK(h);
     k_qual_zrun<<<1, 1024, 0, h->stream>>>(t.logs, t.dtab_fix, t.dom_sym, t.cid, t.zrun, t.zinfo);
     FQ28_LAUNCH_CHECK(h);
     uint32_t zi[QZ_MAX + 1];
     FQ28_CUDA(h, cudaMemcpyAsync(&t.h_n_touched, t.n_touched, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    FQ28_CUDA(h, cudaMemcpyAsync(&t.h_n_v, t.qdinfo, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
     FQ28_CUDA(h, cudaMemcpyAsync(zi, t.zinfo, sizeof(zi), cudaMemcpyDeviceToHost, h->stream));
     FQ28_CUDA(h, cudaStreamSynchronize(h->stream));
     t.h_n_z = zi[0];

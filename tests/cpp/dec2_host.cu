@@ -1,0 +1,175 @@
+// dec2_host.cu -- TEST INFRASTRUCTURE.  Compiles the product's per-stream decoders
+// (fqcomp28_b200/csrc/fq28_dec2.cuh, __host__ __device__) for the CPU so that
+// tests/test_dec2_host.py can check the algorithm -- cached cells, deferred
+// refresh, STALE protocol, zero-bit runs, slow path -- against the oracle without
+// a GPU.  Shared memory is a byte array and there is one lane.  The derived
+// tables (W tables, dense alphabet, run tables) are rebuilt here on the host with
+// the same rules as the device kernels in fq28_tables.cu.  Never linked into
+// libfq28.so.
+#define DEC2_STATS 1
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../fqcomp28_b200/csrc/fq28_dec2.cuh"
+#include "../../oracle/fq28_oracle.h"
+
+namespace fq28 { namespace dec2 {
+thread_local uint8_t *g_host_smem = nullptr;
+thread_local unsigned long long g_stats[8];
+} }
+using namespace fq28::dec2;
+
+namespace {
+
+struct Tables {
+  std::vector<uint32_t> logs, logsuf, dtab_fix;
+  unsigned n = 0;
+};
+
+void build_dtabs(Tables &t, const int16_t *norm, const uint32_t *logs, unsigned n_models, unsigned alphabet) {
+  t.n = n_models;
+  t.logs.assign(logs, logs + n_models);
+  t.logsuf.assign(n_models + 1, 0);
+  uint32_t suf = 0;
+  for (unsigned c = n_models; c > 0; --c) { t.logsuf[c - 1] = suf; suf += logs[c - 1]; }
+  t.logsuf[n_models] = suf;
+  t.dtab_fix.assign((size_t)n_models << TAB_LOG, 0);
+  for (unsigned c = 0; c < n_models; c++)
+    fq28o_build_dtable(&t.dtab_fix[(size_t)c << TAB_LOG], norm + (size_t)c * alphabet, alphabet - 1, logs[c]);
+}
+
+void fill_args(StreamArgs &a, const uint8_t *src, uint32_t len, const uint16_t *readlens, const uint16_t *hdr_lens,
+               uint32_t n_rec, std::vector<uint32_t> &recscan, char *out, const Tables &t, const uint32_t *wtab) {
+  recscan.assign(n_rec + 1, 0);
+  for (uint32_t r = 0; r < n_rec; r++) recscan[r + 1] = recscan[r] + hdr_lens[r] + 2u * readlens[r] + 5u;
+  a.src = src; a.len = len; a.rec0 = 0; a.n_rec = n_rec;
+  a.readlens = readlens; a.hdr_lens = hdr_lens; a.recscan = recscan.data();
+  a.out = out; a.logs = t.logs.data(); a.logsuf = t.logsuf.data(); a.wtab = wtab;
+  a.ring = nullptr; a.live = true;
+}
+
+}  // namespace
+
+extern "C" {
+
+// event counters since the last call: [0] seq drains, [1] seq inline refreshes, [2] qual drains,
+// [3] zero-bit runs, [4] single steps in a run context, [5] slow-path entries, [6] slow-path
+// symbols in dense contexts, [7] slow-path symbols in contexts outside the dense set
+void dec2h_stats(unsigned long long *out) {
+  for (int i = 0; i < 8; i++) { out[i] = g_stats[i]; g_stats[i] = 0; }
+}
+
+// ft = FreqTable<256,4> image.  The stream is copied to `misalign` bytes past an 8-byte boundary.
+int dec2h_seq(const uint8_t *ft, const uint8_t *stream, uint32_t len, unsigned misalign, const uint16_t *readlens,
+              const uint16_t *hdr_lens, uint32_t n_rec, char *out) {
+  const int16_t *norm = reinterpret_cast<const int16_t *>(ft);
+  const uint32_t *logs = reinterpret_cast<const uint32_t *>(ft + 256 * 4 * 2);
+  Tables t;
+  build_dtabs(t, norm, logs, 256, 4);
+  std::vector<uint32_t> wtab((size_t)256 << TAB_LOG, 0);
+  for (unsigned c = 0; c < 256; c++)
+    for (unsigned u = 0; u < (1u << logs[c]); u++)
+      wtab[((size_t)c << TAB_LOG) + u] = make_w_seq(t.dtab_fix[((size_t)c << TAB_LOG) + u], c);
+  // shared memory image: 4 homopolymer tables | S | scratch
+  const uint32_t ht = 0, sb = 4 * (4u << TAB_LOG), scratch = sb + 1024;
+  std::vector<uint8_t> smem(scratch + 64, 0);
+  for (unsigned j = 0; j < 4; j++)
+    memcpy(&smem[ht + j * (4u << TAB_LOG)], &wtab[(size_t)(j * 0x55u) << TAB_LOG], 4u << TAB_LOG);
+  g_host_smem = smem.data();
+  std::vector<uint64_t> buf((len + 64) / 8 + 4, 0);
+  uint8_t *src = reinterpret_cast<uint8_t *>(buf.data()) + 8 + (misalign & 7);
+  memcpy(src, stream, len);
+  StreamArgs a;
+  std::vector<uint32_t> recscan;
+  fill_args(a, src, len, readlens, hdr_lens, n_rec, recscan, out, t, wtab.data());
+  const bool ok = decode_seq_stream(a, sb, ht, scratch);
+  g_host_smem = nullptr;
+  return ok ? 0 : -8;
+}
+
+// ft = FreqTable<8192,64> image.  stats (may be NULL): [0] = |V|, [1] = run slots
+int dec2h_qual(const uint8_t *ft, const uint8_t *stream, uint32_t len, unsigned misalign, const uint16_t *readlens,
+               const uint16_t *hdr_lens, uint32_t n_rec, char *out, uint32_t *stats) {
+  const int16_t *norm = reinterpret_cast<const int16_t *>(ft);
+  const uint32_t *logs = reinterpret_cast<const uint32_t *>(ft + (size_t)8192 * 64 * 2);
+  Tables t;
+  build_dtabs(t, norm, logs, 8192, 64);
+  // touched contexts (k_qual_cid): table differs from the prior-only pattern
+  std::vector<uint16_t> cid(8192, 0xFFFF);
+  bool inV[64] = {false};
+  inV[0] = true;
+  unsigned nt = 0;
+  for (unsigned c = 0; c < 8192; c++) {
+    bool touched = logs[c] != 7;
+    for (unsigned s = 0; s < 64 && !touched; s++) touched = norm[(size_t)c * 64 + s] != 2;
+    if (touched) { cid[c] = (uint16_t)nt++; inV[c & 63] = true; }
+  }
+  uint8_t rk[64];
+  unsigned nv = 0;
+  for (unsigned qv = 0; qv < 64; qv++) rk[qv] = inV[qv] ? (uint8_t)nv++ : (uint8_t)0xFF;
+  uint8_t vq[64] = {0};
+  for (unsigned qv = 0; qv < 64; qv++) if (rk[qv] != 0xFF) vq[rk[qv]] = (uint8_t)qv;
+  // dense W table
+  const unsigned n_dense = 2 * nv * 64;
+  std::vector<uint32_t> wtab((size_t)n_dense << TAB_LOG, 0);
+  for (unsigned rm = 0; rm < nv; rm++)
+    for (unsigned eq = 0; eq < 2; eq++)
+      for (unsigned rq = 0; rq < nv; rq++) {
+        const unsigned cx = ((unsigned)vq[rm] << 6) + vq[rq] + (eq << 12);
+        const unsigned d = qual_dense_id(rm, eq, rq);
+        for (unsigned u = 0; u < (1u << logs[cx]); u++)
+          wtab[((size_t)d << TAB_LOG) + u] = make_w_qual(t.dtab_fix[((size_t)cx << TAB_LOG) + u], rk);
+      }
+  // zero-bit run slots (k_qual_zrun): ctx(d,d,d) with a dominant d, high qualities first
+  unsigned nz = 0, zsym[4];
+  for (int d = 63; d >= 0 && nz < 4; --d) {
+    const unsigned cx = qual_ctx13((unsigned)d, (unsigned)d, (unsigned)d);
+    const int T = 1 << logs[cx];
+    if (cid[cx] != 0xFFFF && norm[(size_t)cx * 64 + d] > T / 2) {
+      cid[cx] = (uint16_t)(cid[cx] | ((nz + 1) << 13));
+      zsym[nz++] = (unsigned)d;
+    }
+  }
+  // shared memory image: rk | zc | zt | hz | S | scratch
+  const uint32_t rk_a = 0, zc_a = 64, zt_a = 128, hz_a = zt_a + nz * (2u << TAB_LOG);
+  const uint32_t sb = (hz_a + nz * (4u << TAB_LOG) + 255) & ~255u;
+  const uint32_t scratch = sb + n_dense * 4;
+  std::vector<uint8_t> smem(scratch + 64, 0);
+  memcpy(&smem[rk_a], rk, 64);
+  for (unsigned j = 0; j < nz; j++) {
+    const unsigned d = zsym[j], cx = qual_ctx13(d, d, d), T = 1u << logs[cx];
+    const uint32_t ch = d + QUAL_CHAR0;
+    memcpy(&smem[zc_a + j * 4], &ch, 4);
+    for (unsigned x = 0; x < (1u << TAB_LOG); x++) {
+      unsigned k = 0, y = x;
+      while (x < T && k < 15) {
+        const uint32_t e = t.dtab_fix[((size_t)cx << TAB_LOG) + y];
+        if (((e >> 16) & 63u) != d || (e >> 24) != 0) break;
+        y = e & 0xFFFFu;
+        k++;
+      }
+      const uint16_t z = (uint16_t)((k << 11) | y);
+      memcpy(&smem[zt_a + j * (2u << TAB_LOG) + x * 2], &z, 2);
+    }
+    const unsigned dd = qual_dense_id(rk[d], 1, rk[d]);
+    memcpy(&smem[hz_a + j * (4u << TAB_LOG)], &wtab[(size_t)dd << TAB_LOG], 4u << TAB_LOG);
+  }
+  g_host_smem = smem.data();
+  std::vector<uint64_t> buf((len + 64) / 8 + 4, 0);
+  uint8_t *src = reinterpret_cast<uint8_t *>(buf.data()) + 8 + (misalign & 7);
+  memcpy(src, stream, len);
+  std::vector<uint16_t> cold(8192, 0);
+  StreamArgs a;
+  std::vector<uint32_t> recscan;
+  fill_args(a, src, len, readlens, hdr_lens, n_rec, recscan, out, t, wtab.data());
+  QualShared qs{rk_a, zt_a, hz_a, zc_a};
+  const bool ok = decode_qual_stream(a, qs, sb, scratch, t.dtab_fix.data(), cid.data(), cold.data());
+  g_host_smem = nullptr;
+  if (stats) { stats[0] = nv; stats[1] = nz; }
+  return ok ? 0 : -8;
+}
+
+}  // extern "C"
