@@ -11,10 +11,13 @@
 // its current state* (W) in shared memory instead of the state:
 //     W = S[ctx]  ->  symbol  ->  ctx'                (ONE shared load + 1 ALU)
 // and the remaining work (bit read, new state, fetching the cell of the new
-// state from the L2-resident table) is off the recurrence: the fetch is issued
-// into one of D pending slots and stored back to S[ctx] D symbols later.  A
-// context whose refresh is pending is marked STALE in S; reading STALE drains
-// the slots first.  Contexts that loop onto themselves (sequence homopolymers,
+// state from the L2-resident table) is off the recurrence: the fetch is a 4-byte
+// cp.async from the table straight into S[ctx] -- no destination register, hence
+// no scoreboard wait in the instruction stream (ptxas puts every in-flight LDG of
+// an unrolled loop on ONE scoreboard, so a register-based software pipeline waits
+// for the youngest load at every step; measured, 400 cycles per symbol).  A
+// context whose refresh is in flight holds STALE in S; reading STALE waits for
+// the thread's async copies and reads again.  Contexts that loop onto themselves (sequence homopolymers,
 // quality ctx(d,d,d) with a dominant d) are refreshed inline from shared-memory
 // copies of their tables; the latter also use the zero-bit run tables.
 //
@@ -56,8 +59,10 @@ FQ_HD uint32_t make_w_seq(uint32_t cell /* newState | sym<<16 | nb<<24 */, unsig
 //  [0] UNSEEN (symbol outside the dense alphabet V)   [1] ZENT (S entry of a
 //  zero-bit-run context: holds a state, not a cell)   [2,8) rank of the symbol in V
 //  [8,12) nbBits   [12,23) newState base   [23,30) output char   [31] STALE
+//  [30] DONE: not a cell -- the lane has nothing to decode in this trip (register only)
 //  ZENT entry: [8,19) state   [20,22) run slot
-constexpr uint32_t QW_UNSEEN = 1u, QW_ZENT = 2u, QW_STALE = 1u << 31, QW_SPECIAL = QW_UNSEEN | QW_ZENT | QW_STALE;
+constexpr uint32_t QW_UNSEEN = 1u, QW_ZENT = 2u, QW_DONE = 1u << 30, QW_STALE = 1u << 31,
+                   QW_SPECIAL = QW_UNSEEN | QW_ZENT | QW_DONE | QW_STALE;
 constexpr unsigned QROW_BYTES = 256;  // 64 entries per (max, eq) row
 FQ_HD uint32_t make_w_qual(uint32_t cell, const uint8_t *rk /*[64] rank in V or 0xFF*/) {
   const unsigned sym = (cell >> 16) & 63u, nb = cell >> 24, ns = cell & 0x7FFu;
@@ -73,7 +78,7 @@ FQ_HD unsigned qual_ctx13(unsigned q, unsigned q1, unsigned q2) {  // calcContex
 
 // host-only event counters for tests (drains, inline refreshes, runs, slow-path entries)
 #if !defined(__CUDA_ARCH__) && defined(DEC2_STATS)
-extern thread_local unsigned long long g_stats[8];
+extern thread_local unsigned long long g_stats[12];
 #define DEC2_COUNT(i) (++g_stats[i])
 #else
 #define DEC2_COUNT(i) ((void)0)
@@ -128,6 +133,58 @@ FQ_HD uint32_t gl_ld32(const uint32_t *p) {
   return *p;
 #endif
 }
+// S[a] <- *p, asynchronously (device: cp.async, lands after the L1/L2 latency; host: a FIFO
+// that delivers after a few steps, so that the STALE protocol is exercised by the CPU tests too)
+#ifndef __CUDA_ARCH__
+struct HostAsync { uint32_t addr[64], val[64], due[64]; unsigned n, now; };
+extern thread_local HostAsync g_host_async;
+constexpr unsigned HOST_ASYNC_LATENCY = 5;
+inline void host_async_deliver(bool all) {
+  HostAsync &q = g_host_async;
+  unsigned k = 0;
+  for (unsigned i = 0; i < q.n; i++) {
+    if (all || q.due[i] <= q.now) memcpy(g_host_smem + q.addr[i], &q.val[i], 4);
+    else { q.addr[k] = q.addr[i]; q.val[k] = q.val[i]; q.due[k] = q.due[i]; k++; }
+  }
+  q.n = k;
+}
+#endif
+FQ_HD void sm_async_ld32(uint32_t a, const uint32_t *p) {
+#ifdef __CUDA_ARCH__
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(a), "l"(p));
+#else
+  HostAsync &q = g_host_async;
+  if (q.n == 64) host_async_deliver(true);
+  q.addr[q.n] = a; q.val[q.n] = *p; q.due[q.n] = q.now + HOST_ASYNC_LATENCY; q.n++;
+#endif
+}
+FQ_HD void sm_async_wait_all() {  // every async copy of this thread has landed
+#ifdef __CUDA_ARCH__
+  asm volatile("cp.async.wait_all;" ::: "memory");
+#else
+  host_async_deliver(true);
+#endif
+}
+FQ_HD void sm_async_tick() {  // host only: one decoding step of time passes
+#ifndef __CUDA_ARCH__
+  g_host_async.now++;
+  host_async_deliver(false);
+#endif
+}
+// S[a] holds a STALE marker: its refresh is in flight.  Poll the slot -- the wait then ends when
+// THIS copy lands (it was issued some steps ago), whereas cp.async.wait_all waits for the
+// youngest copy of the whole warp, a full L2 round trip.  Bounded: falls back to the wait.
+template <uint32_t STALE_BIT>
+FQ_HD uint32_t sm_resolve_stale(uint32_t a) {
+#ifdef __CUDA_ARCH__
+  for (int k = 0; k < 64; k++) {
+    const uint32_t w = sm_ld32(a);
+    if (!(w & STALE_BIT)) return w;
+  }
+#endif
+  sm_async_wait_all();
+  return sm_ld32(a);
+}
 FQ_HD unsigned hb32(unsigned v) {
 #ifdef __CUDA_ARCH__
   return 31u - (unsigned)__clz((int)v);
@@ -143,6 +200,13 @@ FQ_HD uint32_t fshl(uint32_t lo, uint32_t hi, unsigned s) {  // (hi:lo << s) >> 
   if (s == 0) return hi;
   if (s >= 32) return lo;
   return (hi << s) | (lo >> (32 - s));
+#endif
+}
+FQ_HD bool warp_any(bool p) {
+#ifdef __CUDA_ARCH__
+  return __any_sync(0xffffffffu, p) != 0;
+#else
+  return p;
 #endif
 }
 FQ_HD uint32_t warp_min(uint32_t v) {
@@ -178,6 +242,9 @@ struct BitReader {
     if (pidx >= 0 && 2 * pidx + 1 <= last_word) {
       const unsigned sa = (unsigned)__cvta_generic_to_shared(const_cast<uint32_t *>(slot));
       asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(w + 2 * pidx) : "memory");
+      // own group: the refill that consumes the pair waits for the committed groups only, not
+      // for the table refreshes issued since (those stay uncommitted until the next prefetch)
+      asm volatile("cp.async.commit_group;\n" ::: "memory");
     } else {
       slot[0] = load_word(2 * pidx);
       slot[1] = load_word(2 * pidx + 1);
@@ -229,7 +296,7 @@ struct BitReader {
 #ifdef __CUDA_ARCH__
     const int pidx = wq >> 1;
     if (wq & 1) {  // first touch of pair pidx (copy issued two refills ago); the other slot is free
-      asm volatile("cp.async.wait_all;\n" ::: "memory");
+      asm volatile("cp.async.wait_group 0;\n" ::: "memory");
       nxw = ring[((pidx & 1) << 1) + 1];
       prefetch_pair(pidx - 1);
     } else {
@@ -249,6 +316,16 @@ struct BitReader {
     if (avail <= 32) refill();
     return v;
   }
+  // the same without the refill: the caller refills before its next read when avail <= 32
+  // (the hot loops fold that test into their single "anything unusual" branch)
+  FQ_HD unsigned read_nr(unsigned nb) {
+    const unsigned v = fshl(hi, 0u, nb);
+    hi = fshl(lo, hi, nb);
+    lo <<= nb;
+    avail -= (int)nb;
+    return v;
+  }
+  FQ_HD bool low() const { return avail <= 32; }
   FQ_HD long long position() const { return 32ll * (wq + 2) + avail; }  // P
   FQ_HD bool finished() const { return position() == floor_; }            // BIT_endOfDStream
 };
@@ -274,14 +351,14 @@ struct StreamArgs {
   bool live;                 // false: idle lane (takes part in the warp votes only)
 };
 
-constexpr int PEND = 8;  // pending refresh slots (software pipeline depth of the table fetch)
+constexpr int UNROLL = 4;  // symbols per loop trip
 
 // ---------------------------------------------------------------------------
 // Sequence.  Shared memory: S = 256 words at sb (1 KB aligned), the four
-// homopolymer tables at ht (4 x 2048 words), one scratch word at scratch.
+// homopolymer tables at ht (4 x 2048 words).
 // Returns true when the stream was consumed exactly.
 // ---------------------------------------------------------------------------
-FQ_HD bool decode_seq_stream(const StreamArgs &c, uint32_t sb, uint32_t ht, uint32_t scratch) {
+FQ_HD bool decode_seq_stream(const StreamArgs &c, uint32_t sb, uint32_t ht) {
   BitReader br;
   bool ok = true;
   unsigned rr = 0;
@@ -309,29 +386,26 @@ FQ_HD bool decode_seq_stream(const StreamArgs &c, uint32_t sb, uint32_t ht, uint
   if (rr > 1) nxt = load_meta(c.readlens, c.hdr_lens, c.recscan, c.rec0 + rr - 2);
   char *dst = c.out + (cur.scan - scan0) + cur.hl + 1;
   unsigned i = 0;
-  uint32_t pval[PEND], paddr[PEND];
-#pragma unroll
-  for (int u = 0; u < PEND; u++) { pval[u] = 0; paddr[u] = scratch; }
   const uint32_t a_init = sb + SEQ_INIT_CTX * 4;
   uint32_t a = a_init, W = sm_ld32(a);
   uint32_t T = sb | ((a >> 2) & 0xFCu);  // next S address without the symbol bits
-  auto drain = [&]() {
-#pragma unroll
-    for (int u = 0; u < PEND; u++) { sm_st32(paddr[u], pval[u]); paddr[u] = scratch; }
-  };
   // W table biased so that ((a << 9) + ns) indexes it directly (a = sb + ctx * 4, sb < 2^18)
   const uint32_t *wadj = c.wtab - ((size_t)sb << (TAB_LOG - 2));
-  // one symbol; u = pending slot of this step
-  auto step = [&](int u, char *o) {
-    sm_st32(a, SW_STALE);                // (before the retire: slot u may hold this very context)
-    sm_st32(paddr[u], pval[u]);          // retire the refresh issued PEND symbols ago
+  // One symbol.  A taken branch costs ~25 cycles of fixed latency here (predicate -> BRA ->
+  // BSYNC), so the common case has exactly one: everything unusual -- refill due, context
+  // STALE, homopolymer context -- hides behind a single test.
+  auto step = [&](char *o) {
+    sm_async_tick();
+    // mark the context before the speculative load of the next one (the two may coincide); a
+    // context that is already STALE keeps its marker: its refresh may land at any moment
+    if (!(W & SW_STALE)) sm_st32(a, SW_STALE);
     uint32_t an = T | (W & 0x300u);      // ctx' = (ctx >> 2) + (sym << 6), as a word address
     uint32_t Wn = sm_ld32(an);           // speculative: W may still turn out to be STALE
-    if (W & SW_SPECIAL) {
-      if (W & SW_STALE) {
+    if (((W & SW_SPECIAL) != 0) | br.low()) {
+      if (br.low()) br.refill();
+      if (W & SW_STALE) {                // refresh in flight: wait for it and start over
         DEC2_COUNT(0);
-        drain();
-        W = sm_ld32(a);
+        W = sm_resolve_stale<SW_STALE>(a);
         sm_st32(a, SW_STALE);
         an = T | (W & 0x300u);
         Wn = sm_ld32(an);
@@ -339,11 +413,10 @@ FQ_HD bool decode_seq_stream(const StreamArgs &c, uint32_t sb, uint32_t ht, uint
       if (W & SW_INLINE) {               // homopolymer context: table in shared memory
         DEC2_COUNT(1);
         *o = (char)(W & 0xFFu);
-        const unsigned ns = ((W >> 16) & 0x7FFu) + br.read((W >> 12) & 15u);
+        const unsigned ns = ((W >> 16) & 0x7FFu) + br.read_nr((W >> 12) & 15u);
         const uint32_t W2 = sm_ld32(ht + (((W >> 27) & 3u) << (TAB_LOG + 2)) + ns * 4);
         sm_st32(a, W2);
         if (an == a) Wn = W2;
-        paddr[u] = scratch;
         T = sb | ((an >> 2) & 0xFCu);
         a = an;
         W = Wn;
@@ -351,13 +424,65 @@ FQ_HD bool decode_seq_stream(const StreamArgs &c, uint32_t sb, uint32_t ht, uint
       }
     }
     *o = (char)(W & 0xFFu);
-    const unsigned ns = ((W >> 16) & 0x7FFu) + br.read((W >> 12) & 15u);
-    pval[u] = gl_ld32(wadj + ((a << (TAB_LOG - 2)) + ns));
-    paddr[u] = a;
+    const unsigned ns = ((W >> 16) & 0x7FFu) + br.read_nr((W >> 12) & 15u);
+    sm_async_ld32(a, wadj + ((a << (TAB_LOG - 2)) + ns));  // S[a] <- cell of the new state, when it arrives
     T = sb | ((an >> 2) & 0xFCu);
     a = an;
     W = Wn;
   };
+  // Four symbols at once.  The contexts and cells of the four symbols are chained through
+  // shared-memory loads WITHOUT side effects, then validated in one go -- no special cell, no
+  // context twice among them (a later load must not see an unmarked earlier context), enough bits
+  // in the window -- and only then committed.  Straight-line code lets the in-order pipeline
+  // overlap the four dependent loads with the bit arithmetic; an invalid block is redone by
+  // step(), which takes every case.
+  auto block = [&](char *o) {
+    if (br.low()) br.refill();
+    const uint32_t a0 = a, W0 = W;
+    const uint32_t a1 = T | (W0 & 0x300u);
+    const uint32_t W1 = sm_ld32(a1);
+    const uint32_t a2 = sb | ((a1 >> 2) & 0xFCu) | (W1 & 0x300u);
+    const uint32_t W2 = sm_ld32(a2);
+    const uint32_t a3 = sb | ((a2 >> 2) & 0xFCu) | (W2 & 0x300u);
+    const uint32_t W3 = sm_ld32(a3);
+    const uint32_t a4 = sb | ((a3 >> 2) & 0xFCu) | (W3 & 0x300u);
+    const uint32_t W4 = sm_ld32(a4);
+    // bit reads on a copy of the window
+    uint32_t hi = br.hi, lo = br.lo;
+    const unsigned n0 = (W0 >> 12) & 15u, n1 = (W1 >> 12) & 15u, n2 = (W2 >> 12) & 15u, n3 = (W3 >> 12) & 15u;
+    const unsigned v0 = fshl(hi, 0u, n0); hi = fshl(lo, hi, n0); lo <<= n0;
+    const unsigned v1 = fshl(hi, 0u, n1); hi = fshl(lo, hi, n1); lo <<= n1;
+    const unsigned v2 = fshl(hi, 0u, n2); hi = fshl(lo, hi, n2); lo <<= n2;
+    const unsigned v3 = fshl(hi, 0u, n3); hi = fshl(lo, hi, n3); lo <<= n3;
+    const int avail = br.avail - (int)(n0 + n1 + n2 + n3);
+    const bool bad = (((W0 | W1 | W2 | W3) & SW_SPECIAL) != 0) | (avail < 0) | (a2 == a0) | (a3 == a0) | (a3 == a1) |
+                     (a4 == a0) | (a4 == a1) | (a4 == a2);
+    if (bad) {
+      DEC2_COUNT(8);
+#pragma unroll
+      for (int u = 0; u < UNROLL; u++) step(o + u);
+      return;
+    }
+    DEC2_COUNT(9);
+    sm_async_tick(); sm_async_tick(); sm_async_tick(); sm_async_tick();
+    sm_st32(a0, SW_STALE);
+    sm_st32(a1, SW_STALE);
+    sm_st32(a2, SW_STALE);
+    sm_st32(a3, SW_STALE);
+    o[0] = (char)(W0 & 0xFFu);
+    o[1] = (char)(W1 & 0xFFu);
+    o[2] = (char)(W2 & 0xFFu);
+    o[3] = (char)(W3 & 0xFFu);
+    sm_async_ld32(a0, wadj + ((a0 << (TAB_LOG - 2)) + ((W0 >> 16) & 0x7FFu) + v0));
+    sm_async_ld32(a1, wadj + ((a1 << (TAB_LOG - 2)) + ((W1 >> 16) & 0x7FFu) + v1));
+    sm_async_ld32(a2, wadj + ((a2 << (TAB_LOG - 2)) + ((W2 >> 16) & 0x7FFu) + v2));
+    sm_async_ld32(a3, wadj + ((a3 << (TAB_LOG - 2)) + ((W3 >> 16) & 0x7FFu) + v3));
+    br.hi = hi; br.lo = lo; br.avail = avail;
+    a = a4;
+    W = W4;
+    T = sb | ((a4 >> 2) & 0xFCu);
+  };
+  static_assert(UNROLL == 4, "block() is written for four symbols");
   for (;;) {
     // uniform trip count: symbols until the first lane of the warp reaches a record end
     const unsigned n = warp_min(rr > 0 ? cur.L - i : 0xFFFFFFFFu);
@@ -365,13 +490,10 @@ FQ_HD bool decode_seq_stream(const StreamArgs &c, uint32_t sb, uint32_t ht, uint
     if (rr > 0) {
       char *o = dst + i;
       unsigned t = n;
-      for (; t >= PEND; t -= PEND, o += PEND) {
+      for (; t >= UNROLL; t -= UNROLL, o += UNROLL) block(o);
 #pragma unroll
-        for (int u = 0; u < PEND; u++) step(u, o + u);
-      }
-#pragma unroll
-      for (int u = 0; u < PEND - 1; u++)
-        if ((unsigned)u < t) step(u, o + u);
+      for (int u = 0; u < UNROLL - 1; u++)
+        if ((unsigned)u < t) step(o + u);
       i += n;
       if (i >= cur.L) {  // record done: records n-1 .. 0 (src/workspace.cpp:84-87)
         --rr;
@@ -394,14 +516,14 @@ FQ_HD bool decode_seq_stream(const StreamArgs &c, uint32_t sb, uint32_t ht, uint
 // tables zt (n_z x 2048 u16: (k << 11) | state after k zero-bit steps) at zt_a;
 // the run contexts' W tables at hz_a (n_z x 2048 words); zc (n_z words: output
 // char of run slot j) at zc_a.  Per stream: S = 2 * |V| rows of 64 words at sb
-// (256-byte aligned), one scratch word.  V = {0} + the quality values that occur
+// (256-byte aligned).  V = {0} + the quality values that occur
 // in a context of the sample: every context made of values in V has a dense id
 // (row = rank(max) * 2 + eq, column = rank(q)).  Contexts outside the dense set
 // keep their state in `cold` (global, u16[8192]) and decode through dtab_fix.
 // ---------------------------------------------------------------------------
 struct QualShared { uint32_t rk_a, zt_a, hz_a, zc_a; };
 
-FQ_HD bool decode_qual_stream(const StreamArgs &c, const QualShared &q, uint32_t sb, uint32_t scratch,
+FQ_HD bool decode_qual_stream(const StreamArgs &c, const QualShared &q, uint32_t sb,
                               const uint32_t *dtab_fix, const uint16_t *cid /*[8192]: run slot + 1 in bits 13..15*/,
                               uint16_t *cold) {
   BitReader br;
@@ -440,19 +562,12 @@ FQ_HD bool decode_qual_stream(const StreamArgs &c, const QualShared &q, uint32_t
   if (rr > 1) nxt = load_meta(c.readlens, c.hdr_lens, c.recscan, c.rec0 + rr - 2);
   char *dst = c.out + (cur.scan - scan0) + cur.hl + 1 + cur.L + 3;
   unsigned i = 0;
-  uint32_t pval[PEND], paddr[PEND];
-#pragma unroll
-  for (int u = 0; u < PEND; u++) { pval[u] = 0; paddr[u] = scratch; }
   // record start: the three previous symbols are 0 (rank 0): row (max 0, eq 1), column 0
   const uint32_t row_init = sb + QROW_BYTES;
-  uint32_t a = row_init, W = sm_ld32(a);
+  uint32_t a = row_init, W = QW_DONE;
   uint32_t R1 = row_init;   // row of the NEXT symbol's context (from the two symbols before this one)
   uint32_t r4p = 0;         // rank * 4 of the previous symbol
-  unsigned lim = 0;         // end of the current trip; 0 = leave the fast loop for the slow path
-  auto drain = [&]() {
-#pragma unroll
-    for (int u = 0; u < PEND; u++) { sm_st32(paddr[u], pval[u]); paddr[u] = scratch; }
-  };
+  bool cold_pending = false;  // a symbol outside V was decoded: the slow path continues after this block
   const uint32_t *wadj = c.wtab - ((size_t)sb << (TAB_LOG - 2));  // ((a << 9) + ns) indexes it directly
   auto row_of = [&](uint32_t r4a, uint32_t r4b) -> uint32_t {  // row of (max, eq) of two symbols, ranks * 4
     const uint32_t mx4 = r4a > r4b ? r4a : r4b;
@@ -462,7 +577,7 @@ FQ_HD bool decode_qual_stream(const StreamArgs &c, const QualShared &q, uint32_t
   // explicit q values, blocking table loads, until the record ends or the last three
   // symbols are in V again.  o = the record's quality slot, t = next position, rem = record length.
   auto cold_run = [&](char *o, unsigned t, unsigned rem) -> unsigned {
-    drain();
+    sm_async_wait_all();
     unsigned qa = (unsigned)(unsigned char)o[t - 1] - QUAL_CHAR0;
     unsigned qb = t >= 2 ? (unsigned)(unsigned char)o[t - 2] - QUAL_CHAR0 : 0u;
     unsigned qc = t >= 3 ? (unsigned)(unsigned char)o[t - 3] - QUAL_CHAR0 : 0u;
@@ -504,19 +619,21 @@ FQ_HD bool decode_qual_stream(const StreamArgs &c, const QualShared &q, uint32_t
       qc = qb; qb = qa; qa = sym;
     }
   };
-  // one decoding event at position t of the record (rem symbols long): a symbol, a zero-bit
-  // run, or a slow-path stretch; returns the new position.  u = pending slot of this step.
-  auto step = [&](int u, char *o, unsigned t, unsigned rem) -> unsigned {
-    sm_st32(a, QW_STALE);                // (before the retire: slot u may hold this very context)
-    sm_st32(paddr[u], pval[u]);          // retire the refresh issued PEND steps ago
-    paddr[u] = scratch;
+  // One decoding event at position t of the record (rem symbols long): a symbol or a zero-bit
+  // run; returns the new position.  As in the sequence decoder the common case has a single
+  // branch; behind it: lane idle in this trip (DONE), refill due, STALE, run context, symbol
+  // outside V.  When the lane reaches `stop` (or must hand over to the slow path) W becomes DONE.
+  auto step = [&](char *o, unsigned t, unsigned rem, unsigned stop) -> unsigned {
+    sm_async_tick();
+    if (!(W & (QW_STALE | QW_DONE))) sm_st32(a, QW_STALE);  // see decode_seq_stream
     uint32_t an = R1 | (W & 0xFCu);
     uint32_t Wn = sm_ld32(an);           // speculative
-    if (W & QW_SPECIAL) {
+    if (((W & QW_SPECIAL) != 0) | br.low()) {
+      if (W & QW_DONE) return t;
+      if (br.low()) br.refill();
       if (W & QW_STALE) {
         DEC2_COUNT(2);
-        drain();
-        W = sm_ld32(a);
+        W = sm_resolve_stale<QW_STALE>(a);
         sm_st32(a, QW_STALE);
         an = R1 | (W & 0xFCu);
         Wn = sm_ld32(an);
@@ -536,61 +653,72 @@ FQ_HD bool decode_qual_stream(const StreamArgs &c, const QualShared &q, uint32_t
           W = make_zent(xs, zs);
           sm_st32(a, W);
           const char dc = (char)sm_ld32(q.zc_a + zs * 4);
-          for (unsigned j = 0; j < kz; j++) o[t + j] = dc;
-          return t + kz;
+          if (t + 15 <= rem) {  // the bytes behind the run are rewritten by the record's later symbols
+#pragma unroll
+            for (unsigned j = 0; j < 15; j++) o[t + j] = dc;
+          } else {
+            for (unsigned j = 0; j < kz; j++) o[t + j] = dc;
+          }
+          t += kz;
+          if (t >= stop) W = QW_DONE;
+          return t;
         }
         // one ordinary step in the run context: cell from the shared table, refreshed inline
         DEC2_COUNT(4);
         const uint32_t cell = sm_ld32(q.hz_a + (zs << (TAB_LOG + 2)) + x * 4);
-        const unsigned ns = ((cell >> 12) & 0x7FFu) + br.read((cell >> 8) & 15u);
-        const uint32_t Wz = make_zent(ns, zs);
-        sm_st32(a, Wz);
+        const unsigned ns = ((cell >> 12) & 0x7FFu) + br.read_nr((cell >> 8) & 15u);
+        sm_st32(a, make_zent(ns, zs));
         an = R1 | (cell & 0xFCu);
         Wn = sm_ld32(an);
         W = cell;
       } else {
-        const unsigned ns = ((W >> 12) & 0x7FFu) + br.read((W >> 8) & 15u);
-        pval[u] = gl_ld32(wadj + ((a << (TAB_LOG - 2)) + ns));
-        paddr[u] = a;
+        const unsigned ns = ((W >> 12) & 0x7FFu) + br.read_nr((W >> 8) & 15u);
+        sm_async_ld32(a, wadj + ((a << (TAB_LOG - 2)) + ns));
       }
       o[t] = (char)((W >> 23) & 0x7Fu);
-      if (W & QW_UNSEEN) {  // leave the unrolled loop: the slow path continues from t + 1
+      const uint32_t r4 = W & 0xFCu;
+      R1 = row_of(r4, r4p);
+      r4p = r4;
+      a = an;
+      if (W & QW_UNSEEN) {  // the slow path takes over from t + 1 (after this block of steps)
         DEC2_COUNT(5);
-        lim = 0;
-        return t + 1;
+        cold_pending = true;
+        W = QW_DONE;
+      } else {
+        W = t + 1 >= stop ? QW_DONE : Wn;
       }
-    } else {
-      const unsigned ns = ((W >> 12) & 0x7FFu) + br.read((W >> 8) & 15u);
-      pval[u] = gl_ld32(wadj + ((a << (TAB_LOG - 2)) + ns));
-      paddr[u] = a;
-      o[t] = (char)((W >> 23) & 0x7Fu);
+      return t + 1;
     }
+    const unsigned ns = ((W >> 12) & 0x7FFu) + br.read_nr((W >> 8) & 15u);
+    sm_async_ld32(a, wadj + ((a << (TAB_LOG - 2)) + ns));
+    o[t] = (char)((W >> 23) & 0x7Fu);
     const uint32_t r4 = W & 0xFCu;
     R1 = row_of(r4, r4p);
     r4p = r4;
     a = an;
-    W = Wn;
+    W = t + 1 >= stop ? QW_DONE : Wn;
     return t + 1;
   };
   for (;;) {
     // uniform trip: every lane decodes until it has passed n symbols (n = symbols left in the
-    // warp's shortest current record); runs may overshoot n but never the lane's own record
+    // warp's shortest current record); runs may overshoot n but never the lane's own record.
+    // Lanes without work carry W = DONE through the same instructions.
     const unsigned n = warp_min(rr > 0 ? cur.L - i : 0xFFFFFFFFu);
     if (n == 0xFFFFFFFFu) break;
-    if (rr > 0) {
-      char *o = dst;                 // positions are absolute inside the record
-      const unsigned rem = cur.L, stop = i + n;
-      unsigned t = i;
-      lim = stop;
-      while (t < stop) {
+    char *o = dst;                       // positions are absolute inside the record
+    const unsigned rem = cur.L, stop = rr > 0 ? i + n : 0u;
+    unsigned t = rr > 0 ? i : 0u;
+    W = rr > 0 ? sm_ld32(a) : QW_DONE;
+    do {
 #pragma unroll
-        for (int u = 0; u < PEND; u++)
-          if (t < lim) t = step(u, o, t, rem);
-        if (lim == 0) {  // a symbol outside V was decoded
-          t = cold_run(o, t, rem);
-          lim = stop;
-        }
+      for (int u = 0; u < UNROLL; u++) t = step(o, t, rem, stop);
+      if (cold_pending) {                // a symbol outside V was decoded
+        cold_pending = false;
+        t = cold_run(o, t, rem);         // back with the last three symbols in V, or at the record end
+        if (t >= stop) W = QW_DONE;
       }
+    } while (warp_any(t < stop));
+    if (rr > 0) {
       i = t;
       if (i >= cur.L) {
         --rr;
@@ -599,7 +727,6 @@ FQ_HD bool decode_qual_stream(const StreamArgs &c, const QualShared &q, uint32_t
         dst = c.out + (cur.scan - scan0) + cur.hl + 1 + cur.L + 3;
         if (rr > 1) nxt = load_meta(c.readlens, c.hdr_lens, c.recscan, c.rec0 + rr - 2);
         a = row_init;
-        W = sm_ld32(a);
         R1 = row_init;
         r4p = 0;
       }

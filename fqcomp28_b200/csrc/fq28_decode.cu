@@ -510,20 +510,20 @@ k_decode_qual(const DecChunk *__restrict__ ch, unsigned n_chunks, unsigned lanes
 
 // ---------------------------------------------------------------------------
 // Decoder v2 (fq28_dec2.cuh): every context caches the cell of its current state
-// in shared memory, the table fetch of the next cell is deferred (8 in flight).
+// in shared memory, the table fetch of the next cell is an async copy into that slot.
 // One thread per stream, `lanes` streams per warp in lockstep (few for small
 // batches: one warp per SM sub-partition is the sweet spot of a latency chain;
 // 32 for big ones).  Shared memory per CTA:
-//   sequence: 4 homopolymer tables (32 KB) | ring | scratch | S (1 KB per stream)
-//   quality : rk | zc | run tables (4 + 8 KB per slot) | ring | scratch | S (|V| * 512 B per stream)
+//   sequence: 4 homopolymer tables (32 KB) | ring | S (1 KB per stream)
+//   quality : rk | zc | run tables (4 + 8 KB per slot) | ring | S (|V| * 512 B per stream)
 // ---------------------------------------------------------------------------
 constexpr unsigned D2_HT_BYTES = 4u * (4u << FIX_LOG);
 __host__ __device__ inline size_t d2_seq_smem(unsigned per_cta) {
-  return D2_HT_BYTES + (size_t)per_cta * 16 + (size_t)per_cta * 4 + 1024 /*alignment slack*/ + (size_t)per_cta * 1024;
+  return D2_HT_BYTES + (size_t)per_cta * 16 + 1024 /*alignment slack*/ + (size_t)per_cta * 1024;
 }
 __host__ __device__ inline size_t d2_qual_fixed(unsigned nz) { return 128 + (size_t)nz * ((2u << FIX_LOG) + (4u << FIX_LOG)); }
 __host__ __device__ inline size_t d2_qual_smem(unsigned per_cta, unsigned nz, unsigned nv) {
-  return d2_qual_fixed(nz) + (size_t)per_cta * 16 + (size_t)per_cta * 4 + 256 + (size_t)per_cta * nv * 2 * dec2::QROW_BYTES;
+  return d2_qual_fixed(nz) + (size_t)per_cta * 16 + 256 /*alignment slack*/ + (size_t)per_cta * nv * 2 * dec2::QROW_BYTES;
 }
 
 __device__ __forceinline__ void d2_args(dec2::StreamArgs &a, const DecChunk &c, bool live, const uint8_t *stream, uint32_t len,
@@ -550,8 +550,8 @@ k_dec2_seq(const DecChunk *__restrict__ ch, unsigned n_chunks, unsigned lanes, c
   }
   __syncthreads();
   const uint32_t base = (uint32_t)__cvta_generic_to_shared(smem_raw);
-  const uint32_t ring0 = base + D2_HT_BYTES, scr0 = ring0 + per_cta * 16;
-  const uint32_t s0 = (scr0 + per_cta * 4 + 1023u) & ~1023u;
+  const uint32_t ring0 = base + D2_HT_BYTES;
+  const uint32_t s0 = (ring0 + per_cta * 16 + 1023u) & ~1023u;
   const unsigned lane = threadIdx.x & 31;
   const unsigned slot = (threadIdx.x >> 5) * lanes + lane;
   const unsigned k = blockIdx.x * per_cta + slot;
@@ -563,7 +563,7 @@ k_dec2_seq(const DecChunk *__restrict__ ch, unsigned n_chunks, unsigned lanes, c
   dec2::StreamArgs a;
   d2_args(a, c, live, arena + c.seq_off, c.seq_len, recscan, readlens, hdr_lens, out, logs, logsuf, wtab,
           smem_raw + (ring0 - base) + sl * 16);
-  const bool ok = dec2::decode_seq_stream(a, s0 + sl * 1024, base, scr0 + sl * 4);
+  const bool ok = dec2::decode_seq_stream(a, s0 + sl * 1024, base);
   if (live && !ok) set_error(st, FQ28_ERR_STREAM, k);  // BIT_endOfDStream, src/fse_common.hpp:141
 }
 
@@ -580,7 +580,7 @@ k_dec2_qual(const DecChunk *__restrict__ ch, unsigned n_chunks, unsigned lanes, 
   dec2::QualShared qs;
   qs.rk_a = base; qs.zc_a = base + 64; qs.zt_a = base + 128; qs.hz_a = qs.zt_a + nz * (2u << FIX_LOG);
   {
-    if (threadIdx.x < 64) smem_raw[threadIdx.x] = qrk[threadIdx.x];
+    for (unsigned i = threadIdx.x; i < 64; i += blockDim.x) smem_raw[i] = qrk[i];  // (a CTA may be one warp)
     const unsigned zc[4] = {zctx.x, zctx.y, zctx.z, zctx.w};
     for (unsigned j = 0; j < nz; j++) {
       const unsigned d = zc[j] & 63u;        // run context = ctx(d, d, d)
@@ -596,8 +596,8 @@ k_dec2_qual(const DecChunk *__restrict__ ch, unsigned n_chunks, unsigned lanes, 
     }
   }
   __syncthreads();
-  const uint32_t ring0 = qs.hz_a + nz * (4u << FIX_LOG), scr0 = ring0 + per_cta * 16;
-  const uint32_t s0 = (scr0 + per_cta * 4 + 255u) & ~255u;
+  const uint32_t ring0 = qs.hz_a + nz * (4u << FIX_LOG);
+  const uint32_t s0 = (ring0 + per_cta * 16 + 255u) & ~255u;
   const unsigned s_bytes = nv * 2 * dec2::QROW_BYTES;
   const unsigned lane = threadIdx.x & 31;
   const unsigned slot = (threadIdx.x >> 5) * lanes + lane;
@@ -610,7 +610,7 @@ k_dec2_qual(const DecChunk *__restrict__ ch, unsigned n_chunks, unsigned lanes, 
   dec2::StreamArgs a;
   d2_args(a, c, live, arena + c.qual_off, c.qual_len, recscan, readlens, hdr_lens, out, logs, logsuf, wtab,
           smem_raw + (ring0 - base) + sl * 16);
-  const bool ok = dec2::decode_qual_stream(a, qs, s0 + sl * s_bytes, scr0 + sl * 4, dtab_fix, cid,
+  const bool ok = dec2::decode_qual_stream(a, qs, s0 + sl * s_bytes, dtab_fix, cid,
                                           cold_states + (size_t)(live ? k : 0) * QUAL_N);
   if (live && !ok) set_error(st, FQ28_ERR_STREAM, k);
 }

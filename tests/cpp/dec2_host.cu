@@ -18,7 +18,8 @@
 
 namespace fq28 { namespace dec2 {
 thread_local uint8_t *g_host_smem = nullptr;
-thread_local unsigned long long g_stats[8];
+thread_local unsigned long long g_stats[12];
+thread_local HostAsync g_host_async;
 } }
 using namespace fq28::dec2;
 
@@ -57,9 +58,10 @@ extern "C" {
 
 // event counters since the last call: [0] seq drains, [1] seq inline refreshes, [2] qual drains,
 // [3] zero-bit runs, [4] single steps in a run context, [5] slow-path entries, [6] slow-path
-// symbols in dense contexts, [7] slow-path symbols in contexts outside the dense set
+// symbols in dense contexts, [7] slow-path symbols in contexts outside the dense set,
+// [8] sequence blocks redone step by step, [9] sequence blocks committed at once
 void dec2h_stats(unsigned long long *out) {
-  for (int i = 0; i < 8; i++) { out[i] = g_stats[i]; g_stats[i] = 0; }
+  for (int i = 0; i < 12; i++) { out[i] = g_stats[i]; g_stats[i] = 0; }
 }
 
 // ft = FreqTable<256,4> image.  The stream is copied to `misalign` bytes past an 8-byte boundary.
@@ -74,8 +76,8 @@ int dec2h_seq(const uint8_t *ft, const uint8_t *stream, uint32_t len, unsigned m
     for (unsigned u = 0; u < (1u << logs[c]); u++)
       wtab[((size_t)c << TAB_LOG) + u] = make_w_seq(t.dtab_fix[((size_t)c << TAB_LOG) + u], c);
   // shared memory image: 4 homopolymer tables | S | scratch
-  const uint32_t ht = 0, sb = 4 * (4u << TAB_LOG), scratch = sb + 1024;
-  std::vector<uint8_t> smem(scratch + 64, 0);
+  const uint32_t ht = 0, sb = 4 * (4u << TAB_LOG);
+  std::vector<uint8_t> smem(sb + 1024 + 64, 0);
   for (unsigned j = 0; j < 4; j++)
     memcpy(&smem[ht + j * (4u << TAB_LOG)], &wtab[(size_t)(j * 0x55u) << TAB_LOG], 4u << TAB_LOG);
   g_host_smem = smem.data();
@@ -85,7 +87,8 @@ int dec2h_seq(const uint8_t *ft, const uint8_t *stream, uint32_t len, unsigned m
   StreamArgs a;
   std::vector<uint32_t> recscan;
   fill_args(a, src, len, readlens, hdr_lens, n_rec, recscan, out, t, wtab.data());
-  const bool ok = decode_seq_stream(a, sb, ht, scratch);
+  g_host_async = HostAsync();
+  const bool ok = decode_seq_stream(a, sb, ht);
   g_host_smem = nullptr;
   return ok ? 0 : -8;
 }
@@ -136,8 +139,7 @@ int dec2h_qual(const uint8_t *ft, const uint8_t *stream, uint32_t len, unsigned 
   // shared memory image: rk | zc | zt | hz | S | scratch
   const uint32_t rk_a = 0, zc_a = 64, zt_a = 128, hz_a = zt_a + nz * (2u << TAB_LOG);
   const uint32_t sb = (hz_a + nz * (4u << TAB_LOG) + 255) & ~255u;
-  const uint32_t scratch = sb + n_dense * 4;
-  std::vector<uint8_t> smem(scratch + 64, 0);
+  std::vector<uint8_t> smem(sb + n_dense * 4 + 64, 0);
   memcpy(&smem[rk_a], rk, 64);
   for (unsigned j = 0; j < nz; j++) {
     const unsigned d = zsym[j], cx = qual_ctx13(d, d, d), T = 1u << logs[cx];
@@ -166,7 +168,8 @@ int dec2h_qual(const uint8_t *ft, const uint8_t *stream, uint32_t len, unsigned 
   std::vector<uint32_t> recscan;
   fill_args(a, src, len, readlens, hdr_lens, n_rec, recscan, out, t, wtab.data());
   QualShared qs{rk_a, zt_a, hz_a, zc_a};
-  const bool ok = decode_qual_stream(a, qs, sb, scratch, t.dtab_fix.data(), cid.data(), cold.data());
+  g_host_async = HostAsync();
+  const bool ok = decode_qual_stream(a, qs, sb, t.dtab_fix.data(), cid.data(), cold.data());
   g_host_smem = nullptr;
   if (stats) { stats[0] = nv; stats[1] = nz; }
   return ok ? 0 : -8;
