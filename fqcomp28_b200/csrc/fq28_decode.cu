@@ -744,50 +744,46 @@ int decode_batch(fq28_handle *h, const fq28_dec_arenas *in, const fq28_chunk_inf
   FQ28_LAUNCH_CHECK(h);
   stage_end(h, ST_LAYOUT);
 
-  // the two stream types are independent: quality runs on the side stream
-  FQ28_TRY(side_fork(h));
-  if (!h->cfg.dec_v1) {
-    // Lanes (streams per warp): a stream is one latency chain, and one warp per SM sub-partition
-    // (592 on the GPU) runs it without issue contention; beyond that, lockstep lanes are cheaper
-    // than more warps.  Both stream types run at the same time, hence 2 * n_chunks streams.
-    unsigned lanes = (unsigned)((2 * n_chunks + 591) / 592);
-    lanes = lanes < 1 ? 1 : lanes > 32 ? 32 : lanes;
-    auto shape = [&](unsigned want_lanes, unsigned want_warps, unsigned &l, unsigned &w) {
-      l = want_lanes ? (want_lanes > 32 ? 32 : want_lanes) : lanes;
-      w = want_warps ? (want_warps > 8 ? 8 : want_warps) : 4;
-    };
-    stage_begin(h, ST_DECODE_SEQ);
-    {
-      unsigned l, w;
+  // the two stream types are independent: quality runs on the side stream (FQ28_DEC_SERIAL puts
+  // both on the main stream, one after the other, to time each kernel on its own)
+  cudaStream_t qstream = h->cfg.dec_serial ? h->stream : h->side;
+  if (!h->cfg.dec_serial) FQ28_TRY(side_fork(h));
+  // Lanes (streams per warp) of the v2 kernels: a stream is one latency chain; lockstep lanes
+  // save issue slots but every lane waits for the slowest path taken in its warp
+  unsigned lanes = (unsigned)(((h->cfg.qual_v2 ? 2 : 1) * n_chunks + 1183) / 1184);
+  lanes = lanes < 1 ? 1 : lanes > 32 ? 32 : lanes;
+  auto shape = [&](unsigned want_lanes, unsigned want_warps, unsigned &l, unsigned &w) {
+    l = want_lanes ? (want_lanes > 32 ? 32 : want_lanes) : lanes;
+    w = want_warps ? (want_warps > 8 ? 8 : want_warps) : 4;
+  };
+  stage_begin(h, ST_DECODE_SEQ);
+  if (!h->cfg.seq_v1) {
+    unsigned l, w;
+    size_t smem;
+    if (h->cfg.qual_v2 || h->cfg.dec_serial) {
       shape(h->cfg.seq_lanes, h->cfg.seq_warps, l, w);
       while (d2_seq_smem(l * w) > 200 * 1024 && w > 1) w >>= 1;
-      const unsigned per_cta = l * w;
-      k_dec2_seq<<<(unsigned)((n_chunks + per_cta - 1) / per_cta), w * 32, d2_seq_smem(per_cta), h->stream>>>(
-          ch, (unsigned)n_chunks, l, in->seq, h->seq.wtab, h->seq.logs, h->seq.logsuf, recscan, in->readlens, in->hdr_lens,
-          d_out, h->d_status);
-      FQ28_LAUNCH_CHECK(h);
+      smem = d2_seq_smem(l * w);
+    } else {
+      // Next to the state-table quality decoder the two kernels must not share SMs: measured, the
+      // quality kernel takes 76 ms instead of 37 when sequence CTAs live on its SMs (its DTable
+      // cells are L1 hits only as long as nothing else streams tables through that L1).  So the
+      // sequence CTAs are made fat -- 8 warps and a shared-memory request no other CTA fits
+      // beside -- and sized to cover about 65 of the 148 SMs; quality gets the rest.
+      w = h->cfg.seq_warps ? (h->cfg.seq_warps > 8 ? 8 : h->cfg.seq_warps) : 8;
+      l = (unsigned)((n_chunks + 65 * w - 1) / (65 * w));
+      if (h->cfg.seq_lanes) l = h->cfg.seq_lanes;
+      l = l < 1 ? 1 : l > 32 ? 32 : l;
+      while (d2_seq_smem(l * w) > 220 * 1024 && l > 1) --l;
+      smem = d2_seq_smem(l * w);
+      if (smem < 200 * 1024) smem = 200 * 1024;
     }
-    stage_end(h, ST_DECODE_SEQ);
-    {
-      unsigned l, w;
-      shape(h->cfg.qual_lanes, h->cfg.qual_warps, l, w);
-      const unsigned nz = h->cfg.no_zrun ? 0u : h->qual.h_n_z, nv = h->qual.h_n_v;
-      // the per-stream context arrays (|V| * 512 B) must fit: fewer warps first, then fewer lanes
-      while (d2_qual_smem(l * w, nz, nv) > 200 * 1024 && l * w > 1) {
-        if (w > 1) w >>= 1; else l = (l + 1) / 2;
-      }
-      const unsigned per_cta = l * w;
-      uint4 zctx = make_uint4(h->qual.h_zctx[0], h->qual.h_zctx[1], h->qual.h_zctx[2], h->qual.h_zctx[3]);
-      side_stage_begin(h, ST_DECODE_QUAL);
-      k_dec2_qual<<<(unsigned)((n_chunks + per_cta - 1) / per_cta), w * 32, d2_qual_smem(per_cta, nz, nv), h->side>>>(
-          ch, (unsigned)n_chunks, l, in->qual, h->qual.wtab, h->qual.logs, h->qual.logsuf, h->qual.dtab_fix, h->qual.cid,
-          h->qual.qrk, nv, h->qual.zrun, nz, zctx, h->dec_cold.as<uint16_t>(), recscan, in->readlens, in->hdr_lens, d_out,
-          h->d_status);
-      FQ28_LAUNCH_CHECK(h);
-      side_stage_end(h, ST_DECODE_QUAL);
-    }
+    const unsigned per_cta = l * w;
+    k_dec2_seq<<<(unsigned)((n_chunks + per_cta - 1) / per_cta), w * 32, smem, h->stream>>>(
+        ch, (unsigned)n_chunks, l, in->seq, h->seq.wtab, h->seq.logs, h->seq.logsuf, recscan, in->readlens, in->hdr_lens,
+        d_out, h->d_status);
+    FQ28_LAUNCH_CHECK(h);
   } else {
-  stage_begin(h, ST_DECODE_SEQ);
   {
     // streams per CTA (= per SM): few per warp keeps the homopolymer path from
     // stalling the other streams of a warp; big batches fill 32 slots per SM
@@ -809,7 +805,28 @@ int decode_batch(fq28_handle *h, const fq28_dec_arenas *in, const fq28_chunk_inf
         recscan, in->readlens, in->hdr_lens, d_out, h->d_status);
     FQ28_LAUNCH_CHECK(h);
   }
+  }
   stage_end(h, ST_DECODE_SEQ);
+  if (h->cfg.qual_v2) {
+    {
+      unsigned l, w;
+      shape(h->cfg.qual_lanes, h->cfg.qual_warps, l, w);
+      const unsigned nz = h->cfg.no_zrun ? 0u : h->qual.h_n_z, nv = h->qual.h_n_v;
+      // the per-stream context arrays (|V| * 512 B) must fit: fewer warps first, then fewer lanes
+      while (d2_qual_smem(l * w, nz, nv) > 200 * 1024 && l * w > 1) {
+        if (w > 1) w >>= 1; else l = (l + 1) / 2;
+      }
+      const unsigned per_cta = l * w;
+      uint4 zctx = make_uint4(h->qual.h_zctx[0], h->qual.h_zctx[1], h->qual.h_zctx[2], h->qual.h_zctx[3]);
+      const int qslot = stage_open(h, ST_DECODE_QUAL, qstream);
+      k_dec2_qual<<<(unsigned)((n_chunks + per_cta - 1) / per_cta), w * 32, d2_qual_smem(per_cta, nz, nv), qstream>>>(
+          ch, (unsigned)n_chunks, l, in->qual, h->qual.wtab, h->qual.logs, h->qual.logsuf, h->qual.dtab_fix, h->qual.cid,
+          h->qual.qrk, nv, h->qual.zrun, nz, zctx, h->dec_cold.as<uint16_t>(), recscan, in->readlens, in->hdr_lens, d_out,
+          h->d_status);
+      FQ28_LAUNCH_CHECK(h);
+      stage_close(h, qslot, qstream);
+    }
+  } else {
   {
     const unsigned nt = h->qual.h_n_touched;
     // Streams per warp.  The DTable cells come through L1/L2, so the streams of
@@ -849,15 +866,15 @@ int decode_batch(fq28_handle *h, const fq28_dec_arenas *in, const fq28_chunk_inf
         h->qual_carve_set = pct;
       }
     }
-    side_stage_begin(h, ST_DECODE_QUAL);
-    k_decode_qual<<<(unsigned)((n_chunks + q_per_cta - 1) / q_per_cta), q_warps * 32, smem, h->side>>>(
+    const int qslot = stage_open(h, ST_DECODE_QUAL, qstream);
+    k_decode_qual<<<(unsigned)((n_chunks + q_per_cta - 1) / q_per_cta), q_warps * 32, smem, qstream>>>(
         ch, (unsigned)n_chunks, lanes, in->qual, h->qual.logs, h->qual.logsuf, h->qual.dtab_fix, h->qual.cid, nt,
         h->qual.zrun, nz, zctx, h->dec_cold.as<uint16_t>(), recscan, in->readlens, in->hdr_lens, d_out, h->d_status);
     FQ28_LAUNCH_CHECK(h);
-    side_stage_end(h, ST_DECODE_QUAL);
+    stage_close(h, qslot, qstream);
   }
-  }
-  FQ28_TRY(side_join(h));
+    }
+  if (!h->cfg.dec_serial) FQ28_TRY(side_join(h));
 
   stage_begin(h, ST_NINSERT);
   if (n_rec && in->n_pos_entries) {

@@ -181,7 +181,9 @@ struct fq28_handle {
 
   // policy knobs, read from the environment once at fq28_create (diagnostics)
   struct Cfg {
-    bool dec_v1 = false;           // FQ28_DEC_V1: round-1 decoders (thread per stream over state tables)
+    bool seq_v1 = false;           // FQ28_SEQ_V1 / FQ28_DEC_V1: round-1 sequence decoder (rank-directory tables)
+    bool qual_v2 = false;          // FQ28_QUAL_V2: cached-cell quality decoder (fq28_dec2.cuh) instead of the state-table one
+    bool dec_serial = false;       // FQ28_DEC_SERIAL: the two decode kernels one after the other (per-kernel timing)
     unsigned seq_lanes = 0, seq_warps = 0, qual_lanes = 0, qual_warps = 0;  // 0 = automatic
     int qual_carveout = -2;        // -2 = automatic
     bool no_zrun = false, no_dom = false, no_rankc = false, serial = false, full_overlap = false;
