@@ -113,6 +113,7 @@ SYMBOLS = [
     "fq28_compress_fetch", "fq28_bound_seq", "fq28_bound_qual", "fq28_decompress",
     "fq28_decompress_dev", "fq28_get_ctable", "fq28_get_dtable", "fq28_compress_dev_arenas",
     "fq28_last_timings", "fq28_stage_name", "fq28_tokenize_headers", "fq28_detokenize_headers",
+    "fq28_device_count", "fq28_stage", "fq28_plan", "fq28_plan_dev",
 ]
 
 _lib = None
@@ -149,6 +150,10 @@ def load() -> C.CDLL:
     L.fq28_compress.argtypes = [vp, vp, sz, sz, sz, i32, vp, vp, C.POINTER(EncArenas), C.POINTER(ChunkInfo), sz, C.POINTER(EncSummary)]
     L.fq28_compress_dev.argtypes = [vp, vp, sz, sz, sz, i32, vp, vp, C.POINTER(ChunkInfo), sz, C.POINTER(EncSummary)]
     L.fq28_compress_fetch.argtypes = [vp, C.POINTER(EncArenas)]
+    L.fq28_device_count.argtypes = []
+    L.fq28_stage.argtypes = [vp, vp, sz]
+    L.fq28_plan.argtypes = [vp, vp, sz, sz, i32, C.POINTER(C.c_uint64), psz]
+    L.fq28_plan_dev.argtypes = [vp, vp, sz, sz, i32, C.POINTER(C.c_uint64), psz]
     L.fq28_bound_seq.argtypes = [sz]
     L.fq28_bound_seq.restype = sz
     L.fq28_bound_qual.argtypes = [sz]
@@ -310,6 +315,24 @@ class Handle:
         n = C.c_size_t(0)
         self._ck(self.L.fq28_split(self.h, _ptr(data), data.size, reading_size, int(eof), _ptr(offs), cap, C.byref(n)))
         return offs[: n.value + 1].copy()
+
+    def stage(self, data: np.ndarray | None) -> None:
+        """fq28_stage: start the H2D copy of a host range early (None forgets it)."""
+        if data is None:
+            self._ck(self.L.fq28_stage(self.h, None, 0))
+        else:
+            self._ck(self.L.fq28_stage(self.h, _ptr(data), data.size))
+
+    def plan(self, data: np.ndarray, reading_size: int, eof: bool = True):
+        """fq28_plan: parseRecords + chunk boundary walk only -> (consumed, n_chunks)."""
+        cons, n = C.c_uint64(0), C.c_size_t(0)
+        self._ck(self.L.fq28_plan(self.h, _ptr(data), data.size, reading_size, int(eof), C.byref(cons), C.byref(n)))
+        return cons.value, n.value
+
+    def plan_dev(self, d_fastq: int, n_bytes: int, reading_size: int, eof: bool = True):
+        cons, n = C.c_uint64(0), C.c_size_t(0)
+        self._ck(self.L.fq28_plan_dev(self.h, d_fastq, n_bytes, reading_size, int(eof), C.byref(cons), C.byref(n)))
+        return cons.value, n.value
 
     # ------------------------------------------------------------ tables
     def hist(self, data: np.ndarray, cs: np.ndarray | None = None, cq: np.ndarray | None = None):

@@ -171,7 +171,27 @@ static int ft_image_in(fq28_handle *h, DevTables &t, const void *image) {
 
 static int stage_in(fq28_handle *h, const char *fastq, size_t n_bytes) {
   FQ28_TRY(ensure(h, h->in_fastq, n_bytes + 64));
+  if (h->stage_host && fastq >= h->stage_host && fastq + n_bytes <= h->stage_host + h->stage_bytes) {
+    // already on the device (fq28_stage): move it to the aligned work buffer instead of a second H2D
+    FQ28_CUDA(h, cudaMemcpyAsync(h->in_fastq.p, h->in_raw.as<char>() + (fastq - h->stage_host), n_bytes,
+                                 cudaMemcpyDeviceToDevice, h->stream));
+    return FQ28_OK;
+  }
   FQ28_CUDA(h, cudaMemcpyAsync(h->in_fastq.p, fastq, n_bytes, cudaMemcpyHostToDevice, h->stream));
+  return FQ28_OK;
+}
+
+// the host FreqTable images follow the device tables (one source of truth: norm / logs on the device)
+static int ensure_ft_images(fq28_handle *h) {
+  if (h->ft_img_gen == h->tables_gen && h->ft_img_seq.size() == FQ28_FT_SEQ_BYTES && h->ft_img_qual.size() == FQ28_FT_QUAL_BYTES)
+    return FQ28_OK;
+  if (!h->seq.ready || !h->qual.ready) return fail(h, FQ28_ERR_ARG, "frequency tables not built/loaded");
+  h->ft_img_seq.resize(FQ28_FT_SEQ_BYTES);
+  h->ft_img_qual.resize(FQ28_FT_QUAL_BYTES);
+  FQ28_TRY(ft_image_out(h, h->seq, h->ft_img_seq.data()));
+  FQ28_TRY(ft_image_out(h, h->qual, h->ft_img_qual.data()));
+  FQ28_CUDA(h, cudaStreamSynchronize(h->stream));
+  h->ft_img_gen = h->tables_gen;
   return FQ28_OK;
 }
 
@@ -180,6 +200,11 @@ static int stage_in(fq28_handle *h, const char *fastq, size_t n_bytes) {
 using namespace fq28;
 
 extern "C" {
+
+int fq28_device_count(void) {
+  int n = 0;
+  return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0;
+}
 
 int fq28_create(int device, fq28_handle **out) {
   if (!out) return FQ28_ERR_ARG;
@@ -381,13 +406,14 @@ int fq28_load_tables(fq28_handle *h, const void *ft_seq, const void *ft_qual) {
   stage_reset(h);
   FQ28_TRY(ft_image_in(h, h->seq, ft_seq));
   FQ28_TRY(ft_image_in(h, h->qual, ft_qual));
-  h->ft_img_seq.assign(static_cast<const uint8_t *>(ft_seq), static_cast<const uint8_t *>(ft_seq) + FQ28_FT_SEQ_BYTES);
-  h->ft_img_qual.assign(static_cast<const uint8_t *>(ft_qual), static_cast<const uint8_t *>(ft_qual) + FQ28_FT_QUAL_BYTES);
   stage_begin(h, ST_TABLES);
   FQ28_TRY(tables_from_norm(h, h->seq));
   FQ28_TRY(tables_from_norm(h, h->qual));
   stage_end(h, ST_TABLES);
   FQ28_CUDA(h, cudaStreamSynchronize(h->stream));
+  h->ft_img_seq.assign(static_cast<const uint8_t *>(ft_seq), static_cast<const uint8_t *>(ft_seq) + FQ28_FT_SEQ_BYTES);
+  h->ft_img_qual.assign(static_cast<const uint8_t *>(ft_qual), static_cast<const uint8_t *>(ft_qual) + FQ28_FT_QUAL_BYTES);
+  h->ft_img_gen = h->tables_gen;
   return FQ28_OK;
 }
 
@@ -428,19 +454,59 @@ int fq28_compress_dev(fq28_handle *h, const char *d_fastq, size_t n_bytes, size_
     FQ28_TRY(ft_image_out(h, h->seq, ft_seq_out));
     FQ28_TRY(ft_image_out(h, h->qual, ft_qual_out));
   }
+  const bool planned = sample_bytes == 0 && h->plan.valid && h->plan.d_fastq == d_fastq && h->plan.n_bytes == n_bytes &&
+                       h->plan.reading_size == reading_size && h->plan.eof == (eof != 0);
+  if (!planned) {
+    stage_begin(h, ST_PARSE);
+    FQ28_TRY(parse_slab(h, d_fastq, n_bytes, true));
+    FQ28_TRY(split_slab(h, reading_size, eof != 0, 0));
+    stage_end(h, ST_PARSE);
+  }
+  h->plan.valid = false;
+  return encode_slab(h, infos, infos_cap, summary);
+}
+
+// parseRecords + the chunk boundary walk of one slab, without encoding (src/fastq_io.cpp:23-125).
+// *consumed = where the next slab must start.  The plan is kept: fq28_compress_dev with the same
+// slab / reading size / eof and sample_bytes == 0 then goes straight to the encode.  This is what
+// lets several GPUs share one file: slab i+1 starts at the `consumed` of slab i, which is known
+// after this cheap step, long before slab i is encoded.
+int fq28_plan_dev(fq28_handle *h, const char *d_fastq, size_t n_bytes, size_t reading_size, int eof, uint64_t *consumed,
+                  size_t *n_chunks) {
+  if (!h) return FQ28_ERR_ARG;
+  FQ28_TRY(bind(h));
+  stage_reset(h);
   stage_begin(h, ST_PARSE);
   FQ28_TRY(parse_slab(h, d_fastq, n_bytes, true));
   FQ28_TRY(split_slab(h, reading_size, eof != 0, 0));
   stage_end(h, ST_PARSE);
-  FQ28_TRY(encode_slab(h, infos, infos_cap, summary));
-  if (sample_bytes > 0 && ft_seq_out && ft_qual_out && ft_seq_out != h->ft_img_seq.data()) {
-    // keep the images: a later host-buffer call with sample_bytes == 0 may hand them to the sibling handle
-    h->ft_img_seq.assign(static_cast<const uint8_t *>(ft_seq_out), static_cast<const uint8_t *>(ft_seq_out) + FQ28_FT_SEQ_BYTES);
-    h->ft_img_qual.assign(static_cast<const uint8_t *>(ft_qual_out), static_cast<const uint8_t *>(ft_qual_out) + FQ28_FT_QUAL_BYTES);
-  } else if (sample_bytes > 0 && !(ft_seq_out && ft_qual_out)) {
-    h->ft_img_seq.clear();
-    h->ft_img_qual.clear();
-  }
+  h->plan.valid = true;
+  h->plan.d_fastq = d_fastq; h->plan.n_bytes = n_bytes; h->plan.reading_size = reading_size; h->plan.eof = eof != 0;
+  if (consumed) *consumed = h->h_chunk_byte[h->n_chunks];
+  if (n_chunks) *n_chunks = h->n_chunks;
+  return FQ28_OK;
+}
+
+int fq28_stage(fq28_handle *h, const char *fastq, size_t n_bytes) {
+  if (!h) return FQ28_ERR_ARG;
+  FQ28_TRY(bind(h));
+  h->stage_host = nullptr;
+  h->stage_bytes = 0;
+  if (!fastq || n_bytes == 0) return FQ28_OK;  // forget the staged range
+  FQ28_TRY(ensure(h, h->in_raw, n_bytes + 64));
+  FQ28_CUDA(h, cudaMemcpyAsync(h->in_raw.p, fastq, n_bytes, cudaMemcpyHostToDevice, h->stream));
+  h->stage_host = fastq;
+  h->stage_bytes = n_bytes;
+  return FQ28_OK;
+}
+
+int fq28_plan(fq28_handle *h, const char *fastq, size_t n_bytes, size_t reading_size, int eof, uint64_t *consumed,
+              size_t *n_chunks) {
+  if (!h || !fastq) return FQ28_ERR_ARG;
+  FQ28_TRY(bind(h));
+  FQ28_TRY(stage_in(h, fastq, n_bytes));
+  FQ28_TRY(fq28_plan_dev(h, h->in_fastq.as<char>(), n_bytes, reading_size, eof, consumed, n_chunks));
+  h->plan_host = fastq;
   return FQ28_OK;
 }
 
@@ -501,21 +567,21 @@ static int compress_two_stage(fq28_handle *h, const char *fastq, size_t n_bytes,
   FQ28_CUDA(h, cudaStreamWaitEvent(s->stream, h->ev_copy, 0));
   FQ28_CUDA(h, cudaMemcpyAsync(s->in_raw.p, fastq + h1, n_bytes - h1, cudaMemcpyHostToDevice, s->stream));
   // first half
-  h->ft_img_seq.resize(FQ28_FT_SEQ_BYTES);
-  h->ft_img_qual.resize(FQ28_FT_QUAL_BYTES);
   fq28_enc_summary sa;
-  FQ28_TRY(fq28_compress_dev(h, h->in_fastq.as<char>(), h1, sample_bytes, reading_size, 0,
-                             sample_bytes ? h->ft_img_seq.data() : nullptr, sample_bytes ? h->ft_img_qual.data() : nullptr,
-                             infos, infos_cap, &sa));
+  FQ28_TRY(fq28_compress_dev(h, h->in_fastq.as<char>(), h1, sample_bytes, reading_size, 0, nullptr, nullptr, infos, infos_cap,
+                             &sa));
+  FQ28_TRY(ensure_ft_images(h));  // read back from the device tables unless they are the ones last loaded
   if (sample_bytes) {
     if (ft_seq_out) memcpy(ft_seq_out, h->ft_img_seq.data(), FQ28_FT_SEQ_BYTES);
     if (ft_qual_out) memcpy(ft_qual_out, h->ft_img_qual.data(), FQ28_FT_QUAL_BYTES);
   }
   FQ28_TRY(fetch_async(h, out));  // device->host of the first half overlaps the second half's kernels
-  // second half: same tables, FASTQ = [consumed, n) moved to an aligned buffer
-  if (!(s->seq.ready && s->qual.ready && s->ft_img_seq == h->ft_img_seq && s->ft_img_qual == h->ft_img_qual)) {
+  // second half: same tables (checked by generation, not by what some earlier call left behind),
+  // FASTQ = [consumed, n) moved to an aligned buffer
+  if (!(s->seq.ready && s->qual.ready && h->sibling_gen == h->tables_gen)) {
     const int rc = fq28_load_tables(s, h->ft_img_seq.data(), h->ft_img_qual.data());
     if (rc != FQ28_OK) return fail(h, rc, "second half: %s", fq28_last_error(s));
+    h->sibling_gen = h->tables_gen;
   }
   const size_t ca = (size_t)sa.consumed;
   FQ28_CUDA(h, cudaMemcpyAsync(s->in_fastq.p, h->in_fastq.as<char>() + ca, h1 - ca, cudaMemcpyDeviceToDevice, s->stream));
@@ -569,12 +635,16 @@ int fq28_compress(fq28_handle *h, const char *fastq, size_t n_bytes, size_t samp
     const size_t win = sample_bytes < n_bytes ? sample_bytes : n_bytes;
     size_t h1 = (n_bytes / 2) & ~(size_t)15;
     if (win > h1) h1 = (win + 15) & ~(size_t)15;
-    const bool tables_ok = sample_bytes > 0 || (h->ft_img_seq.size() == FQ28_FT_SEQ_BYTES && h->ft_img_qual.size() == FQ28_FT_QUAL_BYTES);
-    if (n_bytes >= h->cfg.pipe_min_bytes && h1 + ((size_t)16 << 20) <= n_bytes && tables_ok)
+    const bool tables_ok = sample_bytes > 0 || (h->seq.ready && h->qual.ready);
+    const bool planned = h->plan.valid && sample_bytes == 0;  // a planned slab is encoded as planned, in one piece
+    if (n_bytes >= h->cfg.pipe_min_bytes && h1 + ((size_t)16 << 20) <= n_bytes && tables_ok && !planned)
       return compress_two_stage(h, fastq, n_bytes, h1, sample_bytes, reading_size, eof, ft_seq_out, ft_qual_out, out, infos,
                                 infos_cap, summary);
   }
-  FQ28_TRY(stage_in(h, fastq, n_bytes));
+  const bool planned = sample_bytes == 0 && h->plan.valid && h->plan.d_fastq == h->in_fastq.as<char>() &&
+                       h->plan.n_bytes == n_bytes && h->plan.reading_size == reading_size && h->plan.eof == (eof != 0) &&
+                       h->plan_host == fastq;
+  if (!planned) FQ28_TRY(stage_in(h, fastq, n_bytes));
   FQ28_TRY(fq28_compress_dev(h, h->in_fastq.as<char>(), n_bytes, sample_bytes, reading_size, eof, ft_seq_out, ft_qual_out,
                              infos, infos_cap, summary));
   return fq28_compress_fetch(h, out);

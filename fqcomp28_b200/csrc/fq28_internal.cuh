@@ -175,7 +175,20 @@ struct fq28_handle {
   // host-buffer compress of a large slab runs as two overlapped halves: the second half is
   // staged and encoded by a sibling handle (own streams and buffers) while the first one computes
   fq28_handle *sibling = nullptr;
-  fq28::DevBuf in_raw;                   // sibling: second half as copied from the host (before alignment)
+  fq28::DevBuf in_raw;                   // sibling: second half as copied from the host (before alignment);
+                                         // fq28_stage: the speculatively copied host range
+  // fq28_stage: host range [stage_host, stage_host + stage_bytes) already copied (or being copied,
+  // same stream) to in_raw; host-buffer entry points whose input lies inside it skip their H2D
+  const char *stage_host = nullptr;
+  size_t stage_bytes = 0;
+  // fq28_plan / fq28_plan_dev: parse + chunk walk done for exactly this slab; a following
+  // fq28_compress(_dev) with the same arguments and sample_bytes == 0 goes straight to the encode
+  struct Plan { bool valid = false; const char *d_fastq = nullptr; size_t n_bytes = 0, reading_size = 0; int eof = 0; } plan;
+  // generation of the device tables (bumped whenever they are rebuilt) and the generation the
+  // host FreqTable images below were taken from: the sibling handle is only ever loaded from
+  // images that match the current tables
+  uint64_t tables_gen = 0, ft_img_gen = ~0ull, sibling_gen = ~0ull;
+  const char *plan_host = nullptr;       // host slab of the last fq28_plan
   cudaEvent_t ev_copy = nullptr;
   std::vector<uint8_t> ft_img_seq, ft_img_qual;   // host copies of the FreqTable images (for the sibling)
 

@@ -274,6 +274,7 @@ int parse_slab(fq28_handle *h, const char *d_fastq, size_t n_bytes, bool need_sy
   h->n_bytes = n_bytes;
   h->n_lines = h->n_rec = 0;
   h->n_chunks = 0;
+  h->plan.valid = false;  // the record table of any earlier plan is gone
   FQ28_CUDA(h, cudaMemsetAsync(h->d_status, 0, sizeof(DevStatus), h->stream));
   const size_t n_tiles = (n_bytes + NL_TILE - 1) / NL_TILE;
   FQ28_TRY(ensure(h, h->tile_cnt, (n_tiles + 1) * sizeof(uint32_t)));

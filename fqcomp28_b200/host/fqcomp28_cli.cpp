@@ -17,15 +17,19 @@
 //     streams and every integer field are the reference's; only the payload
 //     of the bsc-coded buffers differs, so archives are self-consistent but
 //     not exchangeable with a libbsc build.  Magic "FQ28STOR" marks them.
-// Divergence kept on purpose: n_count / n_pos are written per block, not
-// accumulated across blocks (SURVEY Q2 makes archives quadratic in size).
+// Divergence by default: n_count / n_pos are written per block, not accumulated
+// across blocks (SURVEY Q2 makes archives quadratic in size); --ref-compat writes
+// them the reference's way (what `--threads 1` produces).
+#include <atomic>
 #include <charconv>
 #include <chrono>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
 #include <iostream>
 #include <numeric>
+#include <thread>
 #include <variant>
 
 #include "fqcomp28_gpu.hpp"
@@ -37,8 +41,10 @@ struct Settings {  // src/settings.h:15-39
   std::string mates1, archive;
   unsigned sample_mb = 128, reading_mb = 256, n_threads = 1;
   bool verbose = false;
-  std::size_t slab_mb = 1024;  // FASTQ bytes handed to the GPU per pass
+  std::size_t slab_mb = 1024;  // FASTQ bytes handed to a GPU per pass
   bool host_headers = false;   // tokenise headers on the host instead of the GPU (row N2)
+  unsigned n_gpus = 1, first_gpu = 0;  // --gpus N [--device D]: one worker per GPU, chunk ranges in file order
+  bool ref_compat = false;     // --ref-compat: accumulate n_count / n_pos over blocks like `--threads 1`
 };
 
 // ---------------------------------------------------------------- headers
@@ -504,6 +510,98 @@ static std::size_t printReport(const InputStats &inp, const Archive &ar, std::FI
   return archive_size;
 }
 
+// ---------------------------------------------------------------- pipeline plumbing
+/** results come back from the workers in any order and leave in index order */
+template <class T> class OrderedQueue {
+public:
+  void put(std::size_t index, T &&v) {
+    std::lock_guard<std::mutex> lk(mu_);
+    items_.emplace(index, std::move(v));
+    cv_.notify_all();
+  }
+  /** blocks until item `index` is there (or a worker failed) */
+  bool take(std::size_t index, T &out) {
+    std::unique_lock<std::mutex> lk(mu_);
+    cv_.wait(lk, [&] { return failed_ || items_.count(index); });
+    if (failed_) return false;
+    out = std::move(items_.at(index));
+    items_.erase(index);
+    return true;
+  }
+  void fail() {
+    std::lock_guard<std::mutex> lk(mu_);
+    failed_ = true;
+    cv_.notify_all();
+  }
+
+private:
+  std::mutex mu_;
+  std::condition_variable cv_;
+  std::map<std::size_t, T> items_;
+  bool failed_ = false;
+};
+
+/** counting semaphore: bounds the slabs / batches in flight (host memory) */
+class Tokens {
+public:
+  explicit Tokens(std::size_t n) : n_(n) {}
+  void acquire() {
+    std::unique_lock<std::mutex> lk(mu_);
+    cv_.wait(lk, [&] { return n_ > 0; });
+    --n_;
+  }
+  void release() {
+    std::lock_guard<std::mutex> lk(mu_);
+    ++n_;
+    cv_.notify_one();
+  }
+  void abort() {  // a stage failed: nobody may stay blocked here
+    std::lock_guard<std::mutex> lk(mu_);
+    n_ = static_cast<std::size_t>(1) << 40;
+    cv_.notify_all();
+  }
+
+private:
+  std::mutex mu_;
+  std::condition_variable cv_;
+  std::size_t n_;
+};
+
+static void warnFewChunks(std::size_t n_chunks, std::size_t per_gpu_mb, unsigned reading_mb) {
+  static std::atomic<bool> warned{false};
+  if (n_chunks >= 64 || warned.exchange(true)) return;
+  std::fprintf(stderr,
+               "fqcomp28: note: only %zu chunks per %zu MB GPU pass at -R %u; a chunk is one serial tANS stream per\n"
+               "          stream type (src/fse_common.hpp:77-141), so the GPU decodes chunks in parallel, not symbols.\n"
+               "          Archives written with -R 1..16 decompress one to two orders of magnitude faster here.\n",
+               n_chunks, per_gpu_mb, reading_mb);
+}
+
+/** one context (= one fq28 handle, own streams and buffers) per worker; worker g runs on device
+ *  first_gpu + g, wrapping around the visible devices (two workers on one GPU are legal: they
+ *  just share it, which is also how the pipeline is tested on a single-GPU box) */
+static std::vector<std::shared_ptr<GpuContext>> workerContexts(const Settings &set) {
+  const int visible = fq28_device_count();
+  if (visible <= 0) throw std::runtime_error("no CUDA device (the fqcomp28 GPU path has no CPU fallback)");
+  const unsigned n = std::max(1u, set.n_gpus);
+  if (static_cast<int>(n) > visible)
+    std::fprintf(stderr, "fqcomp28: note: --gpus %u with %d visible device(s): workers share devices\n", n, visible);
+  std::vector<std::shared_ptr<GpuContext>> ctxs;
+  for (unsigned g = 0; g < n; ++g) ctxs.push_back(std::make_shared<GpuContext>(static_cast<int>((set.first_gpu + g) % visible)));
+  return ctxs;
+}
+
+// ---------------------------------------------------------------- c
+/** processReads, src/process.cpp:32-82, as a pipeline over one or several GPUs:
+ *    reader thread  : file -> slab buffers (slab i = [i*B, (i+1)*B + R), so that it holds the start of
+ *                     its first chunk whatever the previous slab consumed)
+ *    worker per GPU : slab i goes to GPU i mod N.  H2D copy (fq28_stage) right away; then, in slab
+ *                     order, the cheap boundary step (fq28_plan: parseRecords + chunk walk) that tells
+ *                     where slab i+1 starts -- the only sequential dependency between GPUs, ~2 ms per
+ *                     GB -- then encodeChunks + header tokenisation, overlapped between GPUs
+ *    this thread    : writes blocks in slab order = chunk order (idx), like `--threads 1`
+ *  The chunk boundaries are those of a single sequential walk, so the archive is byte-identical
+ *  for any number of GPUs. */
 static int compress(const Settings &set) {
   std::ifstream in(set.mates1, std::ios::binary);
   if (!in) throw std::system_error(errno, std::generic_category(), set.mates1);
@@ -511,55 +609,138 @@ static int compress(const Settings &set) {
   const std::size_t file_size = static_cast<std::size_t>(in.tellg());
   in.seekg(0);
   const std::size_t R = static_cast<std::size_t>(set.reading_mb) << 20, S = static_cast<std::size_t>(set.sample_mb) << 20;
-  const std::size_t slab_cap = std::max(set.slab_mb << 20, 2 * R);
-  auto ctx = GpuContext::shared();
+  const std::size_t B = std::max(set.slab_mb << 20, 2 * R);   // nominal slab
+  const unsigned n_gpus = std::max(1u, set.n_gpus);
+  std::vector<std::shared_ptr<GpuContext>> ctxs = workerContexts(set);
   Archive ar;
   ar.fs.open(set.archive, std::ios::binary | std::ios::out | std::ios::trunc);
   if (!ar.fs) throw std::system_error(errno, std::generic_category(), set.archive);
 
-  std::vector<char> slab;
-  std::size_t file_pos = 0, carry = 0;
+  const double t_start = now_s();
+  {  // analyzeDataset (src/prepare.cpp:42-47): first chunk of a reader with reading size S, on the first GPU
+    FastqChunk sample;
+    sample.raw_data.resize(std::min(S, file_size));
+    in.read(sample.raw_data.data(), static_cast<std::streamsize>(sample.raw_data.size()));
+    const std::size_t used = FastqReader::parseRecords(sample, *ctxs[0]);
+    sample.raw_data.resize(used);
+    if (sample.records.empty()) throw std::invalid_argument("no complete FASTQ record in the sample window");
+    ar.setMeta(DatasetMeta(sample, *ctxs[0]));
+    ar.writeMeta();
+  }
+  const std::size_t n_slabs = file_size == 0 ? 0 : std::max<std::size_t>(1, (file_size + B - 1) / B);
+  // slab i is the last one when its buffer reaches the end of the file
+  auto slab_end = [&](std::size_t i) { return std::min(file_size, (i + 1) * B + R); };
+  std::size_t last_slab = 0;
+  while (last_slab + 1 < n_slabs && slab_end(last_slab) < file_size) ++last_slab;
+
+  struct Slab { std::size_t base = 0; std::vector<char> buf; };
+  struct Result {
+    std::vector<CompressedBuffersDst> blocks;
+    std::vector<std::vector<headers::FieldStorage>> fields;
+    double t_gpu = 0, t_hdr = 0;
+  };
+  OrderedQueue<Slab> slabs;
+  OrderedQueue<Result> results;
+  Tokens in_flight(2 * n_gpus + 1);
+  std::exception_ptr error;
+  std::mutex error_mu;
+  std::mutex baton_mu;
+  std::condition_variable baton_cv;
+  bool aborted = false;
+  auto fail = [&](std::exception_ptr e) {
+    { std::lock_guard<std::mutex> lk(error_mu); if (!error) error = e; }
+    slabs.fail();
+    results.fail();
+    in_flight.abort();
+    { std::lock_guard<std::mutex> lk(baton_mu); aborted = true; baton_cv.notify_all(); }
+  };
+
+  std::thread reader([&] {
+    try {
+      std::ifstream f(set.mates1, std::ios::binary);
+      for (std::size_t i = 0; i <= last_slab; ++i) {
+        in_flight.acquire();
+        Slab s;
+        s.base = i * B;
+        s.buf.resize(slab_end(i) - s.base);
+        f.seekg(static_cast<std::streamoff>(s.base));
+        f.read(s.buf.data(), static_cast<std::streamsize>(s.buf.size()));
+        if (!f) throw std::runtime_error("short read from " + set.mates1);
+        slabs.put(i, std::move(s));
+      }
+    } catch (...) { fail(std::current_exception()); }
+  });
+
+  // the baton: start offset of slab i, published by the worker of slab i-1 after its boundary step
+  std::vector<std::size_t> start(last_slab + 2, 0);
+  std::size_t known = 0;  // start[0..known] are valid
+
+  std::vector<std::thread> workers;
+  for (unsigned g = 0; g < n_gpus; ++g) {
+    workers.emplace_back([&, g] {
+      try {
+        GpuContext &ctx = *ctxs[g];
+        CompressionWorkspace wksp(&ar.meta, ctxs[g]);
+        for (std::size_t i = g; i <= last_slab; i += n_gpus) {
+          Slab s;
+          if (!slabs.take(i, s)) return;
+          ctx.check(fq28_stage(ctx.handle(), s.buf.data(), s.buf.size()));  // async H2D, before the start is known
+          std::size_t s_i;
+          {
+            std::unique_lock<std::mutex> lk(baton_mu);
+            baton_cv.wait(lk, [&] { return aborted || known >= i; });
+            if (aborted) return;
+            s_i = start[i];
+          }
+          const bool eof = i == last_slab;
+          if (s_i < s.base || s_i > s.base + s.buf.size()) throw std::runtime_error("slab does not hold its first chunk; raise --slab-mb");
+          const char *p = s.buf.data() + (s_i - s.base);
+          const std::size_t n = s.buf.size() - (s_i - s.base);
+          double t0 = now_s();
+          uint64_t consumed = 0;
+          std::size_t n_chunks = 0;
+          wksp.useTables();
+          ctx.check(fq28_plan(ctx.handle(), p, n, R, eof ? 1 : 0, &consumed, &n_chunks));
+          if (!eof && consumed == 0) throw std::runtime_error("no whole chunk fits the slab; raise --slab-mb");
+          {
+            std::lock_guard<std::mutex> lk(baton_mu);
+            start[i + 1] = s_i + consumed;
+            known = i + 1;
+            baton_cv.notify_all();
+          }
+          Result r;
+          std::size_t consumed2 = 0;
+          wksp.encodeChunks(p, n, R, eof, r.blocks, &consumed2);  // reuses the plan: straight to the encode
+          if (consumed2 != consumed) throw std::runtime_error("boundary step and encode disagree");
+          r.t_gpu = now_s() - t0;
+          t0 = now_s();
+          if (!set.host_headers) headers::tokenizeOnGpu(ctx, r.blocks, ar.fmt, ar.first_fields, r.fields);
+          r.t_hdr = now_s() - t0;
+          ctx.check(fq28_stage(ctx.handle(), nullptr, 0));
+          warnFewChunks(r.blocks.size(), s.buf.size() >> 20, set.reading_mb);
+          results.put(i, std::move(r));
+        }
+      } catch (...) { fail(std::current_exception()); }
+    });
+  }
+
   double t_gpu = 0, t_host = 0;
   uint32_t next_idx = 0;
   std::size_t tot_seq = 0, tot_qual = 0, n_records = 0;
   InputStats istats;
-  bool have_meta = false;
-  std::unique_ptr<CompressionWorkspace> wksp;
-  while (file_pos < file_size || carry) {
-    const std::size_t want = std::min(slab_cap - carry, file_size - file_pos);
-    slab.resize(carry + want);
-    in.read(slab.data() + carry, static_cast<std::streamsize>(want));
-    file_pos += want;
-    const bool eof = file_pos == file_size;
-    if (!have_meta) {
-      // analyzeDataset (src/prepare.cpp:42-47): first chunk of a reader with reading size S
-      if (slab.size() < std::min(S, file_size)) throw std::runtime_error("slab smaller than the sample window; raise --slab-mb");
-      FastqChunk sample;
-      const std::size_t win = std::min(S, slab.size());
-      sample.raw_data.assign(slab.begin(), slab.begin() + static_cast<std::ptrdiff_t>(win));
-      const std::size_t used = FastqReader::parseRecords(sample, *ctx);
-      sample.raw_data.resize(used);
-      if (sample.records.empty()) throw std::invalid_argument("no complete FASTQ record in the sample window");
-      ar.setMeta(DatasetMeta(sample, *ctx));
-      ar.writeMeta();
-      wksp = std::make_unique<CompressionWorkspace>(&ar.meta, ctx);
-      have_meta = true;
-    }
-    std::vector<CompressedBuffersDst> blocks;
-    std::size_t consumed = 0;
-    double t0 = now_s();
-    wksp->encodeChunks(slab.data(), slab.size(), R, eof, blocks, &consumed);
-    t_gpu += now_s() - t0;
-    t0 = now_s();
+  std::vector<std::byte> acc_n_count, acc_n_pos;  // --ref-compat: SURVEY Q2
+  try {
+  for (std::size_t i = 0; i <= last_slab && n_slabs; ++i) {
+    Result r;
+    if (!results.take(i, r)) break;
+    in_flight.release();
+    t_gpu += r.t_gpu;
+    const double t0 = now_s();
     std::vector<headers::FieldStorage> fields;
-    std::vector<std::vector<headers::FieldStorage>> gpu_fields;
-    if (!set.host_headers) headers::tokenizeOnGpu(*ctx, blocks, ar.fmt, ar.first_fields, gpu_fields);
     std::size_t bi = 0;
-    for (auto &cb : blocks) {
+    for (auto &cb : r.blocks) {
       cb.chunk_idx = next_idx++;
       if (set.host_headers) headers::tokenize(cb.raw_headers, cb.header_lengths, ar.fmt, ar.first_fields, fields);
-      ar.writeBlock(cb, set.host_headers ? fields : gpu_fields[bi]);
-      ++bi;
       tot_seq += cb.seq.size();
       tot_qual += cb.qual.size();
       n_records += cb.original_size.n_records;
@@ -567,13 +748,25 @@ static int compress(const Settings &set) {
       istats.header += cb.raw_headers.size();
       for (std::size_t q = 0; q + 1 < cb.readlens.size(); q += 2)  // readlens: u16 LE per record
         istats.seq += std::to_integer<std::size_t>(cb.readlens[q]) | (std::to_integer<std::size_t>(cb.readlens[q + 1]) << 8);
+      if (set.ref_compat) {
+        // src/compressed_buffers.h:58-68: the reference never clears n_count / n_pos between the
+        // chunks of a worker thread, so with --threads 1 block k carries the N data of blocks 0..k
+        acc_n_count.insert(acc_n_count.end(), cb.n_count.begin(), cb.n_count.end());
+        acc_n_pos.insert(acc_n_pos.end(), cb.n_pos.begin(), cb.n_pos.end());
+        cb.n_count = acc_n_count;
+        cb.n_pos = acc_n_pos;
+        cb.original_size.n_count = narrow_cast<uint32_t>(cb.n_count.size());
+        cb.original_size.n_pos = narrow_cast<uint32_t>(cb.n_pos.size());
+      }
+      ar.writeBlock(cb, set.host_headers ? fields : r.fields[bi]);
+      ++bi;
     }
-    t_host += now_s() - t0;
-    if (eof) break;  // a trailing partial record is dropped, like the reference (src/fastq_io.cpp:31-32)
-    if (consumed == 0) throw std::runtime_error("no whole chunk fits the slab; raise --slab-mb");
-    carry = slab.size() - consumed;
-    std::memmove(slab.data(), slab.data() + consumed, carry);
+    t_host += now_s() - t0 + r.t_hdr;
   }
+  } catch (...) { fail(std::current_exception()); }
+  reader.join();
+  for (auto &w : workers) w.join();
+  if (error) std::rethrow_exception(error);
   ar.writeIndex();
   ar.fs.flush();
   {  // src/process.cpp:80-81: flush, then the report; the reference asserts archive_size == file size
@@ -583,15 +776,18 @@ static int compress(const Settings &set) {
     if (archive_size != on_disk)
       std::fprintf(stderr, "warning: report assumes an archive of %zu bytes, the file has %zu\n", archive_size, on_disk);
   }
-  if (set.verbose || true) {
-    std::fprintf(stderr, "fqcomp28 (B200 path): %zu records, %u blocks, seq %zu B, qual %zu B; codec %.3f s, host (headers + archive) %.3f s\n",
-                 n_records, next_idx, tot_seq, tot_qual, t_gpu, t_host);
-  }
+  const double wall = now_s() - t_start;
+  std::fprintf(stderr,
+               "fqcomp28 (B200 path): %zu records, %u blocks, seq %zu B, qual %zu B; %u GPU(s); wall %.3f s = %.0f MB/s "
+               "(codec passes %.3f s summed over GPUs, headers + archive writes %.3f s)\n",
+               n_records, next_idx, tot_seq, tot_qual, n_gpus, wall, file_size / 1e6 / std::max(wall, 1e-9), t_gpu, t_host);
   return 0;
 }
 
 // ---------------------------------------------------------------- d
-/** processArchiveParts, src/process.cpp:84-105 */
+/** processArchiveParts, src/process.cpp:84-105: this thread reads blocks (sorted index) into
+ *  batches, batch j is decoded on GPU j mod N, a writer thread emits the chunks in idx order
+ *  (FastqWriter::writeChunk, src/fastq_io.cpp:131-143). */
 static int decompress(const Settings &set) {
   Archive ar;
   ar.fs.open(set.archive, std::ios::binary | std::ios::in);
@@ -599,37 +795,105 @@ static int decompress(const Settings &set) {
   ar.readHeader();
   std::ofstream out(set.mates1, std::ios::binary | std::ios::trunc);
   if (!out) throw std::system_error(errno, std::generic_category(), set.mates1);
-  auto ctx = GpuContext::shared();
-  DecompressionWorkspace wksp(&ar.meta, ctx);
+  const unsigned n_gpus = std::max(1u, set.n_gpus);
+  std::vector<std::shared_ptr<GpuContext>> ctxs = workerContexts(set);
   const std::size_t batch_bytes = set.slab_mb << 20;
-  std::size_t i = 0;
-  while (i < ar.index.size()) {
+  const double t_start = now_s();
+
+  struct Batch {
     std::vector<CompressedBuffersSrc> srcs;
-    std::vector<headers::FieldStorage> fields;
-    std::vector<std::vector<headers::FieldStorage>> batch_fields;
-    std::vector<std::size_t> batch_records;
-    std::size_t bytes = 0;
-    while (i < ar.index.size() && (srcs.empty() || bytes < batch_bytes)) {
-      srcs.emplace_back();
-      ar.readBlock(ar.index[i++], srcs.back(), fields);
-      auto &cb = srcs.back();
-      if (set.host_headers) {
-        headers::detokenize(fields, ar.fmt, ar.first_fields, cb.original_size.n_records, cb.raw_headers, cb.header_lengths);
-      } else {
-        batch_fields.push_back(fields);
-        batch_records.push_back(cb.original_size.n_records);
-      }
-      bytes += cb.original_size.total;
-    }
-    if (!set.host_headers) headers::detokenizeOnGpu(*ctx, batch_fields, batch_records, ar.fmt, ar.first_fields, srcs);
-    std::vector<CompressedBuffersSrc *> ps;
-    std::vector<FastqChunk> chunks(srcs.size());
-    std::vector<FastqChunk *> pc;
-    for (std::size_t k = 0; k < srcs.size(); ++k) { ps.push_back(&srcs[k]); pc.push_back(&chunks[k]); }
-    wksp.decodeChunks(ps, pc);
-    for (auto &c : chunks) out.write(c.raw_data.data(), static_cast<std::streamsize>(c.raw_data.size()));  // idx order
+    std::vector<std::vector<headers::FieldStorage>> fields;
+    std::vector<std::size_t> records;
+  };
+  using Chunks = std::vector<FastqChunk>;
+  OrderedQueue<Batch> batches;
+  OrderedQueue<Chunks> decoded;
+  Tokens in_flight(2 * n_gpus + 1);
+  std::exception_ptr error;
+  std::mutex error_mu;
+  std::size_t n_batches = 0;
+  std::mutex nb_mu;
+  std::condition_variable nb_cv;
+  bool all_read = false;
+  auto fail = [&](std::exception_ptr e) {
+    { std::lock_guard<std::mutex> lk(error_mu); if (!error) error = e; }
+    batches.fail();
+    decoded.fail();
+    in_flight.abort();
+    { std::lock_guard<std::mutex> lk(nb_mu); all_read = true; nb_cv.notify_all(); }
+  };
+  auto batch_exists = [&](std::size_t j) {  // waits until batch j has been read or the archive is exhausted
+    std::unique_lock<std::mutex> lk(nb_mu);
+    nb_cv.wait(lk, [&] { return all_read || n_batches > j; });
+    return n_batches > j;
+  };
+
+  std::vector<std::thread> workers;
+  for (unsigned g = 0; g < n_gpus; ++g) {
+    workers.emplace_back([&, g] {
+      try {
+        GpuContext &ctx = *ctxs[g];
+        DecompressionWorkspace wksp(&ar.meta, ctxs[g]);
+        for (std::size_t j = g; batch_exists(j); j += n_gpus) {
+          Batch b;
+          if (!batches.take(j, b)) return;
+          if (!set.host_headers) headers::detokenizeOnGpu(ctx, b.fields, b.records, ar.fmt, ar.first_fields, b.srcs);
+          std::vector<CompressedBuffersSrc *> ps;
+          Chunks chunks(b.srcs.size());
+          std::vector<FastqChunk *> pc;
+          for (std::size_t k = 0; k < b.srcs.size(); ++k) { ps.push_back(&b.srcs[k]); pc.push_back(&chunks[k]); }
+          wksp.decodeChunks(ps, pc);
+          decoded.put(j, std::move(chunks));
+        }
+      } catch (...) { fail(std::current_exception()); }
+    });
   }
+  std::thread writer([&] {
+    try {
+      for (std::size_t j = 0; batch_exists(j); ++j) {
+        Chunks chunks;
+        if (!decoded.take(j, chunks)) return;
+        for (auto &c : chunks) out.write(c.raw_data.data(), static_cast<std::streamsize>(c.raw_data.size()));  // idx order
+        in_flight.release();
+      }
+    } catch (...) { fail(std::current_exception()); }
+  });
+
+  try {
+    std::size_t i = 0;
+    while (i < ar.index.size()) {
+      in_flight.acquire();
+      Batch b;
+      std::vector<headers::FieldStorage> fields;
+      std::size_t bytes = 0;
+      while (i < ar.index.size() && (b.srcs.empty() || bytes < batch_bytes)) {
+        b.srcs.emplace_back();
+        ar.readBlock(ar.index[i++], b.srcs.back(), fields);
+        auto &cb = b.srcs.back();
+        if (set.host_headers) {
+          headers::detokenize(fields, ar.fmt, ar.first_fields, cb.original_size.n_records, cb.raw_headers, cb.header_lengths);
+        } else {
+          b.fields.push_back(fields);
+          b.records.push_back(cb.original_size.n_records);
+        }
+        bytes += cb.original_size.total;
+      }
+      warnFewChunks(b.srcs.size(), bytes >> 20, static_cast<unsigned>((bytes / std::max<std::size_t>(1, b.srcs.size())) >> 20));
+      std::size_t j;
+      { std::lock_guard<std::mutex> lk(nb_mu); j = n_batches; }
+      batches.put(j, std::move(b));
+      { std::lock_guard<std::mutex> lk(nb_mu); ++n_batches; nb_cv.notify_all(); }
+    }
+  } catch (...) { fail(std::current_exception()); }
+  { std::lock_guard<std::mutex> lk(nb_mu); all_read = true; nb_cv.notify_all(); }
+  for (auto &w : workers) w.join();
+  writer.join();
+  if (error) std::rethrow_exception(error);
   out.flush();
+  if (set.verbose) {
+    const double wall = now_s() - t_start;
+    std::fprintf(stderr, "fqcomp28 d (B200 path): %zu blocks on %u GPU(s), wall %.3f s\n", ar.index.size(), n_gpus, wall);
+  }
   return out ? 0 : 1;
 }
 
@@ -640,8 +904,12 @@ static void usage() {
   std::fprintf(stderr,
                "fqcomp28 (B200 codec path)\n"
                "  fqcomp28 c --i1|--input1 FILE -o|--output ARCHIVE [-S|--sample-size-Mb N=128] [-R|--reading-size-Mb N=256]\n"
-               "             [-t|--threads N] [--verbose] [--slab-mb N=1024] [--host-headers]\n"
-               "  fqcomp28 d -i|--input ARCHIVE --o1|--output1 FILE [-t|--threads N] [--verbose] [--slab-mb N=1024] [--host-headers]\n");
+               "             [-t|--threads N] [--verbose] [--slab-mb N=1024] [--host-headers] [--gpus N] [--device D] [--ref-compat]\n"
+               "  fqcomp28 d -i|--input ARCHIVE --o1|--output1 FILE [-t|--threads N] [--verbose] [--slab-mb N=1024] [--host-headers]\n"
+               "             [--gpus N] [--device D]\n"
+               "  --gpus N      one worker per GPU; chunk boundaries come from one sequential walk, so the archive does not\n"
+               "                depend on N (blocks in file order, like --threads 1)\n"
+               "  --ref-compat  n_count / n_pos accumulate over blocks as in the reference (src/compressed_buffers.h:58-68)\n");
 }
 
 int main(int argc, char **argv) {
@@ -670,6 +938,9 @@ int main(int argc, char **argv) {
     else if (a == "--slab-mb") set.slab_mb = mb(need(i));
     else if (a == "--verbose") set.verbose = true;
     else if (a == "--host-headers") set.host_headers = true;
+    else if (a == "--gpus") set.n_gpus = mb(need(i));
+    else if (a == "--device") set.first_gpu = static_cast<unsigned>(std::strtol(need(i).c_str(), nullptr, 10));
+    else if (cmd == "c" && a == "--ref-compat") set.ref_compat = true;
     else { std::fprintf(stderr, "unknown option %s\n", a.c_str()); usage(); return 109; }
   }
   if ((cmd != "c" && cmd != "d") || set.mates1.empty() || set.archive.empty()) { usage(); return 106; }

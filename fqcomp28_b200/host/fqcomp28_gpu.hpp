@@ -28,7 +28,9 @@
 #include <cstddef>
 #include <cstdint>
 #include <cstring>
+#include <map>
 #include <memory>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <string_view>
@@ -162,14 +164,30 @@ public:
     throw std::runtime_error(msg);
   }
 
+  /** process-wide context of one device (device 0 unless told otherwise) */
   static std::shared_ptr<GpuContext> shared(int device = 0) {
-    static std::shared_ptr<GpuContext> ctx;
-    if (!ctx) ctx = std::make_shared<GpuContext>(device);
-    return ctx;
+    static std::mutex mu;
+    static std::map<int, std::shared_ptr<GpuContext>> ctxs;
+    std::lock_guard<std::mutex> lk(mu);
+    auto &c = ctxs[device];
+    if (!c) c = std::make_shared<GpuContext>(device);
+    return c;
   }
+
+  /** The handle holds ONE set of tables and several facade objects share it (encoders, decoders,
+   * workspaces, calculateFreqTable).  Whoever changes the tables names itself as the owner; a
+   * workspace re-loads its DatasetMeta's tables before a batch whenever somebody else did. */
+  void loadTables(const void *owner, const void *ft_seq, const void *ft_qual) {
+    if (owner != nullptr && owner == tables_owner_) return;
+    tables_owner_ = nullptr;
+    check(fq28_load_tables(h_, ft_seq, ft_qual));
+    tables_owner_ = owner;
+  }
+  void tablesChanged() { tables_owner_ = nullptr; }
 
 private:
   fq28_handle *h_ = nullptr;
+  const void *tables_owner_ = nullptr;
 };
 
 namespace detail {
@@ -280,6 +298,7 @@ public:
     detail::histChunk(ctx, chunk, cs, cq);
     auto ft = std::make_unique<FreqTableT>();
     auto fq = std::make_unique<QualFreqTable>();
+    ctx.tablesChanged();
     ctx.check(fq28_build_tables(ctx.handle(), cs.data(), cq.data(), ft.get(), fq.get()));
     return ft;
   }
@@ -300,6 +319,7 @@ public:
     detail::histChunk(ctx, chunk, cs, cq);
     auto fs = std::make_unique<SeqFreqTable>();
     auto ft = std::make_unique<FreqTableT>();
+    ctx.tablesChanged();
     ctx.check(fq28_build_tables(ctx.handle(), cs.data(), cq.data(), fs.get(), ft.get()));
     return ft;
   }
@@ -319,6 +339,7 @@ struct DatasetMeta {
     detail::histChunk(ctx, chunk, cs, cq);
     ft_seq = std::make_unique<SeqFreqTable>();
     ft_qual = std::make_unique<QualFreqTable>();
+    ctx.tablesChanged();
     ctx.check(fq28_build_tables(ctx.handle(), cs.data(), cq.data(), ft_seq.get(), ft_qual.get()));
   }
   std::string first_header;
@@ -403,8 +424,9 @@ class CompressionWorkspace : public Workspace {
 public:
   explicit CompressionWorkspace(const DatasetMeta *meta, std::shared_ptr<GpuContext> ctx = GpuContext::shared())
       : meta_(meta), ctx_(std::move(ctx)) {
-    ctx_->check(fq28_load_tables(ctx_->handle(), meta_->ft_seq.get(), meta_->ft_qual.get()));
+    useTables();
   }
+  void useTables() { ctx_->loadTables(this, meta_->ft_seq.get(), meta_->ft_qual.get()); }
 
   /** src/workspace.cpp:14-45.  chunk.raw_data must be the chunk's FASTQ bytes
    * (what FastqReader::readNextChunk leaves there).  Like the reference, the
@@ -412,6 +434,7 @@ public:
    * same cbs, and N bases in chunk.raw_data are replaced by 'A'
    * (src/fse_sequence.cpp:45). */
   void encodeChunk(FastqChunk &chunk, CompressedBuffersDst &cbs) {
+    useTables();
     std::vector<std::byte> keep_nc = std::move(cbs.n_count), keep_np = std::move(cbs.n_pos);
     std::vector<CompressedBuffersDst> one;
     detail::encodeSlab(*ctx_, chunk.raw_data.data(), chunk.raw_data.size(), std::max<std::size_t>(chunk.raw_data.size(), 1), true,
@@ -438,6 +461,7 @@ public:
   /** batched form: all chunks of a slab in one GPU pass (thousands in flight) */
   void encodeChunks(const char *fastq, std::size_t n, std::size_t reading_size, bool eof,
                     std::vector<CompressedBuffersDst> &out, std::size_t *consumed = nullptr) {
+    useTables();
     detail::encodeSlab(*ctx_, fastq, n, reading_size, eof, out, consumed);
   }
 
@@ -450,8 +474,9 @@ class DecompressionWorkspace : public Workspace {
 public:
   explicit DecompressionWorkspace(const DatasetMeta *meta, std::shared_ptr<GpuContext> ctx = GpuContext::shared())
       : meta_(meta), ctx_(std::move(ctx)) {
-    ctx_->check(fq28_load_tables(ctx_->handle(), meta_->ft_seq.get(), meta_->ft_qual.get()));
+    useTables();
   }
+  void useTables() { ctx_->loadTables(this, meta_->ft_seq.get(), meta_->ft_qual.get()); }
 
   /** src/workspace.cpp:47-88: resizes chunk, lays out records, decodes */
   void decodeChunk(FastqChunk &chunk, CompressedBuffersSrc &cbs) {
@@ -462,6 +487,7 @@ public:
 
   /** batched form */
   void decodeChunks(const std::vector<CompressedBuffersSrc *> &cbs, const std::vector<FastqChunk *> &chunks) {
+    useTables();
     const std::size_t n = cbs.size();
     std::vector<uint8_t> seq, qual, headers;
     std::vector<uint16_t> readlens, n_count, n_pos, hdr_lens;
@@ -486,6 +512,9 @@ public:
       app8(seq, c.seq);
       app8(qual, c.qual);
       app8(headers, c.raw_headers);
+      // side information comes from an archive: check the sizes before anything indexes with them
+      if (c.readlens.size() < nrec * sizeof(uint16_t)) throw std::runtime_error("readlens shorter than n_records");
+      if (c.header_lengths.size() != nrec) throw std::runtime_error("header_lengths does not match n_records");
       const auto *rl = reinterpret_cast<const uint16_t *>(c.readlens.data());
       readlens.insert(readlens.end(), rl, rl + nrec);
       hdr_lens.insert(hdr_lens.end(), c.header_lengths.begin(), c.header_lengths.end());
@@ -595,10 +624,12 @@ protected:
     if constexpr (IS_SEQ) {
       auto other = std::make_unique<QualFreqTable>();
       detail::fillUniform(*other);
+      ctx_->tablesChanged();
       ctx_->check(fq28_load_tables(ctx_->handle(), ft_, other.get()));
     } else {
       auto other = std::make_unique<SeqFreqTable>();
       detail::fillUniform(*other);
+      ctx_->tablesChanged();
       ctx_->check(fq28_load_tables(ctx_->handle(), other.get(), ft_));
     }
   }
@@ -677,10 +708,12 @@ protected:
     if constexpr (IS_SEQ) {
       uq = std::make_unique<QualFreqTable>();
       detail::fillUniform(*uq);
+      ctx_->tablesChanged();
       ctx_->check(fq28_load_tables(ctx_->handle(), ft_, uq.get()));
     } else {
       us = std::make_unique<SeqFreqTable>();
       detail::fillUniform(*us);
+      ctx_->tablesChanged();
       ctx_->check(fq28_load_tables(ctx_->handle(), us.get(), ft_));
     }
     detail::RecordQueue q;

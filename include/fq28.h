@@ -51,6 +51,7 @@ typedef struct fq28_handle fq28_handle;
  * CompressionWorkspace / DecompressionWorkspace of src/process.cpp:49-67,94-103.
  * Not thread-safe; use one handle per host thread. */
 int fq28_create(int device, fq28_handle **out);
+int fq28_device_count(void);   /* visible CUDA devices (0 when there is none) */
 void fq28_destroy(fq28_handle *h);
 const char *fq28_last_error(const fq28_handle *h);
 /* Launch on an existing cudaStream_t (e.g. the caller's current stream). */
@@ -166,6 +167,22 @@ int fq28_compress_dev(fq28_handle *h, const char *d_fastq, size_t n_bytes,
                       void *ft_seq_out, void *ft_qual_out,
                       fq28_chunk_info *infos, size_t infos_cap,
                       fq28_enc_summary *summary);
+/* -- one file, several GPUs --------------------------------------------------
+ * The chunk boundaries of a file are a sequential recurrence (src/fastq_io.cpp:23-65):
+ * a slab can only be cut where the previous one stopped.  fq28_plan runs just
+ * parseRecords + the boundary walk of a slab and returns *consumed, the offset at
+ * which the next slab starts -- known a millisecond after the data is on the GPU, so
+ * the next GPU can start while this one encodes.  The plan is kept: fq28_compress
+ * (or _dev) with the same slab, reading size and eof, and sample_bytes == 0, reuses it.
+ * fq28_stage starts the host-to-device copy of a host range early (before the
+ * slab's exact start is known); host-buffer calls whose input lies inside the staged
+ * range take it from there instead of copying again (a snapshot: it stays in use until
+ * the next fq28_stage; fq28_stage(h, NULL, 0) forgets it). */
+int fq28_stage(fq28_handle *h, const char *fastq, size_t n_bytes);
+int fq28_plan(fq28_handle *h, const char *fastq, size_t n_bytes, size_t reading_size,
+              int eof, uint64_t *consumed, size_t *n_chunks);
+int fq28_plan_dev(fq28_handle *h, const char *d_fastq, size_t n_bytes, size_t reading_size,
+                  int eof, uint64_t *consumed, size_t *n_chunks);
 /* Copies the device-resident result of the last fq28_compress_dev out. */
 int fq28_compress_fetch(fq28_handle *h, const fq28_enc_arenas *out);
 /* Upper bounds for sizing arenas: Workspace::compressBoundSequence/Quality,

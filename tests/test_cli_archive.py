@@ -20,7 +20,7 @@ CLI = os.path.join(ROOT, "fqcomp28_b200", "fqcomp28")
 
 def build_cli():
     pkg = os.path.join(ROOT, "fqcomp28_b200")
-    subprocess.check_call(["g++", "-std=c++20", "-O2", "-Wall", "-Wextra", "-o", CLI, os.path.join(pkg, "host", "fqcomp28_cli.cpp"),
+    subprocess.check_call(["g++", "-std=c++20", "-O2", "-Wall", "-Wextra", "-pthread", "-o", CLI, os.path.join(pkg, "host", "fqcomp28_cli.cpp"),
                            "-L", pkg, "-lfq28", "-Wl,-rpath,$ORIGIN"])
 
 

@@ -15,7 +15,7 @@ def build_facade_test(tmp_path):
     exe = str(tmp_path / "test_facade")
     lib_dir = os.path.join(ROOT, "fqcomp28_b200")
     subprocess.check_call(
-        ["g++", "-std=c++20", "-O1", "-Wall", "-Wextra", "-o", exe, os.path.join(ROOT, "tests", "cpp", "test_facade.cpp"),
+        ["g++", "-std=c++20", "-O1", "-Wall", "-Wextra", "-pthread", "-o", exe, os.path.join(ROOT, "tests", "cpp", "test_facade.cpp"),
          "-L", lib_dir, "-lfq28", f"-Wl,-rpath,{lib_dir}"]
     )
     return exe
