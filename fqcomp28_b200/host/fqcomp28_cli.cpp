@@ -916,6 +916,20 @@ int main(int argc, char **argv) {
   using namespace fqcomp28;
   if (argc < 2) { usage(); return 106; }
   const std::string cmd = argv[1];
+  if (cmd == "header-format" && argc == 3) {
+    // HeaderFormatSpeciciation::fromHeader (src/headers.cpp:43-73) on one header line: field count,
+    // field types (S = STRING, N = NUMERIC), separators.  Test hook for test/headers_test.cpp:12-33.
+    try {
+      const auto fmt = headers::Format::fromHeader(argv[2]);
+      std::string types, seps(fmt.separators.begin(), fmt.separators.end());
+      for (auto t : fmt.field_types) types += t == headers::FieldType::STRING ? 'S' : 'N';
+      std::printf("%zu\n%s\n%s\n", fmt.n_fields(), types.c_str(), seps.c_str());
+      return 0;
+    } catch (const std::exception &e) {
+      std::fprintf(stderr, "fqcomp28: %s\n", e.what());
+      return 1;
+    }
+  }
   Settings set;
   auto need = [&](int &i) -> std::string {
     if (i + 1 >= argc) { usage(); std::exit(106); }

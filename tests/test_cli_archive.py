@@ -30,6 +30,25 @@ def test_cli_builds():
     assert r.returncode == 106 and "fqcomp28 c" in r.stderr  # usage, like CLI11's RequiredError exit
 
 
+# test/headers_test.cpp:12-33 ("HeaderFormatSpec"), the reference's only literal expectations
+HEADER_FORMAT_CASES = [
+    ("@SRR22543904.1 1 length=150", 5, "SNNSN", ". \x20="),
+    ("@SRR065390.1000 HWUSI-EAS687_61DAJ:8:1:1174:9158 length=100", 11, "SNSSSNNNNSN", ". -_:::: ="),
+]
+
+
+@pytest.mark.parametrize("header,n,types,seps", HEADER_FORMAT_CASES)
+def test_header_format_spec(header, n, types, seps):
+    """Format::fromHeader of the CLI == the reference's REQUIREs (field types and separators)."""
+    build_cli()
+    seps = seps.replace("\x20", " ")
+    r = subprocess.run([CLI, "header-format", header], capture_output=True, text=True, check=True)
+    got = r.stdout.split("\n")
+    assert (int(got[0]), got[1], got[2]) == (n, types, seps)
+    bad = subprocess.run([CLI, "header-format", "@ends.in.separator."], capture_output=True, text=True)
+    assert bad.returncode == 1 and "should end in alnum" in bad.stderr   # src/headers.cpp:64-66
+
+
 def parse_archive(buf: bytes, n_fields_types):
     """-> (first_header, ft_seq, ft_qual, [blocks sorted by idx])"""
     (n_blocks,) = struct.unpack_from("<I", buf, 0)

@@ -135,6 +135,25 @@ def test_fixture_headers(oracle, H, name):
         run_case(H, lines, [0, 1, n // 2, n - 1, n])  # every chunk restarts from the first header
 
 
+def test_reference_header_format_literals(H):
+    """test/headers_test.cpp:12-33: field types / separators of the two literal headers, as the
+    format handed to fq28_tokenize_headers, and a tokenise -> detokenise round trip on records
+    of each shape."""
+    cases = [
+        (b"@SRR22543904.1 1 length=150", [1, 0, 0, 1, 0], b".  ="),
+        (b"@SRR065390.1000 HWUSI-EAS687_61DAJ:8:1:1174:9158 length=100", [1, 0, 1, 1, 1, 0, 0, 0, 0, 1, 0], b". -_:::: ="),
+    ]
+    for first, types, seps in cases:
+        lines = [first]
+        for i in range(2, 40):
+            if len(types) == 5:
+                lines.append(b"@SRR22543904.%d %d length=%d" % (i, i, 150 - (i % 3)))
+            else:
+                lines.append(b"@SRR065390.%d HWUSI-EAS687_61DAJ:8:%d:%d:%d length=100" % (999 + i, 1 + i // 20, 1174 + 7 * i, 9158 - i))
+        fmt = run_case(H, lines, [0, 10, len(lines)], canonical=True)
+        assert list(fmt["types"]) == types and bytes(fmt["separators"]) == seps
+
+
 def test_synthetic_illumina_headers(oracle, H):
     import synth
 
