@@ -113,7 +113,7 @@ SYMBOLS = [
     "fq28_compress_fetch", "fq28_bound_seq", "fq28_bound_qual", "fq28_decompress",
     "fq28_decompress_dev", "fq28_get_ctable", "fq28_get_dtable", "fq28_compress_dev_arenas",
     "fq28_last_timings", "fq28_stage_name", "fq28_tokenize_headers", "fq28_detokenize_headers",
-    "fq28_device_count", "fq28_stage", "fq28_plan", "fq28_plan_dev",
+    "fq28_device_count", "fq28_stage", "fq28_plan", "fq28_plan_dev", "fq28_preparse_dev", "fq28_plan_cut_dev",
 ]
 
 _lib = None
@@ -154,6 +154,8 @@ def load() -> C.CDLL:
     L.fq28_stage.argtypes = [vp, vp, sz]
     L.fq28_plan.argtypes = [vp, vp, sz, sz, i32, C.POINTER(C.c_uint64), psz]
     L.fq28_plan_dev.argtypes = [vp, vp, sz, sz, i32, C.POINTER(C.c_uint64), psz]
+    L.fq28_preparse_dev.argtypes = [vp, vp, sz]
+    L.fq28_plan_cut_dev.argtypes = [vp, vp, sz, sz, i32, C.c_uint64, C.POINTER(C.c_uint64), psz]
     L.fq28_bound_seq.argtypes = [sz]
     L.fq28_bound_seq.restype = sz
     L.fq28_bound_qual.argtypes = [sz]
@@ -334,6 +336,16 @@ class Handle:
         self._ck(self.L.fq28_plan_dev(self.h, d_fastq, n_bytes, reading_size, int(eof), C.byref(cons), C.byref(n)))
         return cons.value, n.value
 
+    def preparse_dev(self, d_fastq: int, n_bytes: int) -> None:
+        self._ck(self.L.fq28_preparse_dev(self.h, d_fastq, n_bytes))
+
+    def plan_cut_dev(self, d_fastq: int, n_bytes: int, reading_size: int, eof: bool, first_cut: int):
+        """boundary walk of a (pre)parsed slab from `first_cut` -> (consumed, n_chunks); chunk 0 is
+        the dropped head when first_cut > 0"""
+        cons, n = C.c_uint64(0), C.c_size_t(0)
+        self._ck(self.L.fq28_plan_cut_dev(self.h, d_fastq, n_bytes, reading_size, int(eof), first_cut, C.byref(cons), C.byref(n)))
+        return cons.value, n.value
+
     # ------------------------------------------------------------ tables
     def hist(self, data: np.ndarray, cs: np.ndarray | None = None, cq: np.ndarray | None = None):
         data = np.ascontiguousarray(data, dtype=np.uint8)
@@ -432,6 +444,18 @@ class Handle:
     def compress_fetch(self, arenas: dict):
         ea = self._enc_arenas(arenas)
         self._ck(self.L.fq28_compress_fetch(self.h, C.byref(ea)))
+
+    def compress_fetch_all(self, summ) -> dict:
+        """arenas sized from the summary of the last fq28_compress_dev, filled by fq28_compress_fetch"""
+        nr = int(summ.n_records)
+        arenas = {
+            "seq": np.zeros(int(summ.seq_bytes) + 64, np.uint8), "qual": np.zeros(int(summ.qual_bytes) + 64, np.uint8),
+            "readlens": np.zeros(nr + 8, np.uint16), "n_count": np.zeros(nr + 8, np.uint16),
+            "n_pos": np.zeros(int(summ.n_pos_entries) + 8, np.uint16), "hdr_lens": np.zeros(nr + 8, np.uint16),
+            "headers": np.zeros(int(summ.hdr_bytes) + 64, np.uint8),
+        }
+        self.compress_fetch(arenas)
+        return arenas
 
     def compress_dev_arenas(self) -> DecArenas:
         v = DecArenas()

@@ -471,6 +471,37 @@ int fq28_compress_dev(fq28_handle *h, const char *d_fastq, size_t n_bytes, size_
 // slab / reading size / eof and sample_bytes == 0 then goes straight to the encode.  This is what
 // lets several GPUs share one file: slab i+1 starts at the `consumed` of slab i, which is known
 // after this cheap step, long before slab i is encoded.
+int fq28_preparse_dev(fq28_handle *h, const char *d_fastq, size_t n_bytes) {
+  if (!h) return FQ28_ERR_ARG;
+  FQ28_TRY(bind(h));
+  stage_reset(h);
+  stage_begin(h, ST_PARSE);
+  FQ28_TRY(parse_slab(h, d_fastq, n_bytes, true));
+  stage_end(h, ST_PARSE);
+  h->parsed.valid = true;
+  h->parsed.d_fastq = d_fastq;
+  h->parsed.n_bytes = n_bytes;
+  return FQ28_OK;
+}
+
+int fq28_plan_cut_dev(fq28_handle *h, const char *d_fastq, size_t n_bytes, size_t reading_size, int eof, uint64_t first_cut,
+                      uint64_t *consumed, size_t *n_chunks) {
+  if (!h) return FQ28_ERR_ARG;
+  FQ28_TRY(bind(h));
+  const bool have = h->parsed.valid && h->parsed.d_fastq == d_fastq && h->parsed.n_bytes == n_bytes;
+  if (!have) stage_reset(h);
+  stage_begin(h, ST_PARSE);
+  if (!have) FQ28_TRY(parse_slab(h, d_fastq, n_bytes, true));
+  h->parsed.valid = false;
+  FQ28_TRY(split_slab(h, reading_size, eof != 0, 0, (size_t)first_cut));
+  stage_end(h, ST_PARSE);
+  h->plan.valid = true;
+  h->plan.d_fastq = d_fastq; h->plan.n_bytes = n_bytes; h->plan.reading_size = reading_size; h->plan.eof = eof != 0;
+  if (consumed) *consumed = h->h_chunk_byte[h->n_chunks];
+  if (n_chunks) *n_chunks = h->n_chunks;
+  return FQ28_OK;
+}
+
 int fq28_plan_dev(fq28_handle *h, const char *d_fastq, size_t n_bytes, size_t reading_size, int eof, uint64_t *consumed,
                   size_t *n_chunks) {
   if (!h) return FQ28_ERR_ARG;

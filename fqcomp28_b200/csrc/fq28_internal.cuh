@@ -184,6 +184,8 @@ struct fq28_handle {
   // fq28_plan / fq28_plan_dev: parse + chunk walk done for exactly this slab; a following
   // fq28_compress(_dev) with the same arguments and sample_bytes == 0 goes straight to the encode
   struct Plan { bool valid = false; const char *d_fastq = nullptr; size_t n_bytes = 0, reading_size = 0; int eof = 0; } plan;
+  // fq28_preparse_dev: the record table of exactly this slab is in place (consumed by the next plan)
+  struct Parsed { bool valid = false; const char *d_fastq = nullptr; size_t n_bytes = 0; } parsed;
   // generation of the device tables (bumped whenever they are rebuilt) and the generation the
   // host FreqTable images below were taken from: the sibling handle is only ever loaded from
   // images that match the current tables
@@ -261,7 +263,7 @@ int scan_exclusive_u32_to_u64(fq28_handle *h, const uint32_t *in, uint64_t *out,
 // fq28_parse.cu: K1.  Fills h->nl .. h->symoff, h->n_lines, h->n_rec.
 int parse_slab(fq28_handle *h, const char *d_fastq, size_t n_bytes, bool need_symoff);
 // chunk walk (A9); fills h->chunk_rec, h_chunk_*, n_chunks
-int split_slab(fq28_handle *h, size_t reading_size, bool eof, size_t max_chunks);
+int split_slab(fq28_handle *h, size_t reading_size, bool eof, size_t max_chunks, size_t first_cut = 0);
 // fq28_tables.cu: K3 / K4
 int tokenize_headers(fq28_handle *h, const uint8_t *headers, size_t headers_bytes, const uint16_t *hdr_lens, size_t n_rec,
                      const uint64_t *chunk_rec, size_t n_chunks, const fq28_hdr_format *fmt, uint8_t *arena, size_t arena_cap,

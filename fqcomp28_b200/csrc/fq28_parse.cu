@@ -135,7 +135,7 @@ __global__ void k_records(const char *__restrict__ d, const uint32_t *__restrict
 // out: chunk_rec[k] / chunk_sym[k] / chunk_byte[k] for k = 0..n_chunks.
 __global__ void __launch_bounds__(32)
 k_chunk_walk(const uint32_t *__restrict__ hdr_off, const uint32_t *__restrict__ symoff, size_t n_rec,
-             size_t n_bytes, size_t R, int eof, size_t cap, uint32_t *__restrict__ chunk_rec,
+             size_t n_bytes, size_t R, int eof, size_t first_cut, size_t cap, uint32_t *__restrict__ chunk_rec,
              uint32_t *__restrict__ chunk_sym, uint32_t *__restrict__ chunk_byte,
              uint64_t *__restrict__ n_chunks_out, DevStatus *st) {
   // Speculation: the walk is a chain of dependent loads (one per chunk).  The
@@ -155,6 +155,33 @@ k_chunk_walk(const uint32_t *__restrict__ hdr_off, const uint32_t *__restrict__ 
   const size_t avg = n_rec ? ((size_t)hdr_off[n_rec] - hdr_off[0] + n_rec - 1) / n_rec : 1;
   size_t s = n_rec ? hdr_off[0] : 0;  // byte start of the current chunk (carried, never re-loaded)
   size_t last_recs = n_rec ? n_rec : 1, last_bytes = n_rec ? (size_t)hdr_off[n_rec] - hdr_off[0] : 1;
+  if (first_cut > s && n_rec) {
+    // The slab starts inside a chunk that belongs to the previous slab (several GPUs, one file):
+    // that chunk ends at byte `first_cut`, which must be a record boundary.  Emit the head
+    // [0, first_cut) as chunk 0 (the caller drops it) and walk on from there.
+    size_t lo = 0, hi = n_rec;       // largest r with hdr_off[r] <= first_cut
+    while (lo < hi) {
+      const size_t step = (hi - lo + 31) / 32;
+      size_t p = lo + (size_t)(lane + 1) * step;
+      if (p > hi) p = hi;
+      const bool ok = (size_t)hdr_off[p] <= first_cut;
+      const unsigned c = __popc(__ballot_sync(0xffffffffu, ok));
+      size_t nlo = lo + (size_t)c * step, nhi = lo + (size_t)(c + 1) * step;
+      if (nlo > hi) nlo = hi;
+      if (nhi > hi) nhi = hi;        // probe c was clipped to hi and does not fit
+      lo = nlo;
+      if (c == 32) break;            // every probe fits, the last one is hi itself
+      hi = nhi - 1;
+    }
+    if ((size_t)hdr_off[lo] != first_cut || lo == 0) {
+      if (lane == 0) { set_error(st, FQ28_ERR_FORMAT, (unsigned)lo); *n_chunks_out = 0; }
+      return;
+    }
+    k = 1;
+    if (lane == 0) { chunk_rec[1] = (uint32_t)lo; chunk_byte[1] = (uint32_t)first_cut; }
+    s_rec = lo;
+    s = first_cut;
+  }
   for (;;) {
     if (s_rec >= n_rec) {
       // bytes left but no complete record: in the reference this is a
@@ -275,6 +302,7 @@ int parse_slab(fq28_handle *h, const char *d_fastq, size_t n_bytes, bool need_sy
   h->n_lines = h->n_rec = 0;
   h->n_chunks = 0;
   h->plan.valid = false;  // the record table of any earlier plan is gone
+  h->parsed.valid = false;
   FQ28_CUDA(h, cudaMemsetAsync(h->d_status, 0, sizeof(DevStatus), h->stream));
   const size_t n_tiles = (n_bytes + NL_TILE - 1) / NL_TILE;
   FQ28_TRY(ensure(h, h->tile_cnt, (n_tiles + 1) * sizeof(uint32_t)));
@@ -313,15 +341,16 @@ int parse_slab(fq28_handle *h, const char *d_fastq, size_t n_bytes, bool need_sy
   return FQ28_OK;
 }
 
-int split_slab(fq28_handle *h, size_t reading_size, bool eof, size_t max_chunks) {
+int split_slab(fq28_handle *h, size_t reading_size, bool eof, size_t max_chunks, size_t first_cut) {
   if (reading_size == 0) return fail(h, FQ28_ERR_ARG, "reading_size must be >= 1 (SURVEY Q6)");
-  size_t cap = 2 * (h->n_bytes / reading_size) + 4;
+  if (first_cut >= h->n_bytes && first_cut) return fail(h, FQ28_ERR_ARG, "first_cut beyond the slab");
+  size_t cap = 2 * (h->n_bytes / reading_size) + 5;
   if (max_chunks && cap > max_chunks) cap = max_chunks;
   FQ28_TRY(ensure(h, h->chunk_rec, 3 * (cap + 1) * sizeof(uint32_t)));
   h->chunk_stride = cap + 1;
   uint32_t *cr = h->chunk_rec.as<uint32_t>();
   k_chunk_walk<<<1, 32, 0, h->stream>>>(h->hdr_off.as<uint32_t>(), h->symoff.as<uint32_t>(), h->n_rec, h->n_bytes,
-                                       reading_size, eof ? 1 : 0, cap, cr, cr + (cap + 1), cr + 2 * (cap + 1),
+                                       reading_size, eof ? 1 : 0, first_cut, cap, cr, cr + (cap + 1), cr + 2 * (cap + 1),
                                        h->d_scalars, h->d_status);
   FQ28_LAUNCH_CHECK(h);
   FQ28_CUDA(h, cudaMemcpyAsync(h->h_scalars, h->d_scalars, sizeof(uint64_t), cudaMemcpyDeviceToHost, h->stream));

@@ -183,6 +183,17 @@ int fq28_plan(fq28_handle *h, const char *fastq, size_t n_bytes, size_t reading_
               int eof, uint64_t *consumed, size_t *n_chunks);
 int fq28_plan_dev(fq28_handle *h, const char *d_fastq, size_t n_bytes, size_t reading_size,
                   int eof, uint64_t *consumed, size_t *n_chunks);
+/* A slab that starts at a record boundary INSIDE a chunk owned by the previous slab (one rank
+ * per GPU, each holding its own record range of the file plus reading_size bytes of lookahead):
+ * fq28_preparse_dev builds the record table as soon as the data is there -- it does not depend on
+ * the other ranks -- and fq28_plan_cut_dev then only walks the boundaries, starting at
+ * `first_cut`, the slab-relative offset at which the previous rank's last chunk ends (0: the slab
+ * starts a chunk).  With first_cut > 0 the head [0, first_cut) is emitted as chunk 0 and must be
+ * dropped by the caller: it is the tail of the previous rank's last chunk.  first_cut must be a
+ * record boundary (else FQ28_ERR_FORMAT).  Between ranks only this one offset travels. */
+int fq28_preparse_dev(fq28_handle *h, const char *d_fastq, size_t n_bytes);
+int fq28_plan_cut_dev(fq28_handle *h, const char *d_fastq, size_t n_bytes, size_t reading_size,
+                      int eof, uint64_t first_cut, uint64_t *consumed, size_t *n_chunks);
 /* Copies the device-resident result of the last fq28_compress_dev out. */
 int fq28_compress_fetch(fq28_handle *h, const fq28_enc_arenas *out);
 /* Upper bounds for sizing arenas: Workspace::compressBoundSequence/Quality,

@@ -234,3 +234,44 @@ def test_rebuilt_tables_reach_both_halves_of_a_large_slab(P, oracle, data, monke
         assert ar["seq"][ci.seq_off : ci.seq_off + ci.seq_len].tobytes() == e["seq"].tobytes(), k
         assert ar["qual"][ci.qual_off : ci.qual_off + ci.qual_len].tobytes() == e["qual"].tobytes(), k
     h.close()
+
+
+# ---------------------------------------------------------------- one rank per GPU: record ranges + first_cut
+def test_record_ranges_with_first_cut_equal_one_pass(P, oracle, data):
+    """What bench.py does with N ranks: rank r holds records [r*M, (r+1)*M) of the file plus
+    reading_size bytes of lookahead, pre-parses them at once, and learns from rank r-1 only the
+    offset at which that rank's last chunk ends (fq28_preparse_dev + fq28_plan_cut_dev).  The
+    blocks of all ranks, minus each rank's dropped head, are the blocks of the one-pass run."""
+    import torch
+
+    R = 1 << 20
+    fs, fq = tables(oracle, data, 2 << 20)
+    h = P.Handle(0)
+    h.load_tables(fs, fq)
+    ref = blocks_of(*h.compress(data, R, eof=True))
+    recs, _ = oracle.parse_records(data)
+    ends = np.append(recs["hdr_off"].astype(np.int64), data.size)
+    for n_ranks in (2, 3, 5):
+        M = (len(recs) + n_ranks - 1) // n_ranks
+        out, cut_global = [], 0
+        for r in range(n_ranks):
+            b0 = int(ends[min(r * M, len(recs))])                    # global offset of the rank's first record
+            b1 = int(ends[min((r + 1) * M, len(recs))])
+            last = r == n_ranks - 1
+            stop = data.size if last else min(data.size, b1 + R - 1)  # exactly R - 1 bytes of lookahead:
+            slab = torch.from_numpy(data[b0:stop].copy()).cuda()      # chunks starting at >= b1 cannot be emitted
+            h.preparse_dev(slab.data_ptr(), slab.numel())
+            first_cut = cut_global - b0
+            assert 0 <= first_cut < R
+            consumed, n = h.plan_cut_dev(slab.data_ptr(), slab.numel(), R, last, first_cut)
+            infos, summ = h.compress_dev(slab.data_ptr(), slab.numel(), R, eof=last)
+            assert int(summ.consumed) == consumed and int(summ.n_chunks) == n
+            ar = h.compress_fetch_all(summ)
+            blocks = blocks_of(infos, summ, ar)
+            out += blocks[1:] if first_cut else blocks
+            cut_global = b0 + consumed
+        assert out == ref, n_ranks
+    with pytest.raises(P.capi.Fq28Error):  # a cut that is not a record boundary
+        slab = torch.from_numpy(data[: 3 << 20].copy()).cuda()
+        h.plan_cut_dev(slab.data_ptr(), slab.numel(), R, False, 12345)
+    h.close()
