@@ -48,6 +48,12 @@ def parse_args():
                     help="quality model of the synthetic reads; ont = BASELINE config 4 (1-50 kb reads)")
     ap.add_argument("--cpu-mb", type=int, default=2048, help="bounded sample (MB of the slab) for the CPU legs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the reading-size / chunks-resident sweep")
+    ap.add_argument("--sweep-reading-mb", default="16,256", help="extra -R values measured on the same slab (few steps each)")
+    ap.add_argument("--resident-mb", type=int, default=3840, help="slab size (MB) of the many-chunks decompress point; 0 = skip")
+    ap.add_argument("--resident-slabs", type=int, default=3, help="slabs decoded concurrently for the largest chunks-resident point")
+    ap.add_argument("--no-parity", action="store_true", help="skip the per-rank oracle check")
+    ap.add_argument("--parity-chunks", type=int, default=48, help="chunks per rank checked stream by stream against the oracle")
     ap.add_argument("--threads", type=int, default=0, help="CPU threads (0 = all)")
     return ap.parse_args()
 
@@ -126,20 +132,25 @@ class ClockSampler:
         return out
 
 
-def make_data(args, rank: int, device: str):
-    """Rank r's slab: records [r*M, (r+1)*M) of the virtual global file."""
+def make_data(args, rank: int, device: str, extra_bytes: int = 0):
+    """Rank r's slab: records [r*M, (r+1)*M) of the virtual global file, plus (extra_bytes > 0)
+    enough of the following records to cover extra_bytes of lookahead."""
     import synth
+    import torch
 
     if args.profile == "ont":  # variable-length long reads, ~24.5 kB per record on average
-        import torch
-
         m = max(1, (args.size_mb << 20) // 24500)
-        parts = [synth.ont(rank * m + a, min(1024, m - a), seed=32, device=device) for a in range(0, m, 1024)]
+        extra = (extra_bytes // 2000 + 8) if extra_bytes else 0   # a record is at least 1000 bases
+        n = m + extra
+        parts = [synth.ont(rank * m + a, min(1024, n - a), seed=32, device=device) for a in range(0, n, 1024)]
         return torch.cat(parts), m
     per = 150 * 2 + 52
     m = (args.size_mb << 20) // per
-    t = synth.illumina(rank * m, m, seed=30, profile=args.profile, device=device)
-    return t, m
+    extra = (extra_bytes // 300 + 64) if extra_bytes else 0       # a record is at least ~340 bytes
+    n = m + extra
+    step = (1 << 30) // per                                        # generate in <= 1 GB pieces (temporaries are 8 B per byte)
+    parts = [synth.illumina(rank * m + a, min(step, n - a), seed=30, profile=args.profile, device=device) for a in range(0, n, step)]
+    return (parts[0] if len(parts) == 1 else torch.cat(parts)), m
 
 
 # --------------------------------------------------------------------------- reference arm
@@ -202,6 +213,33 @@ def workload_config(args, n_bytes):
 
 
 # --------------------------------------------------------------------------- our arm
+class Baton:
+    """The one number that travels between ranks: the global file offset at which the previous
+    rank's last chunk ends (the chunk boundary walk is sequential, src/fastq_io.cpp:23-65).
+    Host-side, through the process group's TCP store -- control metadata, not a data-path
+    collective.  One key per (step, rank)."""
+
+    def __init__(self, rank, world):
+        self.rank, self.world, self.step = rank, world, 0
+        self.store = None
+        if world > 1:
+            from torch.distributed.distributed_c10d import _get_default_store
+
+            self.store = _get_default_store()
+
+    def next_step(self):
+        self.step += 1
+
+    def recv(self) -> int:
+        if self.rank == 0:
+            return 0
+        return int(self.store.get(f"fq28/cut/{self.step}/{self.rank}").decode())
+
+    def send(self, cut: int):
+        if self.rank + 1 < self.world:
+            self.store.set(f"fq28/cut/{self.step}/{self.rank + 1}", str(int(cut)))
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -220,134 +258,27 @@ def run_ours(args):
     if world > 1:
         os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout: one JSON line only
         dist.init_process_group("nccl", device_id=dev)
-    R, S = args.reading_mb << 20, args.sample_mb << 20
-
-    d_fastq, n_rec = make_data(args, rank, str(dev))
-    n_bytes = d_fastq.numel()
-    # sample shard of this rank: the sample is the head of the virtual global
-    # file = head of rank 0's slab; shard r = its records [K r/N, K (r+1)/N)
-    if world > 1:
-        import synth
-
-        k = torch.zeros(1, dtype=torch.int64, device=dev)
-        if rank == 0:
-            k[0] = int((d_fastq[: min(S, n_bytes)] == 10).sum().item()) // 4
-        dist.broadcast(k, 0)
-        K = int(k.item())
-        a, b = MG.shard_range(K, rank, world)
-        d_sample = (synth.ont(a, b - a, seed=32, device=str(dev)) if args.profile == "ont"
-                    else synth.illumina(a, b - a, seed=30, profile=args.profile, device=str(dev)))
-        sample_window = d_sample.numel()
-    else:
-        d_sample = d_fastq
-        sample_window = min(S, n_bytes)
-
+    S = args.sample_mb << 20
+    last = rank == world - 1
+    baton = Baton(rank, world)
     stream = torch.cuda.current_stream()
     h = P.Handle(local, stream=stream.cuda_stream)
-    cs = torch.zeros(256 * 4, dtype=torch.int32, device=dev)
-    cq = torch.zeros(8192 * 64, dtype=torch.int32, device=dev)
-    max_chunks = 2 * (n_bytes // R) + 8
-    infos = (P.ChunkInfo * max_chunks)()
-    fs = np.zeros(P.capi.FT_SEQ_BYTES, np.uint8)
-    fq = np.zeros(P.capi.FT_QUAL_BYTES, np.uint8)
-    state = {}
+    peak, peak_src = load_peaks()
+    traffic_db = load_traffic()
 
-    def analyze_dev():
-        cs.zero_()
-        cq.zero_()
-        h.hist_dev(d_sample.data_ptr(), sample_window, cs.data_ptr(), cq.data_ptr())
-        if world > 1:
-            MG.allreduce_counts(cs, cq)  # the path's only collective (C1): 525 312 u32 counters over NCCL
-        f = h.build_tables_dev(cs.data_ptr(), cq.data_ptr())
-        state["ft"] = f
+    def allmax(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
-    def compress_step_dev():
-        t = {}
-        analyze_dev()
-        t.update({k: v for k, v in h.timings().items() if v})
-        _, summ = h.compress_dev(d_fastq.data_ptr(), n_bytes, R, eof=True, max_chunks=max_chunks, infos=infos)
-        for k, v in h.timings().items():
-            t[k] = t.get(k, 0.0) + v
-        state["summ"], state["t_c"] = summ, t
-
-    # ---- device-resident decode setup (after one compress)
-    def setup_decode():
-        compress_step_dev()
-        summ = state["summ"]
-        state["enc_summ"] = summ
-        setup_e2e()  # pinned host arenas, filled by fq28_compress_fetch
-        h.compress_fetch(state["hp"]["arenas"])
-        # private device copies: the handle's arenas are overwritten by the next compress
-        keep = {k: torch.from_numpy(v.view(np.uint8)).to(dev) for k, v in state["hp"]["arenas"].items()}
-        nr = int(summ.n_records)
-        d = P.DecArenas()
-        d.seq, d.seq_bytes = keep["seq"].data_ptr(), int(summ.seq_bytes)
-        d.qual, d.qual_bytes = keep["qual"].data_ptr(), int(summ.qual_bytes)
-        d.readlens, d.n_count = keep["readlens"].data_ptr(), keep["n_count"].data_ptr()
-        d.n_pos, d.n_pos_entries = keep["n_pos"].data_ptr(), int(summ.n_pos_entries)
-        d.hdr_lens = keep["hdr_lens"].data_ptr()
-        d.headers, d.headers_bytes = keep["headers"].data_ptr(), int(summ.hdr_bytes)
-        d.n_records = nr
-        state["dec"] = (d, keep, int(summ.n_chunks))
-        state["dec_infos"] = (P.ChunkInfo * int(summ.n_chunks))(*[infos[i] for i in range(int(summ.n_chunks))])
-        state["d_out"] = torch.empty(n_bytes + 64, dtype=torch.uint8, device=dev)
-
-    def decompress_step_dev():
-        d, _, nch = state["dec"]
-        wrote = h.decompress_dev(d, state["dec_infos"], nch, state["d_out"].data_ptr(), n_bytes)
-        state["t_d"] = {k: v for k, v in h.timings().items() if v}
-        state["wrote"] = wrote
-
-    # ---- host-buffer (e2e) setup
-    def pinned(n, dtype=np.uint8):
-        t = torch.empty(n, dtype=torch.uint8).pin_memory()
-        return t, t.numpy()
-
-    def setup_e2e():
-        summ = state["enc_summ"]
-        hp = {}
-        hp["fastq_t"], hp["fastq"] = pinned(n_bytes)
-        hp["fastq_t"].copy_(d_fastq.cpu())
-        if world > 1:
-            hp["sample_t"], hp["sample"] = pinned(sample_window)
-            hp["sample_t"].copy_(d_sample.cpu())
-        nr = int(summ.n_records)
-        caps = {"seq": int(summ.seq_bytes) + 4096, "qual": int(summ.qual_bytes) + 4096, "readlens": nr * 2 + 64,
-                "n_count": nr * 2 + 64, "n_pos": int(summ.n_pos_entries) * 2 + 64, "hdr_lens": nr * 2 + 64,
-                "headers": int(summ.hdr_bytes) + 64}
-        ar = {}
-        for k, nb in caps.items():
-            t, a = pinned(nb)
-            hp[k + "_t"] = t
-            ar[k] = a if k in ("seq", "qual", "headers") else a.view(np.uint16)
-        hp["arenas"] = ar
-        hp["out_t"], hp["out"] = pinned(n_bytes + 64)
-        state["hp"] = hp
-
-    def compress_step_e2e():
-        hp = state["hp"]
-        if world > 1:
-            cs.zero_()
-            cq.zero_()
-            hs = np.zeros((256, 4), np.uint32)
-            # H2D of the sample shard + histogram through the host-buffer ABI would
-            # need a host-side reduction; keep the collective on device instead:
-            d_tmp = torch.empty(sample_window + 64, dtype=torch.uint8, device=dev)
-            d_tmp[:sample_window].copy_(hp["sample_t"], non_blocking=True)
-            h.hist_dev(d_tmp.data_ptr(), sample_window, cs.data_ptr(), cq.data_ptr())
-            MG.allreduce_counts(cs, cq)
-            h.build_tables_dev(cs.data_ptr(), cq.data_ptr())
-            _, summ, _ = h.compress(hp["fastq"], R, eof=True, arenas=hp["arenas"])
-        else:
-            _, summ, _ = h.compress(hp["fastq"], R, eof=True, arenas=hp["arenas"], sample_bytes=S, ft_out=(fs, fq))
-        state["e2e_summ"] = summ
-
-    def decompress_step_e2e():
-        hp = state["hp"]
-        summ = state["enc_summ"]
-        out = h.decompress(hp["arenas"], state["dec_infos"], int(summ.n_chunks), hp["arenas"]["headers"][: int(summ.hdr_bytes)],
-                           int(summ.n_records), out=hp["out"], n_pos_entries=int(summ.n_pos_entries))
-        state["e2e_wrote"] = out.size
+    def allsum(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t)
+        return float(t.item())
 
     def timed(fn, steps, warmup):
         for _ in range(warmup):
@@ -364,49 +295,267 @@ def run_ours(args):
         e1.record(stream)
         torch.cuda.synchronize()
         w1 = time.perf_counter()
-        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        ms = allmax(e0.elapsed_time(e1))
         if world > 1:
             dist.barrier()
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item()) / steps, (w1 - w0) * 1e3 / steps, (h.launches - l0) // steps
+        return ms / steps, (w1 - w0) * 1e3 / steps, (h.launches - l0) // steps
 
-    setup_decode()
-    decompress_step_dev()
-    roundtrip_ok = bool(state["wrote"] == n_bytes and torch.equal(state["d_out"][:n_bytes], d_fastq))
+    def pinned(n):
+        t = torch.empty(n, dtype=torch.uint8).pin_memory()
+        return t, t.numpy()
 
-    sampler = ClockSampler(local) if rank == 0 else None
-    ms_c, wall_c, launches_c = timed(compress_step_dev, args.steps, args.warmup)
-    t_c = dict(state["t_c"])
-    ms_d, wall_d, launches_d = timed(decompress_step_dev, args.steps, args.warmup)
-    t_d = dict(state["t_d"])
-    clocks = sampler.stop() if sampler else {}
-    ms_ce, _, _ = timed(compress_step_e2e, args.steps, args.warmup)
-    ms_de, _, _ = timed(decompress_step_e2e, args.steps, args.warmup)
-    # e2e correctness: the host round trip restores the slab
-    e2e_ok = bool(state["e2e_wrote"] == n_bytes and np.array_equal(state["hp"]["out"][:n_bytes], state["hp"]["fastq"]))
+    # ------------------------------------------------------------------ the file
+    # One virtual file of `world` x size_mb: rank r owns records [r*M, (r+1)*M).  With several ranks
+    # the chunks are those of ONE boundary walk over the whole file: a rank also holds
+    # the next R - 1 bytes, so that the chunk that starts in its range and ends in the next one is
+    # its own, and it starts encoding where the previous rank's last chunk ended (Baton).
+    class Workload:
+        def __init__(self, R, size_mb=None):
+            self.R = R
+            a = argparse.Namespace(**vars(args))
+            if size_mb:
+                a.size_mb = size_mb
+            t, self.M = make_data(a, rank, str(dev), extra_bytes=(R if (world > 1 and not last) else 0))
+            if world > 1:
+                nl = torch.nonzero(t == 10).flatten()
+                own = int(nl[4 * self.M - 1].item()) + 1
+                del nl
+                self.slab = t[: own + R - 1] if not last else t[:own]
+            else:
+                own = t.numel()
+                self.slab = t
+            self.own_bytes = own
+            sizes = [own]
+            if world > 1:
+                g = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+                dist.all_gather(g, torch.tensor([own], dtype=torch.int64, device=dev))
+                sizes = [int(x.item()) for x in g]
+            self.base = sum(sizes[:rank])          # global offset of this rank's first record
+            self.file_bytes = sum(sizes)
+            self.n = self.slab.numel()
+            self.ptr = self.slab.data_ptr()
+            self.max_chunks = 2 * (self.n // R) + 8
+            self.infos = (P.ChunkInfo * self.max_chunks)()
 
-    summ = state["enc_summ"]
-    tot_bytes = torch.tensor([n_bytes], dtype=torch.float64, device=dev)
+    wl = Workload(args.reading_mb << 20)
+
+    # sample shard of this rank: the sample is the head of the file = head of rank 0's slab;
+    # shard r = its records [K r/N, K (r+1)/N)
     if world > 1:
-        dist.all_reduce(tot_bytes)
-    total_mb = float(tot_bytes.item()) / 1e6
-    peak, peak_src = load_peaks()
-    traffic_db = load_traffic()
-    nsym = int(summ.n_symbols)
-    side = 2 * int(summ.n_records) * 2 + 2 * int(summ.n_pos_entries) + int(summ.hdr_bytes)
-    algo_pipeline = n_bytes + int(summ.seq_bytes) + int(summ.qual_bytes) + side  # SURVEY 8(d) `B`
+        import synth
 
-    def roofline(stage_ms: dict, kind: str):
+        k = torch.zeros(1, dtype=torch.int64, device=dev)
+        if rank == 0:
+            k[0] = int((wl.slab[: min(S, wl.own_bytes)] == 10).sum().item()) // 4
+        dist.broadcast(k, 0)
+        K = int(k.item())
+        a, b = MG.shard_range(K, rank, world)
+        d_sample = (synth.ont(a, b - a, seed=32, device=str(dev)) if args.profile == "ont"
+                    else synth.illumina(a, b - a, seed=30, profile=args.profile, device=str(dev)))
+        sample_window = d_sample.numel()
+    else:
+        d_sample = wl.slab
+        sample_window = min(S, wl.n)
+    cs = torch.zeros(256 * 4, dtype=torch.int32, device=dev)
+    cq = torch.zeros(8192 * 64, dtype=torch.int32, device=dev)
+    tables = {}
+
+    def analyze_dev(t=None):
+        cs.zero_()
+        cq.zero_()
+        h.hist_dev(d_sample.data_ptr(), sample_window, cs.data_ptr(), cq.data_ptr())
+        if t is not None:  # stage timers are reset by every ABI call: read them call by call
+            for kk, v in h.timings().items():
+                t[kk] = t.get(kk, 0.0) + v
+        if world > 1:
+            MG.allreduce_counts(cs, cq)  # the path's only collective (C1): 525 312 u32 counters over NCCL
+        tables["ft"] = h.build_tables_dev(cs.data_ptr(), cq.data_ptr())
+        if t is not None:
+            for kk, v in h.timings().items():
+                t[kk] = t.get(kk, 0.0) + v
+
+    # ------------------------------------------------------------------ one (workload, reading size)
+    class Run:
+        def __init__(self, w):
+            self.w = w
+            self.st = {}
+
+        # ---- compress, slab resident
+        def compress_dev(self):
+            w, t = self.w, {}
+            analyze_dev(t)
+            baton.next_step()
+            if world > 1:
+                h.preparse_dev(w.ptr, w.n)                      # does not wait for anybody
+                cut = baton.recv()                               # where the previous rank's last chunk ends
+                consumed, _ = h.plan_cut_dev(w.ptr, w.n, w.R, last, cut - w.base)
+                baton.send(w.base + consumed)
+                self.st["cut_local"] = cut - w.base
+            _, summ = h.compress_dev(w.ptr, w.n, w.R, eof=last, max_chunks=w.max_chunks, infos=w.infos)
+            for kk, v in h.timings().items():
+                t[kk] = t.get(kk, 0.0) + v
+            self.st["summ"], self.st["t_c"] = summ, t
+
+        # chunks of this rank: with a cut inside the slab, chunk 0 is the dropped head
+        def kept(self):
+            summ = self.st["summ"]
+            k0 = 1 if self.st.get("cut_local", 0) > 0 else 0
+            return k0, int(summ.n_chunks)
+
+        def setup(self):
+            """after one compress: pinned host arenas (= what the e2e legs use), private device
+            copies for the device-resident decode, chunk infos rebased to this rank's chunks"""
+            w = self.w
+            self.compress_dev()
+            summ = self.st["summ"]
+            nr = int(summ.n_records)
+            hp = {}
+            hp["fastq_t"], hp["fastq"] = pinned(w.n)
+            hp["fastq_t"].copy_(w.slab.cpu())
+            if world > 1:
+                hp["sample_t"], hp["sample"] = pinned(sample_window)
+                hp["sample_t"].copy_(d_sample.cpu())
+            caps = {"seq": int(summ.seq_bytes) + 4096, "qual": int(summ.qual_bytes) + 4096, "readlens": nr * 2 + 64,
+                    "n_count": nr * 2 + 64, "n_pos": int(summ.n_pos_entries) * 2 + 64, "hdr_lens": nr * 2 + 64,
+                    "headers": int(summ.hdr_bytes) + 64}
+            ar = {}
+            for kk, nb in caps.items():
+                t, a = pinned(nb)
+                hp[kk + "_t"] = t
+                ar[kk] = a if kk in ("seq", "qual", "headers") else a.view(np.uint16)
+            hp["arenas"] = ar
+            self.hp = hp
+            h.compress_fetch(ar)
+            k0, k1 = self.kept()
+            b = w.infos[k0]
+            r0, p0, h0 = int(b.rec_off), int(b.n_pos_off), int(b.hdr_off)
+            self.abs_infos = [w.infos[i] for i in range(k0, k1)]
+            dec = (P.ChunkInfo * (k1 - k0))()
+            out_bytes = 0
+            for i in range(k0, k1):
+                ci = P.ChunkInfo.from_buffer_copy(bytes(w.infos[i]))
+                ci.rec_off -= r0
+                ci.n_pos_off -= p0
+                ci.hdr_off -= h0
+                dec[i - k0] = ci
+                out_bytes += int(ci.total)
+            self.dec_infos, self.n_dec, self.out_bytes = dec, k1 - k0, out_bytes
+            self.first_byte = int(b.fastq_off)
+            # host views of this rank's chunks (e2e decompress)
+            self.host_ar = {"seq": ar["seq"], "qual": ar["qual"], "readlens": ar["readlens"][r0:], "n_count": ar["n_count"][r0:],
+                            "n_pos": ar["n_pos"][p0:], "hdr_lens": ar["hdr_lens"][r0:], "headers": ar["headers"][h0 : int(summ.hdr_bytes)]}
+            self.n_rec_dec, self.n_pos_dec = nr - r0, int(summ.n_pos_entries) - p0
+            keep = {kk: torch.from_numpy(v.view(np.uint8)).to(dev) for kk, v in ar.items()}
+            d = P.DecArenas()
+            d.seq, d.seq_bytes = keep["seq"].data_ptr(), int(summ.seq_bytes)
+            d.qual, d.qual_bytes = keep["qual"].data_ptr(), int(summ.qual_bytes)
+            d.readlens, d.n_count = keep["readlens"].data_ptr() + 2 * r0, keep["n_count"].data_ptr() + 2 * r0
+            d.n_pos, d.n_pos_entries = keep["n_pos"].data_ptr() + 2 * p0, self.n_pos_dec
+            d.hdr_lens = keep["hdr_lens"].data_ptr() + 2 * r0
+            d.headers, d.headers_bytes = keep["headers"].data_ptr() + h0, int(summ.hdr_bytes) - h0
+            d.n_records = self.n_rec_dec
+            self.dec, self.keep = d, keep
+            self.d_out = torch.empty(out_bytes + 64, dtype=torch.uint8, device=dev)
+            hp["out_t"], hp["out"] = pinned(out_bytes + 64)
+            self.enc_summ = summ
+            self.out_bytes_c = int(summ.seq_bytes) + int(summ.qual_bytes) + 3 * 2 * nr + 2 * int(summ.n_pos_entries) + int(summ.hdr_bytes)
+
+        def decompress_dev(self):
+            self.st["wrote"] = h.decompress_dev(self.dec, self.dec_infos, self.n_dec, self.d_out.data_ptr(), self.out_bytes)
+            self.st["t_d"] = {kk: v for kk, v in h.timings().items() if v}
+
+        def roundtrip_dev(self):
+            want = self.w.slab[self.first_byte : self.first_byte + self.out_bytes]
+            return bool(self.st["wrote"] == self.out_bytes and torch.equal(self.d_out[: self.out_bytes], want))
+
+        # ---- the same through the host-buffer C ABI (pinned host memory, copies inside the call)
+        def compress_e2e(self):
+            w, hp = self.w, self.hp
+            baton.next_step()
+            if world > 1:
+                cs.zero_()
+                cq.zero_()
+                # the sample shard goes H2D, the histogram is reduced on the device (no host-side sum)
+                d_tmp = torch.empty(sample_window + 64, dtype=torch.uint8, device=dev)
+                d_tmp[:sample_window].copy_(hp["sample_t"], non_blocking=True)
+                h.hist_dev(d_tmp.data_ptr(), sample_window, cs.data_ptr(), cq.data_ptr())
+                MG.allreduce_counts(cs, cq)
+                h.build_tables_dev(cs.data_ptr(), cq.data_ptr())
+                h.preparse(hp["fastq"])                         # H2D + record table, before the cut is known
+                cut = baton.recv()
+                consumed, _ = h.plan_cut(hp["fastq"], w.R, last, cut - w.base)
+                baton.send(w.base + consumed)
+                _, summ, _ = h.compress(hp["fastq"], w.R, eof=last, arenas=hp["arenas"])
+            else:
+                fs = np.zeros(P.capi.FT_SEQ_BYTES, np.uint8)
+                fq = np.zeros(P.capi.FT_QUAL_BYTES, np.uint8)
+                _, summ, _ = h.compress(hp["fastq"], w.R, eof=True, arenas=hp["arenas"], sample_bytes=S, ft_out=(fs, fq))
+            self.st["e2e_summ"] = summ
+
+        def decompress_e2e(self):
+            out = h.decompress(self.host_ar, self.dec_infos, self.n_dec, self.host_ar["headers"], self.n_rec_dec,
+                               out=self.hp["out"], n_pos_entries=self.n_pos_dec)
+            self.st["e2e_wrote"] = out.size
+
+        def roundtrip_e2e(self):
+            want = self.hp["fastq"][self.first_byte : self.first_byte + self.out_bytes]
+            return bool(np.array_equal(self.hp["out"][: self.out_bytes], want))
+
+        # ---- host link ceiling: the same bytes, the same pinned buffers, copies only
+        def copy_legs(self, steps):
+            w, hp = self.w, self.hp
+            d_in = torch.empty(w.n + 64, dtype=torch.uint8, device=dev)
+            d_res = torch.empty(self.out_bytes_c + 64, dtype=torch.uint8, device=dev)
+            h_res_t, _ = pinned(self.out_bytes_c + 64)
+            side = torch.cuda.Stream()
+
+            def h2d_in():
+                d_in[: w.n].copy_(hp["fastq_t"], non_blocking=True)
+
+            def d2h_res():
+                h_res_t[: self.out_bytes_c].copy_(d_res[: self.out_bytes_c], non_blocking=True)
+
+            def h2d_res():
+                d_res[: self.out_bytes_c].copy_(h_res_t[: self.out_bytes_c], non_blocking=True)
+
+            def d2h_out():
+                hp["out_t"][: self.out_bytes].copy_(self.d_out[: self.out_bytes], non_blocking=True)
+
+            def both_c():   # compress direction: input down, result up, at the same time
+                side.wait_stream(stream)
+                h2d_in()
+                with torch.cuda.stream(side):
+                    d2h_res()
+                stream.wait_stream(side)
+
+            def both_d():
+                side.wait_stream(stream)
+                h2d_res()
+                with torch.cuda.stream(side):
+                    d2h_out()
+                stream.wait_stream(side)
+
+            r = {}
+            for name, fn in (("h2d_fastq", h2d_in), ("d2h_result", d2h_res), ("h2d_result", h2d_res), ("d2h_fastq", d2h_out),
+                             ("compress_both_ways", both_c), ("decompress_both_ways", both_d)):
+                r[name + "_ms"] = timed(fn, steps, 1)[0]
+            return r
+
+    def roofline(run, stage_ms: dict):
+        summ, w = run.enc_summ, run.w
+        nsym = int(summ.n_symbols)
+        side = 2 * int(summ.n_records) * 2 + 2 * int(summ.n_pos_entries) + int(summ.hdr_bytes)
+        algo_pipeline = w.n + int(summ.seq_bytes) + int(summ.qual_bytes) + side  # SURVEY 8(d) `B`
         # dominant kernel = longest stage; algorithmic bytes per launch stated in DESIGN.md section 5
         algo = {
             "chain_seq": nsym * 3, "chain_qual": nsym * 3,          # 1 B symbol read + 2 B field written
             "decode_seq": nsym + int(summ.seq_bytes), "decode_qual": nsym + int(summ.qual_bytes),  # stream read + 1 B/sym written
             "part_seq": nsym * (2 + 1 + 4), "part_qual": nsym * (4 + 4 + 1 + 4),
-            "pack_seq": nsym * (4 + 2) * 2, "pack_qual": nsym * (4 + 2) * 2, "extract": 2 * nsym + nsym * 6, "parse": 2 * n_bytes,
-            "layout": int(summ.hdr_bytes) * 2 + 5 * int(summ.n_records), "hist": 2 * min(S, n_bytes), "tables": 8448 * 2048 * 10,
+            "pack_seq": nsym * (4 + 2) * 2, "pack_qual": nsym * (4 + 2) * 2, "extract": 2 * nsym + nsym * 6, "parse": 2 * w.n,
+            "layout": int(summ.hdr_bytes) * 2 + 5 * int(summ.n_records), "hist": 2 * min(S, w.n), "tables": 8448 * 2048 * 10,
             "ninsert": 4 * int(summ.n_records),
         }
-        name = max(stage_ms, key=lambda k: stage_ms[k])
+        name = max(stage_ms, key=lambda kk: stage_ms[kk])
         ach = algo.get(name, 0) / (stage_ms[name] * 1e-3) / 1e9
         kern_ms = sum(stage_ms.values())
         return {
@@ -414,31 +563,111 @@ def run_ours(args):
             "traffic": (traffic_db.get(name, {}).get("dram_bytes_per_symbol") or 0) * nsym or None,
             "traffic_source": "ncu dram__bytes_read+write per symbol of the committed capture x symbols of this run" if name in traffic_db else None,
             "peak_source": peak_src, "kernel_ms": stage_ms[name], "kernel_share_of_step": stage_ms[name] / kern_ms,
-            "stage_ms": {k: round(v, 4) for k, v in stage_ms.items()},
+            "stage_ms": {kk: round(v, 4) for kk, v in stage_ms.items()},
             "pipeline": {"algorithmic_bytes": algo_pipeline, "kernels_ms": kern_ms,
                          "achieved": algo_pipeline / (kern_ms * 1e-3) / 1e9, "frac": algo_pipeline / (kern_ms * 1e-3) / 1e9 / peak},
         }
 
-    out_bytes_c = int(summ.seq_bytes) + int(summ.qual_bytes) + 3 * 2 * int(summ.n_records) + 2 * int(summ.n_pos_entries) + int(summ.hdr_bytes)
+    # ------------------------------------------------------------------ headline measurement
+    run = Run(wl)
+    run.setup()
+    run.decompress_dev()
+    roundtrip_ok = run.roundtrip_dev()
+    total_mb = allsum(float(wl.own_bytes)) / 1e6
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms_c, wall_c, launches_c = timed(run.compress_dev, args.steps, args.warmup)
+    t_c = dict(run.st["t_c"])
+    ms_d, wall_d, launches_d = timed(run.decompress_dev, args.steps, args.warmup)
+    t_d = dict(run.st["t_d"])
+    clocks = sampler.stop() if sampler else {}
+    ms_ce, _, _ = timed(run.compress_e2e, args.steps, args.warmup)
+    ms_de, _, _ = timed(run.decompress_e2e, args.steps, args.warmup)
+    e2e_ok = bool(run.st["e2e_wrote"] == run.out_bytes) and run.roundtrip_e2e()
+    copies = run.copy_legs(max(2, args.steps))
+    summ = run.enc_summ
+
     comp = {
         "value": total_mb / (ms_c * 1e-3), "ms_per_step": ms_c, "wall_ms_per_step": wall_c,
         "e2e": {"value": total_mb / (ms_ce * 1e-3), "unit": "MB/s", "ms_per_step": ms_ce,
-                "h2d_bytes_per_step": n_bytes + (sample_window if world > 1 else 0), "d2h_bytes_per_step": out_bytes_c},
-        "gpu_launches": int(launches_c), "roofline": roofline(t_c, "c"),
+                "h2d_bytes_per_step": wl.n + (sample_window if world > 1 else 0), "d2h_bytes_per_step": run.out_bytes_c,
+                "copy_only_ms": copies["compress_both_ways_ms"], "fraction_of_copy_ceiling": copies["compress_both_ways_ms"] / ms_ce},
+        "gpu_launches": int(launches_c), "roofline": roofline(run, t_c),
     }
     deco = {
         "value": total_mb / (ms_d * 1e-3), "ms_per_step": ms_d, "wall_ms_per_step": wall_d,
         "e2e": {"value": total_mb / (ms_de * 1e-3), "unit": "MB/s", "ms_per_step": ms_de,
-                "h2d_bytes_per_step": out_bytes_c, "d2h_bytes_per_step": n_bytes},
-        "gpu_launches": int(launches_d), "roofline": roofline(t_d, "d"),
+                "h2d_bytes_per_step": run.out_bytes_c, "d2h_bytes_per_step": run.out_bytes,
+                "copy_only_ms": copies["decompress_both_ways_ms"], "fraction_of_copy_ceiling": copies["decompress_both_ways_ms"] / ms_de},
+        "gpu_launches": int(launches_d), "roofline": roofline(run, t_d),
     }
+
+    # ------------------------------------------------------------------ parity of THIS rank against the oracle
+    def parity_rank():
+        """chunk boundaries, a spread of chunk streams and side buffers of this rank's slab, and (rank 0)
+        the all-reduced FreqTable images, against the CPU oracle.  Returns (ok, detail)."""
+        from oracle import oracle as O
+
+        host, ar = run.hp["fastq"], run.hp["arenas"]
+        fs, fq = tables["ft"]
+        detail = {}
+        ok = True
+        if rank == 0:  # tables of the sharded sample + all-reduce == tables of the whole sample in one pass
+            win = host[: min(S, wl.own_bytes)]
+            recs, used = O.parse_records(win)
+            ofs, ofq = O.make_ft(*O.hist(win[:used], recs))
+            detail["tables_match_single_pass"] = bool(np.array_equal(ofs, fs) and np.array_equal(ofq, fq))
+            ok &= detail["tables_match_single_pass"]
+        first = run.first_byte
+        offs = O.split_chunks(host[first:], wl.R)             # the oracle's walk from this rank's first chunk
+        mine = [int(ci.fastq_off) for ci in run.abs_infos] + [int(run.abs_infos[-1].fastq_off) + int(run.abs_infos[-1].total)]
+        ncmp = len(mine) if last else min(len(mine), len(offs) - 1)
+        detail["boundaries_match"] = bool([int(o) + first for o in offs[:ncmp]] == mine[:ncmp])
+        ok &= detail["boundaries_match"]
+        cod = O.Codec(fs, fq)
+        nk = len(run.abs_infos)
+        pick = sorted(set(list(range(min(nk, args.parity_chunks // 2))) + list(range(max(0, nk - args.parity_chunks // 2), nk))))
+        bad = 0
+        for kk in pick:
+            ci = run.abs_infos[kk]
+            sub = host[int(ci.fastq_off) : int(ci.fastq_off) + int(ci.total)]
+            recs, used = O.parse_records(sub)
+            enc = cod.encode_chunk(sub, recs)
+            r0, n = int(ci.rec_off), int(ci.n_records)
+            same = (used == sub.size and n == len(recs)
+                    and np.array_equal(ar["seq"][ci.seq_off : ci.seq_off + ci.seq_len], enc["seq"])
+                    and np.array_equal(ar["qual"][ci.qual_off : ci.qual_off + ci.qual_len], enc["qual"])
+                    and np.array_equal(ar["readlens"][r0 : r0 + n], enc["readlens"])
+                    and np.array_equal(ar["n_count"][r0 : r0 + n], enc["n_count"])
+                    and np.array_equal(ar["n_pos"][ci.n_pos_off : ci.n_pos_off + ci.n_pos_len], enc["n_pos"]))
+            bad += not same
+        detail["chunks_checked"], detail["chunks_differ"] = len(pick), bad
+        ok &= bad == 0
+        return ok, detail
+
+    parity = {"roundtrip_device": roundtrip_ok, "roundtrip_e2e": e2e_ok}
+    if not args.no_parity:
+        try:
+            ok, detail = parity_rank()
+        except Exception as e:
+            ok, detail = False, {"error": repr(e)}
+        parity["rank0_vs_oracle"] = detail if rank == 0 else None
+        parity["this_rank_vs_oracle"] = bool(ok)
+        parity["all_ranks_vs_oracle"] = bool(allsum(0.0 if ok else 1.0) == 0.0)
+        parity["all_ranks_roundtrip"] = bool(allsum(0.0 if (roundtrip_ok and e2e_ok) else 1.0) == 0.0)
+        if world > 1:  # the global chunk chain is gap-free: each rank starts where the previous one stopped
+            ends = [torch.zeros(2, dtype=torch.int64, device=dev) for _ in range(world)]
+            a0 = wl.base + run.first_byte
+            dist.all_gather(ends, torch.tensor([a0, a0 + run.out_bytes], dtype=torch.int64, device=dev))
+            e = [(int(x[0]), int(x[1])) for x in ends]
+            parity["chunk_chain_contiguous"] = bool(e[0][0] == 0 and all(e[i][1] == e[i + 1][0] for i in range(world - 1))
+                                                    and e[-1][1] == wl.file_bytes)
 
     def gpu_fnv(O):
         """FNV-1a over (seq stream, qual stream) of every chunk in order, on the
         bytes the e2e leg fetched to the host -- same walk as fq28o_bench."""
-        ar, hh = state["hp"]["arenas"], 1469598103934665603
-        for kk in range(int(summ.n_chunks)):
-            ci = state["dec_infos"][kk]
+        ar, hh = run.hp["arenas"], 1469598103934665603
+        for ci in run.abs_infos:
             hh = O.fnv1a(ar["seq"][ci.seq_off : ci.seq_off + ci.seq_len], hh)
             hh = O.fnv1a(ar["qual"][ci.qual_off : ci.qual_off + ci.qual_len], hh)
         return hh
@@ -449,39 +678,126 @@ def run_ours(args):
             from oracle import oracle as O
 
             threads = args.threads or os.cpu_count() or 1
-            nb = min(n_bytes, args.cpu_mb << 20)
-            host = state["hp"]["fastq"][:nb]
+            nb = min(wl.n, args.cpu_mb << 20)
+            host = run.hp["fastq"][:nb]
             # cut at a record boundary so the sample is a valid FASTQ prefix
-            offs = O.split_chunks(host, R)
+            offs = O.split_chunks(host, wl.R)
             host = host[: int(offs[-1])]
-            res = O.bench(host, S, R, threads, True)
+            res = O.bench(host, S, wl.R, threads, True)
             vc = host.size / 1e6 / (res.t_analyze_s + res.t_compress_s)
             vd = host.size / 1e6 / res.t_decompress_s
-            # parity of this run: FNV over all chunk streams of the same prefix
             cpu_baseline = {
                 "value": vc if args.mode == "compress" else vd, "unit": "MB/s", "cores": threads, "kind": "port",
                 "sample": f"leading {host.size} bytes of the rank-0 slab ({res.n_chunks} chunks), one pass",
                 "compress_MBps": vc, "decompress_MBps": vd, "roundtrip_ok": bool(res.roundtrip_ok),
-                "streams_match_gpu": bool(host.size == n_bytes
-                                          and res.seq_bytes == sum(int(state["dec_infos"][kk].seq_len) for kk in range(int(summ.n_chunks)))
-                                          and res.qual_bytes == sum(int(state["dec_infos"][kk].qual_len) for kk in range(int(summ.n_chunks)))
+                "streams_match_gpu": bool(host.size == wl.n
+                                          and res.seq_bytes == sum(int(ci.seq_len) for ci in run.abs_infos)
+                                          and res.qual_bytes == sum(int(ci.qual_len) for ci in run.abs_infos)
                                           and res.checksum == gpu_fnv(O)),
             }
         except Exception as e:  # the oracle is a checker, never a dependency of the product arm
             cpu_baseline = {"error": repr(e)}
 
+    # ------------------------------------------------------------------ sweep: reading sizes, chunks resident
+    sweep = None
+    if not args.no_sweep:
+        sweep = {"note": "same slab; tables from the same -S sample; few steps per point (the -R 256 decode takes seconds)",
+                 "reading_size_mb": {}, "chunks_resident": {}}
+        sweep["reading_size_mb"][str(args.reading_mb)] = {
+            "n_chunks_per_gpu": run.n_dec, "compress_MBps": comp["value"], "compress_e2e_MBps": comp["e2e"]["value"],
+            "decompress_MBps": deco["value"], "decompress_e2e_MBps": deco["e2e"]["value"], "roundtrip": roundtrip_ok and e2e_ok}
+        sweep["chunks_resident"][str(int(allsum(run.n_dec) / world))] = {
+            "slabs_in_flight": 1, "fastq_MB_per_gpu": wl.own_bytes / 1e6, "decompress_MBps": deco["value"], "ms": ms_d}
+        # (several ranks: the resident slabs hold R - 1 bytes of lookahead for the headline R only)
+        for rmb in [int(x) for x in args.sweep_reading_mb.split(",") if x and int(x) != args.reading_mb and world == 1]:
+            try:
+                w2 = Workload.__new__(Workload)
+                w2.__dict__.update(wl.__dict__)
+                w2.R = rmb << 20
+                w2.max_chunks = 2 * (w2.n // w2.R) + 8
+                w2.infos = (P.ChunkInfo * w2.max_chunks)()
+                r2 = Run(w2)
+                r2.setup()
+                heavy = rmb >= 64
+                c_ms = timed(r2.compress_dev, 1 if heavy else 2, 1)[0]
+                d_ms = timed(r2.decompress_dev, 1, 0 if heavy else 1)[0]
+                ok2 = r2.roundtrip_dev()
+                ce_ms = timed(r2.compress_e2e, 1 if heavy else 2, 1)[0]
+                de_ms = timed(r2.decompress_e2e, 1, 0 if heavy else 1)[0]
+                ok2 = ok2 and bool(r2.st["e2e_wrote"] == r2.out_bytes) and r2.roundtrip_e2e()
+                mb2 = w2.own_bytes / 1e6
+                sweep["reading_size_mb"][str(rmb)] = {
+                    "n_chunks_per_gpu": r2.n_dec, "compress_MBps": mb2 / (c_ms * 1e-3), "compress_e2e_MBps": mb2 / (ce_ms * 1e-3),
+                    "decompress_MBps": mb2 / (d_ms * 1e-3), "decompress_e2e_MBps": mb2 / (de_ms * 1e-3), "roundtrip": ok2,
+                    "stage_ms_compress": {kk: round(v, 3) for kk, v in r2.st["t_c"].items() if v},
+                    "stage_ms_decompress": {kk: round(v, 3) for kk, v in r2.st["t_d"].items() if v}}
+                del r2
+            except Exception as e:
+                sweep["reading_size_mb"][str(rmb)] = {"error": repr(e)}
+        # BASELINE config 5's shape: decompress only, thousands of chunks resident per GPU.  A slab is
+        # < 4 GiB (FQ28_MAX_SLAB), so more chunks = several slabs in flight on separate handles.
+        if args.resident_mb and world == 1:
+            try:
+                import threading
+
+                w3 = Workload(args.reading_mb << 20, size_mb=args.resident_mb)
+                r3 = Run(w3)
+                r3.setup()
+                r3.decompress_dev()
+                ok3 = r3.roundtrip_dev()
+                d_ms = timed(r3.decompress_dev, 2, 1)[0]
+                sweep["chunks_resident"][str(r3.n_dec)] = {"slabs_in_flight": 1, "fastq_MB_per_gpu": w3.own_bytes / 1e6,
+                                                           "decompress_MBps": w3.own_bytes / 1e6 / (d_ms * 1e-3), "ms": d_ms, "roundtrip": ok3}
+                nh = max(1, args.resident_slabs)
+                if nh > 1:
+                    hs = [P.Handle(local) for _ in range(nh - 1)]
+                    outs = [torch.empty(r3.out_bytes + 64, dtype=torch.uint8, device=dev) for _ in hs]
+                    for hh in hs:
+                        hh.load_tables(*tables["ft"])
+
+                    def all_at_once():
+                        ths = [threading.Thread(target=lambda hh=hh, o=o: hh.decompress_dev(r3.dec, r3.dec_infos, r3.n_dec, o.data_ptr(), r3.out_bytes))
+                               for hh, o in zip(hs, outs)]
+                        for t in ths:
+                            t.start()
+                        r3.decompress_dev()
+                        for t in ths:
+                            t.join()
+
+                    all_at_once()
+                    ok3 = all(bool(torch.equal(o[: r3.out_bytes], r3.d_out[: r3.out_bytes])) for o in outs)
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                    all_at_once()
+                    torch.cuda.synchronize()
+                    d_ms = (time.perf_counter() - t0) * 1e3
+                    sweep["chunks_resident"][str(nh * r3.n_dec)] = {
+                        "slabs_in_flight": nh, "fastq_MB_per_gpu": nh * w3.own_bytes / 1e6, "decompress_MBps": nh * w3.own_bytes / 1e6 / (d_ms * 1e-3),
+                        "ms": d_ms, "roundtrip": ok3, "timer": "host wall clock around the concurrent calls (one handle and host thread per slab)",
+                        "note": "the slabs are copies of one slab (same streams decoded into separate outputs)"}
+                    for hh in hs:
+                        hh.close()
+                del r3, w3
+            except Exception as e:
+                sweep["chunks_resident"]["error"] = repr(e)
+
     if rank == 0:
         head, other = (comp, deco) if args.mode == "compress" else (deco, comp)
+        cfg = workload_config(args, wl.own_bytes)
+        if world > 1:
+            cfg["multi_gpu"] = ("one virtual file of %d bytes; chunk boundaries from one sequential walk (each rank starts where the "
+                                "previous rank's last chunk ends; that offset is the only thing exchanged, via the process group's "
+                                "store); sample sharded by record range + one NCCL all-reduce of the 525 312 counters" % wl.file_bytes)
         line = {
             "metric": METRIC, "value": head["value"], "unit": "MB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "u8", "data": "synthetic", "config": workload_config(args, n_bytes), "mode": args.mode,
+            "dtype": "u8", "data": "synthetic", "config": cfg, "mode": args.mode,
             "e2e": head["e2e"], "gpu_launches": head["gpu_launches"], "roofline": head["roofline"],
             "clocks": clocks, "cpu_baseline": cpu_baseline,
-            "compress": {k: v for k, v in comp.items()}, "decompress": {k: v for k, v in deco.items()},
-            "parity": {"roundtrip_device": roundtrip_ok, "roundtrip_e2e": e2e_ok},
-            "stats": {"n_chunks": int(summ.n_chunks), "n_records": int(summ.n_records), "seq_bytes": int(summ.seq_bytes),
-                      "qual_bytes": int(summ.qual_bytes), "ratio_seq_qual": n_bytes / max(1, int(summ.seq_bytes) + int(summ.qual_bytes))},
+            "compress": {kk: v for kk, v in comp.items()}, "decompress": {kk: v for kk, v in deco.items()},
+            "host_link": copies, "parity": parity, "sweep": sweep,
+            "stats": {"n_chunks": run.n_dec, "n_records": run.n_rec_dec, "seq_bytes": int(summ.seq_bytes),
+                      "qual_bytes": int(summ.qual_bytes), "ratio_seq_qual": wl.n / max(1, int(summ.seq_bytes) + int(summ.qual_bytes))},
         }
         print(json.dumps(line), flush=True)
     h.close()

@@ -114,6 +114,7 @@ SYMBOLS = [
     "fq28_decompress_dev", "fq28_get_ctable", "fq28_get_dtable", "fq28_compress_dev_arenas",
     "fq28_last_timings", "fq28_stage_name", "fq28_tokenize_headers", "fq28_detokenize_headers",
     "fq28_device_count", "fq28_stage", "fq28_plan", "fq28_plan_dev", "fq28_preparse_dev", "fq28_plan_cut_dev",
+    "fq28_preparse", "fq28_plan_cut",
 ]
 
 _lib = None
@@ -155,6 +156,8 @@ def load() -> C.CDLL:
     L.fq28_plan.argtypes = [vp, vp, sz, sz, i32, C.POINTER(C.c_uint64), psz]
     L.fq28_plan_dev.argtypes = [vp, vp, sz, sz, i32, C.POINTER(C.c_uint64), psz]
     L.fq28_preparse_dev.argtypes = [vp, vp, sz]
+    L.fq28_preparse.argtypes = [vp, vp, sz]
+    L.fq28_plan_cut.argtypes = [vp, vp, sz, sz, i32, C.c_uint64, C.POINTER(C.c_uint64), psz]
     L.fq28_plan_cut_dev.argtypes = [vp, vp, sz, sz, i32, C.c_uint64, C.POINTER(C.c_uint64), psz]
     L.fq28_bound_seq.argtypes = [sz]
     L.fq28_bound_seq.restype = sz
@@ -334,6 +337,14 @@ class Handle:
     def plan_dev(self, d_fastq: int, n_bytes: int, reading_size: int, eof: bool = True):
         cons, n = C.c_uint64(0), C.c_size_t(0)
         self._ck(self.L.fq28_plan_dev(self.h, d_fastq, n_bytes, reading_size, int(eof), C.byref(cons), C.byref(n)))
+        return cons.value, n.value
+
+    def preparse(self, data: np.ndarray) -> None:
+        self._ck(self.L.fq28_preparse(self.h, _ptr(data), data.size))
+
+    def plan_cut(self, data: np.ndarray, reading_size: int, eof: bool, first_cut: int):
+        cons, n = C.c_uint64(0), C.c_size_t(0)
+        self._ck(self.L.fq28_plan_cut(self.h, _ptr(data), data.size, reading_size, int(eof), first_cut, C.byref(cons), C.byref(n)))
         return cons.value, n.value
 
     def preparse_dev(self, d_fastq: int, n_bytes: int) -> None:

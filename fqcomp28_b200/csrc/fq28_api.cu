@@ -531,6 +531,27 @@ int fq28_stage(fq28_handle *h, const char *fastq, size_t n_bytes) {
   return FQ28_OK;
 }
 
+int fq28_preparse(fq28_handle *h, const char *fastq, size_t n_bytes) {
+  if (!h || !fastq) return FQ28_ERR_ARG;
+  FQ28_TRY(bind(h));
+  FQ28_TRY(stage_in(h, fastq, n_bytes));
+  FQ28_TRY(fq28_preparse_dev(h, h->in_fastq.as<char>(), n_bytes));
+  h->plan_host = fastq;
+  return FQ28_OK;
+}
+
+int fq28_plan_cut(fq28_handle *h, const char *fastq, size_t n_bytes, size_t reading_size, int eof, uint64_t first_cut,
+                  uint64_t *consumed, size_t *n_chunks) {
+  if (!h || !fastq) return FQ28_ERR_ARG;
+  FQ28_TRY(bind(h));
+  const bool have = h->parsed.valid && h->parsed.d_fastq == h->in_fastq.as<char>() && h->parsed.n_bytes == n_bytes &&
+                    h->plan_host == fastq;
+  if (!have) FQ28_TRY(stage_in(h, fastq, n_bytes));
+  FQ28_TRY(fq28_plan_cut_dev(h, h->in_fastq.as<char>(), n_bytes, reading_size, eof, first_cut, consumed, n_chunks));
+  h->plan_host = fastq;
+  return FQ28_OK;
+}
+
 int fq28_plan(fq28_handle *h, const char *fastq, size_t n_bytes, size_t reading_size, int eof, uint64_t *consumed,
               size_t *n_chunks) {
   if (!h || !fastq) return FQ28_ERR_ARG;

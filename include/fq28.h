@@ -192,6 +192,11 @@ int fq28_plan_dev(fq28_handle *h, const char *d_fastq, size_t n_bytes, size_t re
  * dropped by the caller: it is the tail of the previous rank's last chunk.  first_cut must be a
  * record boundary (else FQ28_ERR_FORMAT).  Between ranks only this one offset travels. */
 int fq28_preparse_dev(fq28_handle *h, const char *d_fastq, size_t n_bytes);
+/* host-buffer forms: fq28_preparse copies the slab to the device and builds the record table;
+ * fq28_plan_cut / fq28_compress on the same buffer then reuse both */
+int fq28_preparse(fq28_handle *h, const char *fastq, size_t n_bytes);
+int fq28_plan_cut(fq28_handle *h, const char *fastq, size_t n_bytes, size_t reading_size,
+                  int eof, uint64_t first_cut, uint64_t *consumed, size_t *n_chunks);
 int fq28_plan_cut_dev(fq28_handle *h, const char *d_fastq, size_t n_bytes, size_t reading_size,
                       int eof, uint64_t first_cut, uint64_t *consumed, size_t *n_chunks);
 /* Copies the device-resident result of the last fq28_compress_dev out. */
