@@ -213,33 +213,6 @@ def workload_config(args, n_bytes):
 
 
 # --------------------------------------------------------------------------- our arm
-class Baton:
-    """The one number that travels between ranks: the global file offset at which the previous
-    rank's last chunk ends (the chunk boundary walk is sequential, src/fastq_io.cpp:23-65).
-    Host-side, through the process group's TCP store -- control metadata, not a data-path
-    collective.  One key per (step, rank)."""
-
-    def __init__(self, rank, world):
-        self.rank, self.world, self.step = rank, world, 0
-        self.store = None
-        if world > 1:
-            from torch.distributed.distributed_c10d import _get_default_store
-
-            self.store = _get_default_store()
-
-    def next_step(self):
-        self.step += 1
-
-    def recv(self) -> int:
-        if self.rank == 0:
-            return 0
-        return int(self.store.get(f"fq28/cut/{self.step}/{self.rank}").decode())
-
-    def send(self, cut: int):
-        if self.rank + 1 < self.world:
-            self.store.set(f"fq28/cut/{self.step}/{self.rank + 1}", str(int(cut)))
-
-
 def run_ours(args):
     import numpy as np
     import torch
@@ -260,7 +233,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     S = args.sample_mb << 20
     last = rank == world - 1
-    baton = Baton(rank, world)
+    baton = MG.Baton(rank, world)
     stream = torch.cuda.current_stream()
     h = P.Handle(local, stream=stream.cuda_stream)
     peak, peak_src = load_peaks()
@@ -320,7 +293,7 @@ def run_ours(args):
                 nl = torch.nonzero(t == 10).flatten()
                 own = int(nl[4 * self.M - 1].item()) + 1
                 del nl
-                self.slab = t[: own + R - 1] if not last else t[:own]
+                self.slab = t[: MG.slab_end(own, R, t.numel(), last)] if not last else t[:own]
             else:
                 own = t.numel()
                 self.slab = t

@@ -1,12 +1,20 @@
 """Host-side multi-GPU logic of the path.
 
 The path shards by chunk range: every GPU encodes / decodes its own contiguous
-range of chunks independently.  The only exchange is the sum of the sample
+range of chunks independently.  The only collective is the sum of the sample
 histograms (256*4 + 8192*64 = 525 312 u32 counters, 2.1 MB) when the sample is
 histogrammed cooperatively; integer sums are order independent, so the tables
 every rank builds afterwards are bit-identical to a single-GPU run.  The +1
 prior (src/fse_sequence.cpp:149-150, src/fse_quality.cpp:75-76) is added after
 the reduction, inside fq28_build_tables.
+
+Chunk boundaries are a sequential recurrence over the file (FastqReader::
+readNextChunk, src/fastq_io.cpp:23-65).  With one rank per GPU, rank r holds its
+record range plus reading_size - 1 bytes of lookahead (`slab_end`), pre-parses
+it at once, and learns from rank r-1 one number -- the file offset at which that
+rank's last chunk ends (`Baton`) -- from which its own boundary walk starts
+(fq28_plan_cut_dev).  The chunks of all ranks are then exactly those of the
+single-process walk.
 
 Backend agnostic: NCCL over NVLink on the GPU box, gloo in the CPU tests.
 """
@@ -59,3 +67,41 @@ def allreduce_counts(seq_counts, qual_counts, group=None):
         dist.all_reduce(seq_counts, group=group)
         dist.all_reduce(qual_counts, group=group)
     return seq_counts, qual_counts
+
+
+def slab_end(own_end: int, reading_size: int, file_size: int, is_last: bool) -> int:
+    """End (global offset, exclusive) of the bytes rank r must hold when its records end at
+    `own_end`: reading_size - 1 bytes of lookahead.  With exactly that much, a chunk that
+    starts before own_end has its whole window inside the slab (so the walk, which only emits
+    chunks whose window fits, emits it), and a chunk that starts at or after own_end does not
+    (it belongs to the next rank)."""
+    if is_last:
+        return file_size
+    return min(file_size, own_end + reading_size - 1)
+
+
+class Baton:
+    """The one number that travels between ranks: the global file offset at which the previous
+    rank's last chunk ends.  Host-side, through the process group's store (TCP) -- control
+    metadata, not a data-path collective.  One key per (step, rank): rank r blocks in recv()
+    until rank r-1 has walked its boundaries."""
+
+    def __init__(self, rank: int, world: int, store=None):
+        self.rank, self.world, self.step = rank, world, 0
+        self.store = store
+        if world > 1 and store is None:
+            from torch.distributed.distributed_c10d import _get_default_store
+
+            self.store = _get_default_store()
+
+    def next_step(self) -> None:
+        self.step += 1
+
+    def recv(self) -> int:
+        if self.rank == 0:
+            return 0
+        return int(self.store.get(f"fq28/cut/{self.step}/{self.rank}").decode())
+
+    def send(self, cut: int) -> None:
+        if self.rank + 1 < self.world:
+            self.store.set(f"fq28/cut/{self.step}/{self.rank + 1}", str(int(cut)))

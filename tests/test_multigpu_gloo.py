@@ -86,6 +86,74 @@ def test_two_rank_tables_and_streams_match_single_process(oracle):
     assert gathered[0][3][1] == gathered[1][3][0]
 
 
+def _chain_worker(rank, world, port, q):
+    """the N-rank chunking of bench.py / DESIGN.md section 7 with the oracle's walk standing in for
+    fq28_plan_cut_dev: record ranges + lookahead (slab_end), one cut offset per rank (Baton)"""
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from fqcomp28_b200 import multigpu as M
+    from oracle import oracle as O
+
+    d = np.concatenate([load_fixture("SRR065390_sub_1"), load_fixture("SRR065390_sub_2"), load_fixture("without_ns")])
+    R = 50_000
+    recs, _ = O.parse_records(d)
+    ends = np.append(recs["hdr_off"].astype(np.int64), d.size)
+    per = (len(recs) + world - 1) // world
+    b0, b1 = int(ends[min(rank * per, len(recs))]), int(ends[min((rank + 1) * per, len(recs))])
+    last = rank == world - 1
+    slab = d[b0 : M.slab_end(b1, R, d.size, last)]
+    baton = M.Baton(rank, world)
+    out = []
+    for step in range(2):                       # two steps: the keys of one step must not leak into the next
+        baton.next_step()
+        cut = baton.recv()
+        first = cut - b0
+        assert 0 <= first < R
+        # walk from the cut; like the GPU walk with eof = 0, only chunks whose window fits are the rank's own
+        offs = [int(o) + first for o in O.split_chunks(slab[first:], R)]
+        if not last:
+            offs = [o for i, o in enumerate(offs) if i == 0 or offs[i - 1] + R <= slab.size]
+        baton.send(b0 + offs[-1])
+        out.append([(b0 + offs[i], b0 + offs[i + 1]) for i in range(len(offs) - 1)])
+    assert out[0] == out[1]
+    gathered = [None] * world
+    dist.all_gather_object(gathered, out[0])
+    if rank == 0:
+        q.put(gathered)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("world", [2, 3])
+def test_cut_chain_tiles_the_file_like_one_walk(oracle, world):
+    port = 31500 + (os.getpid() % 2000) + world
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_chain_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    gathered = q.get(timeout=240)
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    d = np.concatenate([load_fixture("SRR065390_sub_1"), load_fixture("SRR065390_sub_2"), load_fixture("without_ns")])
+    offs = [int(o) for o in oracle.split_chunks(d, 50_000)]
+    chunks = [c for g in gathered for c in g]
+    assert chunks == [(offs[i], offs[i + 1]) for i in range(len(offs) - 1)]
+    assert all(len(g) >= 2 for g in gathered)
+
+
+def test_slab_end():
+    from fqcomp28_b200 import multigpu as M
+
+    assert M.slab_end(1000, 100, 5000, False) == 1099
+    assert M.slab_end(1000, 100, 1050, False) == 1050
+    assert M.slab_end(1000, 100, 5000, True) == 5000
+
+
 def test_shard_helpers():
     from fqcomp28_b200 import multigpu as M
 
