@@ -59,10 +59,8 @@ FQ_HD uint32_t make_w_seq(uint32_t cell /* newState | sym<<16 | nb<<24 */, unsig
 //  [0] UNSEEN (symbol outside the dense alphabet V)   [1] ZENT (S entry of a
 //  zero-bit-run context: holds a state, not a cell)   [2,8) rank of the symbol in V
 //  [8,12) nbBits   [12,23) newState base   [23,30) output char   [31] STALE
-//  [30] DONE: not a cell -- the lane has nothing to decode in this trip (register only)
 //  ZENT entry: [8,19) state   [20,22) run slot
-constexpr uint32_t QW_UNSEEN = 1u, QW_ZENT = 2u, QW_DONE = 1u << 30, QW_STALE = 1u << 31,
-                   QW_SPECIAL = QW_UNSEEN | QW_ZENT | QW_DONE | QW_STALE;
+constexpr uint32_t QW_UNSEEN = 1u, QW_ZENT = 2u, QW_STALE = 1u << 31, QW_SPECIAL = QW_UNSEEN | QW_ZENT | QW_STALE;
 constexpr unsigned QROW_BYTES = 256;  // 64 entries per (max, eq) row
 FQ_HD uint32_t make_w_qual(uint32_t cell, const uint8_t *rk /*[64] rank in V or 0xFF*/) {
   const unsigned sym = (cell >> 16) & 63u, nb = cell >> 24, ns = cell & 0x7FFu;
@@ -564,10 +562,9 @@ FQ_HD bool decode_qual_stream(const StreamArgs &c, const QualShared &q, uint32_t
   unsigned i = 0;
   // record start: the three previous symbols are 0 (rank 0): row (max 0, eq 1), column 0
   const uint32_t row_init = sb + QROW_BYTES;
-  uint32_t a = row_init, W = QW_DONE;
+  uint32_t a = row_init, W = 0;
   uint32_t R1 = row_init;   // row of the NEXT symbol's context (from the two symbols before this one)
   uint32_t r4p = 0;         // rank * 4 of the previous symbol
-  bool cold_pending = false;  // a symbol outside V was decoded: the slow path continues after this block
   const uint32_t *wadj = c.wtab - ((size_t)sb << (TAB_LOG - 2));  // ((a << 9) + ns) indexes it directly
   auto row_of = [&](uint32_t r4a, uint32_t r4b) -> uint32_t {  // row of (max, eq) of two symbols, ranks * 4
     const uint32_t mx4 = r4a > r4b ? r4a : r4b;
@@ -619,106 +616,92 @@ FQ_HD bool decode_qual_stream(const StreamArgs &c, const QualShared &q, uint32_t
       qc = qb; qb = qa; qa = sym;
     }
   };
-  // One decoding event at position t of the record (rem symbols long): a symbol or a zero-bit
-  // run; returns the new position.  As in the sequence decoder the common case has a single
-  // branch; behind it: lane idle in this trip (DONE), refill due, STALE, run context, symbol
-  // outside V.  When the lane reaches `stop` (or must hand over to the slow path) W becomes DONE.
-  auto step = [&](char *o, unsigned t, unsigned rem, unsigned stop) -> unsigned {
-    sm_async_tick();
-    if (!(W & (QW_STALE | QW_DONE))) sm_st32(a, QW_STALE);  // see decode_seq_stream
-    uint32_t an = R1 | (W & 0xFCu);
-    uint32_t Wn = sm_ld32(an);           // speculative
-    if (((W & QW_SPECIAL) != 0) | br.low()) {
-      if (W & QW_DONE) return t;
-      if (br.low()) br.refill();
-      if (W & QW_STALE) {
-        DEC2_COUNT(2);
-        W = sm_resolve_stale<QW_STALE>(a);
-        sm_st32(a, QW_STALE);
-        an = R1 | (W & 0xFCu);
-        Wn = sm_ld32(an);
-      }
-      if (W & QW_ZENT) {
-        const unsigned zs = (W >> 20) & 3u, x = (W >> 8) & 0x7FFu;
-        const unsigned z = sm_ld16(q.zt_a + (zs << (TAB_LOG + 1)) + x * 2);
-        unsigned kz = z >> 11;
-        if (kz) {  // the next kz symbols are d, read no bits, and stay in this context
-          DEC2_COUNT(3);
-          unsigned xs = z & 0x7FFu;
-          if (kz > rem - t) {  // the record ends inside the run: single steps
-            kz = rem - t;
-            xs = x;
-            for (unsigned j = 0; j < kz; j++) xs = (sm_ld32(q.hz_a + (zs << (TAB_LOG + 2)) + xs * 4) >> 12) & 0x7FFu;
-          }
-          W = make_zent(xs, zs);
-          sm_st32(a, W);
-          const char dc = (char)sm_ld32(q.zc_a + zs * 4);
-          if (t + 15 <= rem) {  // the bytes behind the run are rewritten by the record's later symbols
-#pragma unroll
-            for (unsigned j = 0; j < 15; j++) o[t + j] = dc;
-          } else {
-            for (unsigned j = 0; j < kz; j++) o[t + j] = dc;
-          }
-          t += kz;
-          if (t >= stop) W = QW_DONE;
-          return t;
-        }
-        // one ordinary step in the run context: cell from the shared table, refreshed inline
-        DEC2_COUNT(4);
-        const uint32_t cell = sm_ld32(q.hz_a + (zs << (TAB_LOG + 2)) + x * 4);
-        const unsigned ns = ((cell >> 12) & 0x7FFu) + br.read_nr((cell >> 8) & 15u);
-        sm_st32(a, make_zent(ns, zs));
-        an = R1 | (cell & 0xFCu);
-        Wn = sm_ld32(an);
-        W = cell;
-      } else {
-        const unsigned ns = ((W >> 12) & 0x7FFu) + br.read_nr((W >> 8) & 15u);
-        sm_async_ld32(a, wadj + ((a << (TAB_LOG - 2)) + ns));
-      }
-      o[t] = (char)((W >> 23) & 0x7Fu);
-      const uint32_t r4 = W & 0xFCu;
-      R1 = row_of(r4, r4p);
-      r4p = r4;
-      a = an;
-      if (W & QW_UNSEEN) {  // the slow path takes over from t + 1 (after this block of steps)
-        DEC2_COUNT(5);
-        cold_pending = true;
-        W = QW_DONE;
-      } else {
-        W = t + 1 >= stop ? QW_DONE : Wn;
-      }
-      return t + 1;
+  // Everything that is not "a plain cell, bits at hand": lane idle (never here), refill due, context
+  // STALE, run context, symbol outside V.  Out of the hot loop on purpose -- the loop below is a
+  // dozen instructions around one shared-memory load, and a taken branch costs ~25 cycles.
+  // Returns the new position; W / a / R1 / r4p are left ready for the next symbol.
+  auto special = [&](char *o, unsigned t, unsigned rem) -> unsigned {
+    if (br.low()) br.refill();
+    if (W & QW_STALE) {
+      DEC2_COUNT(2);
+      W = sm_resolve_stale<QW_STALE>(a);
     }
-    const unsigned ns = ((W >> 12) & 0x7FFu) + br.read_nr((W >> 8) & 15u);
-    sm_async_ld32(a, wadj + ((a << (TAB_LOG - 2)) + ns));
+    uint32_t an;
+    if (W & QW_ZENT) {
+      const unsigned zs = (W >> 20) & 3u, x = (W >> 8) & 0x7FFu;
+      const unsigned z = sm_ld16(q.zt_a + (zs << (TAB_LOG + 1)) + x * 2);
+      unsigned kz = z >> 11;
+      if (kz) {  // the next kz symbols are d, read no bits, and stay in this context
+        DEC2_COUNT(3);
+        unsigned xs = z & 0x7FFu;
+        if (kz > rem - t) {  // the record ends inside the run: single steps
+          kz = rem - t;
+          xs = x;
+          for (unsigned j = 0; j < kz; j++) xs = (sm_ld32(q.hz_a + (zs << (TAB_LOG + 2)) + xs * 4) >> 12) & 0x7FFu;
+        }
+        W = make_zent(xs, zs);
+        sm_st32(a, W);
+        const char dc = (char)sm_ld32(q.zc_a + zs * 4);
+        if (t + 15 <= rem) {  // the bytes behind the run are rewritten by the record's later symbols
+#pragma unroll
+          for (unsigned j = 0; j < 15; j++) o[t + j] = dc;
+        } else {
+          for (unsigned j = 0; j < kz; j++) o[t + j] = dc;
+        }
+        return t + kz;
+      }
+      // one ordinary step in the run context: cell from the shared table, refreshed inline
+      DEC2_COUNT(4);
+      const uint32_t cell = sm_ld32(q.hz_a + (zs << (TAB_LOG + 2)) + x * 4);
+      const unsigned ns = ((cell >> 12) & 0x7FFu) + br.read_nr((cell >> 8) & 15u);
+      sm_st32(a, make_zent(ns, zs));
+      W = cell;
+    } else {
+      const unsigned ns = ((W >> 12) & 0x7FFu) + br.read_nr((W >> 8) & 15u);
+      sm_st32(a, QW_STALE);
+      sm_async_ld32(a, wadj + ((a << (TAB_LOG - 2)) + ns));
+    }
     o[t] = (char)((W >> 23) & 0x7Fu);
+    if (W & QW_UNSEEN) {  // a quality value the sample never showed: explicit q values from here on
+      DEC2_COUNT(5);
+      return cold_run(o, t + 1, rem);   // comes back with a / R1 / r4p / W set, or at the record end
+    }
     const uint32_t r4 = W & 0xFCu;
+    an = R1 | r4;
     R1 = row_of(r4, r4p);
     r4p = r4;
     a = an;
-    W = t + 1 >= stop ? QW_DONE : Wn;
+    W = sm_ld32(a);
     return t + 1;
   };
   for (;;) {
     // uniform trip: every lane decodes until it has passed n symbols (n = symbols left in the
-    // warp's shortest current record); runs may overshoot n but never the lane's own record.
-    // Lanes without work carry W = DONE through the same instructions.
+    // warp's shortest current record); runs may overshoot n but never the lane's own record
     const unsigned n = warp_min(rr > 0 ? cur.L - i : 0xFFFFFFFFu);
     if (n == 0xFFFFFFFFu) break;
-    char *o = dst;                       // positions are absolute inside the record
-    const unsigned rem = cur.L, stop = rr > 0 ? i + n : 0u;
-    unsigned t = rr > 0 ? i : 0u;
-    W = rr > 0 ? sm_ld32(a) : QW_DONE;
-    do {
-#pragma unroll
-      for (int u = 0; u < UNROLL; u++) t = step(o, t, rem, stop);
-      if (cold_pending) {                // a symbol outside V was decoded
-        cold_pending = false;
-        t = cold_run(o, t, rem);         // back with the last three symbols in V, or at the record end
-        if (t >= stop) W = QW_DONE;
-      }
-    } while (warp_any(t < stop));
     if (rr > 0) {
+      char *o = dst;                     // positions are absolute inside the record
+      const unsigned rem = cur.L, stop = i + n;
+      unsigned t = i;
+      W = sm_ld32(a);
+      while (t < stop) {
+        sm_async_tick();
+        if (((W & QW_SPECIAL) != 0) | br.low()) {
+          t = special(o, t, rem);
+          continue;
+        }
+        // the hot path: a cell whose symbol is in V, bits at hand
+        o[t] = (char)((W >> 23) & 0x7Fu);
+        const unsigned ns = ((W >> 12) & 0x7FFu) + br.read_nr((W >> 8) & 15u);
+        sm_st32(a, QW_STALE);
+        sm_async_ld32(a, wadj + ((a << (TAB_LOG - 2)) + ns));   // S[a] <- cell of the new state, when it arrives
+        const uint32_t r4 = W & 0xFCu;
+        a = R1 | r4;
+        W = sm_ld32(a);
+        R1 = row_of(r4, r4p);
+        r4p = r4;
+        ++t;
+      }
       i = t;
       if (i >= cur.L) {
         --rr;

@@ -18,83 +18,102 @@ namespace fq28 {
 // K3
 // ---------------------------------------------------------------------------
 constexpr int HIST_WARPS = 8;
+constexpr unsigned HQ_SLOTS = 4096;          // per-CTA cache of hot quality (ctx, sym) counters
+constexpr uint32_t HQ_EMPTY = 0xFFFFFFFFu;
 
-// One warp per record.  Sequence: N is skipped and leaves the context
-// unchanged (src/fse_sequence.cpp:157-158), so contexts are formed over the
-// N-free compaction of the read; the warp compacts 32 bases at a time through
-// a 36-entry shared window (4 carried bases + 32 new).
+// One warp per record, and inside the warp one CONTIGUOUS segment of the read per lane: a lane
+// walks its symbols with the context in registers (no votes, no shuffles per symbol) and folds
+// runs of equal (context, symbol) pairs into one update.  Round 1 spent ~4.5 warp instructions
+// per symbol here (a vote loop per 32 symbols); this is ~0.3.
+//   sequence: N is skipped and leaves the context unchanged (src/fse_sequence.cpp:157-158), so a
+//             lane first finds the four non-N bases before its segment (the virtual prefix
+//             T,C,C,T of SEQ_INITIAL_CTX beyond the read start).  Counters: 4 KB in shared memory.
+//   quality : ctx = calcContext(q[i-1], q[i-2], q[i-3]) (src/fse_quality.h:40-44).  The 2 MB table
+//             does not fit shared memory; a direct-mapped cache of 4096 (key, count) slots holds the
+//             hot pairs (binned qualities: a few dozen pairs carry everything) and is flushed with
+//             one RED per used slot; pairs that lose their slot go to L2 with a RED right away.
 __global__ void __launch_bounds__(HIST_WARPS * 32)
 k_hist(const char *__restrict__ d, const uint32_t *__restrict__ seq_off, const uint32_t *__restrict__ qual_off,
        const uint16_t *__restrict__ len, size_t n_rec, uint32_t *__restrict__ g_seq,
        uint32_t *__restrict__ g_qual, DevStatus *st) {
   __shared__ uint32_t s_seq[SEQ_N * SEQ_A];
-  __shared__ unsigned char s_win[HIST_WARPS][36];
+  __shared__ uint32_t s_key[HQ_SLOTS], s_cnt[HQ_SLOTS];
   const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (unsigned i = threadIdx.x; i < SEQ_N * SEQ_A; i += blockDim.x) s_seq[i] = 0;
+  for (unsigned i = threadIdx.x; i < HQ_SLOTS; i += blockDim.x) { s_key[i] = HQ_EMPTY; s_cnt[i] = 0; }
   __syncthreads();
+  auto add_qual = [&](uint32_t key, uint32_t n) {
+    const unsigned slot = (key ^ (key >> 12)) & (HQ_SLOTS - 1);
+    uint32_t cur = s_key[slot];
+    if (cur == HQ_EMPTY) cur = atomicCAS(&s_key[slot], HQ_EMPTY, key), cur = cur == HQ_EMPTY ? key : cur;
+    if (cur == key) atomicAdd(&s_cnt[slot], n);
+    else atomicAdd(&g_qual[key], n);
+  };
   const size_t warps_total = (size_t)gridDim.x * HIST_WARPS;
   for (size_t r = (size_t)blockIdx.x * HIST_WARPS + warp; r < n_rec; r += warps_total) {
     const unsigned L = len[r];
     const unsigned char *sp = reinterpret_cast<const unsigned char *>(d) + seq_off[r];
     const unsigned char *qp = reinterpret_cast<const unsigned char *>(d) + qual_off[r];
+    unsigned K = (L + 31) / 32;          // symbols per lane
+    if (K < 4) K = 4;
+    const unsigned s = lane * K;
+    if (s >= L) continue;
+    const unsigned e = s + K < L ? s + K : L;
     // ---- sequence
-    if (lane < 4) s_win[warp][lane] = (SEQ_INITIAL_CTX >> (2 * lane)) & 3u;  // win[3] = closest = T
-    __syncwarp();
-    for (unsigned base = 0; base < L; base += 32) {
-      const unsigned i = base + lane;
-      int sym = -2;  // -2: past the end
-      if (i < L) {
+    {
+      // the four bases before position s, closest first: real non-N bases, then the prefix T,C,C,T
+      unsigned ctx = 0, found = 0;
+      for (unsigned j = s; j > 0 && found < 4; --j) {
+        const int b = base2bits(sp[j - 1]);
+        if (b >= 0) { ctx |= (unsigned)b << (6 - 2 * found); ++found; }
+      }
+      for (unsigned v = 0; found < 4; ++v, ++found) ctx |= ((SEQ_INITIAL_CTX >> (6 - 2 * v)) & 3u) << (6 - 2 * found);
+      unsigned run_key = 0xFFFFFFFFu, run_n = 0;
+      for (unsigned i = s; i < e; ++i) {
         const unsigned char c = sp[i];
-        sym = (c == 'N') ? -3 : base2bits(c);
-        if (sym == -1) set_error(st, FQ28_ERR_ALPHABET, (unsigned)r);
+        if (c == 'N') continue;
+        const int sym = base2bits(c);
+        if (sym < 0) { set_error(st, FQ28_ERR_ALPHABET, (unsigned)r); break; }
+        const unsigned key = ctx * 4 + (unsigned)sym;
+        if (key == run_key) ++run_n;
+        else {
+          if (run_n) atomicAdd(&s_seq[run_key], run_n);
+          run_key = key;
+          run_n = 1;
+        }
+        ctx = (ctx >> 2) + ((unsigned)sym << 6);
       }
-      const unsigned m = __ballot_sync(0xffffffffu, sym >= 0);
-      const unsigned k = __popc(m & ((1u << lane) - 1u));
-      if (sym >= 0) s_win[warp][4 + k] = (unsigned char)sym;
-      __syncwarp();
-      if (sym >= 0) {
-        const unsigned char *w = &s_win[warp][k];  // w[3] closest ... w[0] farthest
-        const unsigned ctx = ((unsigned)w[3] << 6) | ((unsigned)w[2] << 4) | ((unsigned)w[1] << 2) | w[0];
-        atomicAdd(&s_seq[ctx * 4 + (unsigned)sym], 1u);
-      }
-      __syncwarp();
-      const unsigned tot = __popc(m);
-      unsigned char carry = 0;
-      if (lane < 4) carry = s_win[warp][tot + lane];
-      __syncwarp();
-      if (lane < 4) s_win[warp][lane] = carry;
-      __syncwarp();
+      if (run_n) atomicAdd(&s_seq[run_key], run_n);
     }
-    // ---- quality: ctx_i = calcContext(q[i-1], q[i-2], q[i-3]), q[<0] = 0
-    for (unsigned base = 0; base < L; base += 32) {
-      const unsigned i = base + lane;
-      unsigned key = 0xFFFFFFFFu;
-      if (i < L) {
+    // ---- quality
+    {
+      unsigned q1 = s >= 1 ? (unsigned)qp[s - 1] - QUAL_OFFSET : 0u;
+      unsigned q2 = s >= 2 ? (unsigned)qp[s - 2] - QUAL_OFFSET : 0u;
+      unsigned q3 = s >= 3 ? (unsigned)qp[s - 3] - QUAL_OFFSET : 0u;
+      unsigned run_key = 0xFFFFFFFFu, run_n = 0;
+      for (unsigned i = s; i < e; ++i) {
         const unsigned q = (unsigned)qp[i] - QUAL_OFFSET;
-        const unsigned a = i >= 1 ? (unsigned)qp[i - 1] - QUAL_OFFSET : 0u;
-        const unsigned b = i >= 2 ? (unsigned)qp[i - 2] - QUAL_OFFSET : 0u;
-        const unsigned c = i >= 3 ? (unsigned)qp[i - 3] - QUAL_OFFSET : 0u;
-        if (q > 63u) set_error(st, FQ28_ERR_ALPHABET, (unsigned)r);
-        else key = qual_ctx(a & 63u, b & 63u, c & 63u) * QUAL_A + q;
+        if (q > 63u) { set_error(st, FQ28_ERR_ALPHABET, (unsigned)r); break; }
+        const unsigned key = qual_ctx(q1 & 63u, q2 & 63u, q3 & 63u) * QUAL_A + q;
+        if (key == run_key) ++run_n;
+        else {
+          if (run_n) add_qual(run_key, run_n);
+          run_key = key;
+          run_n = 1;
+        }
+        q3 = q2; q2 = q1; q1 = q;
       }
-      // warp-aggregate equal (ctx, sym) pairs: the hottest pair carries most of
-      // the symbols, so one RED per distinct key instead of one per lane
-      // (one RED per distinct key: vote on the key of the first lane still unserved;
-      // binned qualities settle in 2-4 votes, and a vote is far cheaper than match_any)
-      unsigned todo = __ballot_sync(0xffffffffu, key != 0xFFFFFFFFu);
-      while (todo) {
-        const unsigned leader = (unsigned)__ffs(todo) - 1u;
-        const unsigned lk = __shfl_sync(0xffffffffu, key, leader);
-        const unsigned same = __ballot_sync(0xffffffffu, key == lk);
-        if (lane == leader) atomicAdd(&g_qual[lk], (unsigned)__popc(same));
-        todo &= ~same;
-      }
+      if (run_n) add_qual(run_key, run_n);
     }
   }
   __syncthreads();
   for (unsigned i = threadIdx.x; i < SEQ_N * SEQ_A; i += blockDim.x) {
     const uint32_t v = s_seq[i];
     if (v) atomicAdd(&g_seq[i], v);
+  }
+  for (unsigned i = threadIdx.x; i < HQ_SLOTS; i += blockDim.x) {
+    const uint32_t v = s_cnt[i];
+    if (v) atomicAdd(&g_qual[s_key[i]], v);
   }
 }
 
