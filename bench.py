@@ -360,6 +360,8 @@ def run_ours(args):
             baton.next_step()
             if world > 1:
                 h.preparse_dev(w.ptr, w.n)                      # does not wait for anybody
+                for kk, v in h.timings().items():
+                    t[kk] = t.get(kk, 0.0) + v
                 cut = baton.recv()                               # where the previous rank's last chunk ends
                 consumed, _ = h.plan_cut_dev(w.ptr, w.n, w.R, last, cut - w.base)
                 baton.send(w.base + consumed)

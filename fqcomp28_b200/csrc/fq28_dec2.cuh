@@ -434,7 +434,7 @@ FQ_HD bool decode_seq_stream(const StreamArgs &c, uint32_t sb, uint32_t ht) {
   // in the window -- and only then committed.  Straight-line code lets the in-order pipeline
   // overlap the four dependent loads with the bit arithmetic; an invalid block is redone by
   // step(), which takes every case.
-  auto block = [&](char *o) {
+  auto block = [&](char *o) -> unsigned {
     if (br.low()) br.refill();
     const uint32_t a0 = a, W0 = W;
     const uint32_t a1 = T | (W0 & 0x300u);
@@ -455,11 +455,10 @@ FQ_HD bool decode_seq_stream(const StreamArgs &c, uint32_t sb, uint32_t ht) {
     const int avail = br.avail - (int)(n0 + n1 + n2 + n3);
     const bool bad = (((W0 | W1 | W2 | W3) & SW_SPECIAL) != 0) | (avail < 0) | (a2 == a0) | (a3 == a0) | (a3 == a1) |
                      (a4 == a0) | (a4 == a1) | (a4 == a2);
-    if (bad) {
+    if (bad) {  // one careful step, then blocks again from the next symbol
       DEC2_COUNT(8);
-#pragma unroll
-      for (int u = 0; u < UNROLL; u++) step(o + u);
-      return;
+      step(o);
+      return 1u;
     }
     DEC2_COUNT(9);
     sm_async_tick(); sm_async_tick(); sm_async_tick(); sm_async_tick();
@@ -479,6 +478,7 @@ FQ_HD bool decode_seq_stream(const StreamArgs &c, uint32_t sb, uint32_t ht) {
     a = a4;
     W = W4;
     T = sb | ((a4 >> 2) & 0xFCu);
+    return 4u;
   };
   static_assert(UNROLL == 4, "block() is written for four symbols");
   for (;;) {
@@ -488,10 +488,12 @@ FQ_HD bool decode_seq_stream(const StreamArgs &c, uint32_t sb, uint32_t ht) {
     if (rr > 0) {
       char *o = dst + i;
       unsigned t = n;
-      for (; t >= UNROLL; t -= UNROLL, o += UNROLL) block(o);
-#pragma unroll
-      for (int u = 0; u < UNROLL - 1; u++)
-        if ((unsigned)u < t) step(o + u);
+      while (t >= UNROLL) {
+        const unsigned k = block(o);
+        o += k;
+        t -= k;
+      }
+      for (; t; --t, ++o) step(o);
       i += n;
       if (i >= cur.L) {  // record done: records n-1 .. 0 (src/workspace.cpp:84-87)
         --rr;
