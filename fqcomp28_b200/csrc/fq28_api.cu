@@ -234,8 +234,9 @@ int fq28_create(int device, fq28_handle **out) {
     {  // diagnostic knobs: read once here, never on the per-call paths
       auto env_u = [](const char *n) -> unsigned { const char *e = getenv(n); return e ? (unsigned)atoi(e) : 0u; };
       h->cfg.seq_v1 = getenv("FQ28_DEC_V1") != nullptr || getenv("FQ28_SEQ_V1") != nullptr;
-      h->cfg.qual_v2 = getenv("FQ28_QUAL_V2") != nullptr && getenv("FQ28_DEC_V1") == nullptr;
+      h->cfg.qual_v2 = getenv("FQ28_QUAL_V1") == nullptr && getenv("FQ28_DEC_V1") == nullptr;
       h->cfg.dec_serial = getenv("FQ28_DEC_SERIAL") != nullptr;
+      h->cfg.share_sms = getenv("FQ28_DEC_SHARE_SMS") != nullptr;
       h->cfg.seq_lanes = env_u("FQ28_SEQ_LANES"); h->cfg.seq_warps = env_u("FQ28_SEQ_WARPS");
       h->cfg.qual_lanes = env_u("FQ28_QUAL_LANES"); h->cfg.qual_warps = env_u("FQ28_QUAL_WARPS");
       if (const char *e = getenv("FQ28_QUAL_CARVEOUT")) h->cfg.qual_carveout = atoi(e);

@@ -68,6 +68,13 @@ FQ_HD uint32_t make_w_qual(uint32_t cell, const uint8_t *rk /*[64] rank in V or 
   return (r == 0xFFu ? QW_UNSEEN : (r << 2)) | (nb << 8) | (ns << 12) | ((sym + QUAL_CHAR0) << 23);
 }
 FQ_HD uint32_t make_zent(unsigned state, unsigned slot) { return QW_ZENT | (state << 8) | (slot << 20); }
+// run table of a zero-bit-run context, one 8-byte entry per state x:
+//   .x = the W cell of x (an ordinary step from x)
+//   .y = ZENT entry of the state reached after the k <= 15 zero-bit steps that start at x, with k in
+//        bits [24,28) (k = 0: the cell of x is not a zero-bit cell of the dominant symbol)
+constexpr uint32_t ZQ_K_SHIFT = 24, ZQ_K_MASK = 15u << ZQ_K_SHIFT;
+constexpr unsigned ZQ_SLOT_BYTES = 8u << TAB_LOG;
+FQ_HD uint32_t make_zq_hi(unsigned k, unsigned state_after, unsigned slot) { return make_zent(state_after, slot) | (k << ZQ_K_SHIFT); }
 // dense id of ctx(q, q1, q2) for q, max(q1, q2) in V: row = rank(max) * 2 + eq
 FQ_HD unsigned qual_dense_id(unsigned rank_mx, unsigned eq, unsigned rank_q) { return (rank_mx * 2 + eq) * 64 + rank_q; }
 FQ_HD unsigned qual_ctx13(unsigned q, unsigned q1, unsigned q2) {  // calcContext, src/fse_quality.h:40-44
@@ -102,6 +109,14 @@ FQ_HD void sm_st32(uint32_t a, uint32_t v) {
   asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v));
 #else
   memcpy(g_host_smem + a, &v, 4);
+#endif
+}
+FQ_HD void sm_ld64(uint32_t a, uint32_t &x, uint32_t &y) {
+#ifdef __CUDA_ARCH__
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(x), "=r"(y) : "r"(a));
+#else
+  memcpy(&x, g_host_smem + a, 4);
+  memcpy(&y, g_host_smem + a + 4, 4);
 #endif
 }
 FQ_HD uint32_t sm_ld16(uint32_t a) {
@@ -455,10 +470,11 @@ FQ_HD bool decode_seq_stream(const StreamArgs &c, uint32_t sb, uint32_t ht) {
     const int avail = br.avail - (int)(n0 + n1 + n2 + n3);
     const bool bad = (((W0 | W1 | W2 | W3) & SW_SPECIAL) != 0) | (avail < 0) | (a2 == a0) | (a3 == a0) | (a3 == a1) |
                      (a4 == a0) | (a4 == a1) | (a4 == a2);
-    if (bad) {  // one careful step, then blocks again from the next symbol
+    if (bad) {  // (one careful step and a fresh block attempt was measured slower: 43.5 vs 35.7 ms per GB)
       DEC2_COUNT(8);
-      step(o);
-      return 1u;
+#pragma unroll
+      for (int u = 0; u < UNROLL; u++) step(o + u);
+      return 4u;
     }
     DEC2_COUNT(9);
     sm_async_tick(); sm_async_tick(); sm_async_tick(); sm_async_tick();
@@ -512,16 +528,15 @@ FQ_HD bool decode_seq_stream(const StreamArgs &c, uint32_t sb, uint32_t ht) {
 
 
 // ---------------------------------------------------------------------------
-// Quality.  Shared per CTA: rk[64] (q -> rank in V, 0xFF outside) at rk_a; run
-// tables zt (n_z x 2048 u16: (k << 11) | state after k zero-bit steps) at zt_a;
-// the run contexts' W tables at hz_a (n_z x 2048 words); zc (n_z words: output
-// char of run slot j) at zc_a.  Per stream: S = 2 * |V| rows of 64 words at sb
+// Quality.  Shared per CTA: rk[64] (q -> rank in V, 0xFF outside) at rk_a; the run
+// tables (n_z x 2048 entries of 8 bytes, see make_zq_hi) at zq_a; zc (n_z words:
+// output char of run slot j) at zc_a.  Per stream: S = 2 * |V| rows of 64 words at sb
 // (256-byte aligned).  V = {0} + the quality values that occur
 // in a context of the sample: every context made of values in V has a dense id
 // (row = rank(max) * 2 + eq, column = rank(q)).  Contexts outside the dense set
 // keep their state in `cold` (global, u16[8192]) and decode through dtab_fix.
 // ---------------------------------------------------------------------------
-struct QualShared { uint32_t rk_a, zt_a, hz_a, zc_a; };
+struct QualShared { uint32_t rk_a, zq_a, zc_a; };
 
 FQ_HD bool decode_qual_stream(const StreamArgs &c, const QualShared &q, uint32_t sb,
                               const uint32_t *dtab_fix, const uint16_t *cid /*[8192]: run slot + 1 in bits 13..15*/,
@@ -600,7 +615,7 @@ FQ_HD bool decode_qual_stream(const StreamArgs &c, const QualShared &q, uint32_t
         uint32_t w = sm_ld32(aa);
         if (w & QW_ZENT) {
           const unsigned zs = (w >> 20) & 3u;
-          w = sm_ld32(q.hz_a + (zs << (TAB_LOG + 2)) + ((w >> 8) & 0x7FFu) * 4);
+          w = sm_ld32(q.zq_a + zs * ZQ_SLOT_BYTES + ((w >> 8) & 0x7FFu) * 8);
           sm_st32(aa, make_zent(((w >> 12) & 0x7FFu) + br.read((w >> 8) & 15u), zs));
         } else {
           const unsigned ns = ((w >> 12) & 0x7FFu) + br.read((w >> 8) & 15u);
@@ -631,15 +646,16 @@ FQ_HD bool decode_qual_stream(const StreamArgs &c, const QualShared &q, uint32_t
     uint32_t an;
     if (W & QW_ZENT) {
       const unsigned zs = (W >> 20) & 3u, x = (W >> 8) & 0x7FFu;
-      const unsigned z = sm_ld16(q.zt_a + (zs << (TAB_LOG + 1)) + x * 2);
-      unsigned kz = z >> 11;
+      uint32_t cell, hi;
+      sm_ld64(q.zq_a + zs * ZQ_SLOT_BYTES + x * 8, cell, hi);
+      unsigned kz = (hi >> ZQ_K_SHIFT) & 15u;
       if (kz) {  // the next kz symbols are d, read no bits, and stay in this context
         DEC2_COUNT(3);
-        unsigned xs = z & 0x7FFu;
+        unsigned xs = (hi >> 8) & 0x7FFu;
         if (kz > rem - t) {  // the record ends inside the run: single steps
           kz = rem - t;
           xs = x;
-          for (unsigned j = 0; j < kz; j++) xs = (sm_ld32(q.hz_a + (zs << (TAB_LOG + 2)) + xs * 4) >> 12) & 0x7FFu;
+          for (unsigned j = 0; j < kz; j++) xs = (sm_ld32(q.zq_a + zs * ZQ_SLOT_BYTES + xs * 8) >> 12) & 0x7FFu;
         }
         W = make_zent(xs, zs);
         sm_st32(a, W);
@@ -654,7 +670,6 @@ FQ_HD bool decode_qual_stream(const StreamArgs &c, const QualShared &q, uint32_t
       }
       // one ordinary step in the run context: cell from the shared table, refreshed inline
       DEC2_COUNT(4);
-      const uint32_t cell = sm_ld32(q.hz_a + (zs << (TAB_LOG + 2)) + x * 4);
       const unsigned ns = ((cell >> 12) & 0x7FFu) + br.read_nr((cell >> 8) & 15u);
       sm_st32(a, make_zent(ns, zs));
       W = cell;
@@ -688,21 +703,51 @@ FQ_HD bool decode_qual_stream(const StreamArgs &c, const QualShared &q, uint32_t
       W = sm_ld32(a);
       while (t < stop) {
         sm_async_tick();
-        if (((W & QW_SPECIAL) != 0) | br.low()) {
-          t = special(o, t, rem);
+        if (W & QW_ZENT) {
+          // run context (binned qualities: more than half of all events): one 8-byte shared load
+          // yields either "k symbols d, no bits, state after them" or the cell of an ordinary step
+          const unsigned zs = (W >> 20) & 3u;
+          uint32_t cell, hi;
+          sm_ld64(q.zq_a + zs * ZQ_SLOT_BYTES + ((W >> 8) & 0x7FFu) * 8, cell, hi);
+          const unsigned kz = (hi >> ZQ_K_SHIFT) & 15u;
+          if ((kz != 0) & (t + 15 <= rem)) {
+            DEC2_COUNT(3);
+            const char dc = (char)sm_ld32(q.zc_a + zs * 4);
+#pragma unroll
+            for (unsigned j = 0; j < 15; j++) o[t + j] = dc;   // the bytes behind the run are rewritten later
+            W = hi & ~ZQ_K_MASK;
+            sm_st32(a, W);
+            t += kz;
+            continue;
+          }
+          if ((kz == 0) & !br.low() & !(cell & QW_UNSEEN)) {
+            DEC2_COUNT(4);
+            o[t] = (char)((cell >> 23) & 0x7Fu);
+            const unsigned ns = ((cell >> 12) & 0x7FFu) + br.read_nr((cell >> 8) & 15u);
+            sm_st32(a, make_zent(ns, zs));
+            const uint32_t r4 = cell & 0xFCu;
+            a = R1 | r4;
+            W = sm_ld32(a);
+            R1 = row_of(r4, r4p);
+            r4p = r4;
+            ++t;
+            continue;
+          }
+        } else if (!(((W & QW_SPECIAL) != 0) | br.low())) {
+          // the hot path: a cell whose symbol is in V, bits at hand
+          o[t] = (char)((W >> 23) & 0x7Fu);
+          const unsigned ns = ((W >> 12) & 0x7FFu) + br.read_nr((W >> 8) & 15u);
+          sm_st32(a, QW_STALE);
+          sm_async_ld32(a, wadj + ((a << (TAB_LOG - 2)) + ns));   // S[a] <- cell of the new state, when it arrives
+          const uint32_t r4 = W & 0xFCu;
+          a = R1 | r4;
+          W = sm_ld32(a);
+          R1 = row_of(r4, r4p);
+          r4p = r4;
+          ++t;
           continue;
         }
-        // the hot path: a cell whose symbol is in V, bits at hand
-        o[t] = (char)((W >> 23) & 0x7Fu);
-        const unsigned ns = ((W >> 12) & 0x7FFu) + br.read_nr((W >> 8) & 15u);
-        sm_st32(a, QW_STALE);
-        sm_async_ld32(a, wadj + ((a << (TAB_LOG - 2)) + ns));   // S[a] <- cell of the new state, when it arrives
-        const uint32_t r4 = W & 0xFCu;
-        a = R1 | r4;
-        W = sm_ld32(a);
-        R1 = row_of(r4, r4p);
-        r4p = r4;
-        ++t;
+        t = special(o, t, rem);   // (one call site: the slow paths are long, keep them out of the loop body)
       }
       i = t;
       if (i >= cur.L) {

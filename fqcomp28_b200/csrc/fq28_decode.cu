@@ -515,13 +515,13 @@ k_decode_qual(const DecChunk *__restrict__ ch, unsigned n_chunks, unsigned lanes
 // batches: one warp per SM sub-partition is the sweet spot of a latency chain;
 // 32 for big ones).  Shared memory per CTA:
 //   sequence: 4 homopolymer tables (32 KB) | ring | S (1 KB per stream)
-//   quality : rk | zc | run tables (4 + 8 KB per slot) | ring | S (|V| * 512 B per stream)
+//   quality : rk | zc | run tables (16 KB per slot) | ring | S (|V| * 512 B per stream)
 // ---------------------------------------------------------------------------
 constexpr unsigned D2_HT_BYTES = 4u * (4u << FIX_LOG);
 __host__ __device__ inline size_t d2_seq_smem(unsigned per_cta) {
   return D2_HT_BYTES + (size_t)per_cta * 16 + 1024 /*alignment slack*/ + (size_t)per_cta * 1024;
 }
-__host__ __device__ inline size_t d2_qual_fixed(unsigned nz) { return 128 + (size_t)nz * ((2u << FIX_LOG) + (4u << FIX_LOG)); }
+__host__ __device__ inline size_t d2_qual_fixed(unsigned nz) { return 128 + (size_t)nz * dec2::ZQ_SLOT_BYTES; }
 __host__ __device__ inline size_t d2_qual_smem(unsigned per_cta, unsigned nz, unsigned nv) {
   return d2_qual_fixed(nz) + (size_t)per_cta * 16 + 256 /*alignment slack*/ + (size_t)per_cta * nv * 2 * dec2::QROW_BYTES;
 }
@@ -578,7 +578,7 @@ k_dec2_qual(const DecChunk *__restrict__ ch, unsigned n_chunks, unsigned lanes, 
   const unsigned per_cta = lanes * (blockDim.x >> 5);
   const uint32_t base = (uint32_t)__cvta_generic_to_shared(smem_raw);
   dec2::QualShared qs;
-  qs.rk_a = base; qs.zc_a = base + 64; qs.zt_a = base + 128; qs.hz_a = qs.zt_a + nz * (2u << FIX_LOG);
+  qs.rk_a = base; qs.zc_a = base + 64; qs.zq_a = base + 128;
   {
     for (unsigned i = threadIdx.x; i < 64; i += blockDim.x) smem_raw[i] = qrk[i];  // (a CTA may be one warp)
     const unsigned zc[4] = {zctx.x, zctx.y, zctx.z, zctx.w};
@@ -586,17 +586,18 @@ k_dec2_qual(const DecChunk *__restrict__ ch, unsigned n_chunks, unsigned lanes, 
       const unsigned d = zc[j] & 63u;        // run context = ctx(d, d, d)
       const unsigned r = qrk[d];
       if (threadIdx.x == 0) reinterpret_cast<uint32_t *>(smem_raw + 64)[j] = d + QUAL_OFFSET;
-      // Z part of the run tables ((k << 11) | state after k zero-bit steps); u32 copies of the u16 table
-      const uint32_t *zsrc = reinterpret_cast<const uint32_t *>(gzrun + (size_t)j * 2 * (1u << FIX_LOG));
-      uint32_t *zdst = reinterpret_cast<uint32_t *>(smem_raw + 128 + j * (2u << FIX_LOG));
-      for (unsigned i = threadIdx.x; i < (1u << (FIX_LOG - 1)); i += blockDim.x) zdst[i] = zsrc[i];
+      // run table entry of state x: the W cell of x | ZENT entry after the zero-bit run + its length
+      const uint16_t *zsrc = gzrun + (size_t)j * 2 * (1u << FIX_LOG);   // (k << 11) | state after k zero-bit steps
       const uint32_t *hsrc = wtab + ((size_t)dec2::qual_dense_id(r, 1, r) << FIX_LOG);
-      uint32_t *hdst = reinterpret_cast<uint32_t *>(smem_raw + 128 + nz * (2u << FIX_LOG) + j * (4u << FIX_LOG));
-      for (unsigned i = threadIdx.x; i < (1u << FIX_LOG); i += blockDim.x) hdst[i] = hsrc[i];
+      uint2 *zdst = reinterpret_cast<uint2 *>(smem_raw + 128 + j * dec2::ZQ_SLOT_BYTES);
+      for (unsigned x = threadIdx.x; x < (1u << FIX_LOG); x += blockDim.x) {
+        const unsigned z = zsrc[x];
+        zdst[x] = make_uint2(hsrc[x], dec2::make_zq_hi(z >> 11, z & 0x7FFu, j));
+      }
     }
   }
   __syncthreads();
-  const uint32_t ring0 = qs.hz_a + nz * (4u << FIX_LOG);
+  const uint32_t ring0 = qs.zq_a + nz * dec2::ZQ_SLOT_BYTES;
   const uint32_t s0 = (ring0 + per_cta * 16 + 255u) & ~255u;
   const unsigned s_bytes = nv * 2 * dec2::QROW_BYTES;
   const unsigned lane = threadIdx.x & 31;
@@ -750,7 +751,7 @@ int decode_batch(fq28_handle *h, const fq28_dec_arenas *in, const fq28_chunk_inf
   if (!h->cfg.dec_serial) FQ28_TRY(side_fork(h));
   // Lanes (streams per warp) of the v2 kernels: a stream is one latency chain; lockstep lanes
   // save issue slots but every lane waits for the slowest path taken in its warp
-  unsigned lanes = (unsigned)(((h->cfg.qual_v2 ? 2 : 1) * n_chunks + 1183) / 1184);
+  unsigned lanes = (unsigned)((n_chunks + 1183) / 1184);
   lanes = lanes < 1 ? 1 : lanes > 32 ? 32 : lanes;
   auto shape = [&](unsigned want_lanes, unsigned want_warps, unsigned &l, unsigned &w) {
     l = want_lanes ? (want_lanes > 32 ? 32 : want_lanes) : lanes;
@@ -760,16 +761,17 @@ int decode_batch(fq28_handle *h, const fq28_dec_arenas *in, const fq28_chunk_inf
   if (!h->cfg.seq_v1) {
     unsigned l, w;
     size_t smem;
-    if (h->cfg.qual_v2 || h->cfg.dec_serial) {
+    if (h->cfg.dec_serial || h->cfg.share_sms) {
       shape(h->cfg.seq_lanes, h->cfg.seq_warps, l, w);
       while (d2_seq_smem(l * w) > 200 * 1024 && w > 1) w >>= 1;
       smem = d2_seq_smem(l * w);
     } else {
-      // Next to the state-table quality decoder the two kernels must not share SMs: measured, the
-      // quality kernel takes 76 ms instead of 37 when sequence CTAs live on its SMs (its DTable
-      // cells are L1 hits only as long as nothing else streams tables through that L1).  So the
-      // sequence CTAs are made fat -- 8 warps and a shared-memory request no other CTA fits
-      // beside -- and sized to cover about 65 of the 148 SMs; quality gets the rest.
+      // The two kernels must not share SMs: measured, either quality kernel takes 2-3x longer when
+      // sequence CTAs live on its SMs (76 ms instead of 37 for the state-table one, 95 instead of
+      // 30 for the cached-cell one: the table cells they fetch are L1 hits only as long as nothing
+      // else streams a 2 MB table through that L1).  So the sequence CTAs are made fat -- 8 warps
+      // and a shared-memory request no other CTA fits beside -- and sized to cover about 65 of
+      // the 148 SMs; quality gets the rest.
       w = h->cfg.seq_warps ? (h->cfg.seq_warps > 8 ? 8 : h->cfg.seq_warps) : 8;
       l = (unsigned)((n_chunks + 65 * w - 1) / (65 * w));
       if (h->cfg.seq_lanes) l = h->cfg.seq_lanes;
@@ -811,6 +813,10 @@ int decode_batch(fq28_handle *h, const fq28_dec_arenas *in, const fq28_chunk_inf
     {
       unsigned l, w;
       shape(h->cfg.qual_lanes, h->cfg.qual_warps, l, w);
+      if (!h->cfg.qual_lanes) {  // about 83 SMs = 332 sub-partitions are the quality decoder's: up to ~4 warps on each
+        l = (unsigned)((n_chunks + 4 * 332 - 1) / (4 * 332));
+        l = l < 1 ? 1 : l > 32 ? 32 : l;
+      }
       const unsigned nz = h->cfg.no_zrun ? 0u : h->qual.h_n_z, nv = h->qual.h_n_v;
       // the per-stream context arrays (|V| * 512 B) must fit: fewer warps first, then fewer lanes
       while (d2_qual_smem(l * w, nz, nv) > 200 * 1024 && l * w > 1) {

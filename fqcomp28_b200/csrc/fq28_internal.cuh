@@ -197,8 +197,9 @@ struct fq28_handle {
   // policy knobs, read from the environment once at fq28_create (diagnostics)
   struct Cfg {
     bool seq_v1 = false;           // FQ28_SEQ_V1 / FQ28_DEC_V1: round-1 sequence decoder (rank-directory tables)
-    bool qual_v2 = false;          // FQ28_QUAL_V2: cached-cell quality decoder (fq28_dec2.cuh) instead of the state-table one
+    bool qual_v2 = true;           // cached-cell quality decoder (fq28_dec2.cuh); FQ28_QUAL_V1 / FQ28_DEC_V1: the round-1 state-table one
     bool dec_serial = false;       // FQ28_DEC_SERIAL: the two decode kernels one after the other (per-kernel timing)
+    bool share_sms = false;        // FQ28_DEC_SHARE_SMS: do not keep the sequence decoder on SMs of its own
     unsigned seq_lanes = 0, seq_warps = 0, qual_lanes = 0, qual_warps = 0;  // 0 = automatic
     int qual_carveout = -2;        // -2 = automatic
     bool no_zrun = false, no_dom = false, no_rankc = false, serial = false, full_overlap = false;

@@ -136,15 +136,16 @@ int dec2h_qual(const uint8_t *ft, const uint8_t *stream, uint32_t len, unsigned 
       zsym[nz++] = (unsigned)d;
     }
   }
-  // shared memory image: rk | zc | zt | hz | S | scratch
-  const uint32_t rk_a = 0, zc_a = 64, zt_a = 128, hz_a = zt_a + nz * (2u << TAB_LOG);
-  const uint32_t sb = (hz_a + nz * (4u << TAB_LOG) + 255) & ~255u;
+  // shared memory image: rk | zc | run tables (8 bytes per state) | S
+  const uint32_t rk_a = 0, zc_a = 64, zq_a = 128;
+  const uint32_t sb = (zq_a + nz * ZQ_SLOT_BYTES + 255) & ~255u;
   std::vector<uint8_t> smem(sb + n_dense * 4 + 64, 0);
   memcpy(&smem[rk_a], rk, 64);
   for (unsigned j = 0; j < nz; j++) {
     const unsigned d = zsym[j], cx = qual_ctx13(d, d, d), T = 1u << logs[cx];
     const uint32_t ch = d + QUAL_CHAR0;
     memcpy(&smem[zc_a + j * 4], &ch, 4);
+    const unsigned dd = qual_dense_id(rk[d], 1, rk[d]);
     for (unsigned x = 0; x < (1u << TAB_LOG); x++) {
       unsigned k = 0, y = x;
       while (x < T && k < 15) {
@@ -153,11 +154,9 @@ int dec2h_qual(const uint8_t *ft, const uint8_t *stream, uint32_t len, unsigned 
         y = e & 0xFFFFu;
         k++;
       }
-      const uint16_t z = (uint16_t)((k << 11) | y);
-      memcpy(&smem[zt_a + j * (2u << TAB_LOG) + x * 2], &z, 2);
+      const uint32_t e2[2] = {wtab[((size_t)dd << TAB_LOG) + x], make_zq_hi(k, y, j)};
+      memcpy(&smem[zq_a + j * ZQ_SLOT_BYTES + x * 8], e2, 8);
     }
-    const unsigned dd = qual_dense_id(rk[d], 1, rk[d]);
-    memcpy(&smem[hz_a + j * (4u << TAB_LOG)], &wtab[(size_t)dd << TAB_LOG], 4u << TAB_LOG);
   }
   g_host_smem = smem.data();
   std::vector<uint64_t> buf((len + 64) / 8 + 4, 0);
@@ -167,7 +166,7 @@ int dec2h_qual(const uint8_t *ft, const uint8_t *stream, uint32_t len, unsigned 
   StreamArgs a;
   std::vector<uint32_t> recscan;
   fill_args(a, src, len, readlens, hdr_lens, n_rec, recscan, out, t, wtab.data());
-  QualShared qs{rk_a, zt_a, hz_a, zc_a};
+  QualShared qs{rk_a, zq_a, zc_a};
   g_host_async = HostAsync();
   const bool ok = decode_qual_stream(a, qs, sb, t.dtab_fix.data(), cid.data(), cold.data());
   g_host_smem = nullptr;
