@@ -237,6 +237,7 @@ int fq28_create(int device, fq28_handle **out) {
       h->cfg.qual_v2 = getenv("FQ28_QUAL_V1") == nullptr && getenv("FQ28_DEC_V1") == nullptr;
       h->cfg.dec_serial = getenv("FQ28_DEC_SERIAL") != nullptr;
       h->cfg.share_sms = getenv("FQ28_DEC_SHARE_SMS") != nullptr;
+      h->cfg.dec_concurrent = getenv("FQ28_DEC_CONCURRENT") != nullptr;
       h->cfg.seq_lanes = env_u("FQ28_SEQ_LANES"); h->cfg.seq_warps = env_u("FQ28_SEQ_WARPS");
       h->cfg.qual_lanes = env_u("FQ28_QUAL_LANES"); h->cfg.qual_warps = env_u("FQ28_QUAL_WARPS");
       if (const char *e = getenv("FQ28_QUAL_CARVEOUT")) h->cfg.qual_carveout = atoi(e);

@@ -747,8 +747,13 @@ int decode_batch(fq28_handle *h, const fq28_dec_arenas *in, const fq28_chunk_inf
 
   // the two stream types are independent: quality runs on the side stream (FQ28_DEC_SERIAL puts
   // both on the main stream, one after the other, to time each kernel on its own)
-  cudaStream_t qstream = h->cfg.dec_serial ? h->stream : h->side;
-  if (!h->cfg.dec_serial) FQ28_TRY(side_fork(h));
+  // Many-valued qualities (HiSeq-like, ONT: dozens of values, thousands of live contexts) make the
+  // quality decoder several times slower than the sequence decoder and sensitive to sharing its
+  // SMs' issue slots and L1 (measured, 41-level qualities, 1 GB: 152 ms next to the sequence
+  // kernel on 83 SMs, 55 ms alone on the whole GPU): then the two kernels run one after the other.
+  const bool serial = h->cfg.dec_serial || (h->cfg.qual_v2 && !h->cfg.dec_concurrent && h->qual.h_n_v >= 16);
+  cudaStream_t qstream = serial ? h->stream : h->side;
+  if (!serial) FQ28_TRY(side_fork(h));
   // Lanes (streams per warp) of the v2 kernels: a stream is one latency chain; lockstep lanes
   // save issue slots but every lane waits for the slowest path taken in its warp
   unsigned lanes = (unsigned)((n_chunks + 1183) / 1184);
@@ -761,7 +766,7 @@ int decode_batch(fq28_handle *h, const fq28_dec_arenas *in, const fq28_chunk_inf
   if (!h->cfg.seq_v1) {
     unsigned l, w;
     size_t smem;
-    if (h->cfg.dec_serial || h->cfg.share_sms) {
+    if (serial || h->cfg.share_sms) {
       shape(h->cfg.seq_lanes, h->cfg.seq_warps, l, w);
       while (d2_seq_smem(l * w) > 200 * 1024 && w > 1) w >>= 1;
       smem = d2_seq_smem(l * w);
@@ -813,8 +818,9 @@ int decode_batch(fq28_handle *h, const fq28_dec_arenas *in, const fq28_chunk_inf
     {
       unsigned l, w;
       shape(h->cfg.qual_lanes, h->cfg.qual_warps, l, w);
-      if (!h->cfg.qual_lanes) {  // about 83 SMs = 332 sub-partitions are the quality decoder's: up to ~4 warps on each
-        l = (unsigned)((n_chunks + 4 * 332 - 1) / (4 * 332));
+      if (!h->cfg.qual_lanes) {  // about 83 SMs = 332 sub-partitions are the quality decoder's (all 592 when it runs alone): up to ~4 warps on each
+        const unsigned sub = serial ? 592u : 332u;
+        l = (unsigned)((n_chunks + 4 * sub - 1) / (4 * sub));
         l = l < 1 ? 1 : l > 32 ? 32 : l;
       }
       const unsigned nz = h->cfg.no_zrun ? 0u : h->qual.h_n_z, nv = h->qual.h_n_v;
@@ -880,7 +886,7 @@ int decode_batch(fq28_handle *h, const fq28_dec_arenas *in, const fq28_chunk_inf
     stage_close(h, qslot, qstream);
   }
     }
-  if (!h->cfg.dec_serial) FQ28_TRY(side_join(h));
+  if (!serial) FQ28_TRY(side_join(h));
 
   stage_begin(h, ST_NINSERT);
   if (n_rec && in->n_pos_entries) {

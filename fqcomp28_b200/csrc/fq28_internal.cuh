@@ -200,6 +200,7 @@ struct fq28_handle {
     bool qual_v2 = true;           // cached-cell quality decoder (fq28_dec2.cuh); FQ28_QUAL_V1 / FQ28_DEC_V1: the round-1 state-table one
     bool dec_serial = false;       // FQ28_DEC_SERIAL: the two decode kernels one after the other (per-kernel timing)
     bool share_sms = false;        // FQ28_DEC_SHARE_SMS: do not keep the sequence decoder on SMs of its own
+    bool dec_concurrent = false;   // FQ28_DEC_CONCURRENT: never serialise the two decode kernels
     unsigned seq_lanes = 0, seq_warps = 0, qual_lanes = 0, qual_warps = 0;  // 0 = automatic
     int qual_carveout = -2;        // -2 = automatic
     bool no_zrun = false, no_dom = false, no_rankc = false, serial = false, full_overlap = false;

@@ -27,8 +27,8 @@ for r in rows[1:]:
 tot = sum(a[1] for a in agg.values())
 with open(os.path.join(out, f"{tag}_launches.md"), "w") as f:
     f.write(f"# {tag}: kernel launch list (ncu --metrics gpu__time_duration.sum --clock-control none)\n\n")
-    f.write("Command: `python bench.py --size-mb 256 --sample-mb 64 --steps 1 --warmup 1 --no-cpu-baseline` "
-            "(256 MB slab, -R 1; every launch of the run incl. setup, warm-up, e2e legs).\n"
+    f.write("Command: `python bench.py --size-mb 256 --sample-mb 64 --steps 1 --warmup 1 --no-cpu-baseline --no-sweep --no-parity` "
+            "(256 MB slab, -R 1; every launch of the run incl. setup, warm-up, e2e and copy legs).\n"
             "Per-launch times are cold-cache and serialised: compare SHARES, not absolutes.\n\n")
     f.write("| kernel | launches | total ms | share |\n|---|---:|---:|---:|\n")
     for n, (c, v) in sorted(agg.items(), key=lambda x: -x[1][1]):
@@ -90,7 +90,8 @@ import json
 
 stage_of = [
     ("k_chain<Kind<unsigned int", "chain_qual"), ("k_chain_dom<Kind<unsigned int", "chain_qual"), ("k_chain<Kind<unsigned short", "chain_seq"),
-    ("k_decode_seq", "decode_seq"), ("k_decode_qual", "decode_qual"), ("k_tile_part8", "part_seq"),
+    ("k_decode_seq", "decode_seq"), ("k_decode_qual", "decode_qual"), ("k_dec2_seq", "decode_seq"), ("k_dec2_qual", "decode_qual"),
+    ("k_hist", "hist"), ("k_tile_part8", "part_seq"),
     ("k_tile_rank_compact<Kind<unsigned int", "part_qual"), ("k_tile_hist<Kind<unsigned int", "part_qual"),
     ("k_pack_write<256>", "pack_seq"), ("k_pack_count<256>", "pack_seq"), ("k_pack_write<8192>", "pack_qual"), ("k_pack_count<8192>", "pack_qual"),
     ("k_extract", "extract"), ("k_gather_headers", "extract"), ("k_npos", "extract"),
