@@ -181,20 +181,6 @@ static int stage_in(fq28_handle *h, const char *fastq, size_t n_bytes) {
   return FQ28_OK;
 }
 
-// the host FreqTable images follow the device tables (one source of truth: norm / logs on the device)
-static int ensure_ft_images(fq28_handle *h) {
-  if (h->ft_img_gen == h->tables_gen && h->ft_img_seq.size() == FQ28_FT_SEQ_BYTES && h->ft_img_qual.size() == FQ28_FT_QUAL_BYTES)
-    return FQ28_OK;
-  if (!h->seq.ready || !h->qual.ready) return fail(h, FQ28_ERR_ARG, "frequency tables not built/loaded");
-  h->ft_img_seq.resize(FQ28_FT_SEQ_BYTES);
-  h->ft_img_qual.resize(FQ28_FT_QUAL_BYTES);
-  FQ28_TRY(ft_image_out(h, h->seq, h->ft_img_seq.data()));
-  FQ28_TRY(ft_image_out(h, h->qual, h->ft_img_qual.data()));
-  FQ28_CUDA(h, cudaStreamSynchronize(h->stream));
-  h->ft_img_gen = h->tables_gen;
-  return FQ28_OK;
-}
-
 }  // namespace fq28
 
 using namespace fq28;
@@ -247,6 +233,7 @@ int fq28_create(int device, fq28_handle **out) {
       h->cfg.serial = getenv("FQ28_SERIAL") != nullptr;
       h->cfg.full_overlap = getenv("FQ28_FULL_OVERLAP") != nullptr;
       if (const char *e = getenv("FQ28_PIPE_MIN_MB")) h->cfg.pipe_min_bytes = (size_t)atoll(e) << 20;
+      if (const char *e = getenv("FQ28_PIPE_PARTS")) h->cfg.pipe_parts = (unsigned)std::max(1, std::min(64, atoi(e)));
     }
     // kernel attributes are per device: set them for this handle's device (not once per process)
     rc = encode_init_device(h);
@@ -264,7 +251,12 @@ int fq28_create(int device, fq28_handle **out) {
 
 void fq28_destroy(fq28_handle *h) {
   if (!h) return;
-  if (h->sibling) { fq28_destroy(h->sibling); h->sibling = nullptr; }
+  if (h->sibling) {
+    fq28_handle *s = h->sibling;
+    if (s->borrowing) { s->seq = s->own_seq; s->qual = s->own_qual; s->borrowing = false; }
+    fq28_destroy(s);
+    h->sibling = nullptr;
+  }
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   DevBuf *bufs[] = {&h->in_fastq, &h->tile_cnt, &h->nl, &h->hdr_off, &h->seq_off, &h->qual_off, &h->len, &h->hdr_len,
@@ -285,6 +277,8 @@ void fq28_destroy(fq28_handle *h) {
   for (auto &r : h->ev_pool) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   if (h->side) { cudaStreamSynchronize(h->side); cudaStreamDestroy(h->side); }
   if (h->ev_copy) cudaEventDestroy(h->ev_copy);
+  for (cudaEvent_t e : h->ev_part) cudaEventDestroy(e);
+  if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
@@ -413,9 +407,6 @@ int fq28_load_tables(fq28_handle *h, const void *ft_seq, const void *ft_qual) {
   FQ28_TRY(tables_from_norm(h, h->qual));
   stage_end(h, ST_TABLES);
   FQ28_CUDA(h, cudaStreamSynchronize(h->stream));
-  h->ft_img_seq.assign(static_cast<const uint8_t *>(ft_seq), static_cast<const uint8_t *>(ft_seq) + FQ28_FT_SEQ_BYTES);
-  h->ft_img_qual.assign(static_cast<const uint8_t *>(ft_qual), static_cast<const uint8_t *>(ft_qual) + FQ28_FT_QUAL_BYTES);
-  h->ft_img_gen = h->tables_gen;
   return FQ28_OK;
 }
 
@@ -595,87 +586,118 @@ int fq28_compress_fetch(fq28_handle *h, const fq28_enc_arenas *out) {
   return FQ28_OK;
 }
 
-// Host-buffer compress of a large slab as two overlapped halves.  The chunk
-// walk of the first half (eof = 0) stops at a chunk boundary `consumed`; the
-// second half [consumed, n) is encoded by the sibling handle with the same
-// tables, and its chunk infos are shifted behind the first half's.  Overlap:
-// H2D of the second half with the first half's kernels, D2H of the first
-// half's result with the second half's kernels.  Same bytes as the one-pass
-// path (the walk is deterministic from its start offset).
-static int compress_two_stage(fq28_handle *h, const char *fastq, size_t n_bytes, size_t h1, size_t sample_bytes,
-                              size_t reading_size, int eof, void *ft_seq_out, void *ft_qual_out,
-                              const fq28_enc_arenas *out, fq28_chunk_info *infos, size_t infos_cap,
-                              fq28_enc_summary *summary) {
+// Host-buffer compress of a large slab as K overlapped parts (cfg.pipe_parts, default 4).
+// All host->device copies are queued at once on a copy stream, one event per part; part k is
+// the slab [cut_k, p_{k+1}) where cut_k is where the chunk walk of part k-1 stopped (eof = 0:
+// only chunks whose whole window lies inside the part), so the chunks are exactly those of the
+// one-pass walk (deterministic from its start offset).  Two handles with their own streams and
+// buffers take the parts in turn: the kernels of part k run under the copies of parts k+1..,
+// the device->host copy of its result under the kernels of part k+1.
+static int compress_parts(fq28_handle *h, const char *fastq, size_t n_bytes, unsigned n_parts, size_t p1, size_t sample_bytes,
+                          size_t reading_size, int eof, void *ft_seq_out, void *ft_qual_out,
+                          const fq28_enc_arenas *out, fq28_chunk_info *infos, size_t infos_cap,
+                          fq28_enc_summary *summary) {
   if (!h->sibling) {
     FQ28_TRY(fq28_create(h->device, &h->sibling));
     FQ28_TRY(bind(h));
   }
   fq28_handle *s = h->sibling;
+  if (!h->copy_stream) FQ28_CUDA(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+  while (h->ev_part.size() < n_parts) {
+    cudaEvent_t e;
+    FQ28_CUDA(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    h->ev_part.push_back(e);
+  }
+  // part ends: p[0] = 0, p[1] = p1 (holds the sample window), the rest evenly, 16-byte aligned
+  std::vector<size_t> p(n_parts + 1, 0);
+  p[1] = p1;
+  for (unsigned k = 2; k <= n_parts; k++) p[k] = (p1 + (n_bytes - p1) / (n_parts - 1) * (k - 1)) & ~(size_t)15;
+  p[n_parts] = n_bytes;
+  size_t longest = 0;
+  for (unsigned k = 0; k < n_parts; k++) longest = std::max(longest, p[k + 1] - p[k]);
+  // a part starts at most one window before its nominal start
+  FQ28_TRY(ensure(h, h->in_fastq, longest + reading_size + 64));
+  FQ28_TRY(ensure(s, s->in_fastq, longest + reading_size + 64));
+  FQ28_TRY(ensure(h, h->in_raw, n_bytes + 64));
+  // the copies must not overtake work still queued on the buffers they overwrite
   if (!h->ev_copy) FQ28_CUDA(h, cudaEventCreateWithFlags(&h->ev_copy, cudaEventDisableTiming));
-  FQ28_TRY(ensure(h, h->in_fastq, h1 + 64));
-  FQ28_TRY(ensure(s, s->in_raw, n_bytes - h1 + 64));
-  FQ28_TRY(ensure(s, s->in_fastq, n_bytes + 64));
-  // both host->device copies are queued now; the second one starts when the first is done
-  FQ28_CUDA(h, cudaMemcpyAsync(h->in_fastq.p, fastq, h1, cudaMemcpyHostToDevice, h->stream));
   FQ28_CUDA(h, cudaEventRecord(h->ev_copy, h->stream));
-  FQ28_CUDA(h, cudaStreamWaitEvent(s->stream, h->ev_copy, 0));
-  FQ28_CUDA(h, cudaMemcpyAsync(s->in_raw.p, fastq + h1, n_bytes - h1, cudaMemcpyHostToDevice, s->stream));
-  // first half
-  fq28_enc_summary sa;
-  FQ28_TRY(fq28_compress_dev(h, h->in_fastq.as<char>(), h1, sample_bytes, reading_size, 0, nullptr, nullptr, infos, infos_cap,
-                             &sa));
-  FQ28_TRY(ensure_ft_images(h));  // read back from the device tables unless they are the ones last loaded
-  if (sample_bytes) {
-    if (ft_seq_out) memcpy(ft_seq_out, h->ft_img_seq.data(), FQ28_FT_SEQ_BYTES);
-    if (ft_qual_out) memcpy(ft_qual_out, h->ft_img_qual.data(), FQ28_FT_QUAL_BYTES);
+  FQ28_CUDA(h, cudaStreamWaitEvent(h->copy_stream, h->ev_copy, 0));
+  for (unsigned k = 0; k < n_parts; k++) {
+    // part 0 starts at offset 0: straight into the aligned parse buffer
+    char *dst = k == 0 ? h->in_fastq.as<char>() : h->in_raw.as<char>() + p[k];
+    FQ28_CUDA(h, cudaMemcpyAsync(dst, fastq + p[k], p[k + 1] - p[k], cudaMemcpyHostToDevice, h->copy_stream));
+    FQ28_CUDA(h, cudaEventRecord(h->ev_part[k], h->copy_stream));
   }
-  FQ28_TRY(fetch_async(h, out));  // device->host of the first half overlaps the second half's kernels
-  // second half: same tables (checked by generation, not by what some earlier call left behind),
-  // FASTQ = [consumed, n) moved to an aligned buffer
-  if (!(s->seq.ready && s->qual.ready && h->sibling_gen == h->tables_gen)) {
-    const int rc = fq28_load_tables(s, h->ft_img_seq.data(), h->ft_img_qual.data());
-    if (rc != FQ28_OK) return fail(h, rc, "second half: %s", fq28_last_error(s));
-    h->sibling_gen = h->tables_gen;
-  }
-  const size_t ca = (size_t)sa.consumed;
-  FQ28_CUDA(h, cudaMemcpyAsync(s->in_fastq.p, h->in_fastq.as<char>() + ca, h1 - ca, cudaMemcpyDeviceToDevice, s->stream));
-  FQ28_CUDA(h, cudaMemcpyAsync(s->in_fastq.as<char>() + (h1 - ca), s->in_raw.p, n_bytes - h1, cudaMemcpyDeviceToDevice, s->stream));
-  fq28_enc_arenas ob = *out;
-  ob.seq += sa.seq_bytes; ob.seq_cap -= sa.seq_bytes;
-  ob.qual += sa.qual_bytes; ob.qual_cap -= sa.qual_bytes;
-  ob.readlens += sa.n_records; ob.readlens_cap -= sa.n_records;
-  ob.n_count += sa.n_records; ob.n_count_cap -= sa.n_records;
-  ob.n_pos += sa.n_pos_entries; ob.n_pos_cap -= sa.n_pos_entries;
-  if (ob.hdr_lens) { ob.hdr_lens += sa.n_records; ob.hdr_lens_cap -= sa.n_records; }
-  if (ob.headers) { ob.headers += sa.hdr_bytes; ob.headers_cap -= sa.hdr_bytes; }
-  fq28_chunk_info *ib = infos + sa.n_chunks;
-  fq28_enc_summary sb;
-  {
-    int rc = fq28_compress_dev(s, s->in_fastq.as<char>(), n_bytes - ca, 0, reading_size, eof, nullptr, nullptr, ib,
-                               infos_cap - (size_t)sa.n_chunks, &sb);
-    if (rc == FQ28_OK) rc = fq28_compress_fetch(s, &ob);
-    if (rc != FQ28_OK) {
-      cudaStreamSynchronize(h->stream);
-      return fail(h, rc, "second half: %s", fq28_last_error(s));
+  fq28_enc_summary m;
+  memset(&m, 0, sizeof(m));
+  size_t cut = 0;  // slab offset where the current part starts
+  int rc = FQ28_OK;
+  for (unsigned k = 0; k < n_parts && rc == FQ28_OK; k++) {
+    fq28_handle *g = (k & 1) ? s : h;
+    const size_t len = p[k + 1] - cut;
+    const bool last = k + 1 == n_parts;
+    rc = bind(g);
+    if (rc != FQ28_OK) break;
+    if (cudaStreamWaitEvent(g->stream, h->ev_part[k], 0) != cudaSuccess) { rc = FQ28_ERR_CUDA; break; }
+    if (k > 0) {
+      // [cut, p_k) was copied with part k-1: to h->in_fastq if that was part 0, else to in_raw
+      const char *head = k == 1 ? h->in_fastq.as<char>() + cut : h->in_raw.as<char>() + cut;
+      if (p[k] > cut &&
+          cudaMemcpyAsync(g->in_fastq.p, head, p[k] - cut, cudaMemcpyDeviceToDevice, g->stream) != cudaSuccess) { rc = FQ28_ERR_CUDA; break; }
+      if (cudaMemcpyAsync(g->in_fastq.as<char>() + (p[k] - cut), h->in_raw.as<char>() + p[k], p[k + 1] - p[k],
+                          cudaMemcpyDeviceToDevice, g->stream) != cudaSuccess) { rc = FQ28_ERR_CUDA; break; }
+      if (k == 1) {
+        // same device: the sibling encodes with this handle's tables (built and complete: the first
+        // part has returned); its own stay allocated and come back in fq28_destroy
+        if (!s->borrowing) { s->own_seq = s->seq; s->own_qual = s->qual; s->borrowing = true; }
+        s->seq = h->seq;
+        s->qual = h->qual;
+      }
     }
+    fq28_enc_summary sk;
+    rc = fq28_compress_dev(g, g->in_fastq.as<char>(), len, k == 0 ? sample_bytes : 0, reading_size, last ? eof : 0,
+                           k == 0 ? ft_seq_out : nullptr, k == 0 ? ft_qual_out : nullptr, infos + m.n_chunks,
+                           infos_cap - (size_t)m.n_chunks, &sk);
+    if (rc != FQ28_OK) break;
+    fq28_enc_arenas ob = *out;
+    ob.seq += m.seq_bytes; ob.seq_cap -= m.seq_bytes;
+    ob.qual += m.qual_bytes; ob.qual_cap -= m.qual_bytes;
+    ob.readlens += m.n_records; ob.readlens_cap -= m.n_records;
+    ob.n_count += m.n_records; ob.n_count_cap -= m.n_records;
+    ob.n_pos += m.n_pos_entries; ob.n_pos_cap -= m.n_pos_entries;
+    if (ob.hdr_lens) { ob.hdr_lens += m.n_records; ob.hdr_lens_cap -= m.n_records; }
+    if (ob.headers) { ob.headers += m.hdr_bytes; ob.headers_cap -= m.hdr_bytes; }
+    rc = fetch_async(g, &ob);  // device->host of this part overlaps the next part's kernels
+    if (rc != FQ28_OK) break;
+    for (uint64_t c = 0; c < sk.n_chunks; c++) {
+      fq28_chunk_info &ci = infos[m.n_chunks + c];
+      ci.fastq_off += cut;
+      ci.rec_off += m.n_records;
+      ci.seq_off += m.seq_bytes;
+      ci.qual_off += m.qual_bytes;
+      ci.n_pos_off += m.n_pos_entries;
+      ci.hdr_off += m.hdr_bytes;
+    }
+    m.n_chunks += sk.n_chunks; m.n_records += sk.n_records; m.n_symbols += sk.n_symbols;
+    m.seq_bytes += sk.seq_bytes; m.qual_bytes += sk.qual_bytes; m.n_pos_entries += sk.n_pos_entries;
+    m.hdr_bytes += sk.hdr_bytes;
+    cut += (size_t)sk.consumed;
+  }
+  // nothing may still be writing into the caller's buffers (or reading them) when this returns
+  cudaStreamSynchronize(h->copy_stream);
+  cudaStreamSynchronize(s->stream);
+  cudaStreamSynchronize(h->stream);
+  if (rc != FQ28_OK) {
+    std::string why = s->err.empty() ? h->err : s->err;
+    bind(h);
+    return fail(h, rc, "pipelined compress: %s", why.c_str());
   }
   FQ28_TRY(bind(h));
-  FQ28_CUDA(h, cudaStreamSynchronize(h->stream));
-  for (uint64_t k = 0; k < sb.n_chunks; k++) {
-    fq28_chunk_info &ci = ib[k];
-    ci.fastq_off += ca;
-    ci.rec_off += sa.n_records;
-    ci.seq_off += sa.seq_bytes;
-    ci.qual_off += sa.qual_bytes;
-    ci.n_pos_off += sa.n_pos_entries;
-    ci.hdr_off += sa.hdr_bytes;
-  }
-  fq28_enc_summary m = sa;
-  m.n_chunks += sb.n_chunks; m.n_records += sb.n_records; m.n_symbols += sb.n_symbols;
-  m.seq_bytes += sb.seq_bytes; m.qual_bytes += sb.qual_bytes; m.n_pos_entries += sb.n_pos_entries;
-  m.consumed = ca + sb.consumed; m.hdr_bytes += sb.hdr_bytes;
+  m.consumed = cut;
   if (summary) *summary = m;
-  h->have_result = false;  // the device-resident result is split over two handles: not fetchable again
+  h->have_result = false;  // the device-resident result is split over the parts: not fetchable again
+  s->have_result = false;
   return FQ28_OK;
 }
 
@@ -685,15 +707,21 @@ int fq28_compress(fq28_handle *h, const char *fastq, size_t n_bytes, size_t samp
   if (!h || !out || !infos) return FQ28_ERR_ARG;
   FQ28_TRY(bind(h));
   {
-    // two overlapped halves for large slabs; the sample window must lie inside the first half
+    // overlapped parts for large slabs: every part holds at least 4 windows, the first one the sample window
     const size_t win = sample_bytes < n_bytes ? sample_bytes : n_bytes;
-    size_t h1 = (n_bytes / 2) & ~(size_t)15;
-    if (win > h1) h1 = (win + 15) & ~(size_t)15;
+    unsigned parts = h->cfg.pipe_parts;
+    if (reading_size) parts = (unsigned)std::min<size_t>(parts, n_bytes / (4 * reading_size));
     const bool tables_ok = sample_bytes > 0 || (h->seq.ready && h->qual.ready);
     const bool planned = h->plan.valid && sample_bytes == 0;  // a planned slab is encoded as planned, in one piece
-    if (n_bytes >= h->cfg.pipe_min_bytes && h1 + ((size_t)16 << 20) <= n_bytes && tables_ok && !planned)
-      return compress_two_stage(h, fastq, n_bytes, h1, sample_bytes, reading_size, eof, ft_seq_out, ft_qual_out, out, infos,
-                                infos_cap, summary);
+    if (parts >= 2 && n_bytes >= h->cfg.pipe_min_bytes && tables_ok && !planned) {
+      size_t p1 = (n_bytes / parts) & ~(size_t)15;
+      if (win > p1) p1 = (win + 15) & ~(size_t)15;
+      // the other parts share what is left; fewer of them if the sample window took most of it
+      while (parts > 2 && (n_bytes - p1) / (parts - 1) < 4 * reading_size) parts--;
+      if (p1 + 4 * reading_size <= n_bytes && p1 + ((size_t)16 << 20) <= n_bytes)
+        return compress_parts(h, fastq, n_bytes, parts, p1, sample_bytes, reading_size, eof, ft_seq_out, ft_qual_out, out,
+                              infos, infos_cap, summary);
+    }
   }
   const bool planned = sample_bytes == 0 && h->plan.valid && h->plan.d_fastq == h->in_fastq.as<char>() &&
                        h->plan.n_bytes == n_bytes && h->plan.reading_size == reading_size && h->plan.eof == (eof != 0) &&

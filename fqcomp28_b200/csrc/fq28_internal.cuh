@@ -172,10 +172,15 @@ struct fq28_handle {
   // side stream: the sequence and quality pipelines are independent
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-  // host-buffer compress of a large slab runs as two overlapped halves: the second half is
-  // staged and encoded by a sibling handle (own streams and buffers) while the first one computes
+  // host-buffer compress of a large slab runs as overlapped parts: all host->device copies are
+  // queued on copy_stream (one event per part), the parts are encoded in turn by this handle and
+  // a sibling handle (own streams and buffers)
   fq28_handle *sibling = nullptr;
-  fq28::DevBuf in_raw;                   // sibling: second half as copied from the host (before alignment);
+  bool borrowing = false;                // sibling only: seq / qual are shallow copies of the owner's tables,
+  fq28::DevTables own_seq, own_qual;     // its own (allocated at create) are kept here
+  cudaStream_t copy_stream = nullptr;
+  std::vector<cudaEvent_t> ev_part;
+  fq28::DevBuf in_raw;                   // pipelined compress: the slab as copied from the host (before alignment);
                                          // fq28_stage: the speculatively copied host range
   // fq28_stage: host range [stage_host, stage_host + stage_bytes) already copied (or being copied,
   // same stream) to in_raw; host-buffer entry points whose input lies inside it skip their H2D
@@ -186,13 +191,10 @@ struct fq28_handle {
   struct Plan { bool valid = false; const char *d_fastq = nullptr; size_t n_bytes = 0, reading_size = 0; int eof = 0; } plan;
   // fq28_preparse_dev: the record table of exactly this slab is in place (consumed by the next plan)
   struct Parsed { bool valid = false; const char *d_fastq = nullptr; size_t n_bytes = 0; } parsed;
-  // generation of the device tables (bumped whenever they are rebuilt) and the generation the
-  // host FreqTable images below were taken from: the sibling handle is only ever loaded from
-  // images that match the current tables
-  uint64_t tables_gen = 0, ft_img_gen = ~0ull, sibling_gen = ~0ull;
+  // generation of the device tables (bumped whenever they are rebuilt; the C++ facade compares it)
+  uint64_t tables_gen = 0;
   const char *plan_host = nullptr;       // host slab of the last fq28_plan
   cudaEvent_t ev_copy = nullptr;
-  std::vector<uint8_t> ft_img_seq, ft_img_qual;   // host copies of the FreqTable images (for the sibling)
 
   // policy knobs, read from the environment once at fq28_create (diagnostics)
   struct Cfg {
@@ -204,7 +206,8 @@ struct fq28_handle {
     unsigned seq_lanes = 0, seq_warps = 0, qual_lanes = 0, qual_warps = 0;  // 0 = automatic
     int qual_carveout = -2;        // -2 = automatic
     bool no_zrun = false, no_dom = false, no_rankc = false, serial = false, full_overlap = false;
-    size_t pipe_min_bytes = (size_t)256 << 20;
+    size_t pipe_min_bytes = (size_t)256 << 20;   // FQ28_PIPE_MIN_MB: host-buffer slabs from this size on are pipelined
+    unsigned pipe_parts = 4;                     // FQ28_PIPE_PARTS: ... in this many parts (1 = one piece)
   } cfg;
   int qual_carve_set = -1;         // last shared-memory carve-out set for k_decode_qual on this device
 

@@ -735,7 +735,7 @@ int tables_from_norm(fq28_handle *h, DevTables &t) {
     for (unsigned j = 0; j < QZ_MAX; j++) t.h_zctx[j] = zi[1 + j];
   }
   t.ready = true;
-  h->tables_gen++;  // host images and sibling handles made from older tables are stale now
+  h->tables_gen++;  // anything derived from older tables is stale now
   return FQ28_OK;
 }
 

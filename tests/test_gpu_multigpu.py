@@ -211,14 +211,14 @@ def test_corrupt_side_information_is_an_error_not_a_fault(P, oracle, data):
 # ---------------------------------------------------------------- tables: one source of truth
 def test_rebuilt_tables_reach_both_halves_of_a_large_slab(P, oracle, data, monkeypatch):
     """A handle that loaded tables A and then built tables B must encode a slab that takes the
-    two-half path (sibling handle) with B in BOTH halves."""
-    monkeypatch.setenv("FQ28_PIPE_MIN_MB", "1")  # read at fq28_create: slabs >= 1 MB take the two-half path
+    pipelined path (parts alternate between the handle and a sibling handle) with B in ALL parts."""
+    monkeypatch.setenv("FQ28_PIPE_MIN_MB", "1")  # read at fq28_create: slabs >= 1 MB are pipelined
     R = 1 << 20
     h = P.Handle(0)
     monkeypatch.delenv("FQ28_PIPE_MIN_MB")
     fa = tables(oracle, data, 1 << 20)
     h.load_tables(*fa)
-    h.compress(data, R, eof=True)                      # two halves with A: the sibling now holds A
+    h.compress(data, R, eof=True)                      # pipelined with A: the sibling has encoded with A
     cs, cq = h.hist(data[: 3 << 20][: int(oracle.split_chunks(data[: 3 << 20], 3 << 20)[1])])
     fb = h.build_tables(cs, cq)                        # B, through the counts path
     assert not np.array_equal(fa[1], fb[1])

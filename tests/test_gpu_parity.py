@@ -348,15 +348,19 @@ def test_synthetic_profiles_chunk_parity(oracle, H, profile):
     check_chunks(oracle, H, d, 1 << 20, fs, fq)
 
 
-@pytest.mark.parametrize("eof", [True, False])
-def test_two_stage_host_compress(oracle, H, monkeypatch, eof):
-    """Large host slabs are compressed as two overlapped halves (second half on
-    a sibling handle): same chunks, streams and side arrays as the one-pass
-    walk, with the tables from the sample inside fq28_compress and with
-    pre-loaded tables."""
+@pytest.mark.parametrize("eof,parts", [(True, 4), (False, 4), (True, 2), (False, 7)])
+def test_pipelined_host_compress(oracle, monkeypatch, eof, parts):
+    """Large host slabs are compressed as overlapped parts (copies on a copy
+    stream, parts alternating between the handle and a sibling handle): same
+    chunks, streams and side arrays as the one-pass walk, with the tables from
+    the sample inside fq28_compress and with pre-loaded tables."""
     import synth
 
-    monkeypatch.setenv("FQ28_PIPE_MIN_MB", "1")
+    monkeypatch.setenv("FQ28_PIPE_MIN_MB", "1")      # both read at fq28_create
+    monkeypatch.setenv("FQ28_PIPE_PARTS", str(parts))
+    import fqcomp28_b200 as P
+
+    H = P.Handle(0)
     d = synth.illumina_bytes(40 << 20, seed=31)[0].numpy()
     S, R = 4 << 20, 1 << 20
     sample = d[: int(oracle.split_chunks(d, S)[1])]
@@ -373,8 +377,10 @@ def test_two_stage_host_compress(oracle, H, monkeypatch, eof):
     assert int(summ2.n_chunks) == int(summ.n_chunks) and int(summ2.consumed) == int(summ.consumed)
     assert np.array_equal(ar2["seq"][: int(summ2.seq_bytes)], seq_a)
     # and identical to the one-pass path
-    monkeypatch.setenv("FQ28_PIPE_MIN_MB", "100000")
-    infos1, summ1, ar1 = H.compress(d, R, eof=eof)
+    monkeypatch.setenv("FQ28_PIPE_PARTS", "1")
+    H1 = P.Handle(0)
+    H1.load_tables(fs, fq)
+    infos1, summ1, ar1 = H1.compress(d, R, eof=eof)
     assert int(summ1.n_chunks) == int(summ.n_chunks)
     for k in range(int(summ1.n_chunks)):
         for f in ("fastq_off", "total", "n_records", "rec_off", "seq_off", "qual_off", "seq_len", "qual_len",
@@ -383,6 +389,11 @@ def test_two_stage_host_compress(oracle, H, monkeypatch, eof):
     for key in ("seq", "qual"):
         nb = int(getattr(summ1, key + "_bytes"))
         assert np.array_equal(ar1[key][:nb], ar2[key][:nb]), key
+    for key, n in (("readlens", "n_records"), ("n_count", "n_records"), ("n_pos", "n_pos_entries")):
+        nn = int(getattr(summ1, n))
+        assert np.array_equal(ar1[key][:nn], ar2[key][:nn]), key
+    H.close()
+    H1.close()
 
 
 def _runny_fastq(n_records, seed, levels, p_stay, min_len=40, max_len=260):
