@@ -3,6 +3,12 @@
 #include <stdarg.h>
 #include <stdlib.h>
 
+#include <array>
+#include <chrono>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
+
 #include "fq28_internal.cuh"
 
 namespace fq28 {
@@ -34,6 +40,20 @@ int ensure(fq28_handle *h, DevBuf &b, size_t bytes) {
   }
   FQ28_CUDA(h, cudaMalloc(&b.p, want));
   b.cap = want;
+  return FQ28_OK;
+}
+
+int ensure_pinned(fq28_handle *h, size_t bytes) {
+  if (bytes <= h->h_pin_cap && h->h_pin) return FQ28_OK;
+  if (h->h_pin) {
+    FQ28_CUDA(h, cudaStreamSynchronize(h->stream));
+    FQ28_CUDA(h, cudaFreeHost(h->h_pin));
+    h->h_pin = nullptr;
+    h->h_pin_cap = 0;
+  }
+  const size_t want = (bytes + bytes / 4 + 4095) & ~(size_t)4095;
+  FQ28_CUDA(h, cudaMallocHost(&h->h_pin, want));
+  h->h_pin_cap = want;
   return FQ28_OK;
 }
 
@@ -208,6 +228,7 @@ int fq28_create(int device, fq28_handle **out) {
     {  // the side stream carries the latency-bound chains: its CTAs must not queue behind bulk kernels
       int lo = 0, hi = 0;
       cudaDeviceGetStreamPriorityRange(&lo, &hi);
+      if (getenv("FQ28_SIDE_PRIO_NORMAL")) hi = 0;
       if (cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, hi) != cudaSuccess) { rc = FQ28_ERR_CUDA; break; }
     }
     if (cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess) { rc = FQ28_ERR_CUDA; break; }
@@ -233,6 +254,8 @@ int fq28_create(int device, fq28_handle **out) {
       h->cfg.serial = getenv("FQ28_SERIAL") != nullptr;
       h->cfg.full_overlap = getenv("FQ28_FULL_OVERLAP") != nullptr;
       if (const char *e = getenv("FQ28_PIPE_MIN_MB")) h->cfg.pipe_min_bytes = (size_t)atoll(e) << 20;
+      h->cfg.pipe_trace = getenv("FQ28_PIPE_TRACE") != nullptr;
+      if (const char *e = getenv("FQ28_PIPE_LANES")) h->cfg.pipe_lanes = (unsigned)std::max(1, std::min(8, atoi(e)));
       if (const char *e = getenv("FQ28_PIPE_PARTS")) h->cfg.pipe_parts = (unsigned)std::max(1, std::min(64, atoi(e)));
     }
     // kernel attributes are per device: set them for this handle's device (not once per process)
@@ -251,12 +274,11 @@ int fq28_create(int device, fq28_handle **out) {
 
 void fq28_destroy(fq28_handle *h) {
   if (!h) return;
-  if (h->sibling) {
-    fq28_handle *s = h->sibling;
+  for (fq28_handle *s : h->siblings) {
     if (s->borrowing) { s->seq = s->own_seq; s->qual = s->own_qual; s->borrowing = false; }
     fq28_destroy(s);
-    h->sibling = nullptr;
   }
+  h->siblings.clear();
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   DevBuf *bufs[] = {&h->in_fastq, &h->tile_cnt, &h->nl, &h->hdr_off, &h->seq_off, &h->qual_off, &h->len, &h->hdr_len,
@@ -274,6 +296,7 @@ void fq28_destroy(fq28_handle *h) {
   if (h->h_status) cudaFreeHost(h->h_status);
   if (h->d_scalars) cudaFree(h->d_scalars);
   if (h->h_scalars) cudaFreeHost(h->h_scalars);
+  if (h->h_pin) cudaFreeHost(h->h_pin);
   for (auto &r : h->ev_pool) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   if (h->side) { cudaStreamSynchronize(h->side); cudaStreamDestroy(h->side); }
   if (h->ev_copy) cudaEventDestroy(h->ev_copy);
@@ -420,33 +443,37 @@ size_t fq28_bound_qual(size_t n) {  // src/workspace.h:31-35
   return a > b ? a : b;
 }
 
+// analyzeDataset (src/prepare.cpp:42-47): first chunk of a reader whose reading size is the
+// sample size = records wholly inside the window; histograms, tables, FreqTable images
+static int analyze_dev(fq28_handle *h, const char *d_fastq, size_t n_bytes, size_t sample_bytes, void *ft_seq_out,
+                       void *ft_qual_out) {
+  const size_t win = sample_bytes < n_bytes ? sample_bytes : n_bytes;
+  stage_begin(h, ST_PARSE);
+  FQ28_TRY(parse_slab(h, d_fastq, win, false));
+  stage_end(h, ST_PARSE);
+  if (h->n_rec == 0) return fail(h, FQ28_ERR_FORMAT, "sample window of %zu bytes holds no complete record", win);
+  stage_begin(h, ST_HIST);
+  FQ28_CUDA(h, cudaMemsetAsync(h->seq.counts, 0, (size_t)SEQ_N * SEQ_A * 4, h->stream));
+  FQ28_CUDA(h, cudaMemsetAsync(h->qual.counts, 0, (size_t)QUAL_N * QUAL_A * 4, h->stream));
+  FQ28_TRY(hist_slab(h, h->seq.counts, h->qual.counts));
+  stage_end(h, ST_HIST);
+  stage_begin(h, ST_TABLES);
+  FQ28_TRY(tables_from_counts(h, h->seq, h->seq.counts));
+  FQ28_TRY(tables_from_counts(h, h->qual, h->qual.counts));
+  stage_end(h, ST_TABLES);
+  FQ28_TRY(check_status(h, "analyzeDataset"));
+  FQ28_TRY(ft_image_out(h, h->seq, ft_seq_out));
+  FQ28_TRY(ft_image_out(h, h->qual, ft_qual_out));
+  return FQ28_OK;
+}
+
 int fq28_compress_dev(fq28_handle *h, const char *d_fastq, size_t n_bytes, size_t sample_bytes, size_t reading_size,
                       int eof, void *ft_seq_out, void *ft_qual_out, fq28_chunk_info *infos, size_t infos_cap,
                       fq28_enc_summary *summary) {
   if (!h || !infos) return FQ28_ERR_ARG;
   FQ28_TRY(bind(h));
   stage_reset(h);
-  if (sample_bytes > 0) {
-    // analyzeDataset (src/prepare.cpp:42-47): first chunk of a reader whose
-    // reading size is the sample size = records wholly inside the window
-    const size_t win = sample_bytes < n_bytes ? sample_bytes : n_bytes;
-    stage_begin(h, ST_PARSE);
-    FQ28_TRY(parse_slab(h, d_fastq, win, false));
-    stage_end(h, ST_PARSE);
-    if (h->n_rec == 0) return fail(h, FQ28_ERR_FORMAT, "sample window of %zu bytes holds no complete record", win);
-    stage_begin(h, ST_HIST);
-    FQ28_CUDA(h, cudaMemsetAsync(h->seq.counts, 0, (size_t)SEQ_N * SEQ_A * 4, h->stream));
-    FQ28_CUDA(h, cudaMemsetAsync(h->qual.counts, 0, (size_t)QUAL_N * QUAL_A * 4, h->stream));
-    FQ28_TRY(hist_slab(h, h->seq.counts, h->qual.counts));
-    stage_end(h, ST_HIST);
-    stage_begin(h, ST_TABLES);
-    FQ28_TRY(tables_from_counts(h, h->seq, h->seq.counts));
-    FQ28_TRY(tables_from_counts(h, h->qual, h->qual.counts));
-    stage_end(h, ST_TABLES);
-    FQ28_TRY(check_status(h, "analyzeDataset"));
-    FQ28_TRY(ft_image_out(h, h->seq, ft_seq_out));
-    FQ28_TRY(ft_image_out(h, h->qual, ft_qual_out));
-  }
+  if (sample_bytes > 0) FQ28_TRY(analyze_dev(h, d_fastq, n_bytes, sample_bytes, ft_seq_out, ft_qual_out));
   const bool planned = sample_bytes == 0 && h->plan.valid && h->plan.d_fastq == d_fastq && h->plan.n_bytes == n_bytes &&
                        h->plan.reading_size == reading_size && h->plan.eof == (eof != 0);
   if (!planned) {
@@ -586,22 +613,48 @@ int fq28_compress_fetch(fq28_handle *h, const fq28_enc_arenas *out) {
   return FQ28_OK;
 }
 
-// Host-buffer compress of a large slab as K overlapped parts (cfg.pipe_parts, default 4).
+// Host-buffer compress of a large slab as K overlapped parts (cfg.pipe_parts, default 8) on L lanes
+// (cfg.pipe_lanes, default 4).
 // All host->device copies are queued at once on a copy stream, one event per part; part k is
 // the slab [cut_k, p_{k+1}) where cut_k is where the chunk walk of part k-1 stopped (eof = 0:
 // only chunks whose whole window lies inside the part), so the chunks are exactly those of the
-// one-pass walk (deterministic from its start offset).  Two handles with their own streams and
-// buffers take the parts in turn: the kernels of part k run under the copies of parts k+1..,
-// the device->host copy of its result under the kernels of part k+1.
+// one-pass walk (deterministic from its start offset).  L handles with their own streams and
+// buffers take the parts in turn, each driven by its own host thread, so the kernels of L
+// parts overlap (the chains are latency-bound on a few SMs) and run under the copies of the
+// later parts; the device->host copy of a part's result runs under the kernels of the next.
+// What crosses between the threads: where a part starts and how many chunks precede it (known
+// after the previous part's chunk walk), and the arena offsets of its result (known after the
+// previous part is encoded).
+namespace {
+struct PartSizes { uint64_t n_records = 0, seq_bytes = 0, qual_bytes = 0, n_pos_entries = 0, hdr_bytes = 0, n_symbols = 0; };
+struct PartsShared {
+  std::mutex mu;
+  std::condition_variable cv;
+  std::vector<size_t> cut, cbase;      // part k starts at slab offset cut[k]; cbase[k] chunks precede it
+  std::vector<PartSizes> pre;          // pre[k] = totals of parts < k
+  unsigned planned = 0, sized = 0;     // cut / cbase valid up to index `planned`, pre up to `sized`
+  int rc = FQ28_OK;
+  std::string why;
+  void abort(int code, const std::string &w) {
+    std::lock_guard<std::mutex> lk(mu);
+    if (rc == FQ28_OK) { rc = code; why = w; }
+    cv.notify_all();
+  }
+};
+}  // namespace
+
 static int compress_parts(fq28_handle *h, const char *fastq, size_t n_bytes, unsigned n_parts, size_t p1, size_t sample_bytes,
                           size_t reading_size, int eof, void *ft_seq_out, void *ft_qual_out,
                           const fq28_enc_arenas *out, fq28_chunk_info *infos, size_t infos_cap,
                           fq28_enc_summary *summary) {
-  if (!h->sibling) {
-    FQ28_TRY(fq28_create(h->device, &h->sibling));
+  const unsigned n_lanes = std::max(1u, std::min(h->cfg.pipe_lanes, n_parts));
+  while (h->siblings.size() + 1 < n_lanes) {
+    fq28_handle *s = nullptr;
+    FQ28_TRY(fq28_create(h->device, &s));
+    h->siblings.push_back(s);
     FQ28_TRY(bind(h));
   }
-  fq28_handle *s = h->sibling;
+  auto lane_handle = [&](unsigned k) -> fq28_handle * { return (k % n_lanes) ? h->siblings[k % n_lanes - 1] : h; };
   if (!h->copy_stream) FQ28_CUDA(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
   while (h->ev_part.size() < n_parts) {
     cudaEvent_t e;
@@ -616,8 +669,7 @@ static int compress_parts(fq28_handle *h, const char *fastq, size_t n_bytes, uns
   size_t longest = 0;
   for (unsigned k = 0; k < n_parts; k++) longest = std::max(longest, p[k + 1] - p[k]);
   // a part starts at most one window before its nominal start
-  FQ28_TRY(ensure(h, h->in_fastq, longest + reading_size + 64));
-  FQ28_TRY(ensure(s, s->in_fastq, longest + reading_size + 64));
+  for (unsigned j = 0; j < n_lanes; j++) FQ28_TRY(ensure(lane_handle(j), lane_handle(j)->in_fastq, longest + reading_size + 64));
   FQ28_TRY(ensure(h, h->in_raw, n_bytes + 64));
   // the copies must not overtake work still queued on the buffers they overwrite
   if (!h->ev_copy) FQ28_CUDA(h, cudaEventCreateWithFlags(&h->ev_copy, cudaEventDisableTiming));
@@ -629,75 +681,155 @@ static int compress_parts(fq28_handle *h, const char *fastq, size_t n_bytes, uns
     FQ28_CUDA(h, cudaMemcpyAsync(dst, fastq + p[k], p[k + 1] - p[k], cudaMemcpyHostToDevice, h->copy_stream));
     FQ28_CUDA(h, cudaEventRecord(h->ev_part[k], h->copy_stream));
   }
-  fq28_enc_summary m;
-  memset(&m, 0, sizeof(m));
-  size_t cut = 0;  // slab offset where the current part starts
-  int rc = FQ28_OK;
-  for (unsigned k = 0; k < n_parts && rc == FQ28_OK; k++) {
-    fq28_handle *g = (k & 1) ? s : h;
-    const size_t len = p[k + 1] - cut;
+  // same device: the siblings encode with this handle's tables (complete before the first part's
+  // walk is published); their own stay allocated and come back in fq28_destroy
+  for (unsigned j = 1; j < n_lanes; j++) {
+    fq28_handle *s = lane_handle(j);
+    if (!s->borrowing) { s->own_seq = s->seq; s->own_qual = s->qual; s->borrowing = true; }
+  }
+
+  // FQ28_PIPE_TRACE: host clock (ms since the call started) at the sync points of every part, to stderr
+  const bool trace = h->cfg.pipe_trace;
+  const auto t0 = std::chrono::steady_clock::now();
+  std::vector<std::array<double, 5>> tr(n_parts);
+  auto now_ms = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); };
+  PartsShared sh;
+  sh.cut.assign(n_parts + 1, 0);
+  sh.cbase.assign(n_parts + 1, 0);
+  sh.pre.assign(n_parts + 1, PartSizes());
+  const bool tables_first = sample_bytes > 0;
+
+  // one part, on the handle of its lane (the caller's thread is lane 0 and runs on h)
+  auto run_part = [&](unsigned k) -> int {
+    fq28_handle *g = lane_handle(k);
     const bool last = k + 1 == n_parts;
-    rc = bind(g);
-    if (rc != FQ28_OK) break;
-    if (cudaStreamWaitEvent(g->stream, h->ev_part[k], 0) != cudaSuccess) { rc = FQ28_ERR_CUDA; break; }
+    size_t cut, cbase;
+    {
+      std::unique_lock<std::mutex> lk(sh.mu);
+      sh.cv.wait(lk, [&] { return sh.rc != FQ28_OK || sh.planned >= k; });
+      if (sh.rc != FQ28_OK) return sh.rc;
+      cut = sh.cut[k];
+      cbase = sh.cbase[k];
+    }
+    FQ28_TRY(bind(g));
+    const size_t len = p[k + 1] - cut;
+    tr[k][0] = now_ms();
+    if (trace) { cudaEventSynchronize(h->ev_part[k]); tr[k][1] = now_ms(); }
+    FQ28_CUDA(g, cudaStreamWaitEvent(g->stream, h->ev_part[k], 0));
     if (k > 0) {
-      // [cut, p_k) was copied with part k-1: to h->in_fastq if that was part 0, else to in_raw
+      // [cut, p_k) came with part k-1: in h->in_fastq if that was part 0 (still intact: h's next
+      // part waits for the walks of all parts before it), else in in_raw
       const char *head = k == 1 ? h->in_fastq.as<char>() + cut : h->in_raw.as<char>() + cut;
-      if (p[k] > cut &&
-          cudaMemcpyAsync(g->in_fastq.p, head, p[k] - cut, cudaMemcpyDeviceToDevice, g->stream) != cudaSuccess) { rc = FQ28_ERR_CUDA; break; }
-      if (cudaMemcpyAsync(g->in_fastq.as<char>() + (p[k] - cut), h->in_raw.as<char>() + p[k], p[k + 1] - p[k],
-                          cudaMemcpyDeviceToDevice, g->stream) != cudaSuccess) { rc = FQ28_ERR_CUDA; break; }
-      if (k == 1) {
-        // same device: the sibling encodes with this handle's tables (built and complete: the first
-        // part has returned); its own stay allocated and come back in fq28_destroy
-        if (!s->borrowing) { s->own_seq = s->seq; s->own_qual = s->qual; s->borrowing = true; }
-        s->seq = h->seq;
-        s->qual = h->qual;
+      if (p[k] > cut) FQ28_CUDA(g, cudaMemcpyAsync(g->in_fastq.p, head, p[k] - cut, cudaMemcpyDeviceToDevice, g->stream));
+      FQ28_CUDA(g, cudaMemcpyAsync(g->in_fastq.as<char>() + (p[k] - cut), h->in_raw.as<char>() + p[k], p[k + 1] - p[k],
+                                   cudaMemcpyDeviceToDevice, g->stream));
+    } else if (tables_first) {
+      stage_reset(g);
+      FQ28_TRY(analyze_dev(g, g->in_fastq.as<char>(), len, sample_bytes, ft_seq_out, ft_qual_out));
+    }
+    if (g != h) { g->seq = h->seq; g->qual = h->qual; }   // (pointers: cheap, and h may have rebuilt its tables)
+    uint64_t consumed = 0;
+    size_t nc = 0;
+    FQ28_TRY(fq28_plan_dev(g, g->in_fastq.as<char>(), len, reading_size, last ? eof : 0, &consumed, &nc));
+    if (cbase + nc > infos_cap) return fail(g, FQ28_ERR_CAP, "infos_cap %zu < %zu chunks", infos_cap, cbase + nc);
+    tr[k][2] = now_ms();
+    {
+      std::lock_guard<std::mutex> lk(sh.mu);
+      sh.cut[k + 1] = cut + (size_t)consumed;
+      sh.cbase[k + 1] = cbase + nc;
+      sh.planned = k + 1;
+    }
+    sh.cv.notify_all();
+    fq28_enc_summary sk;
+    FQ28_TRY(fq28_compress_dev(g, g->in_fastq.as<char>(), len, 0, reading_size, last ? eof : 0, nullptr, nullptr,
+                               infos + cbase, infos_cap - cbase, &sk));
+    tr[k][3] = now_ms();
+    PartSizes base;
+    {
+      std::unique_lock<std::mutex> lk(sh.mu);
+      sh.cv.wait(lk, [&] { return sh.rc != FQ28_OK || sh.sized >= k; });
+      if (sh.rc != FQ28_OK) return sh.rc;
+      base = sh.pre[k];
+      PartSizes &nx = sh.pre[k + 1];
+      nx.n_records = base.n_records + sk.n_records; nx.seq_bytes = base.seq_bytes + sk.seq_bytes;
+      nx.qual_bytes = base.qual_bytes + sk.qual_bytes; nx.n_pos_entries = base.n_pos_entries + sk.n_pos_entries;
+      nx.hdr_bytes = base.hdr_bytes + sk.hdr_bytes; nx.n_symbols = base.n_symbols + sk.n_symbols;
+      sh.sized = k + 1;
+    }
+    sh.cv.notify_all();
+    fq28_enc_arenas ob = *out;
+    ob.seq += base.seq_bytes; ob.seq_cap -= std::min<uint64_t>(ob.seq_cap, base.seq_bytes);
+    ob.qual += base.qual_bytes; ob.qual_cap -= std::min<uint64_t>(ob.qual_cap, base.qual_bytes);
+    ob.readlens += base.n_records; ob.readlens_cap -= std::min<uint64_t>(ob.readlens_cap, base.n_records);
+    ob.n_count += base.n_records; ob.n_count_cap -= std::min<uint64_t>(ob.n_count_cap, base.n_records);
+    ob.n_pos += base.n_pos_entries; ob.n_pos_cap -= std::min<uint64_t>(ob.n_pos_cap, base.n_pos_entries);
+    if (ob.hdr_lens) { ob.hdr_lens += base.n_records; ob.hdr_lens_cap -= std::min<uint64_t>(ob.hdr_lens_cap, base.n_records); }
+    if (ob.headers) { ob.headers += base.hdr_bytes; ob.headers_cap -= std::min<uint64_t>(ob.headers_cap, base.hdr_bytes); }
+    FQ28_TRY(fetch_async(g, &ob));  // device->host of this part overlaps the next parts' kernels
+    tr[k][4] = now_ms();
+    for (uint64_t c = 0; c < sk.n_chunks; c++) {
+      fq28_chunk_info &ci = infos[cbase + c];
+      ci.fastq_off += cut;
+      ci.rec_off += base.n_records;
+      ci.seq_off += base.seq_bytes;
+      ci.qual_off += base.qual_bytes;
+      ci.n_pos_off += base.n_pos_entries;
+      ci.hdr_off += base.hdr_bytes;
+    }
+    return FQ28_OK;
+  };
+  auto run_lane = [&](unsigned first) {
+    for (unsigned k = first; k < n_parts; k += n_lanes) {
+      const int rc = run_part(k);
+      if (rc != FQ28_OK) {
+        sh.abort(rc, lane_handle(k)->err);
+        return;
       }
     }
-    fq28_enc_summary sk;
-    rc = fq28_compress_dev(g, g->in_fastq.as<char>(), len, k == 0 ? sample_bytes : 0, reading_size, last ? eof : 0,
-                           k == 0 ? ft_seq_out : nullptr, k == 0 ? ft_qual_out : nullptr, infos + m.n_chunks,
-                           infos_cap - (size_t)m.n_chunks, &sk);
-    if (rc != FQ28_OK) break;
-    fq28_enc_arenas ob = *out;
-    ob.seq += m.seq_bytes; ob.seq_cap -= m.seq_bytes;
-    ob.qual += m.qual_bytes; ob.qual_cap -= m.qual_bytes;
-    ob.readlens += m.n_records; ob.readlens_cap -= m.n_records;
-    ob.n_count += m.n_records; ob.n_count_cap -= m.n_records;
-    ob.n_pos += m.n_pos_entries; ob.n_pos_cap -= m.n_pos_entries;
-    if (ob.hdr_lens) { ob.hdr_lens += m.n_records; ob.hdr_lens_cap -= m.n_records; }
-    if (ob.headers) { ob.headers += m.hdr_bytes; ob.headers_cap -= m.hdr_bytes; }
-    rc = fetch_async(g, &ob);  // device->host of this part overlaps the next part's kernels
-    if (rc != FQ28_OK) break;
-    for (uint64_t c = 0; c < sk.n_chunks; c++) {
-      fq28_chunk_info &ci = infos[m.n_chunks + c];
-      ci.fastq_off += cut;
-      ci.rec_off += m.n_records;
-      ci.seq_off += m.seq_bytes;
-      ci.qual_off += m.qual_bytes;
-      ci.n_pos_off += m.n_pos_entries;
-      ci.hdr_off += m.hdr_bytes;
+  };
+  std::vector<std::thread> lanes;
+  bool threaded = true;
+  try {
+    for (unsigned j = 1; j < n_lanes; j++) lanes.emplace_back([&, j] { run_lane(j); });
+  } catch (...) {
+    threaded = false;  // no more host threads: stop the ones that started, then the parts in order on this one
+    sh.abort(FQ28_ERR_CUDA, "");
+    for (std::thread &t : lanes) t.join();
+    lanes.clear();
+    std::lock_guard<std::mutex> lk(sh.mu);
+    if (sh.planned || sh.sized) return fail(h, FQ28_ERR_CUDA, "pipelined compress: could not start the lane threads");
+    sh.rc = FQ28_OK;
+  }
+  if (threaded) {
+    run_lane(0);
+    for (std::thread &t : lanes) t.join();
+  } else {
+    for (unsigned k = 0; k < n_parts && sh.rc == FQ28_OK; k++) {   // (each part only waits for earlier parts)
+      const int rc = run_part(k);
+      if (rc != FQ28_OK) sh.abort(rc, lane_handle(k)->err);
     }
-    m.n_chunks += sk.n_chunks; m.n_records += sk.n_records; m.n_symbols += sk.n_symbols;
-    m.seq_bytes += sk.seq_bytes; m.qual_bytes += sk.qual_bytes; m.n_pos_entries += sk.n_pos_entries;
-    m.hdr_bytes += sk.hdr_bytes;
-    cut += (size_t)sk.consumed;
   }
   // nothing may still be writing into the caller's buffers (or reading them) when this returns
+  bind(h);
   cudaStreamSynchronize(h->copy_stream);
-  cudaStreamSynchronize(s->stream);
-  cudaStreamSynchronize(h->stream);
-  if (rc != FQ28_OK) {
-    std::string why = s->err.empty() ? h->err : s->err;
-    bind(h);
-    return fail(h, rc, "pipelined compress: %s", why.c_str());
+  for (unsigned j = 0; j < n_lanes; j++) {
+    cudaStreamSynchronize(lane_handle(j)->stream);
+    lane_handle(j)->have_result = false;  // the device-resident result is split over the parts: not fetchable again
   }
-  FQ28_TRY(bind(h));
-  m.consumed = cut;
+  if (sh.rc != FQ28_OK) return fail(h, sh.rc, "pipelined compress: %s", sh.why.c_str());
+  if (trace) {
+    for (unsigned k = 0; k < n_parts; k++)
+      fprintf(stderr, "fq28 pipe part %u/%u [%zu MB]: start %.2f  copied %.2f  walked %.2f  chains done %.2f  fetch queued %.2f ms\n",
+              k, n_parts, (p[k + 1] - p[k]) >> 20, tr[k][0], tr[k][1], tr[k][2], tr[k][3], tr[k][4]);
+    fprintf(stderr, "fq28 pipe end %.2f ms\n", now_ms());
+  }
+  const PartSizes &t = sh.pre[n_parts];
+  fq28_enc_summary m;
+  memset(&m, 0, sizeof(m));
+  m.n_chunks = sh.cbase[n_parts]; m.n_records = t.n_records; m.n_symbols = t.n_symbols;
+  m.seq_bytes = t.seq_bytes; m.qual_bytes = t.qual_bytes; m.n_pos_entries = t.n_pos_entries; m.hdr_bytes = t.hdr_bytes;
+  m.consumed = sh.cut[n_parts];
   if (summary) *summary = m;
-  h->have_result = false;  // the device-resident result is split over the parts: not fetchable again
-  s->have_result = false;
   return FQ28_OK;
 }
 
@@ -711,6 +843,7 @@ int fq28_compress(fq28_handle *h, const char *fastq, size_t n_bytes, size_t samp
     const size_t win = sample_bytes < n_bytes ? sample_bytes : n_bytes;
     unsigned parts = h->cfg.pipe_parts;
     if (reading_size) parts = (unsigned)std::min<size_t>(parts, n_bytes / (4 * reading_size));
+    parts = (unsigned)std::min<size_t>(parts, n_bytes >> 26);   // a part costs ~6 ms of latency whatever its size: >= 64 MB each
     const bool tables_ok = sample_bytes > 0 || (h->seq.ready && h->qual.ready);
     const bool planned = h->plan.valid && sample_bytes == 0;  // a planned slab is encoded as planned, in one piece
     if (parts >= 2 && n_bytes >= h->cfg.pipe_min_bytes && tables_ok && !planned) {

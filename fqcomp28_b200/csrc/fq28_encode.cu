@@ -1326,10 +1326,11 @@ int encode_slab(fq28_handle *h, fq28_chunk_info *infos, size_t infos_cap, fq28_e
     FQ28_TRY(scan_exclusive_u16_to_u32(h, h->n_count.as<uint16_t>(), h->npos_off.as<uint32_t>(), n_rec));
     FQ28_TRY(ensure(h, h->hdrscan, (n_rec + 2) * 4));
     FQ28_TRY(scan_exclusive_u16_to_u32(h, h->hdr_len.as<uint16_t>(), h->hdrscan.as<uint32_t>(), n_rec));
-    uint32_t total_n = 0, total_h = 0;
-    FQ28_CUDA(h, cudaMemcpyAsync(&total_n, h->npos_off.as<uint32_t>() + n_rec, 4, cudaMemcpyDeviceToHost, h->stream));
-    FQ28_CUDA(h, cudaMemcpyAsync(&total_h, h->hdrscan.as<uint32_t>() + n_rec, 4, cudaMemcpyDeviceToHost, h->stream));
+    uint32_t *totals = reinterpret_cast<uint32_t *>(h->h_scalars + 58);   // (pinned)
+    FQ28_CUDA(h, cudaMemcpyAsync(totals, h->npos_off.as<uint32_t>() + n_rec, 4, cudaMemcpyDeviceToHost, h->stream));
+    FQ28_CUDA(h, cudaMemcpyAsync(totals + 1, h->hdrscan.as<uint32_t>() + n_rec, 4, cudaMemcpyDeviceToHost, h->stream));
     FQ28_TRY(check_status(h, "field separation"));
+    const uint32_t total_n = totals[0], total_h = totals[1];
     FQ28_TRY(ensure(h, h->n_pos, ((size_t)total_n + 8) * 2));
     h->last_summary.n_pos_entries = total_n;
     h->last_summary.hdr_bytes = total_h;
@@ -1371,9 +1372,9 @@ int encode_slab(fq28_handle *h, fq28_chunk_info *infos, size_t infos_cap, fq28_e
                                            h->ptile0_qual.as<uint32_t>(), h->pscan_qual.as<unsigned long long>(),
                                            h->d_infos.as<fq28_chunk_info>(), h->d_scalars);
   FQ28_LAUNCH_CHECK(h);
-  h->h_infos.resize(n_chunks);
+  FQ28_TRY(ensure_pinned(h, (size_t)n_chunks * sizeof(fq28_chunk_info)));
   FQ28_CUDA(h, cudaMemcpyAsync(h->h_scalars, h->d_scalars, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, h->stream));
-  FQ28_CUDA(h, cudaMemcpyAsync(h->h_infos.data(), h->d_infos.p, (size_t)n_chunks * sizeof(fq28_chunk_info),
+  FQ28_CUDA(h, cudaMemcpyAsync(h->h_pin, h->d_infos.p, (size_t)n_chunks * sizeof(fq28_chunk_info),
                                cudaMemcpyDeviceToHost, h->stream));
   FQ28_CUDA(h, cudaStreamSynchronize(h->stream));
   const size_t seq_bytes = (size_t)h->h_scalars[0], qual_bytes = (size_t)h->h_scalars[1];
@@ -1390,7 +1391,7 @@ int encode_slab(fq28_handle *h, fq28_chunk_info *infos, size_t infos_cap, fq28_e
   h->last_summary.seq_bytes = seq_bytes;
   h->last_summary.qual_bytes = qual_bytes;
   h->last_summary.consumed = h->h_chunk_byte[n_chunks];
-  memcpy(infos, h->h_infos.data(), (size_t)n_chunks * sizeof(fq28_chunk_info));
+  memcpy(infos, h->h_pin, (size_t)n_chunks * sizeof(fq28_chunk_info));
   if (summary) *summary = h->last_summary;
   h->have_result = true;
   return FQ28_OK;

@@ -150,6 +150,11 @@ struct fq28_handle {
   fq28::DevBuf in_fastq;                 // staging for host-buffer entry points
   fq28::DevBuf tile_cnt, nl, hdr_off, seq_off, qual_off, len, hdr_len, symoff;
   fq28::DevBuf chunk_rec;                // u32 [cap+1]
+  // pinned host scratch for the small device->host reads of the per-call paths (a pageable
+  // destination makes cudaMemcpyAsync wait for the stream inside the runtime, which stalls the
+  // CUDA calls of other host threads -- the two lanes of the pipelined compress)
+  void *h_pin = nullptr;
+  size_t h_pin_cap = 0;
   std::vector<uint32_t> h_chunk_rec;     // host copy
   std::vector<uint32_t> h_chunk_sym;     // symoff at chunk boundaries
   std::vector<uint32_t> h_chunk_byte;    // hdr_off at chunk boundaries
@@ -162,7 +167,6 @@ struct fq28_handle {
   fq28::DevBuf tile0_seq, tile0_qual, tbase_seq, tbase_qual, fstate_seq, fstate_qual;
   fq28::DevBuf ptile0_seq, ptile0_qual, pbits_seq, pbits_qual, pscan_seq, pscan_qual;
   fq28::DevBuf arena_seq, arena_qual, d_infos, scan_tmp, scan_tmp_side, dom_list, present;
-  std::vector<fq28_chunk_info> h_infos;
   fq28_enc_summary last_summary{};
   bool have_result = false;
 
@@ -174,8 +178,8 @@ struct fq28_handle {
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   // host-buffer compress of a large slab runs as overlapped parts: all host->device copies are
   // queued on copy_stream (one event per part), the parts are encoded in turn by this handle and
-  // a sibling handle (own streams and buffers)
-  fq28_handle *sibling = nullptr;
+  // sibling handles (own streams and buffers), each driven by its own host thread (a "lane")
+  std::vector<fq28_handle *> siblings;
   bool borrowing = false;                // sibling only: seq / qual are shallow copies of the owner's tables,
   fq28::DevTables own_seq, own_qual;     // its own (allocated at create) are kept here
   cudaStream_t copy_stream = nullptr;
@@ -207,7 +211,9 @@ struct fq28_handle {
     int qual_carveout = -2;        // -2 = automatic
     bool no_zrun = false, no_dom = false, no_rankc = false, serial = false, full_overlap = false;
     size_t pipe_min_bytes = (size_t)256 << 20;   // FQ28_PIPE_MIN_MB: host-buffer slabs from this size on are pipelined
-    unsigned pipe_parts = 4;                     // FQ28_PIPE_PARTS: ... in this many parts (1 = one piece)
+    bool pipe_trace = false;                     // FQ28_PIPE_TRACE: host-clock timeline of the parts to stderr
+    unsigned pipe_lanes = 4;                     // FQ28_PIPE_LANES: parts in flight (handles and host threads)
+    unsigned pipe_parts = 8;                     // FQ28_PIPE_PARTS: ... in this many parts (1 = one piece)
   } cfg;
   int qual_carve_set = -1;         // last shared-memory carve-out set for k_decode_qual on this device
 
@@ -225,6 +231,7 @@ namespace fq28 {
 int fail(fq28_handle *h, int code, const char *fmt, ...);
 int cuda_fail(fq28_handle *h, cudaError_t e, const char *what);
 int ensure(fq28_handle *h, DevBuf &b, size_t bytes);
+int ensure_pinned(fq28_handle *h, size_t bytes);      // h->h_pin holds at least `bytes`
 int check_status(fq28_handle *h, const char *what);   // syncs + reads d_status
 void stage_reset(fq28_handle *h);
 void stage_begin(fq28_handle *h, Stage s);

@@ -312,10 +312,10 @@ int parse_slab(fq28_handle *h, const char *d_fastq, size_t n_bytes, bool need_sy
     FQ28_LAUNCH_CHECK(h);
   }
   FQ28_TRY(scan_exclusive_u32(h, tile_cnt, tile_cnt, n_tiles));
-  uint32_t n_lines32 = 0;
-  FQ28_CUDA(h, cudaMemcpyAsync(&n_lines32, tile_cnt + n_tiles, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+  uint32_t *n_lines32 = reinterpret_cast<uint32_t *>(h->h_scalars + 60);   // (pinned)
+  FQ28_CUDA(h, cudaMemcpyAsync(n_lines32, tile_cnt + n_tiles, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
   FQ28_CUDA(h, cudaStreamSynchronize(h->stream));
-  h->n_lines = n_lines32;
+  h->n_lines = *n_lines32;
   h->n_rec = h->n_lines / 4;
   const size_t n_rec = h->n_rec;
   FQ28_TRY(ensure(h, h->nl, (h->n_lines + 4) * sizeof(uint32_t)));
@@ -360,10 +360,15 @@ int split_slab(fq28_handle *h, size_t reading_size, bool eof, size_t max_chunks,
   h->h_chunk_rec.resize(n + 1);
   h->h_chunk_sym.resize(n + 1);
   h->h_chunk_byte.resize(n + 1);
-  FQ28_CUDA(h, cudaMemcpyAsync(h->h_chunk_rec.data(), cr, (n + 1) * 4, cudaMemcpyDeviceToHost, h->stream));
-  FQ28_CUDA(h, cudaMemcpyAsync(h->h_chunk_sym.data(), cr + (cap + 1), (n + 1) * 4, cudaMemcpyDeviceToHost, h->stream));
-  FQ28_CUDA(h, cudaMemcpyAsync(h->h_chunk_byte.data(), cr + 2 * (cap + 1), (n + 1) * 4, cudaMemcpyDeviceToHost, h->stream));
+  FQ28_TRY(ensure_pinned(h, 3 * (n + 1) * 4));
+  uint32_t *pin = static_cast<uint32_t *>(h->h_pin);
+  FQ28_CUDA(h, cudaMemcpyAsync(pin, cr, (n + 1) * 4, cudaMemcpyDeviceToHost, h->stream));
+  FQ28_CUDA(h, cudaMemcpyAsync(pin + (n + 1), cr + (cap + 1), (n + 1) * 4, cudaMemcpyDeviceToHost, h->stream));
+  FQ28_CUDA(h, cudaMemcpyAsync(pin + 2 * (n + 1), cr + 2 * (cap + 1), (n + 1) * 4, cudaMemcpyDeviceToHost, h->stream));
   FQ28_CUDA(h, cudaStreamSynchronize(h->stream));
+  memcpy(h->h_chunk_rec.data(), pin, (n + 1) * 4);
+  memcpy(h->h_chunk_sym.data(), pin + (n + 1), (n + 1) * 4);
+  memcpy(h->h_chunk_byte.data(), pin + 2 * (n + 1), (n + 1) * 4);
   return FQ28_OK;
 }
 

@@ -37,7 +37,11 @@ with open(os.path.join(out, f"{tag}_launches.md"), "w") as f:
 
 # ---- full-set metrics
 rep = os.path.join(go, f"prof_{tag}.ncu-rep")
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+raw_csv = os.path.join(go, f"prof_{tag}_raw.csv")   # exported on the GPU box when the report is too big to bring back
+if os.path.exists(rep):
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+else:
+    raw = open(raw_csv).read()
 rr = list(csv.reader(raw.splitlines()))
 h = rr[0]
 want = [

@@ -348,16 +348,17 @@ def test_synthetic_profiles_chunk_parity(oracle, H, profile):
     check_chunks(oracle, H, d, 1 << 20, fs, fq)
 
 
-@pytest.mark.parametrize("eof,parts", [(True, 4), (False, 4), (True, 2), (False, 7)])
-def test_pipelined_host_compress(oracle, monkeypatch, eof, parts):
+@pytest.mark.parametrize("eof,parts,lanes", [(True, 4, 3), (False, 4, 2), (True, 2, 2), (False, 7, 4), (True, 5, 1)])
+def test_pipelined_host_compress(oracle, monkeypatch, eof, parts, lanes):
     """Large host slabs are compressed as overlapped parts (copies on a copy
-    stream, parts alternating between the handle and a sibling handle): same
+    stream, parts dealt to `lanes` handles, one host thread each): same
     chunks, streams and side arrays as the one-pass walk, with the tables from
     the sample inside fq28_compress and with pre-loaded tables."""
     import synth
 
     monkeypatch.setenv("FQ28_PIPE_MIN_MB", "1")      # both read at fq28_create
     monkeypatch.setenv("FQ28_PIPE_PARTS", str(parts))
+    monkeypatch.setenv("FQ28_PIPE_LANES", str(lanes))
     import fqcomp28_b200 as P
 
     H = P.Handle(0)
