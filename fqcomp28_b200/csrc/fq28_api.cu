@@ -836,9 +836,9 @@ static int compress_parts(fq28_handle *h, const char *fastq, size_t n_bytes, uns
 int fq28_compress(fq28_handle *h, const char *fastq, size_t n_bytes, size_t sample_bytes, size_t reading_size, int eof,
                   void *ft_seq_out, void *ft_qual_out, const fq28_enc_arenas *out, fq28_chunk_info *infos,
                   size_t infos_cap, fq28_enc_summary *summary) {
-  if (!h || !out || !infos) return FQ28_ERR_ARG;
+  if (!h || !infos) return FQ28_ERR_ARG;
   FQ28_TRY(bind(h));
-  {
+  if (out) {
     // overlapped parts for large slabs: every part holds at least 4 windows, the first one the sample window
     const size_t win = sample_bytes < n_bytes ? sample_bytes : n_bytes;
     unsigned parts = h->cfg.pipe_parts;
@@ -862,7 +862,9 @@ int fq28_compress(fq28_handle *h, const char *fastq, size_t n_bytes, size_t samp
   if (!planned) FQ28_TRY(stage_in(h, fastq, n_bytes));
   FQ28_TRY(fq28_compress_dev(h, h->in_fastq.as<char>(), n_bytes, sample_bytes, reading_size, eof, ft_seq_out, ft_qual_out,
                              infos, infos_cap, summary));
-  return fq28_compress_fetch(h, out);
+  // out == NULL: the result stays on the device; the caller sizes its arenas from *summary and
+  // calls fq28_compress_fetch (or decodes / reads it in place through fq28_compress_dev_arenas)
+  return out ? fq28_compress_fetch(h, out) : FQ28_OK;
 }
 
 int fq28_compress_dev_arenas(fq28_handle *h, fq28_dec_arenas *v) {

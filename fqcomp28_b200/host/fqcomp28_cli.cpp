@@ -592,6 +592,27 @@ static std::vector<std::shared_ptr<GpuContext>> workerContexts(const Settings &s
 }
 
 // ---------------------------------------------------------------- c
+/** Byte buffers reused from slab to slab: a fresh gigabyte-sized vector costs its zero-fill and
+ *  page faults every time, which is more than the codec takes. */
+class BufferPool {
+public:
+  std::vector<char> get() {
+    std::lock_guard<std::mutex> lk(mu_);
+    if (free_.empty()) return {};
+    std::vector<char> b = std::move(free_.back());
+    free_.pop_back();
+    return b;
+  }
+  void put(std::vector<char> &&b) {
+    std::lock_guard<std::mutex> lk(mu_);
+    free_.push_back(std::move(b));
+  }
+
+private:
+  std::mutex mu_;
+  std::vector<std::vector<char>> free_;
+};
+
 /** processReads, src/process.cpp:32-82, as a pipeline over one or several GPUs:
  *    reader thread  : file -> slab buffers (slab i = [i*B, (i+1)*B + R), so that it holds the start of
  *                     its first chunk whatever the previous slab consumed)
@@ -633,7 +654,8 @@ static int compress(const Settings &set) {
   std::size_t last_slab = 0;
   while (last_slab + 1 < n_slabs && slab_end(last_slab) < file_size) ++last_slab;
 
-  struct Slab { std::size_t base = 0; std::vector<char> buf; };
+  struct Slab { std::size_t base = 0, size = 0; std::vector<char> buf; };   // buf.size() >= size (pooled)
+  BufferPool slab_pool;
   struct Result {
     std::vector<CompressedBuffersDst> blocks;
     std::vector<std::vector<headers::FieldStorage>> fields;
@@ -662,9 +684,11 @@ static int compress(const Settings &set) {
         in_flight.acquire();
         Slab s;
         s.base = i * B;
-        s.buf.resize(slab_end(i) - s.base);
+        s.size = slab_end(i) - s.base;
+        s.buf = slab_pool.get();
+        if (s.buf.size() < s.size) { s.buf.clear(); s.buf.resize(s.size); }
         f.seekg(static_cast<std::streamoff>(s.base));
-        f.read(s.buf.data(), static_cast<std::streamsize>(s.buf.size()));
+        f.read(s.buf.data(), static_cast<std::streamsize>(s.size));
         if (!f) throw std::runtime_error("short read from " + set.mates1);
         slabs.put(i, std::move(s));
       }
@@ -684,7 +708,7 @@ static int compress(const Settings &set) {
         for (std::size_t i = g; i <= last_slab; i += n_gpus) {
           Slab s;
           if (!slabs.take(i, s)) return;
-          ctx.check(fq28_stage(ctx.handle(), s.buf.data(), s.buf.size()));  // async H2D, before the start is known
+          ctx.check(fq28_stage(ctx.handle(), s.buf.data(), s.size));  // async H2D, before the start is known
           std::size_t s_i;
           {
             std::unique_lock<std::mutex> lk(baton_mu);
@@ -693,9 +717,9 @@ static int compress(const Settings &set) {
             s_i = start[i];
           }
           const bool eof = i == last_slab;
-          if (s_i < s.base || s_i > s.base + s.buf.size()) throw std::runtime_error("slab does not hold its first chunk; raise --slab-mb");
+          if (s_i < s.base || s_i > s.base + s.size) throw std::runtime_error("slab does not hold its first chunk; raise --slab-mb");
           const char *p = s.buf.data() + (s_i - s.base);
-          const std::size_t n = s.buf.size() - (s_i - s.base);
+          const std::size_t n = s.size - (s_i - s.base);
           double t0 = now_s();
           uint64_t consumed = 0;
           std::size_t n_chunks = 0;
@@ -717,7 +741,8 @@ static int compress(const Settings &set) {
           if (!set.host_headers) headers::tokenizeOnGpu(ctx, r.blocks, ar.fmt, ar.first_fields, r.fields);
           r.t_hdr = now_s() - t0;
           ctx.check(fq28_stage(ctx.handle(), nullptr, 0));
-          warnFewChunks(r.blocks.size(), s.buf.size() >> 20, set.reading_mb);
+          warnFewChunks(r.blocks.size(), s.size >> 20, set.reading_mb);
+          slab_pool.put(std::move(s.buf));
           results.put(i, std::move(r));
         }
       } catch (...) { fail(std::current_exception()); }
@@ -805,9 +830,10 @@ static int decompress(const Settings &set) {
     std::vector<std::vector<headers::FieldStorage>> fields;
     std::vector<std::size_t> records;
   };
-  using Chunks = std::vector<FastqChunk>;
+  using Bytes = std::vector<char>;   // the FASTQ bytes of a batch, chunks in idx order
+  BufferPool out_pool;
   OrderedQueue<Batch> batches;
-  OrderedQueue<Chunks> decoded;
+  OrderedQueue<Bytes> decoded;
   Tokens in_flight(2 * n_gpus + 1);
   std::exception_ptr error;
   std::mutex error_mu;
@@ -839,11 +865,10 @@ static int decompress(const Settings &set) {
           if (!batches.take(j, b)) return;
           if (!set.host_headers) headers::detokenizeOnGpu(ctx, b.fields, b.records, ar.fmt, ar.first_fields, b.srcs);
           std::vector<CompressedBuffersSrc *> ps;
-          Chunks chunks(b.srcs.size());
-          std::vector<FastqChunk *> pc;
-          for (std::size_t k = 0; k < b.srcs.size(); ++k) { ps.push_back(&b.srcs[k]); pc.push_back(&chunks[k]); }
-          wksp.decodeChunks(ps, pc);
-          decoded.put(j, std::move(chunks));
+          for (std::size_t k = 0; k < b.srcs.size(); ++k) ps.push_back(&b.srcs[k]);
+          Bytes bytes = out_pool.get();
+          wksp.decodeChunksRaw(ps, bytes);
+          decoded.put(j, std::move(bytes));
         }
       } catch (...) { fail(std::current_exception()); }
     });
@@ -851,9 +876,10 @@ static int decompress(const Settings &set) {
   std::thread writer([&] {
     try {
       for (std::size_t j = 0; batch_exists(j); ++j) {
-        Chunks chunks;
-        if (!decoded.take(j, chunks)) return;
-        for (auto &c : chunks) out.write(c.raw_data.data(), static_cast<std::streamsize>(c.raw_data.size()));  // idx order
+        Bytes bytes;
+        if (!decoded.take(j, bytes)) return;
+        out.write(bytes.data(), static_cast<std::streamsize>(bytes.size()));  // FastqWriter::writeChunk, idx order
+        out_pool.put(std::move(bytes));
         in_flight.release();
       }
     } catch (...) { fail(std::current_exception()); }

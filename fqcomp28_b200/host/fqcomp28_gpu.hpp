@@ -185,9 +185,20 @@ public:
   }
   void tablesChanged() { tables_owner_ = nullptr; }
 
+  /** Host staging reused from batch to batch (a context serves one worker at a time).  Fresh
+   * gigabyte-sized vectors per batch cost more in zero-fill and page faults than the codec. */
+  struct Scratch {
+    std::vector<uint8_t> seq, qual, headers;
+    std::vector<uint16_t> readlens, n_count, n_pos, hdr_lens;
+    std::vector<fq28_chunk_info> infos;
+    std::vector<char> out;
+  };
+  Scratch &scratch() { return scratch_; }
+
 private:
   fq28_handle *h_ = nullptr;
   const void *tables_owner_ = nullptr;
+  Scratch scratch_;
 };
 
 namespace detail {
@@ -205,32 +216,6 @@ template <class FT> inline void fillUniform(FT &ft) {
   }
   ft.max_log = log;
 }
-
-struct Arenas {
-  std::vector<uint8_t> seq, qual, headers;
-  std::vector<uint16_t> readlens, n_count, n_pos, hdr_lens;
-  fq28_enc_arenas view() {
-    fq28_enc_arenas a{};
-    a.seq = seq.data(); a.seq_cap = seq.size();
-    a.qual = qual.data(); a.qual_cap = qual.size();
-    a.readlens = readlens.data(); a.readlens_cap = readlens.size();
-    a.n_count = n_count.data(); a.n_count_cap = n_count.size();
-    a.n_pos = n_pos.data(); a.n_pos_cap = n_pos.size();
-    a.hdr_lens = hdr_lens.data(); a.hdr_lens_cap = hdr_lens.size();
-    a.headers = headers.data(); a.headers_cap = headers.size();
-    return a;
-  }
-  void reserveFor(std::size_t fastq_bytes, std::size_t n_chunks) {
-    seq.resize(fastq_bytes / 2 + 4096 * (n_chunks + 1));
-    qual.resize(fastq_bytes + 16384 * (n_chunks + 1));
-    const std::size_t max_rec = fastq_bytes / 12 + 1;
-    readlens.resize(max_rec);
-    n_count.resize(max_rec);
-    hdr_lens.resize(max_rec);
-    n_pos.resize(fastq_bytes / 2 + 16);
-    headers.resize(fastq_bytes / 2 + 64);
-  }
-};
 
 template <typename T> inline void appendBytes(std::vector<std::byte> &dst, const T *src, std::size_t n) {
   const auto *p = reinterpret_cast<const std::byte *>(src);
@@ -390,13 +375,33 @@ namespace detail {
  * CompressedBuffersDst per chunk.  accumulate_ns replicates SURVEY Q2. */
 inline void encodeSlab(GpuContext &ctx, const char *fastq, std::size_t n, std::size_t reading_size, bool eof,
                        std::vector<CompressedBuffersDst> &out, std::size_t *consumed, uint32_t first_idx = 0) {
-  Arenas ar;
   const std::size_t max_chunks = 2 * (n / std::max<std::size_t>(1, reading_size)) + 8;
-  ar.reserveFor(n, max_chunks);
-  std::vector<fq28_chunk_info> infos(max_chunks);
+  GpuContext::Scratch &ar = ctx.scratch();
+  auto &infos = ar.infos;
+  if (infos.size() < max_chunks) infos.resize(max_chunks);
   fq28_enc_summary summ{};
-  auto view = ar.view();
-  ctx.check(fq28_compress(ctx.handle(), fastq, n, 0, reading_size, eof ? 1 : 0, nullptr, nullptr, &view, infos.data(), infos.size(), &summ));
+  // encode first (the result stays on the device), then fetch into arenas of exactly the sizes
+  // the summary names, kept from slab to slab
+  ctx.check(fq28_compress(ctx.handle(), fastq, n, 0, reading_size, eof ? 1 : 0, nullptr, nullptr, nullptr, infos.data(), infos.size(), &summ));
+  auto grow = [](auto &v, std::size_t need) { if (v.size() < need) v.resize(need + need / 8 + 64); };
+  grow(ar.seq, summ.seq_bytes);
+  grow(ar.qual, summ.qual_bytes);
+  grow(ar.readlens, summ.n_records);
+  grow(ar.n_count, summ.n_records);
+  grow(ar.hdr_lens, summ.n_records);
+  grow(ar.n_pos, summ.n_pos_entries);
+  grow(ar.headers, summ.hdr_bytes);
+  if (summ.n_chunks) {
+    fq28_enc_arenas view{};
+    view.seq = ar.seq.data(); view.seq_cap = ar.seq.size();
+    view.qual = ar.qual.data(); view.qual_cap = ar.qual.size();
+    view.readlens = ar.readlens.data(); view.readlens_cap = ar.readlens.size();
+    view.n_count = ar.n_count.data(); view.n_count_cap = ar.n_count.size();
+    view.n_pos = ar.n_pos.data(); view.n_pos_cap = ar.n_pos.size();
+    view.hdr_lens = ar.hdr_lens.data(); view.hdr_lens_cap = ar.hdr_lens.size();
+    view.headers = ar.headers.data(); view.headers_cap = ar.headers.size();
+    ctx.check(fq28_compress_fetch(ctx.handle(), &view));
+  }
   for (std::size_t k = 0; k < summ.n_chunks; ++k) {
     const auto &ci = infos[k];
     out.emplace_back();
@@ -487,16 +492,62 @@ public:
 
   /** batched form */
   void decodeChunks(const std::vector<CompressedBuffersSrc *> &cbs, const std::vector<FastqChunk *> &chunks) {
-    useTables();
+    GpuContext::Scratch &sc = ctx_->scratch();
     const std::size_t n = cbs.size();
-    std::vector<uint8_t> seq, qual, headers;
-    std::vector<uint16_t> readlens, n_count, n_pos, hdr_lens;
-    std::vector<fq28_chunk_info> infos(n);
+    const std::size_t total = stageBatch(cbs);
+    if (sc.out.size() < total) sc.out.resize(total + total / 8);
+    decodeStaged(n, sc.out.data(), total);
+    const auto &infos = sc.infos;
+    std::size_t off = 0, rec = 0;
+    for (std::size_t k = 0; k < n; ++k) {
+      auto &chunk = *chunks[k];
+      chunk.clear();  // prepareFastqChunk, src/workspace.h:127-133
+      chunk.idx = cbs[k]->chunk_idx;
+      chunk.raw_data.assign(sc.out.begin() + static_cast<std::ptrdiff_t>(off), sc.out.begin() + static_cast<std::ptrdiff_t>(off + infos[k].total));
+      chunk.records.resize(infos[k].n_records);
+      char *dst = chunk.raw_data.data();
+      for (std::size_t i = 0; i < infos[k].n_records; ++i, ++rec) {
+        auto &r = chunk.records[i];
+        r.headerp = dst;
+        r.header_length = sc.hdr_lens[rec];
+        dst += r.header_length + 1;
+        r.seqp = dst;
+        r.length = sc.readlens[rec];
+        dst += r.length + 3;
+        r.qualp = dst;
+        dst += r.length + 1;
+        chunk.tot_reads_length += r.length;
+        chunk.headers_length += r.header_length;
+      }
+      off += infos[k].total;
+    }
+  }
+
+  /** batched form without FastqChunk objects: the FASTQ bytes of all chunks, in order, straight
+   * into `out` (resized to the total).  What a writer needs (FastqWriter::writeChunk,
+   * src/fastq_io.cpp:131-143, writes raw_data and nothing else). */
+  void decodeChunksRaw(const std::vector<CompressedBuffersSrc *> &cbs, std::vector<char> &out) {
+    const std::size_t total = stageBatch(cbs);
+    if (out.size() < total) out.resize(total);   // (a pooled buffer only ever grows: no zero-fill after its first use)
+    decodeStaged(cbs.size(), out.data(), total);
+    out.resize(total);
+  }
+
+private:
+  /** gathers the blocks' buffers into the context's staging arenas + chunk infos; @return FASTQ bytes */
+  std::size_t stageBatch(const std::vector<CompressedBuffersSrc *> &cbs) {
+    useTables();
+    GpuContext::Scratch &sc = ctx_->scratch();
+    const std::size_t n = cbs.size();
+    auto &seq = sc.seq; auto &qual = sc.qual; auto &headers = sc.headers;
+    auto &readlens = sc.readlens; auto &n_count = sc.n_count; auto &n_pos = sc.n_pos; auto &hdr_lens = sc.hdr_lens;
+    seq.clear(); qual.clear(); headers.clear(); readlens.clear(); n_count.clear(); n_pos.clear(); hdr_lens.clear();
+    auto &infos = sc.infos;
+    infos.assign(n, fq28_chunk_info{});
     std::size_t total = 0;
     for (std::size_t k = 0; k < n; ++k) {
       auto &c = *cbs[k];
       auto &ci = infos[k];
-      std::memset(&ci, 0, sizeof(ci));
       const std::size_t nrec = c.original_size.n_records;
       ci.total = c.original_size.total;
       ci.n_records = c.original_size.n_records;
@@ -540,41 +591,23 @@ public:
     }
     seq.resize(seq.size() + 16);
     qual.resize(qual.size() + 16);
+    return total;
+  }
+
+  void decodeStaged(std::size_t n, char *out, std::size_t total) {
+    GpuContext::Scratch &sc = ctx_->scratch();
     fq28_dec_arenas in{};
-    in.seq = seq.data(); in.seq_bytes = seq.size();
-    in.qual = qual.data(); in.qual_bytes = qual.size();
-    in.readlens = readlens.data();
-    in.n_count = n_count.data();
-    in.n_pos = n_pos.data(); in.n_pos_entries = n_pos.size();
-    in.hdr_lens = hdr_lens.data();
-    in.headers = headers.data(); in.headers_bytes = headers.size();
-    in.n_records = readlens.size();
-    std::vector<char> out(total);
+    in.seq = sc.seq.data(); in.seq_bytes = sc.seq.size();
+    in.qual = sc.qual.data(); in.qual_bytes = sc.qual.size();
+    in.readlens = sc.readlens.data();
+    in.n_count = sc.n_count.data();
+    in.n_pos = sc.n_pos.data(); in.n_pos_entries = sc.n_pos.size();
+    in.hdr_lens = sc.hdr_lens.data();
+    in.headers = sc.headers.data(); in.headers_bytes = sc.headers.size();
+    in.n_records = sc.readlens.size();
     std::size_t wrote = 0;
-    ctx_->check(fq28_decompress(ctx_->handle(), &in, infos.data(), n, out.data(), out.size(), &wrote));
-    std::size_t off = 0, rec = 0;
-    for (std::size_t k = 0; k < n; ++k) {
-      auto &chunk = *chunks[k];
-      chunk.clear();  // prepareFastqChunk, src/workspace.h:127-133
-      chunk.idx = cbs[k]->chunk_idx;
-      chunk.raw_data.assign(out.begin() + static_cast<std::ptrdiff_t>(off), out.begin() + static_cast<std::ptrdiff_t>(off + infos[k].total));
-      chunk.records.resize(infos[k].n_records);
-      char *dst = chunk.raw_data.data();
-      for (std::size_t i = 0; i < infos[k].n_records; ++i, ++rec) {
-        auto &r = chunk.records[i];
-        r.headerp = dst;
-        r.header_length = hdr_lens[rec];
-        dst += r.header_length + 1;
-        r.seqp = dst;
-        r.length = readlens[rec];
-        dst += r.length + 3;
-        r.qualp = dst;
-        dst += r.length + 1;
-        chunk.tot_reads_length += r.length;
-        chunk.headers_length += r.header_length;
-      }
-      off += infos[k].total;
-    }
+    ctx_->check(fq28_decompress(ctx_->handle(), &in, sc.infos.data(), n, out, total, &wrote));
+    if (wrote != total) throw std::runtime_error("decoded size differs from the blocks' original sizes");
   }
 
 private:

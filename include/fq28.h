@@ -153,7 +153,10 @@ typedef struct {
  * [0, min(sample_bytes, n_bytes)) -- and build the tables from it, which is
  * what `fqcomp28 c` does when it opens the archive (src/archive.cpp:13-20);
  * the raw FreqTable images are returned in ft_seq_out / ft_qual_out (may be
- * NULL).  sample_bytes == 0: use the tables already built / loaded. */
+ * NULL).  sample_bytes == 0: use the tables already built / loaded.
+ * out == NULL: nothing is copied back; the caller reads the sizes from *summary,
+ * sizes its arenas exactly and calls fq28_compress_fetch (compressBound-sized
+ * arenas are ~2.8x the slab: allocating them per call costs more than the codec). */
 int fq28_compress(fq28_handle *h, const char *fastq, size_t n_bytes,
                   size_t sample_bytes, size_t reading_size, int eof,
                   void *ft_seq_out, void *ft_qual_out,
