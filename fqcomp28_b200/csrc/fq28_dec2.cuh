@@ -536,7 +536,10 @@ FQ_HD bool decode_seq_stream(const StreamArgs &c, uint32_t sb, uint32_t ht) {
 // (row = rank(max) * 2 + eq, column = rank(q)).  Contexts outside the dense set
 // keep their state in `cold` (global, u16[8192]) and decode through dtab_fix.
 // ---------------------------------------------------------------------------
-struct QualShared { uint32_t rk_a, zq_a, zc_a; };
+struct QualShared {
+  uint32_t rk_a, zq_a, zc_a;
+  uint32_t n_slots;   // run tables present at zq_a; 0 = the run contexts are decoded as ordinary contexts
+};
 
 FQ_HD bool decode_qual_stream(const StreamArgs &c, const QualShared &q, uint32_t sb,
                               const uint32_t *dtab_fix, const uint16_t *cid /*[8192]: run slot + 1 in bits 13..15*/,
@@ -558,7 +561,7 @@ FQ_HD bool decode_qual_stream(const StreamArgs &c, const QualShared &q, uint32_t
         if (rq != 0xFFu && rm != 0xFFu) {
           const unsigned d = qual_dense_id(rm, cx >> 12, rq);
           const unsigned cv = cid[cx];
-          const unsigned zs = cv == 0xFFFFu ? 0u : (cv >> 13);
+          const unsigned zs = (cv == 0xFFFFu || q.n_slots == 0) ? 0u : (cv >> 13);
           sm_st32(sb + d * 4, zs ? make_zent(x, zs - 1) : gl_ld32(c.wtab + ((size_t)d << TAB_LOG) + x));
         } else {
           cold[cx] = (uint16_t)x;

@@ -578,7 +578,7 @@ k_dec2_qual(const DecChunk *__restrict__ ch, unsigned n_chunks, unsigned lanes, 
   const unsigned per_cta = lanes * (blockDim.x >> 5);
   const uint32_t base = (uint32_t)__cvta_generic_to_shared(smem_raw);
   dec2::QualShared qs;
-  qs.rk_a = base; qs.zc_a = base + 64; qs.zq_a = base + 128;
+  qs.rk_a = base; qs.zc_a = base + 64; qs.zq_a = base + 128; qs.n_slots = nz;
   {
     for (unsigned i = threadIdx.x; i < 64; i += blockDim.x) smem_raw[i] = qrk[i];  // (a CTA may be one warp)
     const unsigned zc[4] = {zctx.x, zctx.y, zctx.z, zctx.w};
@@ -823,9 +823,32 @@ int decode_batch(fq28_handle *h, const fq28_dec_arenas *in, const fq28_chunk_inf
         l = (unsigned)((n_chunks + 4 * sub - 1) / (4 * sub));
         l = l < 1 ? 1 : l > 32 ? 32 : l;
       }
-      const unsigned nz = h->cfg.no_zrun ? 0u : h->qual.h_n_z, nv = h->qual.h_n_v;
+      unsigned nz = h->cfg.no_zrun ? 0u : h->qual.h_n_z;
+      const unsigned nv = h->qual.h_n_v;
+      if (serial && !h->cfg.qual_lanes && !h->cfg.qual_warps) {
+        // Many-valued qualities: the cached cells take |V| * 512 B per stream (20 KB for 40 values),
+        // so shared memory, not warp slots, decides how many streams an SM holds.  One CTA per SM,
+        // one stream per warp (lanes in lockstep cost 1.4x per doubling here), as many warps as
+        // fit; if that covers all streams the launch is ONE wave (measured, 1 028 streams of
+        // 41-valued qualities: 257 CTAs of 150 KB made two waves, 116 ms instead of 58).
+        const size_t budget = 224 * 1024;
+        auto cap_of = [&](unsigned z) {
+          const size_t per_stream = d2_qual_smem(2, z, nv) - d2_qual_smem(1, z, nv);
+          const size_t fixed = d2_qual_smem(0, z, nv);
+          const unsigned c = fixed + per_stream > budget ? 1u : (unsigned)((budget - fixed) / per_stream);
+          return c > 8 ? 8u : c;
+        };
+        auto waves_of = [&](unsigned z) { return (n_chunks + 148ull * cap_of(z) - 1) / (148ull * cap_of(z)); };
+        // the zero-bit run tables (16 KB per slot) are worth less than a wave: without them the run
+        // contexts are ordinary contexts (same bytes)
+        if (nz && waves_of(0) < waves_of(nz)) nz = 0;
+        const unsigned cap = cap_of(nz);
+        const unsigned need = (unsigned)((n_chunks + 147) / 148);   // streams per SM for one wave
+        w = need < cap ? need : cap;
+        l = 1;
+      }
       // the per-stream context arrays (|V| * 512 B) must fit: fewer warps first, then fewer lanes
-      while (d2_qual_smem(l * w, nz, nv) > 200 * 1024 && l * w > 1) {
+      while (d2_qual_smem(l * w, nz, nv) > 224 * 1024 && l * w > 1) {
         if (w > 1) w >>= 1; else l = (l + 1) / 2;
       }
       const unsigned per_cta = l * w;

@@ -916,9 +916,11 @@ static int decompress(const Settings &set) {
   writer.join();
   if (error) std::rethrow_exception(error);
   out.flush();
-  if (set.verbose) {
+  {
     const double wall = now_s() - t_start;
-    std::fprintf(stderr, "fqcomp28 d (B200 path): %zu blocks on %u GPU(s), wall %.3f s\n", ar.index.size(), n_gpus, wall);
+    const std::size_t bytes = static_cast<std::size_t>(out.tellp());
+    std::fprintf(stderr, "fqcomp28 d (B200 path): %zu blocks, %zu bytes on %u GPU(s); wall %.3f s = %.0f MB/s\n", ar.index.size(), bytes,
+                 n_gpus, wall, bytes / 1e6 / std::max(wall, 1e-9));
   }
   return out ? 0 : 1;
 }

@@ -39,6 +39,16 @@ def main():
             f.write(b)
             n += len(b)
     res = {"file_bytes": n, "gpus": a.gpus, "runs": []}
+    # fixed cost of the process (CUDA context, library load, table build): a 3 MB file
+    tiny = os.path.join(d, "tiny.fastq")
+    with open(tiny, "wb") as f:
+        f.write(synth.illumina_bytes(3 << 20, seed=5)[0].numpy().tobytes())
+    t0 = time.time()
+    subprocess.run([CLI, "c", "--i1", tiny, "-o", arc, "-R", "1", "-S", "1"], capture_output=True)
+    res["tiny_file_compress_wall_s"] = time.time() - t0
+    t0 = time.time()
+    subprocess.run([CLI, "d", "-i", arc, "--o1", out], capture_output=True)
+    res["tiny_file_decompress_wall_s"] = time.time() - t0
     for R in a.reading_mb.split(","):
         r = {"reading_mb": int(R)}
         t0 = time.time()

@@ -54,7 +54,13 @@ void fill_args(StreamArgs &a, const uint8_t *src, uint32_t len, const uint16_t *
 
 }  // namespace
 
+// test switch: the tables have run slots (cid carries them) but the decoder is told to ignore them,
+// which is what the product does when the run tables would not leave room for the streams
+static bool g_no_runs = false;
+
 extern "C" {
+
+void dec2h_set_no_runs(int on) { g_no_runs = on != 0; }
 
 // event counters since the last call: [0] seq drains, [1] seq inline refreshes, [2] qual drains,
 // [3] zero-bit runs, [4] single steps in a run context, [5] slow-path entries, [6] slow-path
@@ -166,7 +172,7 @@ int dec2h_qual(const uint8_t *ft, const uint8_t *stream, uint32_t len, unsigned 
   StreamArgs a;
   std::vector<uint32_t> recscan;
   fill_args(a, src, len, readlens, hdr_lens, n_rec, recscan, out, t, wtab.data());
-  QualShared qs{rk_a, zq_a, zc_a};
+  QualShared qs{rk_a, zq_a, zc_a, g_no_runs ? 0u : nz};
   g_host_async = HostAsync();
   const bool ok = decode_qual_stream(a, qs, sb, t.dtab_fix.data(), cid.data(), cold.data());
   g_host_smem = nullptr;

@@ -102,6 +102,26 @@ def test_synthetic_illumina(oracle, D, profile):
         assert stats[1] >= 1, "binned qualities must get a zero-bit run slot"
 
 
+def test_run_tables_ignored(oracle, D):
+    """The tables carry zero-bit run slots but the decoder is told there are none (what the
+    product does when the 16 KB run tables would cost a launch wave): the run contexts are
+    then ordinary contexts, same bytes."""
+    import synth
+
+    D.dec2h_set_no_runs.argtypes = [C.c_int]
+    D.dec2h_set_no_runs(1)
+    try:
+        d = synth.illumina(0, 3000, profile="novaseq").numpy()
+        fs, fq = tables_of(oracle, d[: d.size // 3 * 2])
+        stats = roundtrip(oracle, D, d, fs, fq)
+        assert stats[1] >= 1, "the tables must have run slots for this test to mean anything"
+        d = load_fixture("SRR065390_sub_1")
+        fs, fq = tables_of(oracle, d)
+        roundtrip(oracle, D, d, fs, fq, 5)
+    finally:
+        D.dec2h_set_no_runs(0)
+
+
 def test_synthetic_ont(oracle, D):
     import synth
 
