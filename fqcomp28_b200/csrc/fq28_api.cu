@@ -843,7 +843,8 @@ int fq28_compress(fq28_handle *h, const char *fastq, size_t n_bytes, size_t samp
     const size_t win = sample_bytes < n_bytes ? sample_bytes : n_bytes;
     unsigned parts = h->cfg.pipe_parts;
     if (reading_size) parts = (unsigned)std::min<size_t>(parts, n_bytes / (4 * reading_size));
-    parts = (unsigned)std::min<size_t>(parts, n_bytes >> 26);   // a part costs ~6 ms of latency whatever its size: >= 64 MB each
+    // a part costs ~6 ms of latency whatever its size: at least a quarter of the threshold each (64 MB)
+    parts = (unsigned)std::min<size_t>(parts, n_bytes / std::max<size_t>(h->cfg.pipe_min_bytes / 4, 1));
     const bool tables_ok = sample_bytes > 0 || (h->seq.ready && h->qual.ready);
     const bool planned = h->plan.valid && sample_bytes == 0;  // a planned slab is encoded as planned, in one piece
     if (parts >= 2 && n_bytes >= h->cfg.pipe_min_bytes && tables_ok && !planned) {

@@ -348,8 +348,10 @@ def test_synthetic_profiles_chunk_parity(oracle, H, profile):
     check_chunks(oracle, H, d, 1 << 20, fs, fq)
 
 
-@pytest.mark.parametrize("eof,parts,lanes", [(True, 4, 3), (False, 4, 2), (True, 2, 2), (False, 7, 4), (True, 5, 1)])
-def test_pipelined_host_compress(oracle, monkeypatch, eof, parts, lanes):
+@pytest.mark.parametrize("eof,parts,lanes,kind", [(True, 4, 3, "illumina"), (False, 4, 2, "illumina"), (True, 2, 2, "illumina"),
+                                                  (False, 7, 4, "illumina"), (True, 5, 1, "illumina"), (True, 8, 4, "ont"),
+                                                  (False, 3, 3, "ont")])
+def test_pipelined_host_compress(oracle, monkeypatch, capfd, eof, parts, lanes, kind):
     """Large host slabs are compressed as overlapped parts (copies on a copy
     stream, parts dealt to `lanes` handles, one host thread each): same
     chunks, streams and side arrays as the one-pass walk, with the tables from
@@ -359,18 +361,24 @@ def test_pipelined_host_compress(oracle, monkeypatch, eof, parts, lanes):
     monkeypatch.setenv("FQ28_PIPE_MIN_MB", "1")      # both read at fq28_create
     monkeypatch.setenv("FQ28_PIPE_PARTS", str(parts))
     monkeypatch.setenv("FQ28_PIPE_LANES", str(lanes))
+    monkeypatch.setenv("FQ28_PIPE_TRACE", "1")       # the timeline on stderr proves the parts were taken
     import fqcomp28_b200 as P
 
     H = P.Handle(0)
-    d = synth.illumina_bytes(40 << 20, seed=31)[0].numpy()
+    if kind == "ont":   # reads of 1-50 kb: records straddle the part boundaries
+        d = synth.ont(0, 2000, seed=33).numpy()
+    else:
+        d = synth.illumina_bytes(40 << 20, seed=31)[0].numpy()
     S, R = 4 << 20, 1 << 20
     sample = d[: int(oracle.split_chunks(d, S)[1])]
     recs, _ = oracle.parse_records(sample)
     fs, fq = oracle.make_ft(*oracle.hist(sample, recs))
     ft = (np.zeros(3076, np.uint8), np.zeros(1081348, np.uint8))
+    capfd.readouterr()
     infos, summ, ar = H.compress(d, R, eof=eof, sample_bytes=S, ft_out=ft)
+    assert f"fq28 pipe part {parts - 1}/{parts}" in capfd.readouterr().err, "the slab was not cut into the parts asked for"
     assert np.array_equal(ft[0], fs) and np.array_equal(ft[1], fq)
-    assert int(summ.n_chunks) >= 38
+    assert int(summ.n_chunks) >= d.size // R - 2
     seq_a = ar["seq"][: int(summ.seq_bytes)].copy()
     # pre-loaded tables (sample_bytes == 0), chunk by chunk against the oracle + decode
     H.load_tables(fs, fq)
