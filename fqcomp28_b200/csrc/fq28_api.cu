@@ -155,7 +155,7 @@ static void free_buf(DevBuf &b) {
 static void free_tables(DevTables &t) {
   cudaFree(t.counts); cudaFree(t.norm); cudaFree(t.logs); cudaFree(t.max_log); cudaFree(t.toff);
   cudaFree(t.ctab); cudaFree(t.symtt); cudaFree(t.dtab); cudaFree(t.dtab_fix);
-  cudaFree(t.wtab); cudaFree(t.qrk); cudaFree(t.qdinfo);
+  cudaFree(t.wtab); cudaFree(t.qrk); cudaFree(t.qdinfo); cudaFree(t.qwin); cudaFree(t.wtabw);
   cudaFree(t.logsuf); cudaFree(t.seqdec); cudaFree(t.cid); cudaFree(t.n_touched); cudaFree(t.dom_sym); cudaFree(t.zrun); cudaFree(t.zinfo);
   t = DevTables();
 }
@@ -245,6 +245,8 @@ int fq28_create(int device, fq28_handle **out) {
       h->cfg.dec_serial = getenv("FQ28_DEC_SERIAL") != nullptr;
       h->cfg.share_sms = getenv("FQ28_DEC_SHARE_SMS") != nullptr;
       h->cfg.dec_concurrent = getenv("FQ28_DEC_CONCURRENT") != nullptr;
+      h->cfg.no_win = getenv("FQ28_QUAL_DENSE") != nullptr;
+      h->cfg.force_win = getenv("FQ28_QUAL_WINDOWED") != nullptr;
       h->cfg.seq_lanes = env_u("FQ28_SEQ_LANES"); h->cfg.seq_warps = env_u("FQ28_SEQ_WARPS");
       h->cfg.qual_lanes = env_u("FQ28_QUAL_LANES"); h->cfg.qual_warps = env_u("FQ28_QUAL_WARPS");
       if (const char *e = getenv("FQ28_QUAL_CARVEOUT")) h->cfg.qual_carveout = atoi(e);

@@ -60,7 +60,11 @@ FQ_HD uint32_t make_w_seq(uint32_t cell /* newState | sym<<16 | nb<<24 */, unsig
 //  zero-bit-run context: holds a state, not a cell)   [2,8) rank of the symbol in V
 //  [8,12) nbBits   [12,23) newState base   [23,30) output char   [31] STALE
 //  ZENT entry: [8,19) state   [20,22) run slot
-constexpr uint32_t QW_UNSEEN = 1u, QW_ZENT = 2u, QW_STALE = 1u << 31, QW_SPECIAL = QW_UNSEEN | QW_ZENT | QW_STALE;
+constexpr uint32_t QW_UNSEEN = 1u, QW_ZENT = 2u, QW_STALE = 1u << 31;
+// windowed layout only: the word behind the last column of every row; reading it means "the
+// context (row, column) is outside the row's window": its state is not in shared memory
+constexpr uint32_t QW_OOB = 1u << 30;
+constexpr uint32_t QW_SPECIAL = QW_UNSEEN | QW_ZENT | QW_STALE | QW_OOB;
 constexpr unsigned QROW_BYTES = 256;  // 64 entries per (max, eq) row
 FQ_HD uint32_t make_w_qual(uint32_t cell, const uint8_t *rk /*[64] rank in V or 0xFF*/) {
   const unsigned sym = (cell >> 16) & 63u, nb = cell >> 24, ns = cell & 0x7FFu;
@@ -539,8 +543,18 @@ FQ_HD bool decode_seq_stream(const StreamArgs &c, uint32_t sb, uint32_t ht) {
 struct QualShared {
   uint32_t rk_a, zq_a, zc_a;
   uint32_t n_slots;   // run tables present at zq_a; 0 = the run contexts are decoded as ordinary contexts
+  uint32_t row_a;     // windowed layout: row descriptors, 8 bytes per row (row = rank(max) * 2 + eq)
+  uint32_t n_rows;    //   .x = byte offset of the row's first entry in S, .y = lo * 4 | (width * 4) << 16
 };
 
+// WIN = windowed layout of S for many-valued qualities.  With |V| = 40 values the dense layout
+// takes 2 * 40 rows of 64 columns = 20 KB per stream, of which a few hundred entries are contexts
+// the tables know; shared memory then holds 7 streams per SM.  The windowed layout keeps, for every
+// row, only the columns [lo, lo + width) that span the row's touched contexts, plus one QW_OOB
+// word; a context outside its row's window keeps its state in `cold` and decodes through the
+// slow path, like a quality value outside V.  Address of (row, rank r): base + min(4r - 4lo, 4width)
+// -- two more ALU operations in the symbol chain than the dense layout's OR.  No run tables.
+template <bool WIN>
 FQ_HD bool decode_qual_stream(const StreamArgs &c, const QualShared &q, uint32_t sb,
                               const uint32_t *dtab_fix, const uint16_t *cid /*[8192]: run slot + 1 in bits 13..15*/,
                               uint16_t *cold) {
@@ -553,12 +567,32 @@ FQ_HD bool decode_qual_stream(const StreamArgs &c, const QualShared &q, uint32_t
       ok = false;
     } else {
       rr = c.n_rec;
+      if (WIN) {
+        for (unsigned r = 0; r < q.n_rows; r++) {
+          uint32_t rx, ry;
+          sm_ld64(q.row_a + r * 8, rx, ry);
+          sm_st32(sb + rx + (ry >> 16), QW_OOB);
+        }
+      }
       // FSE_Decoder::startChunk (src/fse_common.hpp:134-138): states for ctx N-1 .. 0
       for (unsigned cc = 8192; cc > 0; --cc) {
         const unsigned cx = cc - 1;
         const unsigned x = br.read(c.logs[cx]);
         const unsigned rq = sm_ld8(q.rk_a + (cx & 63u)), rm = sm_ld8(q.rk_a + ((cx >> 6) & 63u));
-        if (rq != 0xFFu && rm != 0xFFu) {
+        if (WIN) {
+          bool in_s = false;
+          if (rq != 0xFFu && rm != 0xFFu) {
+            uint32_t rx, ry;
+            sm_ld64(q.row_a + (rm * 2 + (cx >> 12)) * 8, rx, ry);
+            const uint32_t rel = rq * 4 - (ry & 0xFFFFu);
+            if (rel < (ry >> 16)) {
+              const uint32_t off = rx + rel;   // byte offset in S = compact id * 4
+              sm_st32(sb + off, gl_ld32(c.wtab + ((size_t)(off >> 2) << TAB_LOG) + x));
+              in_s = true;
+            }
+          }
+          if (!in_s) cold[cx] = (uint16_t)x;
+        } else if (rq != 0xFFu && rm != 0xFFu) {
           const unsigned d = qual_dense_id(rm, cx >> 12, rq);
           const unsigned cv = cid[cx];
           const unsigned zs = (cv == 0xFFFFu || q.n_slots == 0) ? 0u : (cv >> 13);
@@ -581,15 +615,37 @@ FQ_HD bool decode_qual_stream(const StreamArgs &c, const QualShared &q, uint32_t
   char *dst = c.out + (cur.scan - scan0) + cur.hl + 1 + cur.L + 3;
   unsigned i = 0;
   // record start: the three previous symbols are 0 (rank 0): row (max 0, eq 1), column 0
-  const uint32_t row_init = sb + QROW_BYTES;
-  uint32_t a = row_init, W = 0;
+  // Windowed layout: a row is (R1 = address of its first entry, RW = lo * 4 | (width * 4) << 16);
+  // the table builder keeps column 0 of row 1 inside its window.
+  uint32_t RW = 0, RW_init = 0;
+  auto row_of = [&](uint32_t r4a, uint32_t r4b) -> uint32_t {  // row of (max, eq) of two symbols, ranks * 4
+    const uint32_t mx4 = r4a > r4b ? r4a : r4b;
+    if (WIN) {
+      uint32_t rx, ry;
+      sm_ld64(q.row_a + mx4 * 4 + (r4a == r4b ? 8u : 0u), rx, ry);
+      RW = ry;
+      return sb + rx;
+    }
+    return sb + mx4 * (QROW_BYTES / 2) + (r4a == r4b ? QROW_BYTES : 0u);
+  };
+  // entry of column rank r4 / 4 in the row (R1, RW): the OOB word when outside the window
+  auto col_of = [&](uint32_t row, uint32_t rw, uint32_t r4) -> uint32_t {
+    if (WIN) {
+      const uint32_t rel = r4 - (rw & 0xFFFFu), w4 = rw >> 16;
+      return row + (rel < w4 ? rel : w4);
+    }
+    return row | r4;
+  };
+  uint32_t row_init = sb + QROW_BYTES;
+  if (WIN) {
+    row_init = row_of(0, 0);
+    RW_init = RW;
+  }
+  uint32_t a = col_of(row_init, RW_init, 0), W = 0;
+  const uint32_t a_init = a;
   uint32_t R1 = row_init;   // row of the NEXT symbol's context (from the two symbols before this one)
   uint32_t r4p = 0;         // rank * 4 of the previous symbol
   const uint32_t *wadj = c.wtab - ((size_t)sb << (TAB_LOG - 2));  // ((a << 9) + ns) indexes it directly
-  auto row_of = [&](uint32_t r4a, uint32_t r4b) -> uint32_t {  // row of (max, eq) of two symbols, ranks * 4
-    const uint32_t mx4 = r4a > r4b ? r4a : r4b;
-    return sb + mx4 * (QROW_BYTES / 2) + (r4a == r4b ? QROW_BYTES : 0u);
-  };
   // Slow path, entered after a symbol outside V (a quality value the sample never showed):
   // explicit q values, blocking table loads, until the record ends or the last three
   // symbols are in V again.  o = the record's quality slot, t = next position, rem = record length.
@@ -601,20 +657,37 @@ FQ_HD bool decode_qual_stream(const StreamArgs &c, const QualShared &q, uint32_t
     for (;;) {
       const unsigned ra = sm_ld8(q.rk_a + qa), rb = sm_ld8(q.rk_a + qb), rc = sm_ld8(q.rk_a + qc);
       if (ra != 0xFFu && rb != 0xFFu && rc != 0xFFu) {  // back to the fast path
-        a = row_of(rb * 4, rc * 4) | (ra * 4);
-        R1 = row_of(ra * 4, rb * 4);
-        r4p = ra * 4;
-        W = sm_ld32(a);
-        return t;
+        const uint32_t row = row_of(rb * 4, rc * 4);
+        const uint32_t an = col_of(row, RW, ra * 4);
+        const uint32_t wn = sm_ld32(an);
+        if (!WIN || !(wn & QW_OOB)) {   // (windowed: ... if this context is inside its row's window)
+          a = an;
+          R1 = row_of(ra * 4, rb * 4);
+          r4p = ra * 4;
+          W = wn;
+          return t;
+        }
       }
       if (t >= rem) return t;
       const unsigned mx = qb > qc ? qb : qc, eq = qb == qc;
       const unsigned rm = sm_ld8(q.rk_a + mx);
       unsigned sym;
-      if (ra != 0xFFu && rm != 0xFFu) {  // dense context: its cell (or run state) is in S
+      uint32_t aa = 0;
+      bool in_s = ra != 0xFFu && rm != 0xFFu;
+      if (in_s) {
+        if (WIN) {
+          uint32_t rx, ry;
+          sm_ld64(q.row_a + (rm * 2 + eq) * 8, rx, ry);
+          const uint32_t rel = ra * 4 - (ry & 0xFFFFu);
+          in_s = rel < (ry >> 16);
+          aa = sb + rx + rel;
+        } else {
+          aa = sb + qual_dense_id(rm, eq, ra) * 4;
+        }
+      }
+      if (in_s) {  // dense context: its cell (or run state) is in S
         DEC2_COUNT(6);
-        const unsigned d = qual_dense_id(rm, eq, ra);
-        const uint32_t aa = sb + d * 4;
+        const unsigned d = (aa - sb) >> 2;
         uint32_t w = sm_ld32(aa);
         if (w & QW_ZENT) {
           const unsigned zs = (w >> 20) & 3u;
@@ -642,6 +715,11 @@ FQ_HD bool decode_qual_stream(const StreamArgs &c, const QualShared &q, uint32_t
   // Returns the new position; W / a / R1 / r4p are left ready for the next symbol.
   auto special = [&](char *o, unsigned t, unsigned rem) -> unsigned {
     if (br.low()) br.refill();
+    if (WIN && (W & QW_OOB)) {   // the context of this symbol is outside its row's window
+      DEC2_COUNT(5);
+      if (t == 0) return rem + 1;   // (cannot happen: column 0 of the record-start row is always kept) -> stream error
+      return cold_run(o, t, rem);
+    }
     if (W & QW_STALE) {
       DEC2_COUNT(2);
       W = sm_resolve_stale<QW_STALE>(a);
@@ -687,7 +765,7 @@ FQ_HD bool decode_qual_stream(const StreamArgs &c, const QualShared &q, uint32_t
       return cold_run(o, t + 1, rem);   // comes back with a / R1 / r4p / W set, or at the record end
     }
     const uint32_t r4 = W & 0xFCu;
-    an = R1 | r4;
+    an = col_of(R1, RW, r4);
     R1 = row_of(r4, r4p);
     r4p = r4;
     a = an;
@@ -729,7 +807,7 @@ FQ_HD bool decode_qual_stream(const StreamArgs &c, const QualShared &q, uint32_t
             const unsigned ns = ((cell >> 12) & 0x7FFu) + br.read_nr((cell >> 8) & 15u);
             sm_st32(a, make_zent(ns, zs));
             const uint32_t r4 = cell & 0xFCu;
-            a = R1 | r4;
+            a = col_of(R1, RW, r4);
             W = sm_ld32(a);
             R1 = row_of(r4, r4p);
             r4p = r4;
@@ -743,7 +821,7 @@ FQ_HD bool decode_qual_stream(const StreamArgs &c, const QualShared &q, uint32_t
           sm_st32(a, QW_STALE);
           sm_async_ld32(a, wadj + ((a << (TAB_LOG - 2)) + ns));   // S[a] <- cell of the new state, when it arrives
           const uint32_t r4 = W & 0xFCu;
-          a = R1 | r4;
+          a = col_of(R1, RW, r4);
           W = sm_ld32(a);
           R1 = row_of(r4, r4p);
           r4p = r4;
@@ -759,8 +837,9 @@ FQ_HD bool decode_qual_stream(const StreamArgs &c, const QualShared &q, uint32_t
         i = 0;
         dst = c.out + (cur.scan - scan0) + cur.hl + 1 + cur.L + 3;
         if (rr > 1) nxt = load_meta(c.readlens, c.hdr_lens, c.recscan, c.rec0 + rr - 2);
-        a = row_init;
+        a = a_init;
         R1 = row_init;
+        RW = RW_init;
         r4p = 0;
       }
     }

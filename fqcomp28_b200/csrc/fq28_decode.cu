@@ -526,6 +526,12 @@ __host__ __device__ inline size_t d2_qual_smem(unsigned per_cta, unsigned nz, un
   return d2_qual_fixed(nz) + (size_t)per_cta * 16 + 256 /*alignment slack*/ + (size_t)per_cta * nv * 2 * dec2::QROW_BYTES;
 }
 
+// windowed layout: rk | zc | row descriptors (128 x 8 B) | ring | S (n_win * 4 B per stream, 16-byte rounded)
+__host__ __device__ inline size_t d2_qualw_stream(unsigned n_win) { return ((size_t)n_win * 4 + 15) & ~(size_t)15; }
+__host__ __device__ inline size_t d2_qualw_smem(unsigned per_cta, unsigned n_win) {
+  return 128 + 1024 + (size_t)per_cta * 16 + 256 /*alignment slack*/ + (size_t)per_cta * d2_qualw_stream(n_win);
+}
+
 __device__ __forceinline__ void d2_args(dec2::StreamArgs &a, const DecChunk &c, bool live, const uint8_t *stream, uint32_t len,
                                         const uint32_t *recscan, const uint16_t *readlens, const uint16_t *hdr_lens, char *out,
                                         const uint32_t *logs, const uint32_t *logsuf, const uint32_t *wtab, void *ring) {
@@ -567,6 +573,9 @@ k_dec2_seq(const DecChunk *__restrict__ ch, unsigned n_chunks, unsigned lanes, c
   if (live && !ok) set_error(st, FQ28_ERR_STREAM, k);  // BIT_endOfDStream, src/fse_common.hpp:141
 }
 
+// WIN: windowed layout of the cached cells (fq28_dec2.cuh); then nv = entries per stream, gzrun = the
+// row descriptors (uint2[128]), nz = number of rows, and there are no run tables.
+template <bool WIN>
 __global__ void __launch_bounds__(256)
 k_dec2_qual(const DecChunk *__restrict__ ch, unsigned n_chunks, unsigned lanes, const uint8_t *__restrict__ arena,
             const uint32_t *__restrict__ wtab, const uint32_t *__restrict__ logs, const uint32_t *__restrict__ logsuf,
@@ -578,8 +587,13 @@ k_dec2_qual(const DecChunk *__restrict__ ch, unsigned n_chunks, unsigned lanes, 
   const unsigned per_cta = lanes * (blockDim.x >> 5);
   const uint32_t base = (uint32_t)__cvta_generic_to_shared(smem_raw);
   dec2::QualShared qs;
-  qs.rk_a = base; qs.zc_a = base + 64; qs.zq_a = base + 128; qs.n_slots = nz;
-  {
+  qs.rk_a = base; qs.zc_a = base + 64; qs.zq_a = base + 128; qs.n_slots = WIN ? 0u : nz;
+  qs.row_a = base + 128; qs.n_rows = WIN ? nz : 0u;
+  if (WIN) {
+    for (unsigned i = threadIdx.x; i < 64; i += blockDim.x) smem_raw[i] = qrk[i];
+    const uint2 *rows = reinterpret_cast<const uint2 *>(gzrun);
+    for (unsigned i = threadIdx.x; i < 128; i += blockDim.x) reinterpret_cast<uint2 *>(smem_raw + 128)[i] = rows[i];
+  } else {
     for (unsigned i = threadIdx.x; i < 64; i += blockDim.x) smem_raw[i] = qrk[i];  // (a CTA may be one warp)
     const unsigned zc[4] = {zctx.x, zctx.y, zctx.z, zctx.w};
     for (unsigned j = 0; j < nz; j++) {
@@ -597,9 +611,9 @@ k_dec2_qual(const DecChunk *__restrict__ ch, unsigned n_chunks, unsigned lanes, 
     }
   }
   __syncthreads();
-  const uint32_t ring0 = qs.zq_a + nz * dec2::ZQ_SLOT_BYTES;
+  const uint32_t ring0 = WIN ? base + 128 + 1024 : qs.zq_a + nz * dec2::ZQ_SLOT_BYTES;
   const uint32_t s0 = (ring0 + per_cta * 16 + 255u) & ~255u;
-  const unsigned s_bytes = nv * 2 * dec2::QROW_BYTES;
+  const unsigned s_bytes = WIN ? (unsigned)d2_qualw_stream(nv) : nv * 2 * dec2::QROW_BYTES;
   const unsigned lane = threadIdx.x & 31;
   const unsigned slot = (threadIdx.x >> 5) * lanes + lane;
   const unsigned k = blockIdx.x * per_cta + slot;
@@ -611,7 +625,7 @@ k_dec2_qual(const DecChunk *__restrict__ ch, unsigned n_chunks, unsigned lanes, 
   dec2::StreamArgs a;
   d2_args(a, c, live, arena + c.qual_off, c.qual_len, recscan, readlens, hdr_lens, out, logs, logsuf, wtab,
           smem_raw + (ring0 - base) + sl * 16);
-  const bool ok = dec2::decode_qual_stream(a, qs, s0 + sl * s_bytes, dtab_fix, cid,
+  const bool ok = dec2::decode_qual_stream<WIN>(a, qs, s0 + sl * s_bytes, dtab_fix, cid,
                                           cold_states + (size_t)(live ? k : 0) * QUAL_N);
   if (live && !ok) set_error(st, FQ28_ERR_STREAM, k);
 }
@@ -827,39 +841,85 @@ int decode_batch(fq28_handle *h, const fq28_dec_arenas *in, const fq28_chunk_inf
       }
       unsigned nz = h->cfg.no_zrun ? 0u : h->qual.h_n_z;
       const unsigned nv = h->qual.h_n_v;
+      // Many-valued qualities: the cached cells take |V| * 512 B per stream in the dense layout (20 KB
+      // for 40 values), so shared memory, not warp slots, decides how many streams an SM holds.  The
+      // windowed layout keeps only the columns every row's touched contexts span (a few KB).
+      // It costs two ALU operations in the symbol chain and the run tables (measured at 1 028 streams:
+      // 70.9 against 63.1 ms HiSeq-like, 73.9 against 63.8 ms ONT-like), so it is used when the dense
+      // layout cannot hold all streams at once (3 857 / 11 571 streams: 19.2 / 26.5 GB/s against
+      // 13.3 / 14.0 HiSeq-like, 17.0 / 21.3 against 12.0 / 15.5 ONT-like).
+      const unsigned n_win = h->qual.h_n_win;
+      bool win = h->cfg.force_win && n_win > 0;
+      if (serial && !h->cfg.no_win && n_win > 0 && !h->cfg.qual_lanes && !h->cfg.qual_warps) {
+        const size_t per_stream = d2_qual_smem(2, 0, nv) - d2_qual_smem(1, 0, nv);
+        const size_t dense_cap = std::min<size_t>(8, (224 * 1024 - d2_qual_smem(0, 0, nv)) / per_stream);
+        win = win || n_chunks > 148 * std::max<size_t>(dense_cap, 1);
+      }
+      auto smem_of = [&](unsigned per_cta, unsigned z) {
+        return win ? d2_qualw_smem(per_cta, n_win) : d2_qual_smem(per_cta, z, nv);
+      };
       if (serial && !h->cfg.qual_lanes && !h->cfg.qual_warps) {
-        // Many-valued qualities: the cached cells take |V| * 512 B per stream (20 KB for 40 values),
-        // so shared memory, not warp slots, decides how many streams an SM holds.  One CTA per SM,
-        // one stream per warp (lanes in lockstep cost 1.4x per doubling here), as many warps as
-        // fit; if that covers all streams the launch is ONE wave (measured, 1 028 streams of
-        // 41-valued qualities: 257 CTAs of 150 KB made two waves, 116 ms instead of 58).
+        // One stream per warp (lanes in lockstep cost 1.4x per doubling here), CTAs sized so that the
+        // streams an SM can hold are resident at once: if that covers all streams the launch is ONE
+        // wave (measured, 1 028 streams of 41-valued qualities in the dense layout: 257 CTAs of
+        // 150 KB made two waves, 116 ms instead of 58).
         const size_t budget = 224 * 1024;
-        auto cap_of = [&](unsigned z) {
-          const size_t per_stream = d2_qual_smem(2, z, nv) - d2_qual_smem(1, z, nv);
-          const size_t fixed = d2_qual_smem(0, z, nv);
+        auto cap_of = [&](unsigned z) {   // streams per SM that shared memory allows (one or more CTAs)
+          const size_t per_stream = smem_of(2, z) - smem_of(1, z);
+          const size_t fixed = smem_of(0, z);
+          if (win) {   // small CTAs pack: count whole CTAs of 4 streams
+            const size_t cta4 = smem_of(4, z) + 1024;
+            const size_t n = budget / cta4;
+            return (unsigned)(n ? n * 4 : 1);
+          }
           const unsigned c = fixed + per_stream > budget ? 1u : (unsigned)((budget - fixed) / per_stream);
           return c > 8 ? 8u : c;
         };
         auto waves_of = [&](unsigned z) { return (n_chunks + 148ull * cap_of(z) - 1) / (148ull * cap_of(z)); };
         // the zero-bit run tables (16 KB per slot) are worth less than a wave: without them the run
         // contexts are ordinary contexts (same bytes)
-        if (nz && waves_of(0) < waves_of(nz)) nz = 0;
+        if (!win && nz && waves_of(0) < waves_of(nz)) nz = 0;
         const unsigned cap = cap_of(nz);
         const unsigned need = (unsigned)((n_chunks + 147) / 148);   // streams per SM for one wave
         w = need < cap ? need : cap;
+        if (w > 4 && win) w = 4;   // (several 4-warp CTAs per SM rather than one fat one)
+        if (w > 8) w = 8;
         l = 1;
       }
-      // the per-stream context arrays (|V| * 512 B) must fit: fewer warps first, then fewer lanes
-      while (d2_qual_smem(l * w, nz, nv) > 224 * 1024 && l * w > 1) {
+      // the per-stream context arrays must fit: fewer warps first, then fewer lanes
+      while (smem_of(l * w, nz) > 224 * 1024 && l * w > 1) {
         if (w > 1) w >>= 1; else l = (l + 1) / 2;
       }
       const unsigned per_cta = l * w;
       uint4 zctx = make_uint4(h->qual.h_zctx[0], h->qual.h_zctx[1], h->qual.h_zctx[2], h->qual.h_zctx[3]);
       const int qslot = stage_open(h, ST_DECODE_QUAL, qstream);
-      k_dec2_qual<<<(unsigned)((n_chunks + per_cta - 1) / per_cta), w * 32, d2_qual_smem(per_cta, nz, nv), qstream>>>(
-          ch, (unsigned)n_chunks, l, in->qual, h->qual.wtab, h->qual.logs, h->qual.logsuf, h->qual.dtab_fix, h->qual.cid,
-          h->qual.qrk, nv, h->qual.zrun, nz, zctx, h->dec_cold.as<uint16_t>(), recscan, in->readlens, in->hdr_lens, d_out,
-          h->d_status);
+      if (win) {
+        {
+          // The refreshed cells come through L1: reserve only the shared memory the resident CTAs
+          // need (the default carve-out sizes it for as many CTAs as could ever fit and leaves no L1).
+          const size_t n_ctas = (n_chunks + per_cta - 1) / per_cta;
+          const size_t cta_bytes = smem_of(per_cta, 0) + 1024;
+          size_t per_sm = (n_ctas + 147) / 148;
+          const size_t fit = (224 * 1024) / cta_bytes;
+          if (per_sm > fit) per_sm = fit;
+          int pct = (int)((per_sm * cta_bytes * 100 + 228 * 1024 - 1) / (228 * 1024));
+          pct = pct < 1 ? 1 : pct > 100 ? 100 : pct;
+          if (h->cfg.qual_carveout != -2) pct = h->cfg.qual_carveout < 0 ? cudaSharedmemCarveoutDefault : h->cfg.qual_carveout;
+          if (pct != h->qualw_carve_set) {
+            FQ28_CUDA(h, cudaFuncSetAttribute(k_dec2_qual<true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+            h->qualw_carve_set = pct;
+          }
+        }
+        k_dec2_qual<true><<<(unsigned)((n_chunks + per_cta - 1) / per_cta), w * 32, smem_of(per_cta, 0), qstream>>>(
+            ch, (unsigned)n_chunks, l, in->qual, h->qual.wtabw, h->qual.logs, h->qual.logsuf, h->qual.dtab_fix, h->qual.cid,
+            h->qual.qrk, n_win, reinterpret_cast<const uint16_t *>(h->qual.qwin), h->qual.h_n_rows, zctx,
+            h->dec_cold.as<uint16_t>(), recscan, in->readlens, in->hdr_lens, d_out, h->d_status);
+      } else {
+        k_dec2_qual<false><<<(unsigned)((n_chunks + per_cta - 1) / per_cta), w * 32, smem_of(per_cta, nz), qstream>>>(
+            ch, (unsigned)n_chunks, l, in->qual, h->qual.wtab, h->qual.logs, h->qual.logsuf, h->qual.dtab_fix, h->qual.cid,
+            h->qual.qrk, nv, h->qual.zrun, nz, zctx, h->dec_cold.as<uint16_t>(), recscan, in->readlens, in->hdr_lens, d_out,
+            h->d_status);
+      }
       FQ28_LAUNCH_CHECK(h);
       stage_close(h, qslot, qstream);
     }
@@ -932,7 +992,8 @@ int decode_init_device(fq28_handle *h) {
   FQ28_CUDA(h, cudaFuncSetAttribute(k_decode_seq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SEQ_DEC_SMEM));
   FQ28_CUDA(h, cudaFuncSetAttribute(k_decode_qual, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   FQ28_CUDA(h, cudaFuncSetAttribute(k_dec2_seq, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-  FQ28_CUDA(h, cudaFuncSetAttribute(k_dec2_qual, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  FQ28_CUDA(h, cudaFuncSetAttribute(k_dec2_qual<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  FQ28_CUDA(h, cudaFuncSetAttribute(k_dec2_qual<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   return FQ28_OK;
 }
 

@@ -76,6 +76,8 @@ struct DevBuf {
 
 // Device copy of one FreqTable plus the tables built from it
 // (FSE_Encoder / FSE_Decoder ctors, src/fse_common.hpp:46-71,107-127).
+constexpr unsigned QWIN_MAX_ENTRIES = 128 * 65;   // every row all 64 columns + its out-of-window word
+
 struct DevTables {
   unsigned n_models = 0, alphabet = 0;
   uint32_t *counts = nullptr;  // [N*A] scratch for histogram input
@@ -105,8 +107,13 @@ struct DevTables {
   // sequence: [256 << 11]; quality: rows of the dense contexts only, [2 * n_v * 64 << 11]
   uint32_t *wtab = nullptr;
   uint8_t *qrk = nullptr;          // quality only: rk[64] (q -> rank in V, 0xFF outside) then vq[64] (rank -> q)
-  uint32_t *qdinfo = nullptr;      // quality only: [0] = |V|
+  uint32_t *qdinfo = nullptr;      // quality only: [0] = |V|, [1] = entries of the windowed layout, [2] = its rows
   uint32_t h_n_v = 0;
+  // windowed layout of the cached cells (fq28_dec2.cuh, WIN): per row (rank(max) * 2 + eq) the byte offset
+  // of its first entry and lo * 4 | (width * 4) << 16; W table rows in the same compact order
+  uint2 *qwin = nullptr;           // [128]
+  uint32_t *wtabw = nullptr;       // [QWIN_MAX_ENTRIES << 11]
+  uint32_t h_n_win = 0, h_n_rows = 0;
   size_t cells_cap = 0;
   bool ready = false;
 };
@@ -206,6 +213,8 @@ struct fq28_handle {
     bool qual_v2 = true;           // cached-cell quality decoder (fq28_dec2.cuh); FQ28_QUAL_V1 / FQ28_DEC_V1: the round-1 state-table one
     bool dec_serial = false;       // FQ28_DEC_SERIAL: the two decode kernels one after the other (per-kernel timing)
     bool share_sms = false;        // FQ28_DEC_SHARE_SMS: do not keep the sequence decoder on SMs of its own
+    bool force_win = false;        // FQ28_QUAL_WINDOWED: ... the windowed layout whenever the tables have one (A/B, tests)
+    bool no_win = false;           // FQ28_QUAL_DENSE: many-valued qualities keep the dense layout of the cached cells (A/B)
     bool dec_concurrent = false;   // FQ28_DEC_CONCURRENT: never serialise the two decode kernels
     unsigned seq_lanes = 0, seq_warps = 0, qual_lanes = 0, qual_warps = 0;  // 0 = automatic
     int qual_carveout = -2;        // -2 = automatic
@@ -215,6 +224,7 @@ struct fq28_handle {
     unsigned pipe_lanes = 4;                     // FQ28_PIPE_LANES: parts in flight (handles and host threads)
     unsigned pipe_parts = 8;                     // FQ28_PIPE_PARTS: ... in this many parts (1 = one piece)
   } cfg;
+  int qualw_carve_set = -1000;     // ... and for the windowed cached-cell quality decoder
   int qual_carve_set = -1;         // last shared-memory carve-out set for k_decode_qual on this device
 
   // timings

@@ -651,6 +651,62 @@ k_qual_dense(const uint16_t *__restrict__ cid, uint8_t *__restrict__ qrk, uint32
   if (q == 0) qdinfo[0] = nv;
 }
 
+// Windowed layout of the dense contexts: for every row (rank(max) * 2 + eq) the columns [lo, hi]
+// that span its touched contexts (cid != 0xFFFF); a row takes width + 1 entries (the last one is
+// the out-of-window word).  Row 1, column 0 is the record-start context and is always kept.
+// Single CTA of 128 threads, one per row.
+__global__ void __launch_bounds__(128)
+k_qual_win(const uint16_t *__restrict__ cid, const uint8_t *__restrict__ qrk, uint32_t *__restrict__ qdinfo,
+           uint2 *__restrict__ qwin) {
+  __shared__ unsigned wd[128], st[128];
+  const unsigned nv = qdinfo[0];
+  const unsigned row = threadIdx.x, rm = row >> 1, eq = row & 1u;
+  unsigned lo = 64, hi = 0;
+  bool any = false;
+  if (rm < nv) {
+    for (unsigned rq = 0; rq < nv; rq++) {
+      const unsigned cx = ((unsigned)qrk[64 + rm] << 6) + qrk[64 + rq] + (eq << 12);
+      if (cid[cx] != 0xFFFFu) {
+        lo = rq < lo ? rq : lo;
+        hi = rq > hi ? rq : hi;
+        any = true;
+      }
+    }
+    if (row == 1) { lo = 0; any = true; }
+  }
+  const unsigned width = any ? hi - lo + 1 : 0;
+  wd[row] = row < 2 * nv ? width + 1 : 0;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned acc = 0;
+    for (unsigned r = 0; r < 128; r++) { st[r] = acc; acc += wd[r]; }
+    qdinfo[1] = acc;
+    qdinfo[2] = 2 * nv;
+  }
+  __syncthreads();
+  qwin[row] = make_uint2(st[row] * 4, (any ? lo * 4 : 0u) | ((width * 4) << 16));
+}
+
+// W table of the windowed layout: row = compact id of the (row, column) entry.
+__global__ void k_qual_wtabw(const uint32_t *__restrict__ logs, const uint32_t *__restrict__ dtab_fix,
+                             const uint8_t *__restrict__ qrk, const uint32_t *__restrict__ qdinfo,
+                             const uint2 *__restrict__ qwin, uint32_t *__restrict__ wtabw) {
+  __shared__ uint8_t rk[64];
+  const unsigned nv = qdinfo[0];
+  const unsigned rq = blockIdx.x & 63u, eq = (blockIdx.x >> 6) & 1u, rm = blockIdx.x >> 7;
+  if (rq >= nv || rm >= nv) return;
+  const uint2 w = qwin[rm * 2 + eq];
+  const unsigned rel = rq * 4 - (w.y & 0xFFFFu);
+  if (rel >= (w.y >> 16)) return;
+  if (threadIdx.x < 64) rk[threadIdx.x] = qrk[threadIdx.x];
+  __syncthreads();
+  const unsigned cx = ((unsigned)qrk[64 + rm] << 6) + qrk[64 + rq] + (eq << 12);
+  const unsigned d = (w.x + rel) >> 2;
+  const unsigned T = 1u << logs[cx];
+  for (unsigned u = threadIdx.x; u < (1u << FIX_LOG); u += blockDim.x)
+    wtabw[((size_t)d << FIX_LOG) + u] = u < T ? dec2::make_w_qual(dtab_fix[((size_t)cx << FIX_LOG) + u], rk) : 0u;
+}
+
 // Quality W table: one CTA per dense context (row = rank(max) * 2 + eq, column = rank(q)).
 __global__ void k_qual_wtab(const uint32_t *__restrict__ logs, const uint32_t *__restrict__ dtab_fix,
                             const uint8_t *__restrict__ qrk, const uint32_t *__restrict__ qdinfo,
@@ -694,6 +750,8 @@ int tables_alloc(fq28_handle *h, DevTables &t, unsigned n_models, unsigned alpha
   } else {
     FQ28_CUDA(h, cudaMalloc(&t.qrk, 128));
     FQ28_CUDA(h, cudaMalloc(&t.qdinfo, 4 * sizeof(uint32_t)));
+    FQ28_CUDA(h, cudaMalloc(&t.qwin, 128 * sizeof(uint2)));
+    FQ28_CUDA(h, cudaMalloc(&t.wtabw, ((size_t)QWIN_MAX_ENTRIES << FIX_LOG) * sizeof(uint32_t)));
     FQ28_CUDA(h, cudaMalloc(&t.cid, n_models * sizeof(uint16_t)));
     FQ28_CUDA(h, cudaMalloc(&t.n_touched, sizeof(uint32_t)));
     FQ28_CUDA(h, cudaMalloc(&t.zrun, (size_t)QZ_MAX * 2 * (1u << FIX_LOG) * sizeof(uint16_t)));
@@ -724,13 +782,21 @@ int tables_from_norm(fq28_handle *h, DevTables &t) {
     FQ28_LAUNCH_CHECK(h);
     k_qual_wtab<<<2 * 64 * 64, 256, 0, h->stream>>>(t.logs, t.dtab_fix, t.qrk, t.qdinfo, t.wtab);
     FQ28_LAUNCH_CHECK(h);
+    k_qual_win<<<1, 128, 0, h->stream>>>(t.cid, t.qrk, t.qdinfo, t.qwin);
+    FQ28_LAUNCH_CHECK(h);
+    k_qual_wtabw<<<2 * 64 * 64, 256, 0, h->stream>>>(t.logs, t.dtab_fix, t.qrk, t.qdinfo, t.qwin, t.wtabw);
+    FQ28_LAUNCH_CHECK(h);
     k_qual_zrun<<<1, 1024, 0, h->stream>>>(t.logs, t.dtab_fix, t.dom_sym, t.cid, t.zrun, t.zinfo);
     FQ28_LAUNCH_CHECK(h);
     uint32_t zi[QZ_MAX + 1];
     FQ28_CUDA(h, cudaMemcpyAsync(&t.h_n_touched, t.n_touched, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
-    FQ28_CUDA(h, cudaMemcpyAsync(&t.h_n_v, t.qdinfo, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    uint32_t qd[3] = {0, 0, 0};
+    FQ28_CUDA(h, cudaMemcpyAsync(qd, t.qdinfo, sizeof(qd), cudaMemcpyDeviceToHost, h->stream));
     FQ28_CUDA(h, cudaMemcpyAsync(zi, t.zinfo, sizeof(zi), cudaMemcpyDeviceToHost, h->stream));
     FQ28_CUDA(h, cudaStreamSynchronize(h->stream));
+    t.h_n_v = qd[0];
+    t.h_n_win = qd[1];
+    t.h_n_rows = qd[2];
     t.h_n_z = zi[0];
     for (unsigned j = 0; j < QZ_MAX; j++) t.h_zctx[j] = zi[1 + j];
   }

@@ -57,10 +57,13 @@ void fill_args(StreamArgs &a, const uint8_t *src, uint32_t len, const uint16_t *
 // test switch: the tables have run slots (cid carries them) but the decoder is told to ignore them,
 // which is what the product does when the run tables would not leave room for the streams
 static bool g_no_runs = false;
+// test switch: the windowed layout of the cached cells (what the product uses for many-valued qualities)
+static bool g_win = false;
 
 extern "C" {
 
 void dec2h_set_no_runs(int on) { g_no_runs = on != 0; }
+void dec2h_set_win(int on) { g_win = on != 0; }
 
 // event counters since the last call: [0] seq drains, [1] seq inline refreshes, [2] qual drains,
 // [3] zero-bit runs, [4] single steps in a run context, [5] slow-path entries, [6] slow-path
@@ -132,6 +135,59 @@ int dec2h_qual(const uint8_t *ft, const uint8_t *stream, uint32_t len, unsigned 
         for (unsigned u = 0; u < (1u << logs[cx]); u++)
           wtab[((size_t)d << TAB_LOG) + u] = make_w_qual(t.dtab_fix[((size_t)cx << TAB_LOG) + u], rk);
       }
+  if (g_win) {
+    // k_qual_win / k_qual_wtabw: per row the columns spanning its touched contexts + one out-of-window word
+    uint32_t rowx[128] = {0}, rowy[128] = {0};
+    unsigned total = 0;
+    for (unsigned row = 0; row < 2 * nv; row++) {
+      const unsigned rm = row >> 1, eq = row & 1u;
+      unsigned lo = 64, hi = 0;
+      bool any = false;
+      for (unsigned rq = 0; rq < nv; rq++) {
+        const unsigned cx = ((unsigned)vq[rm] << 6) + vq[rq] + (eq << 12);
+        if (cid[cx] != 0xFFFF) { lo = rq < lo ? rq : lo; hi = rq > hi ? rq : hi; any = true; }
+      }
+      if (row == 1) { lo = 0; any = true; }
+      const unsigned width = any ? hi - lo + 1 : 0;
+      rowx[row] = total * 4;
+      rowy[row] = (any ? lo * 4 : 0u) | ((width * 4) << 16);
+      total += width + 1;
+    }
+    std::vector<uint32_t> wtabw((size_t)total << TAB_LOG, 0);
+    for (unsigned rm = 0; rm < nv; rm++)
+      for (unsigned eq = 0; eq < 2; eq++)
+        for (unsigned rq = 0; rq < nv; rq++) {
+          const unsigned row = rm * 2 + eq;
+          const uint32_t rel = rq * 4 - (rowy[row] & 0xFFFFu);
+          if (rel >= (rowy[row] >> 16)) continue;
+          const unsigned cx = ((unsigned)vq[rm] << 6) + vq[rq] + (eq << 12);
+          const unsigned d = (rowx[row] + rel) >> 2;
+          for (unsigned u = 0; u < (1u << logs[cx]); u++)
+            wtabw[((size_t)d << TAB_LOG) + u] = make_w_qual(t.dtab_fix[((size_t)cx << TAB_LOG) + u], rk);
+        }
+    // shared memory image: rk | (zc) | row descriptors | S
+    const uint32_t rk_a = 0, row_a = 128, sbw = 128 + 1024;
+    std::vector<uint8_t> smemw(sbw + total * 4 + 64, 0);
+    memcpy(&smemw[rk_a], rk, 64);
+    for (unsigned r = 0; r < 128; r++) {
+      memcpy(&smemw[row_a + r * 8], &rowx[r], 4);
+      memcpy(&smemw[row_a + r * 8 + 4], &rowy[r], 4);
+    }
+    g_host_smem = smemw.data();
+    std::vector<uint64_t> bufw((len + 64) / 8 + 4, 0);
+    uint8_t *srcw = reinterpret_cast<uint8_t *>(bufw.data()) + 8 + (misalign & 7);
+    memcpy(srcw, stream, len);
+    std::vector<uint16_t> coldw(8192, 0);
+    StreamArgs aw;
+    std::vector<uint32_t> recscanw;
+    fill_args(aw, srcw, len, readlens, hdr_lens, n_rec, recscanw, out, t, wtabw.data());
+    QualShared qsw{rk_a, 128, 64, 0u, row_a, 2 * nv};
+    g_host_async = HostAsync();
+    const bool okw = decode_qual_stream<true>(aw, qsw, sbw, t.dtab_fix.data(), cid.data(), coldw.data());
+    g_host_smem = nullptr;
+    if (stats) { stats[0] = nv; stats[1] = total; }
+    return okw ? 0 : -8;
+  }
   // zero-bit run slots (k_qual_zrun): ctx(d,d,d) with a dominant d, high qualities first
   unsigned nz = 0, zsym[4];
   for (int d = 63; d >= 0 && nz < 4; --d) {
@@ -172,9 +228,9 @@ int dec2h_qual(const uint8_t *ft, const uint8_t *stream, uint32_t len, unsigned 
   StreamArgs a;
   std::vector<uint32_t> recscan;
   fill_args(a, src, len, readlens, hdr_lens, n_rec, recscan, out, t, wtab.data());
-  QualShared qs{rk_a, zq_a, zc_a, g_no_runs ? 0u : nz};
+  QualShared qs{rk_a, zq_a, zc_a, g_no_runs ? 0u : nz, 0u, 0u};
   g_host_async = HostAsync();
-  const bool ok = decode_qual_stream(a, qs, sb, t.dtab_fix.data(), cid.data(), cold.data());
+  const bool ok = decode_qual_stream<false>(a, qs, sb, t.dtab_fix.data(), cid.data(), cold.data());
   g_host_smem = nullptr;
   if (stats) { stats[0] = nv; stats[1] = nz; }
   return ok ? 0 : -8;

@@ -122,6 +122,48 @@ def test_run_tables_ignored(oracle, D):
         D.dec2h_set_no_runs(0)
 
 
+def test_windowed_layout(oracle, D):
+    """decode_qual_stream<WIN>: the cached cells of every row cover only the columns its touched
+    contexts span; everything else (values outside V, contexts outside a row's window) takes the
+    slow path.  On everything the dense layout is tested on, plus tables from a narrow sample
+    against data that leaves the windows all the time."""
+    import synth
+
+    D.dec2h_set_win.argtypes = [C.c_int]
+    D.dec2h_set_win(1)
+    try:
+        for name in FIXTURES:
+            d = load_fixture(name)
+            fs, fq = tables_of(oracle, d)
+            for mis in (0, 3):
+                roundtrip(oracle, D, d, fs, fq, mis)
+        for profile in ("novaseq", "hiseq"):
+            d = synth.illumina(0, 3000, profile=profile).numpy()
+            fs, fq = tables_of(oracle, d[: d.size // 3 * 2])
+            st = roundtrip(oracle, D, d, fs, fq)
+            if profile == "hiseq":
+                assert st[1] * 4 < st[0] * 512 // 2, "the windows must be much smaller than the dense layout"
+        d = synth.ont(0, 40).numpy()
+        fs, fq = tables_of(oracle, d)
+        roundtrip(oracle, D, d, fs, fq, 1)
+        for seed in range(4):
+            d = synth.random_fastq(300, seed=seed)
+            fs, fq = tables_of(oracle, d)
+            roundtrip(oracle, D, d, fs, fq, seed)
+        # windows from a narrow sample (HiSeq-like, values in runs), data = uniformly random qualities:
+        # nearly every context is outside its row's window or outside V
+        d = synth.random_fastq(400, seed=9)
+        fs, fq = tables_of(oracle, synth.illumina(0, 300, profile="hiseq").numpy())
+        roundtrip(oracle, D, d, fs, fq)
+        fs, fq = tables_of(oracle, synth.illumina(0, 300, profile="novaseq").numpy())
+        roundtrip(oracle, D, d, fs, fq)
+        # ... and the other way round: wide tables, narrow data
+        fs, fq = tables_of(oracle, synth.random_fastq(400, seed=9))
+        roundtrip(oracle, D, synth.illumina(0, 800, profile="hiseq").numpy(), fs, fq)
+    finally:
+        D.dec2h_set_win(0)
+
+
 def test_synthetic_ont(oracle, D):
     import synth
 

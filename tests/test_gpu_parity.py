@@ -348,6 +348,37 @@ def test_synthetic_profiles_chunk_parity(oracle, H, profile):
     check_chunks(oracle, H, d, 1 << 20, fs, fq)
 
 
+@pytest.mark.parametrize("kind", ["hiseq", "ont", "fixtures", "novaseq", "outside"])
+def test_windowed_quality_decoder(oracle, monkeypatch, kind):
+    """The windowed layout of the quality decoder's cached cells (used when the dense layout cannot
+    hold all streams of a batch at once) forced on small batches: the decode restores the input
+    for many-valued qualities, long reads, the reference's fixtures, binned qualities, and for data
+    whose contexts fall outside the windows of tables built from a narrow sample."""
+    import synth
+    import fqcomp28_b200 as P
+
+    monkeypatch.setenv("FQ28_QUAL_WINDOWED", "1")   # read at fq28_create
+    h = P.Handle(0)
+    R = 1 << 18
+    if kind == "fixtures":
+        d = np.concatenate([load_fixture(n) for n in FIXTURES])
+        sample = d
+    elif kind == "ont":
+        d = synth.ont(0, 120, seed=34).numpy()
+        sample = d[: d.size // 2]
+    elif kind == "outside":
+        d = synth.random_fastq(3000, seed=11)
+        sample = synth.illumina(0, 600, seed=5, profile="hiseq").numpy()
+    else:
+        d = synth.illumina(0, 6000, seed=36, profile=kind).numpy()
+        sample = d[: d.size // 3]
+    recs, used = oracle.parse_records(sample)
+    fs, fq = oracle.make_ft(*oracle.hist(sample[:used], recs))
+    h.load_tables(fs, fq)
+    check_chunks(oracle, h, d, R, fs, fq)
+    h.close()
+
+
 @pytest.mark.parametrize("eof,parts,lanes,kind", [(True, 4, 3, "illumina"), (False, 4, 2, "illumina"), (True, 2, 2, "illumina"),
                                                   (False, 7, 4, "illumina"), (True, 5, 1, "illumina"), (True, 8, 4, "ont"),
                                                   (False, 3, 3, "ont")])
