@@ -4,6 +4,8 @@ capture (gpurun_out/prof_<tag>_dec.ncu-rep): per source line, warp-stall samples
 executed warp instructions, plus instructions and cycles per decoded symbol.
 
     python profiles/dec_source.py r02      -> profiles/r02_dec_source.md
+    python profiles/dec_source.py r02 REP SUFFIX N_CHUNKS N_RECORDS "TITLE"
+                                           -> profiles/r02_dec_source_SUFFIX.md from another capture
 """
 import csv
 import io
@@ -15,11 +17,17 @@ import sys
 tag = sys.argv[1] if len(sys.argv) > 1 else "r02"
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 rep = os.path.join(root, "gpurun_out", f"prof_{tag}_dec.ncu-rep")
-plain = [l for l in open(os.path.join(root, "gpurun_out", "plain.log")) if l.startswith("{")][-1]
-run = json.loads(plain)
-n_chunks = run["stats"]["n_chunks"]
-# Illumina 150 bp synthetic: every record carries 150 bases and 150 qualities
-nsym = run["stats"]["n_records"] * 150
+suffix, title = "", "256 MB slab"
+if len(sys.argv) > 5:
+    rep, suffix = sys.argv[2], "_" + sys.argv[3]
+    n_chunks, nsym = int(sys.argv[4]), int(sys.argv[5]) * 150
+    title = sys.argv[6] if len(sys.argv) > 6 else sys.argv[3]
+else:
+    plain = [l for l in open(os.path.join(root, "gpurun_out", "plain.log")) if l.startswith("{")][-1]
+    run = json.loads(plain)
+    n_chunks = run["stats"]["n_chunks"]
+    # Illumina 150 bp synthetic: every record carries 150 bases and 150 qualities
+    nsym = run["stats"]["n_records"] * 150
 
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
@@ -53,8 +61,8 @@ def num(x):
         return 0.0
 
 
-with open(os.path.join(root, "profiles", f"{tag}_dec_source.md"), "w") as f:
-    f.write(f"# {tag}: decoder hot loops, ncu source view (256 MB slab, {n_chunks} streams per kind, -R 1)\n\n")
+with open(os.path.join(root, "profiles", f"{tag}_dec_source{suffix}.md"), "w") as f:
+    f.write(f"# {tag}: decoder hot loops, ncu source view ({title}, {n_chunks} streams per kind, -R 1)\n\n")
     f.write("Same command as the launch list; one launch per kernel; `-lineinfo` maps SASS to `fq28_dec2.cuh`.\n"
             "`samples` = warp-stall samples on the line's instructions, `warp inst` = warp-level instructions executed.\n\n")
     seen = set()
@@ -94,4 +102,4 @@ with open(os.path.join(root, "profiles", f"{tag}_dec_source.md"), "w") as f:
         for r in sorted(sass, key=lambda r: -num(r[i_samp]))[:24]:
             f.write(f"| {int(num(r[i_samp]))} | {num(r[i_samp]) / tot_s * 100:.1f}% | {num(r[i_inst]):.3g} | `{r[3].strip()}` |\n")
         f.write("\n")
-print("wrote", f"{tag}_dec_source.md")
+print("wrote", f"{tag}_dec_source{suffix}.md")
