@@ -837,6 +837,7 @@ def run_ours(args):
         }
         print(json.dumps(line), flush=True)
     h.close()
+    baton.close()
     if world > 1:
         dist.destroy_process_group()
     return 0

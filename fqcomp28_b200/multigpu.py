@@ -82,26 +82,99 @@ def slab_end(own_end: int, reading_size: int, file_size: int, is_last: bool) -> 
 
 class Baton:
     """The one number that travels between ranks: the global file offset at which the previous
-    rank's last chunk ends.  Host-side, through the process group's store (TCP) -- control
-    metadata, not a data-path collective.  One key per (step, rank): rank r blocks in recv()
-    until rank r-1 has walked its boundaries."""
+    rank's last chunk ends.  Control metadata, not a data-path collective.  Rank r blocks in
+    recv() until rank r-1 has walked its boundaries, so the hop latency is on the critical path
+    of every step: N - 1 hops in a row.  Measured over the process group's TCP store a hop cost
+    ~0.55 ms (8 GPUs: 81 % of linear for an 18 ms compress step); with all ranks on one node the
+    baton therefore lives in a shared-memory segment (a ring of (step, cut) slots per rank, the
+    receiver spins; a sender may run SLOTS - 1 steps ahead of its receiver, then waits for its
+    acknowledgement), and the store only carries the segment's name once.  Several nodes: the store, one key per
+    (step, rank)."""
 
-    def __init__(self, rank: int, world: int, store=None):
+    TIMEOUT_S = 120.0
+    SLOTS = 64
+
+    def __init__(self, rank: int, world: int, store=None, shared_memory=None):
         self.rank, self.world, self.step = rank, world, 0
         self.store = store
+        self._shm = None
+        self._arr = None
         if world > 1 and store is None:
             from torch.distributed.distributed_c10d import _get_default_store
 
             self.store = _get_default_store()
+        if shared_memory is None:
+            import os
+
+            lws = os.environ.get("LOCAL_WORLD_SIZE")
+            shared_memory = world > 1 and (lws is None or int(lws) == world)
+        if world > 1 and shared_memory:
+            self._attach()
+
+    def _attach(self) -> None:
+        import numpy as np
+        from multiprocessing import shared_memory as shm
+
+        key = "fq28/baton_shm"
+        if self.rank == 0:
+            seg = shm.SharedMemory(create=True, size=8 * self.world * (2 * self.SLOTS + 1))
+            arr = np.ndarray((self.world, 2 * self.SLOTS + 1), dtype=np.int64, buffer=seg.buf)
+            arr[:] = 0
+            self.store.set(key, seg.name)
+        else:
+            seg = shm.SharedMemory(name=self.store.get(key).decode())
+            try:   # (the creator unlinks it; keep Python's resource tracker of this process out of it)
+                from multiprocessing import resource_tracker
+
+                resource_tracker.unregister(seg._name, "shared_memory")
+            except Exception:
+                pass
+            arr = np.ndarray((self.world, 2 * self.SLOTS + 1), dtype=np.int64, buffer=seg.buf)
+        self._shm, self._arr = seg, arr   # row r: SLOTS x (step, cut) written by rank r-1, then the last step rank r has read
+
+    def close(self) -> None:
+        if self._shm is not None:
+            self._arr = None
+            try:
+                self._shm.close()
+                if self.rank == 0:
+                    self._shm.unlink()
+            except Exception:
+                pass
+            self._shm = None
 
     def next_step(self) -> None:
         self.step += 1
 
+    def _spin(self, done, what: str) -> None:
+        import time
+
+        t0, spins = time.monotonic(), 0
+        while not done():
+            spins += 1
+            if (spins & 0x3FFF) == 0 and time.monotonic() - t0 > self.TIMEOUT_S:
+                raise TimeoutError(f"baton, rank {self.rank}: {what}")
+
     def recv(self) -> int:
         if self.rank == 0:
             return 0
+        if self._arr is not None:
+            row, step = self._arr[self.rank], self.step
+            i = 2 * (step % self.SLOTS)
+            self._spin(lambda: int(row[i]) == step, f"no cut from rank {self.rank - 1} for step {step}")
+            cut = int(row[i + 1])
+            row[2 * self.SLOTS] = step   # acknowledged: the slot may be reused SLOTS steps from now
+            return cut
         return int(self.store.get(f"fq28/cut/{self.step}/{self.rank}").decode())
 
     def send(self, cut: int) -> None:
-        if self.rank + 1 < self.world:
-            self.store.set(f"fq28/cut/{self.step}/{self.rank + 1}", str(int(cut)))
+        if self.rank + 1 >= self.world:
+            return
+        if self._arr is not None:
+            row, step = self._arr[self.rank + 1], self.step
+            self._spin(lambda: int(row[2 * self.SLOTS]) > step - self.SLOTS, f"rank {self.rank + 1} is {self.SLOTS} steps behind")
+            i = 2 * (step % self.SLOTS)
+            row[i + 1] = int(cut)   # the value first, then the step that publishes it (x86: stores stay in order)
+            row[i] = step
+            return
+        self.store.set(f"fq28/cut/{self.step}/{self.rank + 1}", str(int(cut)))

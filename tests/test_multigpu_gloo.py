@@ -86,7 +86,7 @@ def test_two_rank_tables_and_streams_match_single_process(oracle):
     assert gathered[0][3][1] == gathered[1][3][0]
 
 
-def _chain_worker(rank, world, port, q):
+def _chain_worker(rank, world, port, q, use_shm):
     """the N-rank chunking of bench.py / DESIGN.md section 7 with the oracle's walk standing in for
     fq28_plan_cut_dev: record ranges + lookahead (slab_end), one cut offset per rank (Baton)"""
     sys.path.insert(0, ROOT)
@@ -104,9 +104,10 @@ def _chain_worker(rank, world, port, q):
     b0, b1 = int(ends[min(rank * per, len(recs))]), int(ends[min((rank + 1) * per, len(recs))])
     last = rank == world - 1
     slab = d[b0 : M.slab_end(b1, R, d.size, last)]
-    baton = M.Baton(rank, world)
+    baton = M.Baton(rank, world, shared_memory=use_shm)
+    assert (baton._arr is not None) == use_shm
     out = []
-    for step in range(2):                       # two steps: the keys of one step must not leak into the next
+    for step in range(70):                      # more steps than ring slots: a slot of one step must not leak into another
         baton.next_step()
         cut = baton.recv()
         first = cut - b0
@@ -117,7 +118,8 @@ def _chain_worker(rank, world, port, q):
             offs = [o for i, o in enumerate(offs) if i == 0 or offs[i - 1] + R <= slab.size]
         baton.send(b0 + offs[-1])
         out.append([(b0 + offs[i], b0 + offs[i + 1]) for i in range(len(offs) - 1)])
-    assert out[0] == out[1]
+    assert all(o == out[0] for o in out)
+    baton.close()
     gathered = [None] * world
     dist.all_gather_object(gathered, out[0])
     if rank == 0:
@@ -127,12 +129,12 @@ def _chain_worker(rank, world, port, q):
 
 
 @pytest.mark.timeout(300)
-@pytest.mark.parametrize("world", [2, 3])
-def test_cut_chain_tiles_the_file_like_one_walk(oracle, world):
-    port = 31500 + (os.getpid() % 2000) + world
+@pytest.mark.parametrize("world,use_shm", [(2, True), (3, True), (3, False)])
+def test_cut_chain_tiles_the_file_like_one_walk(oracle, world, use_shm):
+    port = 31500 + (os.getpid() % 2000) + world + 7 * int(use_shm)
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_chain_worker, args=(r, world, port, q)) for r in range(world)]
+    procs = [ctx.Process(target=_chain_worker, args=(r, world, port, q, use_shm)) for r in range(world)]
     for p in procs:
         p.start()
     gathered = q.get(timeout=240)
