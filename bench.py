@@ -362,10 +362,14 @@ def run_ours(args):
                 h.preparse_dev(w.ptr, w.n)                      # does not wait for anybody
                 for kk, v in h.timings().items():
                     t[kk] = t.get(kk, 0.0) + v
+                t0 = time.perf_counter()
                 cut = baton.recv()                               # where the previous rank's last chunk ends
+                t1 = time.perf_counter()
                 consumed, _ = h.plan_cut_dev(w.ptr, w.n, w.R, last, cut - w.base)
+                t2 = time.perf_counter()
                 baton.send(w.base + consumed)
                 self.st["cut_local"] = cut - w.base
+                self.st["hop_ms"] = {"wait_for_cut": (t1 - t0) * 1e3, "walk_call": (t2 - t1) * 1e3}
             _, summ = h.compress_dev(w.ptr, w.n, w.R, eof=last, max_chunks=w.max_chunks, infos=w.infos)
             for kk, v in h.timings().items():
                 t[kk] = t.get(kk, 0.0) + v
@@ -630,6 +634,10 @@ def run_ours(args):
                 "copy_only_ms": copies["compress_both_ways_ms"], "fraction_of_copy_ceiling": copies["compress_both_ways_ms"] / ms_ce},
         "gpu_launches": int(launches_c), "roofline": roofline(run, t_c),
     }
+    if world > 1:   # the cut chain (last timed step): per rank, how long it waited for its cut and how long its walk took
+        hops = [None] * world
+        dist.all_gather_object(hops, run.st.get("hop_ms"))
+        comp["cut_chain_ms"] = hops
     deco = {
         "value": total_mb / (ms_d * 1e-3), "ms_per_step": ms_d, "wall_ms_per_step": wall_d,
         "e2e": {"value": total_mb / (ms_de * 1e-3), "unit": "MB/s", "ms_per_step": ms_de,
