@@ -69,9 +69,10 @@ static const char *err_name(int code) {
   }
 }
 
-int check_status(fq28_handle *h, const char *what) {
-  FQ28_CUDA(h, cudaMemcpyAsync(h->h_status, h->d_status, sizeof(DevStatus), cudaMemcpyDeviceToHost, h->stream));
-  FQ28_CUDA(h, cudaStreamSynchronize(h->stream));
+int check_status(fq28_handle *h, const char *what, cudaStream_t on) {
+  if (!on) on = h->stream;
+  FQ28_CUDA(h, cudaMemcpyAsync(h->h_status, h->d_status, sizeof(DevStatus), cudaMemcpyDeviceToHost, on));
+  FQ28_CUDA(h, cudaStreamSynchronize(on));
   if (h->h_status->code != 0)
     return fail(h, h->h_status->code, "%s: %s (at index %u)", what, err_name(h->h_status->code), h->h_status->where);
   return FQ28_OK;
@@ -246,6 +247,7 @@ int fq28_create(int device, fq28_handle **out) {
       h->cfg.share_sms = getenv("FQ28_DEC_SHARE_SMS") != nullptr;
       h->cfg.dec_concurrent = getenv("FQ28_DEC_CONCURRENT") != nullptr;
       h->cfg.no_win = getenv("FQ28_QUAL_DENSE") != nullptr;
+      h->cfg.no_eager = getenv("FQ28_NO_EAGER_EXTRACT") != nullptr;
       h->cfg.force_win = getenv("FQ28_QUAL_WINDOWED") != nullptr;
       h->cfg.seq_lanes = env_u("FQ28_SEQ_LANES"); h->cfg.seq_warps = env_u("FQ28_SEQ_WARPS");
       h->cfg.qual_lanes = env_u("FQ28_QUAL_LANES"); h->cfg.qual_warps = env_u("FQ28_QUAL_WARPS");
@@ -302,6 +304,9 @@ void fq28_destroy(fq28_handle *h) {
   for (auto &r : h->ev_pool) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   if (h->side) { cudaStreamSynchronize(h->side); cudaStreamDestroy(h->side); }
   if (h->ev_copy) cudaEventDestroy(h->ev_copy);
+  if (h->bulk) { cudaStreamSynchronize(h->bulk); cudaStreamDestroy(h->bulk); }
+  if (h->ev_parsed) cudaEventDestroy(h->ev_parsed);
+  if (h->ev_extract) cudaEventDestroy(h->ev_extract);
   for (cudaEvent_t e : h->ev_part) cudaEventDestroy(e);
   if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
@@ -503,7 +508,7 @@ int fq28_preparse_dev(fq28_handle *h, const char *d_fastq, size_t n_bytes) {
   h->parsed.valid = true;
   h->parsed.d_fastq = d_fastq;
   h->parsed.n_bytes = n_bytes;
-  return FQ28_OK;
+  return extract_eager(h);   // the field separation does not need the chunk boundaries: it runs under the wait for the cut
 }
 
 int fq28_plan_cut_dev(fq28_handle *h, const char *d_fastq, size_t n_bytes, size_t reading_size, int eof, uint64_t first_cut,

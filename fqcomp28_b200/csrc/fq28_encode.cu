@@ -1292,6 +1292,35 @@ static int pack_kind(fq28_handle *h, const DevTables &tab, KindBufs &b, int whic
   return FQ28_OK;
 }
 
+// Field separation of ALL parsed records, started by fq28_preparse(_dev) on the bulk stream: it
+// needs the record table only, so it runs while the caller waits for its cut (several GPUs, one
+// file: rank r waits r walks).  Buffers are sized by the bound "a symbol takes two bytes".
+int extract_eager(fq28_handle *h) {
+  if (h->cfg.no_eager || h->n_rec == 0) return FQ28_OK;
+  if (!h->bulk) {
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    FQ28_CUDA(h, cudaStreamCreateWithPriority(&h->bulk, cudaStreamNonBlocking, lo));
+    FQ28_CUDA(h, cudaEventCreateWithFlags(&h->ev_parsed, cudaEventDisableTiming));
+    FQ28_CUDA(h, cudaEventCreateWithFlags(&h->ev_extract, cudaEventDisableTiming));
+  }
+  const size_t n_rec = h->n_rec, g_bound = h->n_bytes / 2 + 16;
+  FQ28_TRY(ensure(h, h->key_seq, (g_bound + 8) * 2));
+  FQ28_TRY(ensure(h, h->key_qual, (g_bound + 16) * 4));
+  FQ28_TRY(ensure(h, h->n_count, (n_rec + 2) * 2));
+  FQ28_CUDA(h, cudaEventRecord(h->ev_parsed, h->stream));
+  FQ28_CUDA(h, cudaStreamWaitEvent(h->bulk, h->ev_parsed, 0));
+  const unsigned blocks = (unsigned)((n_rec + EX_WARPS - 1) / EX_WARPS);
+  k_extract<<<blocks, EX_WARPS * 32, 0, h->bulk>>>(h->d_fastq, h->seq_off.as<uint32_t>(), h->qual_off.as<uint32_t>(),
+                                                  h->len.as<uint16_t>(), h->symoff.as<uint32_t>(), n_rec,
+                                                  h->key_seq.as<uint16_t>(), h->key_qual.as<uint32_t>(),
+                                                  h->n_count.as<uint16_t>(), h->d_status);
+  FQ28_LAUNCH_CHECK(h);
+  FQ28_CUDA(h, cudaEventRecord(h->ev_extract, h->bulk));
+  h->extracted = true;
+  return FQ28_OK;
+}
+
 int encode_slab(fq28_handle *h, fq28_chunk_info *infos, size_t infos_cap, fq28_enc_summary *summary) {
   if (!h->seq.ready || !h->qual.ready) return fail(h, FQ28_ERR_ARG, "frequency tables not built/loaded");
   const unsigned n_chunks = (unsigned)h->n_chunks;
@@ -1310,19 +1339,27 @@ int encode_slab(fq28_handle *h, fq28_chunk_info *infos, size_t infos_cap, fq28_e
   const uint32_t *chunk_rec = h->chunk_rec.as<uint32_t>();
   const uint32_t *chunk_sym = chunk_rec + stride, *chunk_byte = chunk_rec + 2 * stride;
 
-  FQ28_TRY(ensure(h, h->key_seq, (G + 8) * 2));
-  FQ28_TRY(ensure(h, h->key_qual, (G + 16) * 4));
-  FQ28_TRY(ensure(h, h->n_count, (n_rec + 2) * 2));
+  const bool eager = h->extracted;   // fq28_preparse(_dev) has started k_extract over all parsed records
+  h->extracted = false;
+  if (!eager) {
+    FQ28_TRY(ensure(h, h->key_seq, (G + 8) * 2));
+    FQ28_TRY(ensure(h, h->key_qual, (G + 16) * 4));
+    FQ28_TRY(ensure(h, h->n_count, (n_rec + 2) * 2));
+  }
   FQ28_TRY(ensure(h, h->npos_off, (n_rec + 2) * 4));
 
   stage_begin(h, ST_EXTRACT);
   {
     const unsigned blocks = (unsigned)((n_rec + EX_WARPS - 1) / EX_WARPS);
-    k_extract<<<blocks, EX_WARPS * 32, 0, h->stream>>>(h->d_fastq, h->seq_off.as<uint32_t>(), h->qual_off.as<uint32_t>(),
-                                                      h->len.as<uint16_t>(), h->symoff.as<uint32_t>(), n_rec,
-                                                      h->key_seq.as<uint16_t>(), h->key_qual.as<uint32_t>(),
-                                                      h->n_count.as<uint16_t>(), h->d_status);
-    FQ28_LAUNCH_CHECK(h);
+    if (eager) {
+      FQ28_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_extract, 0));
+    } else {
+      k_extract<<<blocks, EX_WARPS * 32, 0, h->stream>>>(h->d_fastq, h->seq_off.as<uint32_t>(), h->qual_off.as<uint32_t>(),
+                                                        h->len.as<uint16_t>(), h->symoff.as<uint32_t>(), n_rec,
+                                                        h->key_seq.as<uint16_t>(), h->key_qual.as<uint32_t>(),
+                                                        h->n_count.as<uint16_t>(), h->d_status);
+      FQ28_LAUNCH_CHECK(h);
+    }
     FQ28_TRY(scan_exclusive_u16_to_u32(h, h->n_count.as<uint16_t>(), h->npos_off.as<uint32_t>(), n_rec));
     FQ28_TRY(ensure(h, h->hdrscan, (n_rec + 2) * 4));
     FQ28_TRY(scan_exclusive_u16_to_u32(h, h->hdr_len.as<uint16_t>(), h->hdrscan.as<uint32_t>(), n_rec));

@@ -200,6 +200,12 @@ struct fq28_handle {
   // fq28_plan / fq28_plan_dev: parse + chunk walk done for exactly this slab; a following
   // fq28_compress(_dev) with the same arguments and sample_bytes == 0 goes straight to the encode
   struct Plan { bool valid = false; const char *d_fastq = nullptr; size_t n_bytes = 0, reading_size = 0; int eof = 0; } plan;
+  // fq28_preparse_dev also starts the field separation (k_extract needs the record table, not the
+  // chunk boundaries) on a stream of its own, so that it runs while the caller waits for the cut
+  // that the previous rank owes it; the boundary walk then goes to the high-priority side stream
+  cudaStream_t bulk = nullptr;
+  cudaEvent_t ev_parsed = nullptr, ev_extract = nullptr;
+  bool extracted = false;                // keys / n_count of all h->n_rec parsed records are (being) written
   // fq28_preparse_dev: the record table of exactly this slab is in place (consumed by the next plan)
   struct Parsed { bool valid = false; const char *d_fastq = nullptr; size_t n_bytes = 0; } parsed;
   // generation of the device tables (bumped whenever they are rebuilt; the C++ facade compares it)
@@ -214,6 +220,7 @@ struct fq28_handle {
     bool dec_serial = false;       // FQ28_DEC_SERIAL: the two decode kernels one after the other (per-kernel timing)
     bool share_sms = false;        // FQ28_DEC_SHARE_SMS: do not keep the sequence decoder on SMs of its own
     bool force_win = false;        // FQ28_QUAL_WINDOWED: ... the windowed layout whenever the tables have one (A/B, tests)
+    bool no_eager = false;         // FQ28_NO_EAGER_EXTRACT: fq28_preparse(_dev) does not start the field separation
     bool no_win = false;           // FQ28_QUAL_DENSE: many-valued qualities keep the dense layout of the cached cells (A/B)
     bool dec_concurrent = false;   // FQ28_DEC_CONCURRENT: never serialise the two decode kernels
     unsigned seq_lanes = 0, seq_warps = 0, qual_lanes = 0, qual_warps = 0;  // 0 = automatic
@@ -242,7 +249,7 @@ int fail(fq28_handle *h, int code, const char *fmt, ...);
 int cuda_fail(fq28_handle *h, cudaError_t e, const char *what);
 int ensure(fq28_handle *h, DevBuf &b, size_t bytes);
 int ensure_pinned(fq28_handle *h, size_t bytes);      // h->h_pin holds at least `bytes`
-int check_status(fq28_handle *h, const char *what);   // syncs + reads d_status
+int check_status(fq28_handle *h, const char *what, cudaStream_t on = nullptr);   // syncs (h->stream unless told) + reads d_status
 void stage_reset(fq28_handle *h);
 void stage_begin(fq28_handle *h, Stage s);
 void stage_end(fq28_handle *h, Stage s);
@@ -250,6 +257,8 @@ void stage_end(fq28_handle *h, Stage s);
 // join = main waits for the side stream; side_stage_* time a stage on it
 int side_fork(fq28_handle *h);
 int side_join(fq28_handle *h);
+int extract_eager(fq28_handle *h);   // fq28_encode.cu
+int extract_eager(fq28_handle *h);   // fq28_encode.cu
 void side_stage_begin(fq28_handle *h, Stage s);
 void side_stage_end(fq28_handle *h, Stage s);
 // re-entrant form for stages that overlap on two streams: open returns a slot

@@ -303,6 +303,10 @@ int parse_slab(fq28_handle *h, const char *d_fastq, size_t n_bytes, bool need_sy
   h->n_chunks = 0;
   h->plan.valid = false;  // the record table of any earlier plan is gone
   h->parsed.valid = false;
+  if (h->extracted) {     // an eager field separation nobody consumed still reads the old record table
+    FQ28_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_extract, 0));
+    h->extracted = false;
+  }
   FQ28_CUDA(h, cudaMemsetAsync(h->d_status, 0, sizeof(DevStatus), h->stream));
   const size_t n_tiles = (n_bytes + NL_TILE - 1) / NL_TILE;
   FQ28_TRY(ensure(h, h->tile_cnt, (n_tiles + 1) * sizeof(uint32_t)));
@@ -349,12 +353,20 @@ int split_slab(fq28_handle *h, size_t reading_size, bool eof, size_t max_chunks,
   FQ28_TRY(ensure(h, h->chunk_rec, 3 * (cap + 1) * sizeof(uint32_t)));
   h->chunk_stride = cap + 1;
   uint32_t *cr = h->chunk_rec.as<uint32_t>();
-  k_chunk_walk<<<1, 32, 0, h->stream>>>(h->hdr_off.as<uint32_t>(), h->symoff.as<uint32_t>(), h->n_rec, h->n_bytes,
+  // While an eager field separation fills the GPU (same priority as the main stream), the one-warp
+  // walk would queue behind its CTAs: it goes to the high-priority side stream then.  The record
+  // table it reads was complete before the separation started (ev_parsed).
+  cudaStream_t ws = h->stream;
+  if (h->extracted) {
+    ws = h->side;
+    FQ28_CUDA(h, cudaStreamWaitEvent(ws, h->ev_parsed, 0));
+  }
+  k_chunk_walk<<<1, 32, 0, ws>>>(h->hdr_off.as<uint32_t>(), h->symoff.as<uint32_t>(), h->n_rec, h->n_bytes,
                                        reading_size, eof ? 1 : 0, first_cut, cap, cr, cr + (cap + 1), cr + 2 * (cap + 1),
                                        h->d_scalars, h->d_status);
   FQ28_LAUNCH_CHECK(h);
-  FQ28_CUDA(h, cudaMemcpyAsync(h->h_scalars, h->d_scalars, sizeof(uint64_t), cudaMemcpyDeviceToHost, h->stream));
-  FQ28_TRY(check_status(h, "record splitting"));
+  FQ28_CUDA(h, cudaMemcpyAsync(h->h_scalars, h->d_scalars, sizeof(uint64_t), cudaMemcpyDeviceToHost, ws));
+  FQ28_TRY(check_status(h, "record splitting", ws));
   const size_t n = (size_t)h->h_scalars[0];
   h->n_chunks = n;
   h->h_chunk_rec.resize(n + 1);
@@ -362,10 +374,10 @@ int split_slab(fq28_handle *h, size_t reading_size, bool eof, size_t max_chunks,
   h->h_chunk_byte.resize(n + 1);
   FQ28_TRY(ensure_pinned(h, 3 * (n + 1) * 4));
   uint32_t *pin = static_cast<uint32_t *>(h->h_pin);
-  FQ28_CUDA(h, cudaMemcpyAsync(pin, cr, (n + 1) * 4, cudaMemcpyDeviceToHost, h->stream));
-  FQ28_CUDA(h, cudaMemcpyAsync(pin + (n + 1), cr + (cap + 1), (n + 1) * 4, cudaMemcpyDeviceToHost, h->stream));
-  FQ28_CUDA(h, cudaMemcpyAsync(pin + 2 * (n + 1), cr + 2 * (cap + 1), (n + 1) * 4, cudaMemcpyDeviceToHost, h->stream));
-  FQ28_CUDA(h, cudaStreamSynchronize(h->stream));
+  FQ28_CUDA(h, cudaMemcpyAsync(pin, cr, (n + 1) * 4, cudaMemcpyDeviceToHost, ws));
+  FQ28_CUDA(h, cudaMemcpyAsync(pin + (n + 1), cr + (cap + 1), (n + 1) * 4, cudaMemcpyDeviceToHost, ws));
+  FQ28_CUDA(h, cudaMemcpyAsync(pin + 2 * (n + 1), cr + 2 * (cap + 1), (n + 1) * 4, cudaMemcpyDeviceToHost, ws));
+  FQ28_CUDA(h, cudaStreamSynchronize(ws));
   memcpy(h->h_chunk_rec.data(), pin, (n + 1) * 4);
   memcpy(h->h_chunk_sym.data(), pin + (n + 1), (n + 1) * 4);
   memcpy(h->h_chunk_byte.data(), pin + 2 * (n + 1), (n + 1) * 4);
