@@ -193,7 +193,11 @@ int fq28_plan_dev(fq28_handle *h, const char *d_fastq, size_t n_bytes, size_t re
  * `first_cut`, the slab-relative offset at which the previous rank's last chunk ends (0: the slab
  * starts a chunk).  With first_cut > 0 the head [0, first_cut) is emitted as chunk 0 and must be
  * dropped by the caller: it is the tail of the previous rank's last chunk.  first_cut must be a
- * record boundary (else FQ28_ERR_FORMAT).  Between ranks only this one offset travels. */
+ * record boundary (else FQ28_ERR_FORMAT).  Between ranks only this one offset travels.
+ * fq28_preparse_dev also starts the field separation of the slab (keys, N counts: it needs the
+ * record table, not the chunk boundaries) on a stream of its own, so that it runs while the
+ * caller waits for first_cut; a malformed record anywhere in the slab -- the lookahead included --
+ * is therefore reported by the following fq28_plan_cut / fq28_compress of this slab. */
 int fq28_preparse_dev(fq28_handle *h, const char *d_fastq, size_t n_bytes);
 /* host-buffer forms: fq28_preparse copies the slab to the device and builds the record table;
  * fq28_plan_cut / fq28_compress on the same buffer then reuse both */
