@@ -201,7 +201,9 @@ k_chunk_walk(const uint32_t *__restrict__ hdr_off, const uint32_t *__restrict__ 
       // records per chunk, 8 fractional bits, from the record size of the last chunk (record
       // sizes drift along a file: read ids grow), of the whole slab before the first chunk
       const size_t rpc256 = (size_t)((double)R * 256.0 * (double)last_recs / (double)last_bytes);
-#pragma unroll 8
+      // (fully unrolled: all 32 loads are in flight before the first one is stored -- one memory
+      // latency for the 32 windows instead of one per batch of 8)
+#pragma unroll
       for (unsigned j = 0; j < 32; j++) {
         // chunk j ends about (j+1) chunks of records ahead, minus half a record of slack per chunk
         size_t est = s_rec + (((size_t)(j + 1) * rpc256 - (size_t)j * 128) >> 8);
@@ -287,10 +289,15 @@ k_chunk_walk(const uint32_t *__restrict__ hdr_off, const uint32_t *__restrict__ 
     if (reaches_eof) break;
   }
   if (lane == 0) *n_chunks_out = k;
-  // symbol offsets of the chunk starts: gathered after the walk so that the
-  // loads do not sit in its dependent chain
-  __syncwarp();
-  for (size_t kk = 1 + lane; kk <= k; kk += 32) chunk_sym[kk] = symoff ? symoff[chunk_rec[kk]] : 0u;
+  // (the symbol offsets of the chunk starts are gathered by k_chunk_sym afterwards: in here the
+  // one warp would pay two dependent loads per 32 chunks, ~50 us per 1 000 chunks)
+}
+
+// chunk_sym[k] = symoff[chunk_rec[k]] for the chunks the walk emitted
+__global__ void k_chunk_sym(const uint32_t *__restrict__ symoff, const uint32_t *__restrict__ chunk_rec,
+                            const uint64_t *__restrict__ n_chunks, size_t cap, uint32_t *__restrict__ chunk_sym) {
+  const size_t kk = 1 + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (kk <= *n_chunks && kk <= cap) chunk_sym[kk] = symoff ? symoff[chunk_rec[kk]] : 0u;
 }
 
 int parse_slab(fq28_handle *h, const char *d_fastq, size_t n_bytes, bool need_symoff) {
@@ -364,6 +371,8 @@ int split_slab(fq28_handle *h, size_t reading_size, bool eof, size_t max_chunks,
   k_chunk_walk<<<1, 32, 0, ws>>>(h->hdr_off.as<uint32_t>(), h->symoff.as<uint32_t>(), h->n_rec, h->n_bytes,
                                        reading_size, eof ? 1 : 0, first_cut, cap, cr, cr + (cap + 1), cr + 2 * (cap + 1),
                                        h->d_scalars, h->d_status);
+  FQ28_LAUNCH_CHECK(h);
+  k_chunk_sym<<<(unsigned)((cap + 255) / 256), 256, 0, ws>>>(h->symoff.as<uint32_t>(), cr, h->d_scalars, cap, cr + (cap + 1));
   FQ28_LAUNCH_CHECK(h);
   FQ28_CUDA(h, cudaMemcpyAsync(h->h_scalars, h->d_scalars, sizeof(uint64_t), cudaMemcpyDeviceToHost, ws));
   FQ28_TRY(check_status(h, "record splitting", ws));
