@@ -237,3 +237,60 @@ int dec2h_qual(const uint8_t *ft, const uint8_t *stream, uint32_t len, unsigned 
 }
 
 }  // extern "C"
+
+#ifdef DEC2_FUZZ_MAIN
+// Corrupt-stream fuzzer, built with -fsanitize=address,undefined by tests/test_dec2_host.py:
+// the decoders must never touch memory outside their shared-memory image, their tables or the
+// chunk's output, whatever the stream bits say (compute-sanitizer is not available on the GPU
+// pool; this is the same source).  Input: a blob written by the test (FreqTable image, one
+// chunk's stream, its record lengths); the stream is decoded intact, then with random bit
+// flips, byte overwrites and truncations.  Exit code 0 unless the intact stream fails.
+#include <stdio.h>
+int main(int argc, char **argv) {
+  if (argc < 3) return 2;
+  FILE *f = fopen(argv[1], "rb");
+  if (!f) return 2;
+  uint32_t hd[6];
+  if (fread(hd, 4, 6, f) != 6 || hd[0] != 0x46513238u) return 2;
+  const uint32_t kind = hd[1], ft_bytes = hd[2], len = hd[3], n_rec = hd[4], out_bytes = hd[5];
+  std::vector<uint8_t> ft(ft_bytes), stream(len);
+  std::vector<uint16_t> readlens(n_rec), hdr_lens(n_rec);
+  if (fread(ft.data(), 1, ft_bytes, f) != ft_bytes || fread(stream.data(), 1, len, f) != len ||
+      fread(readlens.data(), 2, n_rec, f) != n_rec || fread(hdr_lens.data(), 2, n_rec, f) != n_rec)
+    return 2;
+  fclose(f);
+  const unsigned iters = (unsigned)atoi(argv[2]);
+  auto run = [&](const std::vector<uint8_t> &s, uint32_t l) -> int {
+    std::vector<char> out(out_bytes, 0);   // exactly the chunk's bytes: an overrun is a heap overflow
+    if (kind == 0) return dec2h_seq(ft.data(), s.data(), l, 0, readlens.data(), hdr_lens.data(), n_rec, out.data());
+    return dec2h_qual(ft.data(), s.data(), l, 0, readlens.data(), hdr_lens.data(), n_rec, out.data(), nullptr);
+  };
+  unsigned long long rng = 0x9E3779B97F4A7C15ull ^ len;
+  auto next = [&]() { rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17; return rng; };
+  unsigned ok = 0, bad = 0;
+  for (int layout = 0; layout < (kind == 1 ? 2 : 1); layout++) {
+    dec2h_set_win(layout);
+    if (run(stream, len) != 0) { fprintf(stderr, "intact stream failed (layout %d)\n", layout); return 1; }
+    for (unsigned it = 0; it < iters; it++) {
+      std::vector<uint8_t> s = stream;
+      uint32_t l = len;
+      const unsigned mode = (unsigned)(next() % 4);
+      if (mode == 0) {                       // a few bit flips anywhere
+        for (unsigned k = 0, n = 1 + (unsigned)(next() % 8); k < n; k++) s[next() % len] ^= (uint8_t)(1u << (next() % 8));
+      } else if (mode == 1) {                // the tail (initial states, end mark) overwritten
+        for (unsigned k = 0, n = 1 + (unsigned)(next() % 16); k < n && k < len; k++) s[len - 1 - k] = (uint8_t)next();
+      } else if (mode == 2) {                // truncated
+        l = (uint32_t)(next() % len);
+        if (l == 0) l = 1;
+      } else {                               // a run of random bytes
+        const size_t a = next() % len, n = 1 + next() % 64;
+        for (size_t k = a; k < len && k < a + n; k++) s[k] = (uint8_t)next();
+      }
+      (run(s, l) == 0 ? ok : bad)++;
+    }
+  }
+  dec2h_set_win(0);
+  printf("fuzz: %u corrupted streams decoded to the end mark, %u rejected\n", ok, bad);
+  return 0;
+}
+#endif

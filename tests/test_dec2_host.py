@@ -230,3 +230,41 @@ def test_corrupt_streams_are_rejected_not_crashing(oracle, D):
         b = D.dec2h_qual(_p(fq), _p(qual), qual.size, 0, _p(readlens), _p(hdr_lens), n, _p(out), None)
         bad += (a != 0) + (b != 0)
     assert bad >= 2  # the truncated pair at least; flips inside symbol fields may go unnoticed
+
+
+def test_corrupt_streams_under_asan(oracle, tmp_path):
+    """The decoders on corrupted streams (bit flips, overwritten tails, truncations, random runs),
+    compiled with AddressSanitizer + UBSan: whatever the bits say, no access outside the
+    shared-memory image, the tables or the chunk's output.  (compute-sanitizer is not available
+    on the GPU pool; fq28_dec2.cuh is the same source for the device.)"""
+    import struct
+    import synth
+
+    exe = str(tmp_path / "dec2_fuzz")
+    r = subprocess.run(["g++", "-x", "c++", "-std=c++17", "-O1", "-g", "-fsanitize=address,undefined", "-fno-omit-frame-pointer",
+                        "-Wno-unknown-pragmas", "-DDEC2_FUZZ_MAIN", SRC, "-o", exe, "-L" + os.path.join(ROOT, "oracle"),
+                        "-lfq28_oracle", "-Wl,-rpath," + os.path.join(ROOT, "oracle")], capture_output=True, text=True)
+    if r.returncode != 0 and "asan" in (r.stderr or "").lower():
+        pytest.skip("no AddressSanitizer runtime in this toolchain")
+    assert r.returncode == 0, r.stderr[-2000:]
+    cases = {"fixture": (load_fixture("SRR065390_sub_1"), 12), "hiseq": (synth.illumina(0, 250, profile="hiseq").numpy(), 60),
+             "novaseq": (synth.illumina(0, 250, profile="novaseq").numpy(), 60)}
+    for name, (d, iters) in cases.items():
+        fs, fq = tables_of(oracle, d)
+        recs, used = oracle.parse_records(d)
+        body = d[:used]
+        enc = oracle.Codec(fs, fq).encode_chunk(body, recs)
+        readlens = np.ascontiguousarray(enc["readlens"], dtype="<u2")
+        hdr_lens = recs["hdr_len"].astype("<u2")
+        for kind, ft, stream in ((0, fs, enc["seq"]), (1, fq, enc["qual"])):
+            blob = tmp_path / f"{name}_{kind}.bin"
+            with open(blob, "wb") as f:
+                f.write(struct.pack("<6I", 0x46513238, kind, ft.size, stream.size, len(recs), body.size))
+                f.write(ft.tobytes())
+                f.write(np.ascontiguousarray(stream).tobytes())
+                f.write(readlens.tobytes())
+                f.write(hdr_lens.tobytes())
+            env = dict(os.environ, ASAN_OPTIONS="detect_leaks=0:abort_on_error=0", UBSAN_OPTIONS="halt_on_error=1:print_stacktrace=1")
+            p = subprocess.run([exe, str(blob), str(iters)], capture_output=True, text=True, env=env, timeout=600)
+            assert p.returncode == 0 and "Sanitizer" not in p.stderr and "runtime error" not in p.stderr, (name, kind, p.stderr[-3000:])
+            assert "fuzz:" in p.stdout
